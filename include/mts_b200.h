@@ -1,0 +1,152 @@
+/* mts_b200.h -- C ABI of libmts_b200.so: the B200 (sm_100a) hot path of the multimodal topic segmenter.
+ *
+ * The reference (Ighina/MultimodalTopicSegmentation) is pure Python: it has no FFI of its own.  The
+ * boundary it offers for this path is the Python duck type that `TextSegmenter` calls on `self.model`
+ * (models/lightning_model.py:293-305, 333-349, 587-594, 682).  Each entry point below replaces the
+ * library call(s) that one reference line makes, so that the host-side mirror in
+ * multimodaltopicsegmentation_b200/modules.py can keep the reference's signatures.  INTEGRATION.md shows
+ * the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; tensors are dense row-major
+ *     fp32 unless stated; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no allocation, no ownership transfer, no host synchronisation inside any call;
+ *   - return value: 0 on success, a positive cudaError_t on a CUDA failure, a negative MTS_E_* code on a
+ *     rejected argument.  Nothing falls back to the CPU.
+ */
+#ifndef MTS_B200_H_
+#define MTS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTS_E_BADARG (-1)    /* null pointer / non-positive size */
+#define MTS_E_UNSUPPORTED (-2) /* shape outside what the kernels implement (message via mts_last_error) */
+#define MTS_E_NODEVICE (-3)  /* no sm_100 device */
+
+int mts_version(void);                 /* ABI version, bumped on any signature change */
+const char *mts_last_error(void);      /* static string describing the last negative return on this thread */
+int mts_device_ok(void);               /* 0 when the current device is compute capability 10.x */
+
+/* ------------------------------------------------------------------------------------------------
+ * Operand preparation.  3xTF32 GEMMs take every fp32 operand as a (hi, lo) pair of TF32-representable
+ * fp32 matrices, K padded with zeros to a multiple of 32.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Early fusion (utils/load_datasets_precomputed.py:158-161 `torch.cat(embs, axis=-1)`) fused with the
+ * time crop to max(lengths) and the hi/lo split:  out[b*T + t, :] = [src1[b,t,:D1] | src2[b,t,:D2] | 0-pad].
+ * src batch strides are in elements (so a [B, T_in, D] tensor cropped to T <= T_in needs no copy);
+ * src2 may be NULL (D2 = 0).  hi/lo: [B*T, Kp], Kp % 32 == 0, Kp >= D1 + D2. */
+int mts_pack_rows_split(const float *src1, int64_t bstride1, int D1, const float *src2, int64_t bstride2, int D2,
+                        int B, int T, int Kp, float *hi, float *lo, void *stream);
+
+/* Generic 2-D split: src [rows, cols] (row stride `ld`) -> hi/lo [rows, Kp]. */
+int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, int Kp, float *hi, float *lo, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ GELU), fp32 in / fp32 out.
+ *   replaces: nn.LSTM's input projection (models/NeuralArchitectures.py:113), nn.Linear heads
+ *   (models/CRF.py:299-310) and HF Longformer's dense layers (modeling_longformer.py:513-515,1067,1112,1126).
+ * mts_gemm_tf32x3: tcgen05 + TMA, error-compensated 3xTF32 (fp32-grade accuracy).  A_hi/A_lo [M,Kp],
+ *   B_hi/B_lo [N,Kp] as produced above; ldc in elements; epilogue: 0 none, 1 +bias, 2 +bias then GELU(erf).
+ *   accumulate != 0 adds into C (used for split weight-gradient sums).
+ * mts_gemm_f32: exact-fp32 CUDA-core GEMM, C[M,N] (+)= op(A) op(B), used for the gradient products whose
+ *   reduction runs over sentences and to validate the tensor-core kernel.  layout 0: A[M,K] B[N,K]^T;
+ *   2: A[M,K] B[K,N]; 3: A[K,M]^T B[K,N].  splits > 1 = split-K with atomics.  shift != 0 (layouts 2,3) reads
+ *   B row k as row k+shift, zero unless 0 <= (k % T) + shift < lengths[k / T]: the h_{t-1}/h_{t+1} operand of
+ *   dW_hh without a shifted copy of the hidden states. */
+int mts_gemm_tf32x3(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
+                    float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, void *stream);
+int mts_gemm_f32(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias, float *C, int64_t ldc,
+                 int M, int N, int K, int layout, int epilogue, int accumulate, int splits, int shift, int T,
+                 const int32_t *lengths, void *stream);
+/* column sums out[n] (+)= sum_m X[m,n]  (bias gradients); ws >= mts_colsum_ws_bytes(M, N) bytes */
+int64_t mts_colsum_ws_bytes(int M, int N);
+int mts_colsum(const float *X, int64_t ld, int M, int N, float *out, int accumulate, void *ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LSTM recurrence  (torch.nn.LSTM as called at models/NeuralArchitectures.py:39-43,113-115).
+ * One call runs BOTH directions of one layer (and, for late fusion, of `n_enc` independent encoders
+ * laid out back to back) over a batch of variable-length episodes.
+ *
+ *   gx      [n_enc, B*T, 2*4H]  input projection + (b_ih + b_hh); columns = [dir][gate i,f,g,o][unit]
+ *   w_hh    [n_enc, 2, 4H, H]   recurrent weights (PyTorch layout, forward then reverse)
+ *   lengths [B] int32           valid length per episode, 1 <= len <= T
+ *   y       [B, T, n_enc*2H]    hidden states, zero at t >= len_b (pad_packed_sequence semantics);
+ *                               columns = [enc][dir][unit]  (late fusion's torch.cat, models/CRF.py:425)
+ *   gates   [n_enc, 2, B, T, 5, H] or NULL: i,f,g,o (post-activation) and c saved for the backward pass
+ *   order   [B] int32 or NULL   episode ids sorted by decreasing length: tile i of the cluster kernel takes
+ *                               order[8i .. 8i+7], so that the episodes of a tile finish together
+ * H == 256 runs the persistent cluster kernel (W_hh resident in registers across 8 CTAs, h exchanged
+ * through distributed shared memory); other H run a generic kernel. */
+int mts_lstm_rec_fwd(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
+                     int B, int T, int H, float *y, float *gates, void *stream);
+
+/* Backward through time of the same layer.
+ *   dy      [B, T, n_enc*2H]    gradient w.r.t. y (ignored at t >= len_b)
+ *   gates   as saved by the forward call;  y as produced by the forward call (h_{t-1} source)
+ *   dgx     [n_enc, B*T, 2*4H]  gradient w.r.t. gx (zero at padded steps).  The weight gradients are GEMMs
+ *                               over dgx issued by the caller: dW_ih = dgx^T X, dW_hh = dgx^T H_prev
+ *                               (mts_gemm_f32 layout 3 with a row shift), db = mts_colsum(dgx).
+ */
+int mts_lstm_rec_bwd(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
+                     const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Head + decode  (models/CRF.py:340,361-369: Linear then sigmoid/softmax threshold)
+ *   feats [B,T,F] (row stride F), w [n_out,F], bias [n_out] -> scores [B,T,n_out];
+ *   tags [B,T] uint8 = (n_out==1 ? sigmoid(s) : softmax(s)[1]) > th  for t < len_b, 0xFF beyond.
+ *   tags may be NULL (training).  n_out in {1,2}.
+ * ---------------------------------------------------------------------------------------------- */
+int mts_head_fwd(const float *feats, const float *w, const float *bias, const int32_t *lengths, int B, int T, int F,
+                 int n_out, float th, float *scores, uint8_t *tags, void *stream);
+/* d_scores [B,T,n_out] -> d_feats [B,T,F], d_w [n_out,F], d_bias [n_out] (all overwritten);
+ * ws: >= mts_head_bwd_ws_bytes() bytes of scratch. */
+int64_t mts_head_bwd_ws_bytes(int B, int T, int F, int n_out);
+int mts_head_bwd(const float *d_scores, const float *feats, const float *w, int B, int T, int F, int n_out,
+                 float *d_feats, float *d_w, float *d_bias, void *ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Segmentation losses over the valid (un-padded) sentences of a batch (models/CRF.py:342-356).
+ *   kind 0: sigmoid focal loss on logits (models/focal_loss.py:38-57), alpha/gamma as given
+ *   kind 1: Sigmoid + nn.BCELoss (log clamped at -100)
+ *   kind 2: CrossEntropyLoss(ignore_index=-1) on [B*T,2] logits over ALL B*T positions
+ *   scores [B,T,n_out]; target [B,*] float with row stride ldt (the collater's tgt_tokens);
+ *   inv_count: 1/N with N = sum(lengths) (kinds 0,1) -- passed in so data-parallel ranks can use the
+ *   GLOBAL N; kind 2 counts its own non-ignored targets when inv_count <= 0.
+ *   loss_out: 2 floats {loss, number of counted positions}.  partial: >= 2*1024 floats of scratch.
+ * ---------------------------------------------------------------------------------------------- */
+int mts_seg_loss_fwd(const float *scores, const float *target, int64_t ldt, const int32_t *lengths, int B, int T,
+                     int kind, float alpha, float gamma, float inv_count, float *loss_out, float *partial,
+                     void *stream);
+/* d_scores = grad_out * d loss / d scores, zero at padded / ignored positions.  count_dev: device pointer to
+ * the count written by the forward call (loss_out + 1), used when inv_count <= 0; may be NULL otherwise. */
+int mts_seg_loss_bwd(const float *scores, const float *target, int64_t ldt, const int32_t *lengths, int B, int T,
+                     int kind, float alpha, float gamma, float inv_count, const float *count_dev,
+                     const float *grad_out, float *d_scores, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear-chain CRF (models/CRF.py:98-240) on emissions [B,L,C], C = tags + 2 (START = C-2, STOP = C-1),
+ * trans[i*C + j] = score of j -> i, lengths int32.  3 <= C <= 8.
+ * ---------------------------------------------------------------------------------------------- */
+/* Viterbi (CRF.py:172-216): sequential fp32 max-plus recurrence, first maximum wins; on-device back-trace.
+ *   best_score [B]; paths [B,L] int32, -1 beyond len_b; bp_ws: B*L uint32 of scratch (packed back-pointers). */
+int mts_crf_viterbi(const float *emis, const int32_t *lengths, const float *trans, int B, int L, int C,
+                    float *best_score, int32_t *paths, uint32_t *bp_ws, void *stream);
+/* NLL pieces (CRF.py:130-170, 218-240): log partition, gold-path score; alphas [B,L,C] saved for backward.
+ *   tags [B,*] float (row stride ldt, values in [0, C-2)). */
+int mts_crf_nll_fwd(const float *emis, const float *tags, int64_t ldt, const int32_t *lengths, const float *trans,
+                    int B, int L, int C, float *log_z, float *gold, float *alphas, void *stream);
+/* scale_dev [B]: d loss / d log_z[b] on the device (= -d loss / d gold[b]; grad_out / B for the mean).
+ * d_emis [B,L,C] (overwritten, zero at padded steps); d_trans [C,C] (overwritten). */
+int mts_crf_nll_bwd(const float *emis, const float *tags, int64_t ldt, const int32_t *lengths, const float *trans,
+                    const float *alphas, const float *log_z, int B, int L, int C, const float *scale_dev, float *d_emis,
+                    float *d_trans, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTS_B200_H_ */

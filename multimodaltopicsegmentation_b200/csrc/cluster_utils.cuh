@@ -1,0 +1,57 @@
+// mbarrier / distributed-shared-memory helpers and the constants shared by the H = 256 LSTM cluster kernels.
+#pragma once
+#include "common.cuh"
+
+namespace mts {
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, DSMEM
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, float4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// H = 256 cluster kernel
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kH = 256;          // hidden size served by the cluster kernel
+constexpr int kCluster = 8;      // CTAs per cluster
+constexpr int kUnits = kH / kCluster;  // 32 hidden units (= 128 gate rows) per CTA
+constexpr int kBT = 8;           // episodes per tile
+constexpr int kThreads = 256;
+constexpr int kHBufFloats = kH * kBT;  // one h_t for the whole tile: 2048 floats = 8 KB
+
+// shared-memory layout of one h buffer: [half (episodes 0-3 / 4-7)][kk 0..31][ks 0..7][4 episodes]
+// with k = ks*32 + kk.  A quarter-warp (8 lanes = 8 k-slices) reads 128 contiguous bytes: conflict-free.
+__device__ __forceinline__ int hbuf_index(int k, int b) { return (((b >> 2) * 32 + (k & 31)) * 8 + (k >> 5)) * 4 + (b & 3); }
+
+
+}  // namespace mts

@@ -1,0 +1,333 @@
+// tcgen05 + TMA GEMM with error-compensated 3xTF32 accumulation (fp32-grade accuracy on the 5th-gen tensor
+// cores, which have no fp32-input mode).   C[M,N] = A[M,K] * B[N,K]^T (+bias) (+GELU)
+//
+//   A = A_hi + A_lo, B = B_hi + B_lo with *_hi the top 19 bits (what kind::tf32 reads) and *_lo the exact
+//   fp32 remainder (<= 13 significant bits).  D += A_hi B_hi + A_hi B_lo + A_lo B_hi ; the dropped
+//   A_lo B_lo term is ~2^-22 relative.  Operands come pre-split from pack.cu, K padded to 32.
+//
+// Structure (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0   : TMA producer  -- 4 tiled tensor maps (SWIZZLE_128B, 32 fp32 = 128 B inner box) per k-block
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs of 128 x BN x 8 per k-block)
+//   warps 2-5: epilogue -- tcgen05.ld 32x32b from the 2-deep TMEM accumulator ring, bias / GELU, global store
+// Pipelines: smem full/empty mbarrier ring (TMA <-> MMA), TMEM full/empty ring (MMA <-> epilogue).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mts {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;      // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TC_UMMA_K = 8;   // tf32
+constexpr int TC_THREADS = 192;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN == 256) ? 2 : 3;
+  static constexpr int kABytes = TC_BM * TC_BK * 4;       // 16 KB per half
+  static constexpr int kBBytes = BN * TC_BK * 4;          // 16/32 KB per half
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kTmemCols = 2 * BN;                // two accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool bar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  while (!bar_try_wait(bar, parity)) {
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 (SW128) [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO: unused for swizzled K-major, canonical value 1
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: 8 rows x 128 B between row groups
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major (InstrDescriptor in the same header)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
+                       int epilogue, int accumulate) {
+  using Cfg = TcCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * Cfg::kStageBytes);
+  uint64_t *full_bar = bars;                    // [kStages]  TMA -> MMA
+  uint64_t *empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
+  uint64_t *tfull_bar = bars + 2 * kStages;     // [2]        MMA -> epilogue
+  uint64_t *tempty_bar = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = Kp / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { bar_init(s_u32(&full_bar[s]), 1); bar_init(s_u32(&empty_bar[s]), 1); }
+    for (int a = 0; a < 2; ++a) { bar_init(s_u32(&tfull_bar[a]), 1); bar_init(s_u32(&tempty_bar[a]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: whole warp, address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
+                 "n"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          bar_wait(s_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = s_u32(&full_bar[stage]);
+          bar_expect_tx(fb, Cfg::kStageBytes);
+          const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
+          tma_load_2d(base, &map_a_hi, kb * TC_BK, m0, fb);
+          tma_load_2d(base + Cfg::kABytes, &map_a_lo, kb * TC_BK, m0, fb);
+          tma_load_2d(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
+          tma_load_2d(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * TC_BK, n0, fb);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        bar_wait(s_u32(&tempty_bar[acc_stage]), acc_phase ^ 1);  // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          bar_wait(s_u32(&full_bar[stage]), phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t a_hi = make_desc_sw128(base), a_lo = make_desc_sw128(base + Cfg::kABytes);
+          const uint64_t b_hi = make_desc_sw128(base + 2 * Cfg::kABytes);
+          const uint64_t b_lo = make_desc_sw128(base + 2 * Cfg::kABytes + Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);  // +32 B per k-step inside the swizzle row
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(s_u32(&empty_bar[stage]));  // smem slot free once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(s_u32(&tfull_bar[acc_stage]));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+      bar_wait(s_u32(&tfull_bar[acc_stage]), acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + q * 32 + lane;
+      float *c_row = C + (int64_t)m * ldc + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN + c0), v);
+        if (m < M) {
+          const bool full = (n0 + c0 + 32 <= N) && ((ldc & 3) == 0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (epilogue >= 1 && n < N) v[j] += __ldg(bias + n);
+            if (epilogue == 2) v[j] = gelu_erf(v[j]);
+          }
+          if (full) {
+            float4 *dst = reinterpret_cast<float4 *>(c_row + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (accumulate) { const float4 p = dst[j]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+              dst[j] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < N) c_row[c0 + j] = accumulate ? c_row[c0 + j] + v[j] : v[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) bar_arrive(s_u32(&tempty_bar[acc_stage]));
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap *map, const float *ptr, int rows, int Kp, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled not available"); return MTS_E_NODEVICE; }
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled failed"); return MTS_E_BADARG; }
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
+                     float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, A_hi, M, Kp, TC_BM))) return rc;
+  if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM))) return rc;
+  if ((rc = make_map(&mb_hi, B_hi, N, Kp, BN))) return rc;
+  if ((rc = make_map(&mb_lo, B_lo, N, Kp, BN))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  gemm_tf32x3_kernel<BN><<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc,
+                                                                   epilogue, accumulate);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mts
+
+using namespace mts;
+
+extern "C" int mts_gemm_tf32x3(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo,
+                               const float *bias, float *C, int M, int N, int Kp, int64_t ldc, int epilogue,
+                               int accumulate, void *stream) {
+  MTS_REQUIRE(A_hi && A_lo && B_hi && B_lo && C, MTS_E_BADARG, "gemm_tf32x3: null pointer");
+  MTS_REQUIRE(M > 0 && N > 0 && Kp > 0, MTS_E_BADARG, "gemm_tf32x3: empty shape");
+  MTS_REQUIRE(Kp % TC_BK == 0, MTS_E_UNSUPPORTED, "gemm_tf32x3: Kp must be a multiple of 32 (use mts_split_tf32)");
+  MTS_REQUIRE(epilogue == 0 || bias, MTS_E_BADARG, "gemm_tf32x3: epilogue needs a bias");
+  MTS_REQUIRE((((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo) & 15) == 0, MTS_E_BADARG,
+              "gemm_tf32x3: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N >= 256) return launch_tc<256>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st);
+  return launch_tc<128>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st);
+}

@@ -1,0 +1,265 @@
+// LSTM recurrence, backward through time.  The reference has no hand-written backward: this must equal
+// autograd through torch.nn.LSTM as called at models/NeuralArchitectures.py:113 (SURVEY.md section 8a').
+//
+// Produces dgx = d loss / d (gate pre-activations) for every valid step; the weight gradients are GEMMs
+// over dgx (dW_ih = dgx^T X, dW_hh = dgx^T H_prev, db = colsum dgx) issued by the host wrapper.
+//
+// H == 256: persistent cluster kernel mirroring the forward one.  CTA r owns the cells of units
+// [32r, 32r+32) x 8 episodes.  Per step:
+//   cell phase   : dh = dy + sum of the 8 partial W_hh^T products received last step; gate derivatives;
+//                  dp (4 x 32 x 8) -> shared memory and -> dgx in HBM;
+//   matvec phase : partial dh_prev[k][e] = sum over this CTA's 128 gate rows of W_hh[row][k] dp[row][e]
+//                  (W_hh slice register-resident: 32 rows x 4 k per thread), reduced across the 4 row
+//                  slices by recursive halving, then pushed (st.async + mbarrier) to the CTA that owns unit k
+//                  -- a reduce-scatter through distributed shared memory, 8 KB per CTA per step.
+#include <cooperative_groups.h>
+
+#include "cluster_utils.cuh"
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mts {
+
+struct GateGrads {
+  float dpi, dpf, dpg, dpo, dc_prev;
+};
+
+__device__ __forceinline__ GateGrads lstm_cell_bwd(float dh, float dc_in, float ig, float fg, float gg, float og,
+                                                   float c, float c_prev) {
+  const float tc = tanhf(c);
+  const float d_o = dh * tc;
+  const float dc = dc_in + dh * og * (1.0f - tc * tc);
+  GateGrads r;
+  r.dpi = dc * gg * ig * (1.0f - ig);
+  r.dpf = dc * c_prev * fg * (1.0f - fg);
+  r.dpg = dc * ig * (1.0f - gg * gg);
+  r.dpo = d_o * og * (1.0f - og);
+  r.dc_prev = dc * fg;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generic kernel: grid (B, 2, n_enc), 256 threads; smem dh[H], dc[H], dp[4H]
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lstm_bwd_generic_kernel(const float *__restrict__ dy,
+                                                               const float *__restrict__ gates,
+                                                               const float *__restrict__ w_hh,
+                                                               const int32_t *__restrict__ lengths, int B, int T,
+                                                               int H, int n_enc, float *__restrict__ dgx) {
+  extern __shared__ float smem[];
+  float *dh = smem, *dc = smem + H, *dp = smem + 2 * H;
+  const int b = blockIdx.x, dir = blockIdx.y, enc = blockIdx.z;
+  const int len = min(max(lengths[b], 0), T);
+  const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * H * H;
+  const int ycols = n_enc * 2 * H;
+  const float *gs_b = gates + (((size_t)enc * 2 + dir) * B + b) * T * 5 * H;
+  float *dgx_b = dgx + (size_t)enc * B * T * 8 * H + (size_t)b * T * 8 * H + (size_t)dir * 4 * H;
+  for (int u = threadIdx.x; u < H; u += blockDim.x) { dh[u] = 0.0f; dc[u] = 0.0f; }
+  __syncthreads();
+  for (int s = 0; s < len; ++s) {
+    const int t = dir ? s : len - 1 - s;
+    const int tp = dir ? t + 1 : t - 1;  // the step the forward pass visited just before t
+    const bool has_prev = dir ? (tp < len) : (tp >= 0);
+    const float *gs = gs_b + (size_t)t * 5 * H;
+    for (int u = threadIdx.x; u < H; u += blockDim.x) {
+      const float dht = dy[((size_t)b * T + t) * ycols + (size_t)enc * 2 * H + dir * H + u] + dh[u];
+      const float c_prev = has_prev ? gs_b[(size_t)tp * 5 * H + 4 * H + u] : 0.0f;
+      const GateGrads g = lstm_cell_bwd(dht, dc[u], gs[u], gs[H + u], gs[2 * H + u], gs[3 * H + u], gs[4 * H + u], c_prev);
+      dc[u] = g.dc_prev;
+      dp[u] = g.dpi; dp[H + u] = g.dpf; dp[2 * H + u] = g.dpg; dp[3 * H + u] = g.dpo;
+      float *o = dgx_b + (size_t)t * 8 * H;
+      o[u] = g.dpi; o[H + u] = g.dpf; o[2 * H + u] = g.dpg; o[3 * H + u] = g.dpo;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < H; k += blockDim.x) {
+      float acc = 0.0f;
+      for (int r = 0; r < 4 * H; ++r) acc = fmaf(__ldg(W + (size_t)r * H + k), dp[r], acc);
+      dh[k] = acc;
+    }
+    __syncthreads();
+  }
+  for (int t = len; t < T; ++t)
+    for (int r = threadIdx.x; r < 4 * H; r += blockDim.x) dgx_b[(size_t)t * 8 * H + r] = 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// H = 256 cluster kernel
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kDpStride = 8;             // floats per dp row (8 episodes)
+constexpr int kDpFloats = 128 * 8 + 4 * 8;  // 128 rows + 8 floats of padding per 32-row slice (bank spread)
+__device__ __forceinline__ int dp_row_base(int lr) { return lr * kDpStride + (lr >> 5) * 8; }
+
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
+    lstm_bwd_cluster_kernel(const float *__restrict__ dy, const float *__restrict__ gates,
+                            const float *__restrict__ w_hh, const int32_t *__restrict__ lengths,
+                            const int32_t *__restrict__ order, int B, int T, int n_enc, int n_tiles,
+                            float *__restrict__ dgx) {
+  __shared__ __align__(16) float recv[2][kCluster][kUnits][kBT];  // partial dh from every CTA, double buffered
+  __shared__ __align__(16) float dpbuf[2][kDpFloats];  // double buffered: step s+1 writes while laggards read step s
+  __shared__ __align__(8) uint64_t full_bar[2];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t rank = cluster.block_rank();
+  const int cid = blockIdx.x / kCluster;
+  const int tile = cid % n_tiles;
+  const int dir = (cid / n_tiles) & 1;
+  const int enc = cid / (2 * n_tiles);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- cell role: (unit u of this CTA, episode slot e) -----------------------------------------------------
+  const int u = tid >> 3, e = tid & 7;
+  const int unit = rank * kUnits + u;
+  const int slot = tile * kBT + e;
+  const int b = (slot < B) ? (order ? order[slot] : slot) : -1;
+  const int len = (b >= 0) ? min(max(lengths[b], 0), T) : 0;
+  int nsteps = len;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
+
+  // ---- matvec role: (k-group kg: k = 4 kg .. 4 kg + 3, row slice rs = gate) ----------------------------------
+  const int rs = lane & 3, kg = warp * 8 + (lane >> 2);
+  float Wb[32][4];
+  {
+    const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * kH * kH;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(rs * kH + rank * kUnits + j) * kH + kg * 4));
+      Wb[j][0] = v.x; Wb[j][1] = v.y; Wb[j][2] = v.z; Wb[j][3] = v.w;
+    }
+  }
+
+  for (int i = tid; i < 2 * kCluster * kUnits * kBT; i += kThreads) (&recv[0][0][0][0])[i] = 0.0f;
+  for (int i = tid; i < 2 * kDpFloats; i += kThreads) (&dpbuf[0][0])[i] = 0.0f;
+  if (tid == 0) {
+    mbar_init(smem_u32(&full_bar[0]), 1);
+    mbar_init(smem_u32(&full_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster.sync();
+
+  // my partial sums for k = 4 kg + rs go to CTA `warp`, unit row `lane` of its recv[.][rank]
+  const uint32_t raddr0 = mapa(smem_u32(&recv[0][rank][lane][0]), (uint32_t)warp);
+  const uint32_t rbar0 = mapa(smem_u32(&full_bar[0]), (uint32_t)warp);
+  constexpr uint32_t kRecvBytes = kCluster * kUnits * kBT * 4;  // 8 KB
+
+  const int ycols = n_enc * 2 * kH;
+  const float *dy_cell = (b >= 0) ? dy + (size_t)b * T * ycols + (size_t)enc * 2 * kH + dir * kH + unit : nullptr;
+  const float *g_cell = (b >= 0) ? gates + ((((size_t)enc * 2 + dir) * B + b) * T) * 5 * kH + unit : nullptr;
+  float *dgx_cell = (b >= 0) ? dgx + (size_t)enc * B * T * 8 * kH + (size_t)b * T * 8 * kH + dir * 4 * kH + unit : nullptr;
+
+  // time visited at backward step s, and prefetch of its saved activations
+  auto time_at = [&](int s) { return dir ? s : len - 1 - s; };
+  float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, dyv = 0.f, c_cur = 0.f, c_nxt = 0.f;
+  if (len > 0) {
+    const float *gs = g_cell + (size_t)time_at(0) * 5 * kH;
+    ig = __ldg(gs); fg = __ldg(gs + kH); gg = __ldg(gs + 2 * kH); og = __ldg(gs + 3 * kH); c_cur = __ldg(gs + 4 * kH);
+    dyv = __ldg(dy_cell + (size_t)time_at(0) * ycols);
+    if (len > 1) c_nxt = __ldg(g_cell + (size_t)time_at(1) * 5 * kH + 4 * kH);
+  }
+  float dc = 0.0f;
+
+  for (int s = 0; s < nsteps; ++s) {
+    const int p = s & 1;
+    if (tid == 0 && s + 1 < nsteps) mbar_arrive_expect_tx(smem_u32(&full_bar[p ^ 1]), kRecvBytes);
+    if (s > 0) mbar_wait(smem_u32(&full_bar[p]), ((s - 1) >> 1) & 1);
+
+    // ---- cell phase ----------------------------------------------------------------------------------------
+    const bool active = s < len;
+    GateGrads g{0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      float dht = dyv;
+      if (s > 0) {
+#pragma unroll
+        for (int src = 0; src < kCluster; ++src) dht += recv[p][src][u][e];
+      }
+      g = lstm_cell_bwd(dht, dc, ig, fg, gg, og, c_cur, (s + 1 < len) ? c_nxt : 0.0f);
+      dc = g.dc_prev;
+      float *o = dgx_cell + (size_t)time_at(s) * 8 * kH;
+      o[0] = g.dpi; o[kH] = g.dpf; o[2 * kH] = g.dpg; o[3 * kH] = g.dpo;
+    }
+    dpbuf[p][dp_row_base(0 * 32 + u) + e] = g.dpi;
+    dpbuf[p][dp_row_base(1 * 32 + u) + e] = g.dpf;
+    dpbuf[p][dp_row_base(2 * 32 + u) + e] = g.dpg;
+    dpbuf[p][dp_row_base(3 * 32 + u) + e] = g.dpo;
+    if (s + 1 < len) {  // prefetch the next step's activations (and the cell state two steps ahead)
+      const float *gs = g_cell + (size_t)time_at(s + 1) * 5 * kH;
+      ig = __ldg(gs); fg = __ldg(gs + kH); gg = __ldg(gs + 2 * kH); og = __ldg(gs + 3 * kH);
+      dyv = __ldg(dy_cell + (size_t)time_at(s + 1) * ycols);
+      c_cur = c_nxt;
+      if (s + 2 < len) c_nxt = __ldg(g_cell + (size_t)time_at(s + 2) * 5 * kH + 4 * kH);
+    }
+    __syncthreads();
+    if (s + 1 >= nsteps) break;  // the last step's dh_prev has no consumer
+
+    // ---- matvec phase: 32 rows (gate rs) x 4 k x 8 episodes ------------------------------------------------
+    float acc[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int x = 0; x < 8; ++x) acc[q][x] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float4 da = *reinterpret_cast<const float4 *>(&dpbuf[p][dp_row_base(rs * 32 + j)]);
+      const float4 db = *reinterpret_cast<const float4 *>(&dpbuf[p][dp_row_base(rs * 32 + j) + 4]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float w = Wb[j][q];
+        acc[q][0] = fmaf(w, da.x, acc[q][0]); acc[q][1] = fmaf(w, da.y, acc[q][1]);
+        acc[q][2] = fmaf(w, da.z, acc[q][2]); acc[q][3] = fmaf(w, da.w, acc[q][3]);
+        acc[q][4] = fmaf(w, db.x, acc[q][4]); acc[q][5] = fmaf(w, db.y, acc[q][5]);
+        acc[q][6] = fmaf(w, db.z, acc[q][6]); acc[q][7] = fmaf(w, db.w, acc[q][7]);
+      }
+    }
+    // reduce over the 4 row slices (gates); lane rs keeps k = 4 kg + rs
+    float r1[2][8], out[8];
+    const bool b1 = rs & 2, b0 = rs & 1;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const float keep = b1 ? acc[2 + q][x] : acc[q][x];
+        const float send = b1 ? acc[q][x] : acc[2 + q][x];
+        r1[q][x] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const float keep = b0 ? r1[1][x] : r1[0][x];
+      const float send = b0 ? r1[0][x] : r1[1][x];
+      out[x] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    const uint32_t boff = (uint32_t)(p ^ 1) * kRecvBytes, moff = (uint32_t)(p ^ 1) * 8;
+    st_async_v4(raddr0 + boff, make_float4(out[0], out[1], out[2], out[3]), rbar0 + moff);
+    st_async_v4(raddr0 + boff + 16, make_float4(out[4], out[5], out[6], out[7]), rbar0 + moff);
+  }
+  // zero the padded tail of my (episode, unit) gate columns
+  if (b >= 0)
+    for (int t = len; t < T; ++t) {
+      float *o = dgx_cell + (size_t)t * 8 * kH;
+      o[0] = 0.0f; o[kH] = 0.0f; o[2 * kH] = 0.0f; o[3 * kH] = 0.0f;
+    }
+  cluster.sync();
+}
+
+}  // namespace mts
+
+using namespace mts;
+
+extern "C" int mts_lstm_rec_bwd(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
+                                const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream) {
+  MTS_REQUIRE(dy && gates && w_hh && lengths && dgx, MTS_E_BADARG, "lstm_rec_bwd: null pointer");
+  MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0 && H > 0, MTS_E_BADARG, "lstm_rec_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H == kH) {
+    const int n_tiles = (B + kBT - 1) / kBT;
+    const unsigned grid = (unsigned)(n_tiles * 2 * n_enc * kCluster);
+    lstm_bwd_cluster_kernel<<<grid, kThreads, 0, st>>>(dy, gates, w_hh, lengths, order, B, T, n_enc, n_tiles, dgx);
+  } else {
+    MTS_REQUIRE(H <= 2048, MTS_E_UNSUPPORTED, "lstm_rec_bwd: H > 2048 not supported by the generic kernel");
+    const size_t smem = (size_t)6 * H * sizeof(float);
+    lstm_bwd_generic_kernel<<<dim3(B, 2, n_enc), 256, smem, st>>>(dy, gates, w_hh, lengths, B, T, H, n_enc, dgx);
+  }
+  MTS_LAUNCH_CHECK();
+  return 0;
+}

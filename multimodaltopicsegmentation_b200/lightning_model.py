@@ -1,0 +1,196 @@
+"""`TextSegmenter` -- the task module the reference's train_fit.py / predict.py drive
+(models/lightning_model.py:178-781), re-hosted on the B200 segmenters of modules.py.
+
+Constructor signature, architecture names, batch-dict keys, logged metric names, threshold handling and
+optimiser settings follow the reference.  When pytorch_lightning is importable the class is a real
+LightningModule; otherwise a small stand-in base provides `log`, `log_dict` and `load_from_checkpoint` with the
+PL checkpoint layout ({'state_dict': ...}) so that reference `.ckpt` files load either way.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .metrics import compute_Pk, compute_window_diff, f1_boundary
+from .modules import BiLSTM, BiLSTMLateFusion, BiRnnCrf
+
+try:  # pragma: no cover - depends on the environment
+    import pytorch_lightning as pl
+
+    _Base = pl.LightningModule
+except Exception:  # pytorch_lightning is not installed in the build image
+    pl = None
+
+    class _Base(nn.Module):
+        """Minimal LightningModule stand-in (logging sink + checkpoint loader)."""
+
+        def __init__(self):
+            super().__init__()
+            self.logged = {}
+
+        def log(self, name, value, **kw):
+            self.logged[name] = value
+
+        def log_dict(self, d, **kw):
+            self.logged.update(d)
+
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            model = cls(**kwargs)
+            state = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+            model.load_state_dict(state, strict=strict)
+            return model
+
+
+class TextSegmenter(_Base):
+    def __init__(self, tagset_size, embedding_dim, hidden_dim, num_layers=1, batch_first=True, LSTM=True,
+                 bidirectional=True, architecture="biLSTMCRF", lr=0.01, dropout_in=0.0, dropout_out=0.0,
+                 optimizer="SGD", positional_encoding=True, nheads=8, end_boundary=False, threshold=None,
+                 search_threshold=False, metric="Pk", cosine_loss=False, zero_baseline=False, loss_fn="CrossEntropy",
+                 no_validation=False, all_results=False, all_scores=False, alpha=0.9, gamma=2, attention_window=120,
+                 switch="dense"):
+        super().__init__()
+        self.validation = not no_validation
+        self.cos = cosine_loss
+        self.double_input = False
+        self.domain = False
+        if architecture == "biLSTMCRF":
+            self.cos = False
+            self.model = BiRnnCrf(tagset_size, embedding_dim, hidden_dim, num_layers=num_layers,
+                                  bidirectional=bidirectional, dropout_in=dropout_in, dropout_out=dropout_out,
+                                  batch_first=batch_first, LSTM=LSTM, architecture="rnn")
+        elif architecture == "BiLSTM":
+            self.model = BiLSTM(tagset_size, embedding_dim, hidden_dim, num_layers=num_layers,
+                                bidirectional=bidirectional, dropout_in=dropout_in, dropout_out=dropout_out,
+                                batch_first=batch_first, LSTM=LSTM, loss_fn=loss_fn, threshold=threshold, alpha=alpha,
+                                gamma=gamma)
+        elif architecture == "BiLSTMLateFusion":
+            self.model = BiLSTMLateFusion(tagset_size, embedding_dim, hidden_dim, num_layers=num_layers,
+                                          bidirectional=bidirectional, dropout_in=dropout_in, dropout_out=dropout_out,
+                                          batch_first=batch_first, LSTM=LSTM, loss_fn=loss_fn, threshold=threshold,
+                                          alpha=alpha, gamma=gamma)
+            self.double_input = True
+        elif architecture == "Transformer":
+            from .transformer import Transformer_segmenter
+
+            self.model = Transformer_segmenter(tagset_size, embedding_dim, hidden_dim, num_layers=num_layers,
+                                               dropout_in=dropout_in, dropout_out=dropout_out, batch_first=batch_first,
+                                               loss_fn=loss_fn, positional_encoding=positional_encoding, nheads=nheads,
+                                               threshold=threshold, alpha=alpha, gamma=gamma,
+                                               window_size=attention_window)
+        else:
+            # SimpleBiLSTM, MLP, Transformer-CRF, RecurrentLongT5, BiLSTMRestrictedMHA, SwitchBiLSTM, SheikhBiLSTM:
+            # outside the hot path this package accelerates
+            raise ValueError("No other architectures implemented yet")
+        self.learning_rate = lr
+        self.optimizer = optimizer
+        self.eb = end_boundary
+        self.threshold = threshold
+        self.s_th = search_threshold
+        self.metric = metric
+        self.best_th, self.losses, self.targets = [], [], []
+        self.zero_base = zero_baseline
+        self.all = bool(all_results)
+        self.results = []
+        self.all_scores = bool(all_scores)
+        self.scores = []
+
+    def forward(self, x):
+        return self.model(x)
+
+    # ---- steps --------------------------------------------------------------------------------------------
+    def _inputs(self, batch):
+        sentence, lengths = batch["src_tokens"], batch["src_lengths"]
+        if self.double_input:
+            return (sentence, batch["src_tokens2"]), lengths
+        return (sentence,), lengths
+
+    def training_step(self, batch, batch_idx):
+        if self.cos:
+            raise NotImplementedError("the auxiliary cosine loss is outside the B200 hot path")
+        xs, lengths = self._inputs(batch)
+        self.best_th, self.losses, self.targets = [], [], []
+        loss = self.model.loss(*xs, lengths, batch["tgt_tokens"])
+        self.log("training_loss", loss, on_step=True, on_epoch=True, prog_bar=True, logger=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        xs, lengths = self._inputs(batch)
+        if self.s_th:
+            scores, _ = self.model(*xs, lengths)
+            target = batch["tgt_tokens"]
+            for index, score in enumerate(scores):
+                n = int(lengths[index])
+                self.losses.append(score[:n].detach().cpu().numpy())
+                self.targets.append(target[index][:n].detach().cpu().numpy())
+            return None
+        with torch.no_grad():
+            loss = self.model.loss(*xs, lengths, batch["tgt_tokens"])
+        self.log_dict({"val_loss": loss, "threshold": 0.5})
+        return loss
+
+    def test_step(self, batch, batch_idx):
+        xs, lengths = self._inputs(batch)
+        target = batch["tgt_tokens"]
+        if self.s_th:
+            raise NotImplementedError()
+        if self.metric.lower() in ("b", "scaiano"):
+            raise NotImplementedError("B / WinPR evaluation is outside the hot path (SURVEY.md section 2 row 9)")
+        lens_host = [int(v) for v in lengths]
+        if self.zero_base:
+            threshold = 0.4
+            tags = [np.zeros(n) for n in lens_host]
+            score = None
+        else:
+            threshold = self.threshold if self.threshold is not None else 0.4
+            if not threshold:
+                threshold = 0.5
+            self.model.th = threshold
+            score, tags = self.model(*xs, lengths)
+        target_host = target.detach().cpu().numpy()
+        loss_pk = loss_f1 = loss_wd = 0.0
+        for i, tag in enumerate(tags):
+            tgt = target_host[i][: lens_host[i]]
+            if self.eb:
+                tag[-1] = 0
+                tgt[-1] = 0
+            loss_pk += float(compute_Pk(np.array(tag), tgt))
+            loss_f1 += f1_boundary(tgt.astype(int), np.array(tag).astype(int))
+            try:
+                loss_wd += float(compute_window_diff(np.array(tag), tgt))
+            except AssertionError:
+                loss_wd += float(compute_Pk(np.array(tag), tgt))
+        n = len(target)
+        results = {"Pk_loss": loss_pk / n, "F1_loss": loss_f1 / n, "WD_loss": loss_wd / n, "threshold": threshold}
+        key = {"F1": "F1_loss", "WD": "WD_loss"}.get(self.metric, "Pk_loss")
+        results["test_loss"] = results.pop(key)
+        if self.all:
+            self.results.append(results)
+        if self.all_scores and score is not None:
+            self.scores.extend([s.detach().cpu().numpy() for s in score])
+        self.log_dict(results, on_epoch=True, prog_bar=True)
+        return results
+
+    def predict_step(self, batch, batch_idx):
+        xs, lengths = self._inputs(batch)
+        _, tags = self.model(*xs, lengths)
+        return tags
+
+    # ---- optimisers (lightning_model.py:759-781) ---------------------------------------------------------------
+    def configure_optimizers(self):
+        if self.optimizer == "SGD":
+            optimizer = torch.optim.SGD(self.parameters(), lr=self.learning_rate, weight_decay=1e-4, momentum=0.9)
+        else:
+            optimizer = torch.optim.Adam(self.parameters(), eps=1e-7, lr=self.learning_rate)
+        mode = "min" if (self.metric.lower() in ("pk", "wd") or not self.s_th) else "max"
+        monitor = "val_loss" if self.validation else "training_loss"
+        scheduler = {"scheduler": torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode, factor=0.8, patience=10),
+                     "monitor": monitor}
+        return {"optimizer": optimizer, "lr_scheduler": scheduler}
+
+
+def launch_count():
+    return ops.launch_count()

@@ -1,0 +1,460 @@
+"""Python face of the C ABI: thin wrappers that hand raw device pointers of torch tensors to
+libmts_b200.so, plus the autograd.Function glue for training.  PyTorch is used here for device memory,
+streams and autograd bookkeeping only -- every arithmetic step of the hot path is one of our kernels.
+
+A global launch counter (`launch_count()`) records how many of OUR kernels were launched; bench.py reports it.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_LAUNCHES = 0
+# kernels launched per ABI call (for the bench's gpu_launches claim)
+_KERNELS_PER_CALL = {
+    "mts_seg_loss_fwd": 2, "mts_head_bwd": 3, "mts_colsum": 2,
+}
+
+
+def launch_count():
+    return _LAUNCHES
+
+
+def reset_launch_count():
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+PROFILE = None  # bench.py sets this to a dict to collect CUDA-event timings per ABI entry point
+# debugging aid for tests only: MTS_GEMM_IMPL=simt routes the input projections through mts_gemm_f32
+GEMM_IMPL = __import__("os").environ.get("MTS_GEMM_IMPL", "tcgen05")
+
+
+def _call(name, *args):
+    global _LAUNCHES
+    _LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
+    if PROFILE is None:
+        return _lib.call(name, *args)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    rc = _lib.call(name, *args)
+    end.record()
+    PROFILE.setdefault(name, []).append((start, end))
+    return rc
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _check(t, name, dtype=torch.float32):
+    if not t.is_cuda:
+        raise _lib.MtsError(f"{name} must live on a CUDA device: this package has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+def _pad32(k):
+    return (k + 31) // 32 * 32
+
+
+def device_ok():
+    return _lib.call("mts_device_ok")
+
+
+# --------------------------------------------------------------------------------------------------------
+# lengths: the reference consumes them on the host (lengths.data.tolist()); we keep a host list, a device
+# int32 copy and the length-sorted episode order used to build the tiles of the recurrence kernels.
+# --------------------------------------------------------------------------------------------------------
+class Lengths:
+    def __init__(self, lengths, device, T_in):
+        if torch.is_tensor(lengths):
+            host = [int(v) for v in lengths.detach().cpu().tolist()]
+        else:
+            host = [int(v) for v in lengths]
+        if not host or min(host) < 1:
+            raise ValueError("every episode must hold at least one sentence")
+        if max(host) > T_in:
+            raise ValueError(f"length {max(host)} exceeds the padded time axis {T_in}")
+        self.host = host
+        self.B = len(host)
+        self.T = max(host)  # pad_packed_sequence crops the time axis to max(lengths)
+        self.N = sum(host)
+        order = sorted(range(self.B), key=lambda i: -host[i])
+        both = torch.tensor([host, order], dtype=torch.int32)
+        both = both.pin_memory() if torch.cuda.is_available() else both
+        dev = both.to(device, non_blocking=True)
+        self.dev = dev[0]
+        self.order = dev[1]
+
+
+# --------------------------------------------------------------------------------------------------------
+# GEMMs
+# --------------------------------------------------------------------------------------------------------
+def split_tf32(src2d, cols=None, ld=None, rows=None):
+    """src [rows, cols] (row stride ld) -> (hi, lo) [rows, pad32(cols)]"""
+    rows = src2d.shape[0] if rows is None else rows
+    cols = src2d.shape[1] if cols is None else cols
+    ld = src2d.stride(0) if ld is None else ld
+    kp = _pad32(cols)
+    out = torch.empty((2, rows, kp), device=src2d.device, dtype=torch.float32)
+    _call("mts_split_tf32", _ptr(src2d), ld, rows, cols, kp, _ptr(out[0]), _ptr(out[1]), _stream())
+    return out[0], out[1]
+
+
+def pack_rows_split(x1, x2, B, T):
+    """[x1[b,:T] | x2[b,:T]] -> (hi, lo) [B*T, pad32(D1+D2)] (early fusion concat + crop + split, one kernel)"""
+    D1 = x1.shape[2]
+    D2 = 0 if x2 is None else x2.shape[2]
+    kp = _pad32(D1 + D2)
+    out = torch.empty((2, B * T, kp), device=x1.device, dtype=torch.float32)
+    _call("mts_pack_rows_split", _ptr(x1), x1.stride(0), D1, _ptr(x2), 0 if x2 is None else x2.stride(0), D2, B, T, kp,
+          _ptr(out[0]), _ptr(out[1]), _stream())
+    return out[0], out[1]
+
+
+def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, out, M, N, epilogue=0, accumulate=False, ldc=None):
+    kp = a_hi.shape[1]
+    assert b_hi.shape[1] == kp
+    _call("mts_gemm_tf32x3", _ptr(a_hi), _ptr(a_lo), _ptr(b_hi), _ptr(b_lo), _ptr(bias), _ptr(out), M, N, kp,
+          out.stride(-2) if ldc is None else ldc, epilogue if bias is not None else 0, int(accumulate), _stream())
+    return out
+
+
+def gemm_f32(a_ptr, lda, b_ptr, ldb, bias, c_ptr, ldc, M, N, K, layout, epilogue=0, accumulate=False, splits=1,
+             shift=0, T=0, lengths=None):
+    _call("mts_gemm_f32", a_ptr, lda, b_ptr, ldb, _ptr(bias), c_ptr, ldc, M, N, K, layout,
+          epilogue if bias is not None else 0, int(accumulate), splits, shift, T, _ptr(lengths), _stream())
+
+
+def colsum(x_ptr, ld, M, N, out, accumulate=False):
+    ws = torch.empty(_lib.load().mts_colsum_ws_bytes(M, N) // 4, device=out.device, dtype=torch.float32)
+    _call("mts_colsum", x_ptr, ld, M, N, _ptr(out), int(accumulate), _ptr(ws), _stream())
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the exact-fp32 GEMM (small output widths: CRF emissions)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _check(x, "x"); _check(w, "weight")
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        M, K = x2.shape
+        N = w.shape[0]
+        wc = w.contiguous()
+        y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        gemm_f32(_ptr(x2), K, _ptr(wc), K, b.contiguous(), _ptr(y), N, M, N, K, layout=0, epilogue=1)
+        ctx.save_for_backward(x2, wc)
+        ctx.xshape = x.shape
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(M, N).contiguous()
+        dx = torch.empty_like(x2)
+        gemm_f32(_ptr(dy2), N, _ptr(w), K, None, _ptr(dx), K, M, K, N, layout=2)
+        dw = torch.empty_like(w)
+        gemm_f32(_ptr(dy2), N, _ptr(x2), K, None, _ptr(dw), K, N, K, M, layout=3, splits=8 if M > 4096 else 1)
+        db = torch.empty(N, device=w.device, dtype=torch.float32)
+        colsum(_ptr(dy2), N, M, N, db)
+        return dx.reshape(ctx.xshape), dw, db
+
+
+# --------------------------------------------------------------------------------------------------------
+# LSTM stack
+# --------------------------------------------------------------------------------------------------------
+class PackedLstm:
+    """GEMM-ready shadow copies of one or two nn.LSTM parameter sets (state-dict layout untouched):
+    per layer  w_ih (hi, lo) [n_enc][8H, pad32(D_l)], bias [n_enc][8H] = b_ih + b_hh, w_hh [n_enc, 2, 4H, H]."""
+
+    def __init__(self, rnns):
+        self.rnns = rnns
+        self.key = None
+        self.layers = None
+
+    def _params(self, rnn, layer):
+        g = lambda n: getattr(rnn, n)
+        sfx = f"_l{layer}"
+        return [g("weight_ih" + sfx), g("weight_hh" + sfx), g("bias_ih" + sfx), g("bias_hh" + sfx),
+                g("weight_ih" + sfx + "_reverse"), g("weight_hh" + sfx + "_reverse"),
+                g("bias_ih" + sfx + "_reverse"), g("bias_hh" + sfx + "_reverse")]
+
+    def flat_params(self):
+        out = []
+        for rnn in self.rnns:
+            for layer in range(rnn.num_layers):
+                out.extend(self._params(rnn, layer))
+        return out
+
+    def get(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.flat_params())
+        if key == self.key:
+            return self.layers
+        rnn0 = self.rnns[0]
+        H, L = rnn0.hidden_size, rnn0.num_layers
+        dev = rnn0.weight_hh_l0.device
+        layers = []
+        with torch.no_grad():
+            for layer in range(L):
+                wih, bias = [], []
+                whh = torch.empty((len(self.rnns), 2, 4 * H, H), device=dev, dtype=torch.float32)
+                for e, rnn in enumerate(self.rnns):
+                    w_f, h_f, bi_f, bh_f, w_r, h_r, bi_r, bh_r = self._params(rnn, layer)
+                    D = w_f.shape[1]
+                    kp = _pad32(D)
+                    pair = torch.empty((2, 8 * H, kp), device=dev, dtype=torch.float32)
+                    for d, w in enumerate((w_f, w_r)):
+                        wc = w.detach().contiguous()
+                        _call("mts_split_tf32", _ptr(wc), D, 4 * H, D, kp, _ptr(pair[0, d * 4 * H:]),
+                              _ptr(pair[1, d * 4 * H:]), _stream())
+                    wih.append((pair[0], pair[1]))
+                    bias.append(torch.cat([bi_f.detach() + bh_f.detach(), bi_r.detach() + bh_r.detach()]))
+                    whh[e, 0].copy_(h_f.detach())
+                    whh[e, 1].copy_(h_r.detach())
+                layers.append({"wih": wih, "bias": bias, "whh": whh})
+        self.key, self.layers = key, layers
+        return layers
+
+
+def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
+    """Runs all layers.  Early fusion: encoders=1, inputs (x1 | x2).  Late fusion: n_enc=2, encoder 0 reads x1,
+    encoder 1 reads xs2.  Returns (y_last [B,T,n_enc*2H], saved list per layer)."""
+    B, T = lens.B, lens.T
+    dev = x1.device
+    layers = packed.get()
+    saved = []
+    y_prev = None
+    for layer in range(L):
+        gx = torch.empty((n_enc, B * T, 8 * H), device=dev, dtype=torch.float32)
+        for e in range(n_enc):
+            if layer == 0:
+                if n_enc == 1:
+                    a_hi, a_lo = pack_rows_split(x1, x2, B, T)
+                else:
+                    a_hi, a_lo = pack_rows_split(x1 if e == 0 else xs2, None, B, T)
+            else:
+                src = y_prev.view(B * T, n_enc * 2 * H)[:, e * 2 * H:(e + 1) * 2 * H]
+                a_hi, a_lo = split_tf32(src, cols=2 * H, ld=n_enc * 2 * H, rows=B * T)
+            w_hi, w_lo = layers[layer]["wih"][e]
+            if GEMM_IMPL == "simt":
+                a, w = a_hi + a_lo, w_hi + w_lo
+                gemm_f32(_ptr(a), a.shape[1], _ptr(w), w.shape[1], layers[layer]["bias"][e], _ptr(gx[e]), 8 * H, B * T,
+                         8 * H, a.shape[1], layout=0, epilogue=1)
+            else:
+                gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, layers[layer]["bias"][e], gx[e], B * T, 8 * H, epilogue=1,
+                            ldc=8 * H)
+        y = torch.empty((B, T, n_enc * 2 * H), device=dev, dtype=torch.float32)
+        gates = torch.empty((n_enc, 2, B, T, 5, H), device=dev, dtype=torch.float32) if save else None
+        _call("mts_lstm_rec_fwd", _ptr(gx), _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order), n_enc, B, T, H,
+              _ptr(y), _ptr(gates), _stream())
+        saved.append((y_prev, y, gates))
+        y_prev = y
+    return y_prev, saved
+
+
+class BiLstmStackFn(torch.autograd.Function):
+    """Differentiable (w.r.t. the LSTM parameters) bi-LSTM stack.  Inputs are data, so layer-0 dX is skipped
+    (SURVEY.md section 8a')."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, xs2, lens, packed, n_enc, *flat):
+        rnn0 = packed.rnns[0]
+        H, L = rnn0.hidden_size, rnn0.num_layers
+        need = any(p.requires_grad for p in flat) and torch.is_grad_enabled()
+        y, saved = _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save=need)
+        if need:
+            ctx.x1, ctx.x2, ctx.xs2, ctx.lens, ctx.packed, ctx.n_enc = x1, x2, xs2, lens, packed, n_enc
+            ctx.saved = saved
+            ctx.HL = (H, L)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        H, L = ctx.HL
+        lens, packed, n_enc = ctx.lens, ctx.packed, ctx.n_enc
+        B, T = lens.B, lens.T
+        N = B * T
+        layers = packed.get()
+        dev = dy.device
+        dy = dy.contiguous()
+        grads = [[None] * (8 * L) for _ in range(n_enc)]
+        splits = max(1, min(16, N // 2048))
+        for layer in range(L - 1, -1, -1):
+            y_in, y_out, gates = ctx.saved[layer]
+            dgx = torch.empty((n_enc, N, 8 * H), device=dev, dtype=torch.float32)
+            _call("mts_lstm_rec_bwd", _ptr(dy), _ptr(gates), _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order),
+                  n_enc, B, T, H, _ptr(dgx), _stream())
+            dy_next = torch.empty((B, T, n_enc * 2 * H), device=dev, dtype=torch.float32) if layer > 0 else None
+            for e in range(n_enc):
+                rnn = packed.rnns[e]
+                w_f, h_f, bi_f, bh_f, w_r, h_r, bi_r, bh_r = packed._params(rnn, layer)
+                D = w_f.shape[1]
+                dg = dgx[e]
+                # biases: column sums of dgx (b_ih and b_hh receive identical gradients)
+                db = torch.empty(8 * H, device=dev, dtype=torch.float32)
+                colsum(_ptr(dg), 8 * H, N, 8 * H, db)
+                # input weights, both directions at once: [8H, D] = dgx^T X
+                dwih = torch.empty((8 * H, D), device=dev, dtype=torch.float32)
+                if layer == 0:
+                    if n_enc == 1:  # early fusion: the two modality blocks of W_ih get their own GEMM (no concat copy)
+                        srcs = [(ctx.x1, 0)] + ([(ctx.x2, ctx.x1.shape[2])] if ctx.x2 is not None else [])
+                    else:
+                        srcs = [(ctx.x1 if e == 0 else ctx.xs2, 0)]
+                    for x, off in srcs:
+                        xc = x if (x.shape[1] == T and x.is_contiguous()) else x[:, :T].contiguous()
+                        Dx = xc.shape[2]
+                        gemm_f32(_ptr(dg), 8 * H, _ptr(xc), Dx, None, dwih.data_ptr() + 4 * off, D, 8 * H, Dx, N,
+                                 layout=3, splits=splits)
+                else:
+                    xin = y_in.view(N, n_enc * 2 * H)
+                    gemm_f32(_ptr(dg), 8 * H, xin.data_ptr() + 4 * e * 2 * H, n_enc * 2 * H, None, _ptr(dwih), D,
+                             8 * H, D, N, layout=3, splits=splits)
+                    # gradient to the lower layer's output: dgx W_ih  (layout 2), written in place into dy_next
+                    wcat = torch.cat([w_f.detach(), w_r.detach()], dim=0)
+                    gemm_f32(_ptr(dg), 8 * H, _ptr(wcat), D, None, dy_next.data_ptr() + 4 * e * 2 * H, n_enc * 2 * H,
+                             N, D, 8 * H, layout=2)
+                # recurrent weights: dW_hh[dir] = dgx_dir^T H_prev  (H_prev = this layer's output shifted in time)
+                dwhh = torch.empty((2, 4 * H, H), device=dev, dtype=torch.float32)
+                yo = y_out.view(N, n_enc * 2 * H)
+                for d, shift in ((0, -1), (1, 1)):
+                    gemm_f32(dg.data_ptr() + 4 * d * 4 * H, 8 * H, yo.data_ptr() + 4 * (e * 2 * H + d * H),
+                             n_enc * 2 * H, None, _ptr(dwhh[d]), H, 4 * H, H, N, layout=3, splits=splits, shift=shift,
+                             T=T, lengths=lens.dev)
+                base = 8 * layer
+                g = grads[e]
+                g[base + 0], g[base + 1] = dwih[:4 * H], dwhh[0]
+                g[base + 2], g[base + 3] = db[:4 * H], db[:4 * H]
+                g[base + 4], g[base + 5] = dwih[4 * H:], dwhh[1]
+                g[base + 6], g[base + 7] = db[4 * H:], db[4 * H:]
+            dy = dy_next
+        flat = [g for e in range(n_enc) for g in grads[e]]
+        ctx.saved = None
+        return (None, None, None, None, None, None, *flat)
+
+
+# --------------------------------------------------------------------------------------------------------
+# head, decode, losses
+# --------------------------------------------------------------------------------------------------------
+class HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, w, b):
+        _check(feats, "features")
+        feats = feats.contiguous()
+        B, T, F = feats.shape
+        n_out = w.shape[0]
+        scores = torch.empty((B, T, n_out), device=feats.device, dtype=torch.float32)
+        wc, bc = w.contiguous(), b.contiguous()
+        _call("mts_head_fwd", _ptr(feats), _ptr(wc), _ptr(bc), 0, B, T, F, n_out, 0.0, _ptr(scores), 0, _stream())
+        ctx.save_for_backward(feats, wc)
+        return scores
+
+    @staticmethod
+    def backward(ctx, ds):
+        feats, w = ctx.saved_tensors
+        B, T, F = feats.shape
+        n_out = w.shape[0]
+        ds = ds.contiguous()
+        dx = torch.empty_like(feats) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(n_out, device=w.device, dtype=torch.float32)
+        ws = torch.empty(_lib.load().mts_head_bwd_ws_bytes(B, T, F, n_out) // 4, device=w.device, dtype=torch.float32)
+        _call("mts_head_bwd", _ptr(ds), _ptr(feats), _ptr(w), B, T, F, n_out, _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws),
+              _stream())
+        return dx, dw, db
+
+
+def head_decode(feats, w, b, lens, th):
+    """scores [B,T,n_out] and uint8 tags [B,T] (0xFF beyond len_b) in one kernel."""
+    feats = _check(feats, "features").contiguous()
+    B, T, F = feats.shape
+    n_out = w.shape[0]
+    scores = torch.empty((B, T, n_out), device=feats.device, dtype=torch.float32)
+    tags = torch.empty((B, T), device=feats.device, dtype=torch.uint8)
+    _call("mts_head_fwd", _ptr(feats), _ptr(w.contiguous()), _ptr(b.contiguous()), _ptr(lens.dev), B, T, F, n_out,
+          float(th), _ptr(scores), _ptr(tags), _stream())
+    return scores, tags
+
+
+LOSS_KINDS = {"FocalLoss": 0, "BinaryCrossEntropy": 1, "CrossEntropy": 2}
+
+
+class SegLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, target, lens, kind, alpha, gamma, inv_count):
+        scores = _check(scores, "scores").contiguous()
+        target = _check(target, "target")
+        if target.stride(-1) != 1:
+            target = target.contiguous()
+        B, T = scores.shape[0], scores.shape[1]
+        out = torch.empty(2, device=scores.device, dtype=torch.float32)
+        partial = torch.empty(2048, device=scores.device, dtype=torch.float32)
+        _call("mts_seg_loss_fwd", _ptr(scores), _ptr(target), target.stride(0), _ptr(lens.dev), B, T, kind, alpha, gamma,
+              inv_count, _ptr(out), _ptr(partial), _stream())
+        ctx.save_for_backward(scores, target, out)
+        ctx.args = (lens, kind, alpha, gamma, inv_count)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        scores, target, out = ctx.saved_tensors
+        lens, kind, alpha, gamma, inv_count = ctx.args
+        B, T = scores.shape[0], scores.shape[1]
+        ds = torch.empty_like(scores)
+        go = grad_out.contiguous().reshape(1)
+        _call("mts_seg_loss_bwd", _ptr(scores), _ptr(target), target.stride(0), _ptr(lens.dev), B, T, kind, alpha, gamma,
+              inv_count, out.data_ptr() + 4, _ptr(go), _ptr(ds), _stream())
+        return ds, None, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------------
+# CRF
+# --------------------------------------------------------------------------------------------------------
+def crf_viterbi(emis, lens, trans):
+    emis = _check(emis, "emissions").contiguous()
+    B, L, C = emis.shape
+    best = torch.empty(B, device=emis.device, dtype=torch.float32)
+    paths = torch.empty((B, L), device=emis.device, dtype=torch.int32)
+    bp = torch.empty((B, L), device=emis.device, dtype=torch.int32)
+    _call("mts_crf_viterbi", _ptr(emis), _ptr(lens.dev), _ptr(trans.detach().contiguous()), B, L, C, _ptr(best),
+          _ptr(paths), _ptr(bp), _stream())
+    return best, paths
+
+
+class CrfNllFn(torch.autograd.Function):
+    """mean_b (log Z_b - gold_b)  (models/CRF.py:130-146 after `fc`)."""
+
+    @staticmethod
+    def forward(ctx, emis, trans, tags, lens):
+        emis = _check(emis, "emissions").contiguous()
+        trans_c = trans.contiguous()
+        B, L, C = emis.shape
+        tags = tags if tags.stride(-1) == 1 else tags.contiguous()
+        stats = torch.empty((2, B), device=emis.device, dtype=torch.float32)
+        alphas = torch.empty((B, L, C), device=emis.device, dtype=torch.float32)
+        _call("mts_crf_nll_fwd", _ptr(emis), _ptr(tags), tags.stride(0), _ptr(lens.dev), _ptr(trans_c), B, L, C,
+              _ptr(stats[0]), _ptr(stats[1]), _ptr(alphas), _stream())
+        ctx.save_for_backward(emis, trans_c, tags, alphas, stats)
+        ctx.lens = lens
+        return stats  # [2, B]: log Z and gold score; the caller takes (stats[0] - stats[1]).mean()
+
+    @staticmethod
+    def backward(ctx, dstats):
+        emis, trans, tags, alphas, stats = ctx.saved_tensors
+        B, L, C = emis.shape
+        # d loss / d logZ_b = dstats[0, b] stays on the device (the loss only ever uses logZ - gold, so
+        # dstats[1] = -dstats[0]); for the reference's mean this is grad_out / B.
+        scale = dstats[0].contiguous()
+        de = torch.empty_like(emis)
+        dt = torch.empty_like(trans)
+        _call("mts_crf_nll_bwd", _ptr(emis), _ptr(tags), tags.stride(0), _ptr(ctx.lens.dev), _ptr(trans), _ptr(alphas),
+              _ptr(stats[0]), B, L, C, _ptr(scale), _ptr(de), _ptr(dt), _stream())
+        return de, dt, None, None

@@ -1,0 +1,406 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every check calls the product through the
+reference-shaped module API, i.e. through the C ABI of libmts_b200.so, and compares with the CPU oracle
+(oracle/ref_numpy.py, oracle/ref_torch.py, oracle/oracle_ref.c) or the committed golden vectors.
+
+Tolerances: integer / index work (Viterbi paths, thresholded tags, Pk, WindowDiff) is bit-exact;
+floating point follows north_star: rtol 1e-4 in fp32 (plus an absolute floor for values near zero).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import params_of
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 2e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import multimodaltopicsegmentation_b200 as m
+
+    m.ops.device_ok()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def load_params(module, fx, dev):
+    sd = {k[2:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("p:")}
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return module.to(dev)
+
+
+def tags_equal(tags, arr):
+    for b, t in enumerate(tags):
+        n = len(t)
+        assert (arr[b, n:] == -1).all()
+        assert [int(v) for v in t] == arr[b, :n].tolist()
+
+
+def close(a, b, rtol=RTOL, atol=ATOL, msg=""):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=msg)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GEMMs
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(300, 256, 96), (1000, 2048, 896), (129, 136, 40), (4096, 1024, 512), (64, 8, 33)])
+def test_gemm_f32_nt(dev, M, N, K):
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator().manual_seed(M + N + K)
+    a, b, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    ref = (a.double() @ b.double().T + bias.double()).float()
+    ad, bd, biasd = a.to(dev), b.to(dev), bias.to(dev)
+    c = torch.empty(M, N, device=dev)
+    ops.gemm_f32(ad.data_ptr(), K, bd.data_ptr(), K, biasd, c.data_ptr(), N, M, N, K, layout=0, epilogue=1)
+    close(c, ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 96), (1000, 2048, 896), (129, 136, 40), (4096, 1024, 512), (19200, 2048, 896)])
+def test_gemm_tf32x3(dev, M, N, K):
+    """tcgen05 3xTF32 vs float64: error must be fp32-grade (no worse than 4x a plain fp32 matmul's)."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    a, b, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    ad, bd, biasd = a.to(dev), b.to(dev), bias.to(dev)
+    ref = (ad.double() @ bd.double().T + biasd.double())
+    a_hi, a_lo = ops.split_tf32(ad)
+    b_hi, b_lo = ops.split_tf32(bd)
+    assert torch.equal(a_hi[:, :K] + a_lo[:, :K], ad)  # the split is exact
+    c = torch.empty(M, N, device=dev)
+    ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, biasd, c, M, N, epilogue=1)
+    err = (c.double() - ref).abs().max().item()
+    err32 = ((ad @ bd.T + biasd).double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= max(4 * err32, 1e-6 * scale), (err, err32, scale)
+    # accumulate and GELU epilogues
+    c2 = c.clone()
+    ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, None, c2, M, N, epilogue=0, accumulate=True)
+    close(c2, (2 * ref - biasd.double()).float(), rtol=1e-5, atol=1e-4 * max(1.0, scale / 50))
+    c3 = torch.empty(M, N, device=dev)
+    ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, biasd, c3, M, N, epilogue=2)
+    close(c3, torch.nn.functional.gelu(ref).float(), rtol=1e-5, atol=1e-4 * max(1.0, scale / 50))
+
+
+def test_gemm_tn_shift(dev):
+    """dW_hh-style product: A^T B with the B rows shifted inside episode boundaries."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    B, T, M, N = 5, 13, 70, 40
+    lengths = torch.tensor([13, 4, 9, 1, 7], dtype=torch.int32)
+    a = torch.randn(B * T, M, generator=g)
+    h = torch.randn(B * T, N, generator=g)
+    for shift in (-1, 1):
+        hs = torch.zeros_like(h).view(B, T, N)
+        hv = h.view(B, T, N)
+        for b, n in enumerate(lengths.tolist()):
+            for t in range(T):
+                if 0 <= t + shift < n:
+                    hs[b, t] = hv[b, t + shift]
+        ref = a.double().T @ hs.view(B * T, N).double()
+        for splits in (1, 4):
+            c = torch.empty(M, N, device=dev)
+            ops.gemm_f32(a.to(dev).data_ptr(), M, h.to(dev).data_ptr(), N, None, c.data_ptr(), N, M, N, B * T, layout=3,
+                         splits=splits, shift=shift, T=T, lengths=lengths.to(dev))
+            close(c, ref.float(), rtol=1e-5, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CRF
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["crf_small", "crf_ragged"])
+def test_crf_golden(dev, golden, name):
+    from multimodaltopicsegmentation_b200 import CRF
+    from oracle import ref_torch as rt
+
+    fx = golden(name)
+    crf = load_params(CRF(16, 2), fx, dev)
+    feats = torch.from_numpy(fx["i:features"]).to(dev)
+    lengths = torch.from_numpy(fx["i:lengths"])
+    masks = rt.length_mask(feats.shape[1], lengths).to(dev)
+    best, paths = crf(feats, masks)
+    tags_equal(paths, fx["o:paths"])
+    close(best, fx["o:best_score"], rtol=1e-5)  # emissions come from our own fc GEMM (rounding differs by ulps)
+    loss = crf.loss(feats, torch.from_numpy(fx["i:ys"]).to(dev), masks)
+    loss.backward()
+    close(loss, fx["o:loss"])
+    for k, p in crf.named_parameters():
+        close(p.grad, fx["g:" + k], atol=3e-6, msg=k)
+
+
+@pytest.mark.parametrize("B,L", [(64, 300), (8, 8192), (300, 77), (3, 1)])
+def test_crf_viterbi_bit_exact_vs_c_oracle(dev, B, L):
+    """Identical emissions => identical paths and bit-identical best scores (north_star)."""
+    from multimodaltopicsegmentation_b200 import ops
+    from oracle import c_oracle
+
+    rng = np.random.default_rng(B * 1000 + L)
+    emis = rng.standard_normal((B, L, 4)).astype(np.float32) * 2
+    # plant exact ties so that first-max-wins is exercised
+    emis[:, ::7, 0] = emis[:, ::7, 1]
+    lengths = rng.integers(1, L + 1, size=B)
+    lengths[0] = L
+    trans = rng.standard_normal((4, 4)).astype(np.float32)
+    trans[2, :] = -1e4
+    trans[:, 3] = -1e4
+    trans[0, 1] = trans[0, 0]
+    best_ref, paths_ref = c_oracle.crf_viterbi(emis, lengths, trans)
+    lens = ops.Lengths(lengths.tolist(), dev, L)
+    best, paths = ops.crf_viterbi(torch.from_numpy(emis).to(dev), lens, torch.from_numpy(trans).to(dev))
+    assert np.array_equal(best.cpu().numpy(), best_ref)
+    assert np.array_equal(paths.cpu().numpy(), paths_ref)
+    # idempotence / size-independent property: the decoded path's own score equals best_score
+    gold = c_oracle.crf_gold(emis, np.maximum(paths_ref, 0), lengths, trans)
+    np.testing.assert_allclose(gold, best_ref, rtol=2e-5, atol=1e-3)
+
+
+def test_crf_nll_vs_oracle_large(dev):
+    from multimodaltopicsegmentation_b200 import ops
+    from oracle import c_oracle, ref_numpy as rn
+
+    rng = np.random.default_rng(11)
+    B, L = 10, 700
+    emis = rng.standard_normal((B, L, 4)).astype(np.float32)
+    lengths = rng.integers(1, L + 1, size=B)
+    lengths[3] = L
+    tags = (rng.random((B, L)) < 0.3).astype(np.float32)
+    trans = rng.standard_normal((4, 4)).astype(np.float32)
+    trans[2, :] = -1e4
+    trans[:, 3] = -1e4
+    lens = ops.Lengths(lengths.tolist(), dev, L)
+    e = torch.from_numpy(emis).to(dev).requires_grad_(True)
+    tr = torch.from_numpy(trans).to(dev).requires_grad_(True)
+    stats = ops.CrfNllFn.apply(e, tr, torch.from_numpy(tags).to(dev), lens)
+    close(stats[0], c_oracle.crf_forward(emis, lengths, trans), rtol=1e-5)
+    close(stats[1], c_oracle.crf_gold(emis, tags, lengths, trans), rtol=1e-5, atol=1e-4)
+    (stats[0] - stats[1]).mean().backward()
+    ge, gt = rn.crf_marginal_grad(emis, tags, lengths, trans)
+    close(e.grad, ge, atol=1e-6)
+    close(tr.grad, gt, rtol=2e-4, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# head + losses
+# ----------------------------------------------------------------------------------------------------------
+def test_losses_golden(dev, golden):
+    from multimodaltopicsegmentation_b200 import ops
+
+    fx = golden("losses")
+    n = len(fx["z"])
+    lens = ops.Lengths([n], dev, n)
+    for kind, key in ((0, "focal"), (1, "bce")):
+        z = torch.from_numpy(fx["z"]).to(dev).view(1, n, 1).requires_grad_(True)
+        y = torch.from_numpy(fx["y"]).to(dev).view(1, n)
+        loss = ops.SegLossFn.apply(z, y, lens, kind, 0.9, 2.0, 1.0 / n)
+        loss.backward()
+        close(loss, fx[key], rtol=1e-5)
+        close(z.grad.view(-1), fx[key + "_grad"], atol=1e-8)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# BiLSTM family on the golden fixtures (generic recurrence kernel, H = 8)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("loss_fn", ["FocalLoss", "BinaryCrossEntropy", "CrossEntropy"])
+def test_bilstm_golden(dev, golden, loss_fn):
+    from multimodaltopicsegmentation_b200 import BiLSTM
+
+    fx = golden("bilstm_" + loss_fn.lower())
+    m = load_params(BiLSTM(2, 12, 8, num_layers=2, loss_fn=loss_fn), fx, dev)
+    x, y = torch.from_numpy(fx["i:x"]).to(dev), torch.from_numpy(fx["i:y"]).to(dev)
+    lengths = torch.from_numpy(fx["i:lengths"])
+    m.th = float(fx["i:th"])
+    scores, tags = m(x, lengths)
+    assert tuple(scores.shape) == fx["o:scores"].shape  # time axis = max(lengths)
+    close(scores, fx["o:scores"])
+    tags_equal(tags, fx["o:tags"])
+    assert all(isinstance(v, bool) for v in tags[0])
+    loss = m.loss(x, lengths, y)
+    loss.backward()
+    close(loss, fx["o:loss"])
+    for k, p in m.named_parameters():
+        close(p.grad, fx["g:" + k], atol=2e-6, msg=k)
+
+
+def test_late_fusion_golden(dev, golden):
+    from multimodaltopicsegmentation_b200 import BiLSTMLateFusion
+
+    fx = golden("latefusion_focal")
+    m = load_params(BiLSTMLateFusion(2, [5, 7], 8, num_layers=2, loss_fn="FocalLoss"), fx, dev)
+    t = lambda k: torch.from_numpy(fx[k]).to(dev)
+    m.th = float(fx["i:th"])
+    scores, tags = m(t("i:x1"), t("i:x2"), torch.from_numpy(fx["i:lengths"]))
+    close(scores, fx["o:scores"])
+    tags_equal(tags, fx["o:tags"])
+    loss = m.loss(t("i:x1"), t("i:x2"), torch.from_numpy(fx["i:lengths"]), t("i:y"))
+    loss.backward()
+    close(loss, fx["o:loss"])
+    for k, p in m.named_parameters():
+        close(p.grad, fx["g:" + k], atol=2e-6, msg=k)
+
+
+def test_bilstm_crf_golden(dev, golden):
+    from multimodaltopicsegmentation_b200 import BiRnnCrf
+
+    fx = golden("bilstm_crf")
+    m = load_params(BiRnnCrf(2, 12, 8, num_layers=2), fx, dev)
+    x = torch.from_numpy(fx["i:x"]).to(dev)
+    lengths = torch.from_numpy(fx["i:lengths"])
+    best, paths = m(x, lengths)
+    tags_equal(paths, fx["o:paths"])
+    close(best, fx["o:best_score"], rtol=1e-4)
+    loss = m.loss(x, lengths, torch.from_numpy(fx["i:ys"]).to(dev))
+    loss.backward()
+    close(loss, fx["o:loss"])
+    for k, p in m.named_parameters():
+        close(p.grad, fx["g:" + k], rtol=2e-4, atol=3e-6, msg=k)
+
+
+def test_early_fusion_pair_input_equals_concat(dev, golden):
+    """Additive API: (text, audio) pair == host-side torch.cat (load_datasets_precomputed.py:158-161)."""
+    from multimodaltopicsegmentation_b200 import BiLSTM
+
+    fx = golden("bilstm_focalloss")
+    m = load_params(BiLSTM(2, 12, 8, num_layers=2, loss_fn="FocalLoss"), fx, dev)
+    x = torch.from_numpy(fx["i:x"]).to(dev)
+    lengths = torch.from_numpy(fx["i:lengths"])
+    s1, _ = m(x, lengths)
+    s2, _ = m((x[:, :, :5].contiguous(), x[:, :, 5:].contiguous()), lengths)
+    assert torch.equal(s1, s2)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# H = 256: the cluster recurrence kernels vs the torch CPU oracle
+# ----------------------------------------------------------------------------------------------------------
+def _oracle_pair(dev, D, H, L, loss_fn="FocalLoss", seed=0):
+    from multimodaltopicsegmentation_b200 import BiLSTM
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(seed)
+    ref = rt.Segmenter(2, D, H, num_layers=L, loss_fn=loss_fn)
+    with torch.no_grad():
+        ref.classification.weight.mul_(4.0)
+    ours = BiLSTM(2, D, H, num_layers=L, loss_fn=loss_fn)
+    ours.load_state_dict(ref.state_dict())
+    return ref, ours.to(dev)
+
+
+@pytest.mark.parametrize("B,T,D,lens", [(11, 37, 40, None), (8, 64, 896, "full"), (17, 300, 64, None)])
+def test_bilstm_h256_forward_backward(dev, B, T, D, lens):
+    g = torch.Generator().manual_seed(B * T)
+    ref, ours = _oracle_pair(dev, D, 256, 2)
+    x = torch.randn(B, T, D, generator=g)
+    if lens == "full":
+        lengths = torch.full((B,), T, dtype=torch.long)
+    else:
+        lengths = torch.randint(1, T + 1, (B,), generator=g)
+        lengths[B // 2] = T
+    y = (torch.rand(B, T, generator=g) < 0.1).float()
+    for b, n in enumerate(lengths.tolist()):
+        y[b, n:] = -1
+    ref.th = ours.th = 0.5
+    s_ref, tags_ref = ref(x, lengths)
+    s, tags = ours(x.to(dev), lengths)
+    close(s, s_ref, msg="scores")
+    # thresholded tags must agree wherever the oracle's probability is not within 1e-6 of the threshold
+    p = torch.sigmoid(s_ref)[:, :, 0]
+    for b, n in enumerate(lengths.tolist()):
+        for t in range(n):
+            if abs(float(p[b, t]) - 0.5) > 1e-6:
+                assert tags[b][t] == tags_ref[b][t]
+    loss_ref = ref.loss(x, lengths, y)
+    loss_ref.backward()
+    loss = ours.loss(x.to(dev), lengths, y.to(dev))
+    loss.backward()
+    close(loss, loss_ref)
+    ref_grads = dict(ref.named_parameters())
+    for k, prm in ours.named_parameters():
+        gr = ref_grads[k].grad
+        tol = 1e-4 * float(gr.abs().max()) + 1e-7  # rtol 1e-4 of the tensor's scale
+        close(prm.grad, gr, rtol=1e-4, atol=tol, msg=k)
+
+
+def test_padding_invariance_and_permutation(dev):
+    """Changing padded inputs leaves valid outputs bit-identical; permuting the batch permutes the outputs."""
+    ref, ours = _oracle_pair(dev, 48, 256, 2, seed=3)
+    g = torch.Generator().manual_seed(9)
+    B, T = 19, 41
+    x = torch.randn(B, T, 48, generator=g)
+    lengths = torch.randint(1, T + 1, (B,), generator=g)
+    lengths[0] = T
+    s1, t1 = ours(x.to(dev), lengths)
+    x2 = x.clone()
+    for b, n in enumerate(lengths.tolist()):
+        x2[b, n:] = 1e3
+    s2, t2 = ours(x2.to(dev), lengths)
+    assert torch.equal(s1, s2) and t1 == t2
+    perm = torch.randperm(B, generator=g)
+    s3, t3 = ours(x[perm].to(dev), lengths[perm])
+    for i, j in enumerate(perm.tolist()):
+        n = int(lengths[j])
+        close(s3[i, :n], s1[j, :n], rtol=1e-5, atol=1e-6)
+    # padded steps: hidden state 0 => logit == classifier bias
+    bias = float(ours.classification.bias)
+    for b, n in enumerate(lengths.tolist()):
+        assert torch.all(s1[b, n:, 0] == bias)
+
+
+def test_cfg1_full_size_properties(dev):
+    """BASELINE configs[0] shape (64 x 300 x 896, H 256, 2 layers): size-independent checks + sampled oracle rows."""
+    from oracle import ref_torch as rt  # noqa: F401
+
+    ref, ours = _oracle_pair(dev, 896, 256, 2, seed=1)
+    g = torch.Generator().manual_seed(1235)
+    B, T = 64, 300
+    x = torch.randn(B, T, 896, generator=g)
+    lengths = torch.randint(84, 301, (B,), generator=g)
+    lengths[5] = 300
+    ours.th = ref.th = 0.5
+    s, tags = ours((x[:, :, :384].contiguous().to(dev), x[:, :, 384:].contiguous().to(dev)), lengths)
+    sub = [0, 5, 17, 63]
+    s_ref, tags_ref = ref(x[sub], lengths[sub])
+    for i, b in enumerate(sub):
+        n = int(lengths[b])
+        close(s[b, :n], s_ref[i, :n], msg=f"episode {b}")
+    assert [len(t) for t in tags] == lengths.tolist()
+
+
+def test_text_segmenter_steps(dev):
+    """The reference-facing task module: training / validation / test / predict steps on a collated batch."""
+    from multimodaltopicsegmentation_b200 import AudioPortionDataset, TextSegmenter, to_device
+
+    g = torch.Generator().manual_seed(4)
+    lines = []
+    for n in (30, 12, 21, 7):
+        labs = (torch.rand(n, generator=g) < 0.2).long().tolist()
+        labs[-1] = 0
+        lines.append((torch.randn(n, 20, generator=g), labs, "f"))
+    ds = AudioPortionDataset(lines, {"0": 0, "1": 1}, CRF=False, truncate=False)
+    batch = to_device(ds.collater([ds[i] for i in range(4)]), dev)
+    torch.manual_seed(0)
+    seg = TextSegmenter(2, 20, 256, num_layers=2, architecture="BiLSTM", loss_fn="FocalLoss", optimizer="Adam",
+                        lr=1e-3, threshold=0.4).to(dev)
+    opt = seg.configure_optimizers()["optimizer"]
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        loss = seg.training_step(batch, 0)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
+    res = seg.test_step(batch, 0)
+    assert set(res) == {"F1_loss", "WD_loss", "threshold", "test_loss"}
+    tags = seg.predict_step(batch, 0)
+    assert [len(t) for t in tags] == [30, 12, 21, 7]
+    with pytest.raises(ValueError):
+        TextSegmenter(2, 20, 256, architecture="nope")
