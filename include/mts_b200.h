@@ -143,7 +143,7 @@ int mts_crf_nll_fwd(const float *emis, const float *tags, int64_t ldt, const int
 /* scale_dev [B]: d loss / d log_z[b] on the device (= -d loss / d gold[b]; grad_out / B for the mean).
  * d_emis [B,L,C] (overwritten, zero at padded steps); d_trans [C,C] (overwritten). */
 int mts_crf_nll_bwd(const float *emis, const float *tags, int64_t ldt, const int32_t *lengths, const float *trans,
-                    const float *alphas, const float *log_z, int B, int L, int C, const float *scale_dev, float *d_emis,
+                    const float *alphas, int B, int L, int C, const float *scale_dev, float *d_emis,
                     float *d_trans, void *stream);
 
 #ifdef __cplusplus

@@ -52,8 +52,14 @@ __device__ __forceinline__ float warp_max(float v) {
 // The reference evaluates torch.sigmoid in fp32; this is the same expression, IEEE division, accurate expf.
 __device__ __forceinline__ float sigmoid_ref(float z) { return __fdiv_rn(1.0f, 1.0f + expf(-z)); }
 
-// Top 19 bits of an fp32 value: what tcgen05 kind::tf32 reads from shared memory.
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// fp32 -> nearest TF32-representable fp32 (low 13 mantissa bits zero), so that what tcgen05 kind::tf32 reads
+// (it ignores those bits) is exactly the value we computed.  x = hi + lo + O(2^-23 |x|) with
+// hi = tf32_rn(x), lo = tf32_rn(x - hi).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

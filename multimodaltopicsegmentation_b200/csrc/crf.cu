@@ -210,67 +210,90 @@ __global__ void __launch_bounds__(128) crf_nll_fwd_kernel(const float *__restric
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Backward: beta recursion + marginals.  d_emis[b,t,i] = scale (P(y_t = i) - 1[y_t = i]);
-// d_trans[i][j] = scale sum_b sum_t (xi_t(i,j) - 1[y_t = i, y_{t-1} = j]) incl. START -> y_0 and y_last -> STOP.
-// Equals autograd through the reference's T-step loop (tests/test_oracle_golden.py::test_crf).
+// Backward.  Same chain of local soft-max Jacobians that autograd walks through the reference's T-step loop
+// (well conditioned for any length: every weight vector is re-normalised from the saved alphas, instead of
+// forming exp(alpha + beta - Z) whose fp32 error grows with the sequence length):
+//   g_last[i]   = softmax_i(alpha_last[i] + T[stop][i])
+//   w_t[i][j]   = softmax_j(alpha_{t-1}[j] + T[i][j])              (alpha_{-1} = START indicator)
+//   d_emis[t,i] = scale (g_t[i] - 1[y_t = i]);  d_trans[i][j] += scale (g_t[i] w_t[i][j] - 1[y_t = i, y_{t-1} = j])
+//   g_{t-1}[j]  = sum_i g_t[i] w_t[i][j]
+// Equals autograd of mean_b(Z_b - gold_b) (tests/test_oracle_golden.py::test_crf pins the closed form).
 // ---------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(128) crf_nll_bwd_kernel(const float *__restrict__ emis, const float *__restrict__ tags,
                                                           int64_t ldt, const int32_t *__restrict__ lengths,
                                                           const float *__restrict__ trans,
-                                                          const float *__restrict__ alphas,
-                                                          const float *__restrict__ log_z, int B, int L, const float *__restrict__ scale_dev,
+                                                          const float *__restrict__ alphas, int B, int L,
+                                                          const float *__restrict__ scale_dev,
                                                           float *__restrict__ d_emis, float *__restrict__ d_trans) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int len = min(max(lengths[b], 0), L);
   constexpr int kStart = C - 2, kStop = C - 1;
-  const float scale = __ldg(scale_dev + b);  // d loss / d logZ_b (= -d loss / d gold_b), e.g. grad_out / B for the mean
-  const int i = lane < C ? lane : C - 1;
+  const float scale = __ldg(scale_dev + b);  // d loss / d logZ_b (= -d loss / d gold_b): grad_out / B for the mean
+  const int i = lane < C ? lane : C - 1;     // lanes >= C mirror lane C-1 (keeps shuffles convergent)
 
-  float Trow[C], Tcol[C], dT[C];
+  float Trow[C], dT[C];
 #pragma unroll
   for (int j = 0; j < C; ++j) {
-    Trow[j] = __ldg(trans + i * C + j);   // T[i][j]: j -> i
-    Tcol[j] = __ldg(trans + j * C + i);   // T[j][i]: i -> j
+    Trow[j] = __ldg(trans + i * C + j);  // T[i][j]: j -> i
     dT[j] = 0.0f;
   }
-  const float *e_b = emis + (size_t)b * L * C;
   const float *a_b = alphas + (size_t)b * L * C;
   const float *y_b = tags + (size_t)b * ldt;
   float *de_b = d_emis + (size_t)b * L * C;
-  const float z = log_z[b];
 
   for (int t = len + (lane >> 3); t < L; t += 4)  // zero the padded tail (8 lanes x 4 rows per pass)
     for (int c = lane & 7; c < C; c += 8) de_b[(size_t)t * C + c] = 0.0f;
   if (len == 0) return;
 
-  // beta at the last valid step: transition to STOP; its gradient term
-  float beta = __ldg(trans + kStop * C + i);
+  // g at the last valid step: soft-max over the transition to STOP
+  float g;
   {
-    const float a_last = a_b[(size_t)(len - 1) * C + i];
+    float x[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) x[j] = a_b[(size_t)(len - 1) * C + j] + __ldg(trans + kStop * C + j);
+    float m = x[0];
+#pragma unroll
+    for (int j = 1; j < C; ++j) m = fmaxf(m, x[j]);
+    float s = 0.0f, mine = 0.0f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { const float ex = expf(x[j] - m); s += ex; if (j == i) mine = ex; }
+    g = mine / s;
     const int y_last = (int)y_b[len - 1];
-    const float g = expf(a_last + beta - z) - (i == y_last ? 1.0f : 0.0f);
-    if (lane < C) atomicAdd(d_trans + kStop * C + lane, scale * g);
+    if (lane < C) atomicAdd(d_trans + kStop * C + lane, scale * (g - (lane == y_last ? 1.0f : 0.0f)));
   }
   for (int t = len - 1; t >= 0; --t) {
-    const float e_i = __ldg(e_b + (size_t)t * C + i);
-    const float a_i = a_b[(size_t)t * C + i];
     const int y = (int)y_b[t];
     const int yp = (t == 0) ? kStart : (int)y_b[t - 1];
-    const float post = expf(a_i + beta - z);
-    if (lane < C) de_b[(size_t)t * C + lane] = scale * (post - (lane == y ? 1.0f : 0.0f));
-    const float xi_base = e_i + beta - z;  // + alpha_{t-1}[j] + T[i][j]
-    const float x_i = e_i + beta;          // message passed back to the state at t-1
-    float nb[C];
+    if (lane < C) de_b[(size_t)t * C + lane] = scale * (g - (lane == y ? 1.0f : 0.0f));
+    float x[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       const float a_prev = (t == 0) ? ((j == kStart) ? 0.0f : kImpossible) : a_b[(size_t)(t - 1) * C + j];
-      dT[j] += expf(a_prev + Trow[j] + xi_base) - ((i == y && j == yp) ? 1.0f : 0.0f);
-      nb[j] = __shfl_sync(0xffffffffu, x_i, j) + Tcol[j];  // T[j][i] + e[j] + beta[j]
+      x[j] = a_prev + Trow[j];
     }
-    beta = lse_over<C>(nb);
+    float m = x[0];
+#pragma unroll
+    for (int j = 1; j < C; ++j) m = fmaxf(m, x[j]);
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { x[j] = expf(x[j] - m); s += x[j]; }
+    const float gi = (lane < C) ? g / s : 0.0f;  // mirrored lanes must not be counted twice below
+    float gn = 0.0f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float c = gi * x[j];  // g_t[i] w_t[i][j]
+      dT[j] += c - ((i == y && j == yp && lane < C) ? 1.0f : 0.0f);
+      // g_{t-1}[j] = sum over lanes i of c: butterfly over the first 8 lanes (C <= 8)
+      float r = c;
+      r += __shfl_xor_sync(0xffffffffu, r, 1);
+      r += __shfl_xor_sync(0xffffffffu, r, 2);
+      r += __shfl_xor_sync(0xffffffffu, r, 4);
+      if (j == i) gn = r;
+    }
+    g = gn;
   }
   if (lane < C) {
 #pragma unroll
@@ -323,15 +346,15 @@ extern "C" int mts_crf_nll_fwd(const float *emis, const float *tags, int64_t ldt
 }
 
 extern "C" int mts_crf_nll_bwd(const float *emis, const float *tags, int64_t ldt, const int32_t *lengths,
-                               const float *trans, const float *alphas, const float *log_z, int B, int L, int C,
+                               const float *trans, const float *alphas, int B, int L, int C,
                                const float *scale_dev, float *d_emis, float *d_trans, void *stream) {
-  MTS_REQUIRE(emis && tags && lengths && trans && alphas && log_z && scale_dev && d_emis && d_trans, MTS_E_BADARG,
+  MTS_REQUIRE(emis && tags && lengths && trans && alphas && scale_dev && d_emis && d_trans, MTS_E_BADARG,
               "crf_nll_bwd: null pointer");
   MTS_REQUIRE(B > 0 && L > 0 && ldt >= L, MTS_E_BADARG, "crf_nll_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   MTS_CUDA(cudaMemsetAsync(d_trans, 0, sizeof(float) * C * C, st));
   MTS_DISPATCH_C(C, (crf_nll_bwd_kernel<kC><<<(B + 3) / 4, 128, 0, st>>>(emis, tags, ldt, lengths, trans, alphas,
-                                                                         log_z, B, L, scale_dev, d_emis, d_trans)));
+                                                                         B, L, scale_dev, d_emis, d_trans)));
   MTS_LAUNCH_CHECK();
   return 0;
 }

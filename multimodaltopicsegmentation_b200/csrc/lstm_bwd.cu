@@ -84,162 +84,224 @@ __global__ void __launch_bounds__(256) lstm_bwd_generic_kernel(const float *__re
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// H = 256 cluster kernel
+// H = 256 cluster kernel (persistent over work items; NT tiles of 8 episodes interleaved per item, as forward)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kDpStride = 8;             // floats per dp row (8 episodes)
 constexpr int kDpFloats = 128 * 8 + 4 * 8;  // 128 rows + 8 floats of padding per 32-row slice (bank spread)
 __device__ __forceinline__ int dp_row_base(int lr) { return lr * kDpStride + (lr >> 5) * 8; }
 
+template <int NT>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     lstm_bwd_cluster_kernel(const float *__restrict__ dy, const float *__restrict__ gates,
                             const float *__restrict__ w_hh, const int32_t *__restrict__ lengths,
                             const int32_t *__restrict__ order, int B, int T, int n_enc, int n_tiles,
                             float *__restrict__ dgx) {
-  __shared__ __align__(16) float recv[2][kCluster][kUnits][kBT];  // partial dh from every CTA, double buffered
-  __shared__ __align__(16) float dpbuf[2][kDpFloats];  // double buffered: step s+1 writes while laggards read step s
-  __shared__ __align__(8) uint64_t full_bar[2];
+  // dynamic shared memory (NT = 2 needs 49.7 KB, above the 48 KB static limit):
+  //   recv  [NT][2][8][32][8]  partial dh from every CTA, double buffered
+  //   dpbuf [NT][2][kDpFloats] double buffered: step s+1 writes while laggards still read step s
+  //   full_bar [NT][2]
+  extern __shared__ __align__(16) float smem_f[];
+  float(*recv)[2][kCluster][kUnits][kBT] = reinterpret_cast<float(*)[2][kCluster][kUnits][kBT]>(smem_f);
+  float(*dpbuf)[2][kDpFloats] = reinterpret_cast<float(*)[2][kDpFloats]>(smem_f + NT * 2 * kCluster * kUnits * kBT);
+  uint64_t(*full_bar)[2] =
+      reinterpret_cast<uint64_t(*)[2]>(smem_f + NT * 2 * kCluster * kUnits * kBT + NT * 2 * kDpFloats);
 
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
-  const int cid = blockIdx.x / kCluster;
-  const int tile = cid % n_tiles;
-  const int dir = (cid / n_tiles) & 1;
-  const int enc = cid / (2 * n_tiles);
+  const int n_clusters = gridDim.x / kCluster;
+  const int groups = (n_tiles + NT - 1) / NT;
+  const int n_items = groups * 2 * n_enc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ycols = n_enc * 2 * kH;
 
-  // ---- cell role: (unit u of this CTA, episode slot e) -----------------------------------------------------
+  // cell role: (unit u of this CTA, episode slot e);  matvec role: (k-group kg: k = 4 kg .. 4 kg + 3, row slice rs = gate)
   const int u = tid >> 3, e = tid & 7;
   const int unit = rank * kUnits + u;
-  const int slot = tile * kBT + e;
-  const int b = (slot < B) ? (order ? order[slot] : slot) : -1;
-  const int len = (b >= 0) ? min(max(lengths[b], 0), T) : 0;
-  int nsteps = len;
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
-
-  // ---- matvec role: (k-group kg: k = 4 kg .. 4 kg + 3, row slice rs = gate) ----------------------------------
   const int rs = lane & 3, kg = warp * 8 + (lane >> 2);
-  float Wb[32][4];
-  {
-    const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * kH * kH;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float4 v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(rs * kH + rank * kUnits + j) * kH + kg * 4));
-      Wb[j][0] = v.x; Wb[j][1] = v.y; Wb[j][2] = v.z; Wb[j][3] = v.w;
-    }
-  }
 
-  for (int i = tid; i < 2 * kCluster * kUnits * kBT; i += kThreads) (&recv[0][0][0][0])[i] = 0.0f;
-  for (int i = tid; i < 2 * kDpFloats; i += kThreads) (&dpbuf[0][0])[i] = 0.0f;
-  if (tid == 0) {
-    mbar_init(smem_u32(&full_bar[0]), 1);
-    mbar_init(smem_u32(&full_bar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  cluster.sync();
-
-  // my partial sums for k = 4 kg + rs go to CTA `warp`, unit row `lane` of its recv[.][rank]
-  const uint32_t raddr0 = mapa(smem_u32(&recv[0][rank][lane][0]), (uint32_t)warp);
-  const uint32_t rbar0 = mapa(smem_u32(&full_bar[0]), (uint32_t)warp);
+  // my partial sums for k = 4 kg + rs go to CTA `warp`, unit row `lane` of its recv[.][.][rank]
+  const uint32_t raddr0 = mapa(smem_u32(&recv[0][0][rank][lane][0]), (uint32_t)warp);
+  const uint32_t rbar0 = mapa(smem_u32(&full_bar[0][0]), (uint32_t)warp);
   constexpr uint32_t kRecvBytes = kCluster * kUnits * kBT * 4;  // 8 KB
 
-  const int ycols = n_enc * 2 * kH;
-  const float *dy_cell = (b >= 0) ? dy + (size_t)b * T * ycols + (size_t)enc * 2 * kH + dir * kH + unit : nullptr;
-  const float *g_cell = (b >= 0) ? gates + ((((size_t)enc * 2 + dir) * B + b) * T) * 5 * kH + unit : nullptr;
-  float *dgx_cell = (b >= 0) ? dgx + (size_t)enc * B * T * 8 * kH + (size_t)b * T * 8 * kH + dir * 4 * kH + unit : nullptr;
+  for (int item = blockIdx.x / kCluster; item < n_items; item += n_clusters) {
+    const int grp = item % groups;
+    const int dir = (item / groups) & 1;
+    const int enc = item / (2 * groups);
 
-  // time visited at backward step s, and prefetch of its saved activations
-  auto time_at = [&](int s) { return dir ? s : len - 1 - s; };
-  float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, dyv = 0.f, c_cur = 0.f, c_nxt = 0.f;
-  if (len > 0) {
-    const float *gs = g_cell + (size_t)time_at(0) * 5 * kH;
-    ig = __ldg(gs); fg = __ldg(gs + kH); gg = __ldg(gs + 2 * kH); og = __ldg(gs + 3 * kH); c_cur = __ldg(gs + 4 * kH);
-    dyv = __ldg(dy_cell + (size_t)time_at(0) * ycols);
-    if (len > 1) c_nxt = __ldg(g_cell + (size_t)time_at(1) * 5 * kH + 4 * kH);
-  }
-  float dc = 0.0f;
-
-  for (int s = 0; s < nsteps; ++s) {
-    const int p = s & 1;
-    if (tid == 0 && s + 1 < nsteps) mbar_arrive_expect_tx(smem_u32(&full_bar[p ^ 1]), kRecvBytes);
-    if (s > 0) mbar_wait(smem_u32(&full_bar[p]), ((s - 1) >> 1) & 1);
-
-    // ---- cell phase ----------------------------------------------------------------------------------------
-    const bool active = s < len;
-    GateGrads g{0.f, 0.f, 0.f, 0.f, 0.f};
-    if (active) {
-      float dht = dyv;
-      if (s > 0) {
+    float Wb[32][4];
+    {
+      const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * kH * kH;
 #pragma unroll
-        for (int src = 0; src < kCluster; ++src) dht += recv[p][src][u][e];
+      for (int j = 0; j < 32; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(rs * kH + rank * kUnits + j) * kH + kg * 4));
+        Wb[j][0] = v.x; Wb[j][1] = v.y; Wb[j][2] = v.z; Wb[j][3] = v.w;
       }
-      g = lstm_cell_bwd(dht, dc, ig, fg, gg, og, c_cur, (s + 1 < len) ? c_nxt : 0.0f);
-      dc = g.dc_prev;
-      float *o = dgx_cell + (size_t)time_at(s) * 8 * kH;
-      o[0] = g.dpi; o[kH] = g.dpf; o[2 * kH] = g.dpg; o[3 * kH] = g.dpo;
     }
-    dpbuf[p][dp_row_base(0 * 32 + u) + e] = g.dpi;
-    dpbuf[p][dp_row_base(1 * 32 + u) + e] = g.dpf;
-    dpbuf[p][dp_row_base(2 * 32 + u) + e] = g.dpg;
-    dpbuf[p][dp_row_base(3 * 32 + u) + e] = g.dpo;
-    if (s + 1 < len) {  // prefetch the next step's activations (and the cell state two steps ahead)
-      const float *gs = g_cell + (size_t)time_at(s + 1) * 5 * kH;
-      ig = __ldg(gs); fg = __ldg(gs + kH); gg = __ldg(gs + 2 * kH); og = __ldg(gs + 3 * kH);
-      dyv = __ldg(dy_cell + (size_t)time_at(s + 1) * ycols);
-      c_cur = c_nxt;
-      if (s + 2 < len) c_nxt = __ldg(g_cell + (size_t)time_at(s + 2) * 5 * kH + 4 * kH);
+
+    int bq[NT], len[NT];
+    int nsteps = 0;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int tile = grp * NT + j;
+      const int slot = tile * kBT + e;
+      bq[j] = (tile < n_tiles && slot < B) ? (order ? order[slot] : slot) : -1;
+      len[j] = (bq[j] >= 0) ? min(max(lengths[bq[j]], 0), T) : 0;
+      nsteps = max(nsteps, len[j]);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
+
+    for (int i = tid; i < NT * 2 * kCluster * kUnits * kBT; i += kThreads) (&recv[0][0][0][0][0])[i] = 0.0f;
+    for (int i = tid; i < NT * 2 * kDpFloats; i += kThreads) (&dpbuf[0][0][0])[i] = 0.0f;
+    if (tid == 0) {
+#pragma unroll
+      for (int j = 0; j < NT * 2; ++j) mbar_init(smem_u32(&full_bar[0][0] + j), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (s + 1 >= nsteps) break;  // the last step's dh_prev has no consumer
+    cluster.sync();
 
-    // ---- matvec phase: 32 rows (gate rs) x 4 k x 8 episodes ------------------------------------------------
-    float acc[4][8];
+    const size_t ycol = (size_t)enc * 2 * kH + dir * kH + unit;
+    const size_t gate_base = ((size_t)enc * 2 + dir) * B;
+    const size_t dgx_enc = (size_t)enc * B * T * 8 * kH;
+    const int gcol = dir * 4 * kH + unit;
+
+    // time visited at backward step s by tile j's cell, and prefetch of its saved activations
+    float ig[NT], fg[NT], gg[NT], og[NT], dyv[NT], c_cur[NT], c_nxt[NT], dc[NT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int x = 0; x < 8; ++x) acc[q][x] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float4 da = *reinterpret_cast<const float4 *>(&dpbuf[p][dp_row_base(rs * 32 + j)]);
-      const float4 db = *reinterpret_cast<const float4 *>(&dpbuf[p][dp_row_base(rs * 32 + j) + 4]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float w = Wb[j][q];
-        acc[q][0] = fmaf(w, da.x, acc[q][0]); acc[q][1] = fmaf(w, da.y, acc[q][1]);
-        acc[q][2] = fmaf(w, da.z, acc[q][2]); acc[q][3] = fmaf(w, da.w, acc[q][3]);
-        acc[q][4] = fmaf(w, db.x, acc[q][4]); acc[q][5] = fmaf(w, db.y, acc[q][5]);
-        acc[q][6] = fmaf(w, db.z, acc[q][6]); acc[q][7] = fmaf(w, db.w, acc[q][7]);
+    for (int j = 0; j < NT; ++j) {
+      ig[j] = fg[j] = gg[j] = og[j] = dyv[j] = c_cur[j] = c_nxt[j] = dc[j] = 0.0f;
+      if (len[j] > 0) {
+        const int t0 = dir ? 0 : len[j] - 1;
+        const float *gs = gates + ((gate_base + bq[j]) * T + t0) * 5 * kH + unit;
+        ig[j] = __ldg(gs); fg[j] = __ldg(gs + kH); gg[j] = __ldg(gs + 2 * kH); og[j] = __ldg(gs + 3 * kH);
+        c_cur[j] = __ldg(gs + 4 * kH);
+        dyv[j] = __ldg(dy + ((size_t)bq[j] * T + t0) * ycols + ycol);
+        if (len[j] > 1) {
+          const int t1 = dir ? 1 : len[j] - 2;
+          c_nxt[j] = __ldg(gates + ((gate_base + bq[j]) * T + t1) * 5 * kH + 4 * kH + unit);
+        }
       }
     }
-    // reduce over the 4 row slices (gates); lane rs keeps k = 4 kg + rs
-    float r1[2][8], out[8];
-    const bool b1 = rs & 2, b0 = rs & 1;
+
+    for (int s = 0; s < nsteps; ++s) {
+      const int p = s & 1;
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+      for (int j = 0; j < NT; ++j) {
+        if (tid == 0 && s + 1 < nsteps) mbar_arrive_expect_tx(smem_u32(&full_bar[j][p ^ 1]), kRecvBytes);
+        if (s > 0) mbar_wait(smem_u32(&full_bar[j][p]), ((s - 1) >> 1) & 1);
+
+        // ---- cell phase --------------------------------------------------------------------------------------
+        const bool active = s < len[j];
+        GateGrads g{0.f, 0.f, 0.f, 0.f, 0.f};
+        if (active) {
+          float dht = dyv[j];
+          if (s > 0) {
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const float keep = b1 ? acc[2 + q][x] : acc[q][x];
-        const float send = b1 ? acc[q][x] : acc[2 + q][x];
-        r1[q][x] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            for (int src = 0; src < kCluster; ++src) dht += recv[j][p][src][u][e];
+          }
+          g = lstm_cell_bwd(dht, dc[j], ig[j], fg[j], gg[j], og[j], c_cur[j], (s + 1 < len[j]) ? c_nxt[j] : 0.0f);
+          dc[j] = g.dc_prev;
+          const int t = dir ? s : len[j] - 1 - s;
+          float *o = dgx + dgx_enc + ((size_t)bq[j] * T + t) * 8 * kH + gcol;
+          o[0] = g.dpi; o[kH] = g.dpf; o[2 * kH] = g.dpg; o[3 * kH] = g.dpo;
+        }
+        float *dpb = &dpbuf[j][p][0];
+        dpb[dp_row_base(0 * 32 + u) + e] = g.dpi;
+        dpb[dp_row_base(1 * 32 + u) + e] = g.dpf;
+        dpb[dp_row_base(2 * 32 + u) + e] = g.dpg;
+        dpb[dp_row_base(3 * 32 + u) + e] = g.dpo;
+        if (s + 1 < len[j]) {  // prefetch the next step's activations (and the cell state two steps ahead)
+          const int tn = dir ? s + 1 : len[j] - 2 - s;
+          const float *gs = gates + ((gate_base + bq[j]) * T + tn) * 5 * kH + unit;
+          ig[j] = __ldg(gs); fg[j] = __ldg(gs + kH); gg[j] = __ldg(gs + 2 * kH); og[j] = __ldg(gs + 3 * kH);
+          dyv[j] = __ldg(dy + ((size_t)bq[j] * T + tn) * ycols + ycol);
+          c_cur[j] = c_nxt[j];
+          if (s + 2 < len[j]) {
+            const int t2 = dir ? s + 2 : len[j] - 3 - s;
+            c_nxt[j] = __ldg(gates + ((gate_base + bq[j]) * T + t2) * 5 * kH + 4 * kH + unit);
+          }
+        }
+        __syncthreads();
+        if (s + 1 >= nsteps) continue;  // the last step's dh_prev has no consumer
+
+        // ---- matvec phase: 32 rows (gate rs) x 4 k x 8 episodes ----------------------------------------------
+        float acc[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int x = 0; x < 8; ++x) acc[q][x] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float4 da = *reinterpret_cast<const float4 *>(&dpb[dp_row_base(rs * 32 + r)]);
+          const float4 db = *reinterpret_cast<const float4 *>(&dpb[dp_row_base(rs * 32 + r) + 4]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float w = Wb[r][q];
+            acc[q][0] = fmaf(w, da.x, acc[q][0]); acc[q][1] = fmaf(w, da.y, acc[q][1]);
+            acc[q][2] = fmaf(w, da.z, acc[q][2]); acc[q][3] = fmaf(w, da.w, acc[q][3]);
+            acc[q][4] = fmaf(w, db.x, acc[q][4]); acc[q][5] = fmaf(w, db.y, acc[q][5]);
+            acc[q][6] = fmaf(w, db.z, acc[q][6]); acc[q][7] = fmaf(w, db.w, acc[q][7]);
+          }
+        }
+        // reduce over the 4 row slices (gates); lane rs keeps k = 4 kg + rs
+        float r1[2][8], out[8];
+        const bool b1 = rs & 2, b0 = rs & 1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const float keep = b1 ? acc[2 + q][x] : acc[q][x];
+            const float send = b1 ? acc[q][x] : acc[2 + q][x];
+            r1[q][x] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          const float keep = b0 ? r1[1][x] : r1[0][x];
+          const float send = b0 ? r1[0][x] : r1[1][x];
+          out[x] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        const uint32_t boff = (uint32_t)(j * 2 + (p ^ 1)) * kRecvBytes, moff = (uint32_t)(j * 2 + (p ^ 1)) * 8;
+        st_async_v4(raddr0 + boff, make_float4(out[0], out[1], out[2], out[3]), rbar0 + moff);
+        st_async_v4(raddr0 + boff + 16, make_float4(out[4], out[5], out[6], out[7]), rbar0 + moff);
       }
-#pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      const float keep = b0 ? r1[1][x] : r1[0][x];
-      const float send = b0 ? r1[0][x] : r1[1][x];
-      out[x] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
     }
-    const uint32_t boff = (uint32_t)(p ^ 1) * kRecvBytes, moff = (uint32_t)(p ^ 1) * 8;
-    st_async_v4(raddr0 + boff, make_float4(out[0], out[1], out[2], out[3]), rbar0 + moff);
-    st_async_v4(raddr0 + boff + 16, make_float4(out[4], out[5], out[6], out[7]), rbar0 + moff);
+    // zero the padded tail of my (episode, unit) gate columns
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      if (bq[j] >= 0)
+        for (int t = len[j]; t < T; ++t) {
+          float *o = dgx + dgx_enc + ((size_t)bq[j] * T + t) * 8 * kH + gcol;
+          o[0] = 0.0f; o[kH] = 0.0f; o[2 * kH] = 0.0f; o[3 * kH] = 0.0f;
+        }
+    cluster.sync();
   }
-  // zero the padded tail of my (episode, unit) gate columns
-  if (b >= 0)
-    for (int t = len; t < T; ++t) {
-      float *o = dgx_cell + (size_t)t * 8 * kH;
-      o[0] = 0.0f; o[kH] = 0.0f; o[2 * kH] = 0.0f; o[3 * kH] = 0.0f;
-    }
-  cluster.sync();
+}
+
+constexpr size_t bwd_smem_bytes(int nt) {
+  return (size_t)nt * 2 * (kCluster * kUnits * kBT + kDpFloats) * sizeof(float) + (size_t)nt * 2 * sizeof(uint64_t);
+}
+
+template <typename K>
+static int max_active_clusters_bwd(K kernel, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCluster * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = kCluster;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 14;
+  }
+  return n;
 }
 
 }  // namespace mts
@@ -252,9 +314,22 @@ extern "C" int mts_lstm_rec_bwd(const float *dy, const float *gates, const float
   MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0 && H > 0, MTS_E_BADARG, "lstm_rec_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (H == kH) {
+    constexpr size_t smem1 = bwd_smem_bytes(1), smem2 = bwd_smem_bytes(2);
+    static int cap = 0;
+    if (!cap) {
+      MTS_CUDA(cudaFuncSetAttribute(lstm_bwd_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      cap = max_active_clusters_bwd(lstm_bwd_cluster_kernel<1>, smem1);
+    }
     const int n_tiles = (B + kBT - 1) / kBT;
-    const unsigned grid = (unsigned)(n_tiles * 2 * n_enc * kCluster);
-    lstm_bwd_cluster_kernel<<<grid, kThreads, 0, st>>>(dy, gates, w_hh, lengths, order, B, T, n_enc, n_tiles, dgx);
+    const int items1 = n_tiles * 2 * n_enc;
+    if (items1 <= cap) {
+      lstm_bwd_cluster_kernel<1><<<(unsigned)(items1 * kCluster), kThreads, smem1, st>>>(dy, gates, w_hh, lengths, order, B,
+                                                                                         T, n_enc, n_tiles, dgx);
+    } else {
+      const int items2 = ((n_tiles + 1) / 2) * 2 * n_enc;
+      lstm_bwd_cluster_kernel<2><<<(unsigned)((items2 < cap ? items2 : cap) * kCluster), kThreads, smem2, st>>>(
+          dy, gates, w_hh, lengths, order, B, T, n_enc, n_tiles, dgx);
+    }
   } else {
     MTS_REQUIRE(H <= 2048, MTS_E_UNSUPPORTED, "lstm_rec_bwd: H > 2048 not supported by the generic kernel");
     const size_t smem = (size_t)6 * H * sizeof(float);

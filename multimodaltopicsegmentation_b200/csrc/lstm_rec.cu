@@ -69,173 +69,218 @@ __global__ void __launch_bounds__(256) lstm_fwd_generic_kernel(const float *__re
       y[((size_t)b * T + t) * ycols + (size_t)enc * 2 * H + dir * H + u] = 0.0f;
 }
 
-template <bool SAVE>
+// One work item = NT tiles of 8 episodes of one (direction, encoder), advanced in lock-step and INTERLEAVED:
+// while tile 0's h_t is in flight through distributed shared memory, the CTA computes tile 1's step, and vice
+// versa, so the exchange latency is hidden behind FMAs.  Clusters are persistent over work items.
+template <bool SAVE, int NT>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     lstm_fwd_cluster_kernel(const float *__restrict__ gx, const float *__restrict__ w_hh,
                             const int32_t *__restrict__ lengths, const int32_t *__restrict__ order, int B, int T,
                             int n_enc, int n_tiles, float *__restrict__ y, float *__restrict__ gates) {
-  __shared__ __align__(16) float hbuf[2][kHBufFloats];
-  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ __align__(16) float hbuf[NT][2][kHBufFloats];
+  __shared__ __align__(8) uint64_t full_bar[NT][2];
 
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
-  const int cid = blockIdx.x / kCluster;  // cluster id -> (tile, dir, enc)
-  const int tile = cid % n_tiles;
-  const int dir = (cid / n_tiles) & 1;
-  const int enc = cid / (2 * n_tiles);
+  const int n_clusters = gridDim.x / kCluster;
+  const int groups = (n_tiles + NT - 1) / NT;  // tile groups per (direction, encoder)
+  const int n_items = groups * 2 * n_enc;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ks = lane & 7;                  // k-slice: k in [32 ks, 32 ks + 32); after the reduction: my episode slot
   const int u = warp * 4 + (lane >> 3);     // hidden unit inside this CTA, 0..31
   const int unit = rank * kUnits + u;       // hidden unit inside the layer, 0..255
-
-  // ---- W_hh slice into registers: 4 gate rows of my unit x my 32 k ---------------------------------------
-  float Wr[4][32];
-  {
-    const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * kH * kH;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float4 *src = reinterpret_cast<const float4 *>(W + (size_t)(g * kH + unit) * kH + ks * 32);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = __ldg(src + q);
-        Wr[g][4 * q + 0] = v.x; Wr[g][4 * q + 1] = v.y; Wr[g][4 * q + 2] = v.z; Wr[g][4 * q + 3] = v.w;
-      }
-    }
-  }
-
-  // ---- my cell: (unit, episode slot ks) ------------------------------------------------------------------
-  const int slot = tile * kBT + ks;
-  const int b = (slot < B) ? (order ? order[slot] : slot) : -1;
-  const int len = (b >= 0) ? min(max(lengths[b], 0), T) : 0;
-  int nsteps = len;  // tile step count = max over the 8 slots (all lanes with the same `ks` pattern agree)
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
-
-  for (int i = tid; i < 2 * kHBufFloats; i += kThreads) (&hbuf[0][0])[i] = 0.0f;
-  if (tid == 0) {
-    mbar_init(smem_u32(&full_bar[0]), 1);
-    mbar_init(smem_u32(&full_bar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  cluster.sync();  // every CTA's barriers and zeroed buffers exist before any remote store
-
   const int ycols = n_enc * 2 * kH;
-  const size_t gx_enc = (size_t)enc * B * T * 8 * kH;
-  const int gcol = dir * 4 * kH + unit;
-  float *y_cell = (b >= 0) ? y + (size_t)b * T * ycols + (size_t)enc * 2 * kH + dir * kH + unit : nullptr;
-  float *g_cell = (SAVE && b >= 0) ? gates + ((((size_t)enc * 2 + dir) * B + b) * T) * 5 * kH + unit : nullptr;
 
   // remote addresses: lane writes the assembled float4 of its 4-episode group to CTAs {2*(ks&3), 2*(ks&3)+1}
+  // (the mapped shared::cluster window is linear in the CTA-local offset, so tile / buffer offsets just add)
   const int half = ks >> 2;
   const uint32_t dst0 = 2 * (ks & 3), dst1 = dst0 + 1;
-  // (the mapped shared::cluster window is linear in the CTA-local offset: buffer 1 = buffer 0 + its size)
-  const uint32_t la = smem_u32(&hbuf[0][((half * 32 + u) * 8 + rank) * 4]);
-  const uint32_t lb = smem_u32(&full_bar[0]);
+  const uint32_t la = smem_u32(&hbuf[0][0][((half * 32 + u) * 8 + rank) * 4]);
+  const uint32_t lb = smem_u32(&full_bar[0][0]);
   const uint32_t raddr0 = mapa(la, dst0), raddr1 = mapa(la, dst1);
   const uint32_t rbar0 = mapa(lb, dst0), rbar1 = mapa(lb, dst1);
 
-  float c = 0.0f;
-  float gxn[4] = {0.f, 0.f, 0.f, 0.f};
-  if (len > 0) {
-    const int t0 = dir ? len - 1 : 0;
-    const float *g_row = gx + gx_enc + ((size_t)b * T + t0) * 8 * kH + gcol;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) gxn[g] = __ldg(g_row + g * kH);
-  }
+  for (int item = blockIdx.x / kCluster; item < n_items; item += n_clusters) {
+    const int grp = item % groups;
+    const int dir = (item / groups) & 1;
+    const int enc = item / (2 * groups);
 
-  for (int s = 0; s < nsteps; ++s) {
-    const int p = s & 1;  // buffer holding h_{s-1}
-    if (tid == 0 && s + 1 < nsteps) mbar_arrive_expect_tx(smem_u32(&full_bar[p ^ 1]), kHBufFloats * 4);
-    if (s > 0) mbar_wait(smem_u32(&full_bar[p]), ((s - 1) >> 1) & 1);
-
-    const bool active = s < len;
-    float gxc[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) gxc[g] = gxn[g];
-    if (s + 1 < len) {  // prefetch the next step's input projection
-      const int tn = dir ? len - 2 - s : s + 1;
-      const float *g_row = gx + gx_enc + ((size_t)b * T + tn) * 8 * kH + gcol;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) gxn[g] = __ldg(g_row + g * kH);
-    }
-
-    // ---- 4 gate rows x 8 episodes x my 32 k --------------------------------------------------------------
-    float acc[4][8];
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[g][e] = 0.0f;
-    const float4 *hp = reinterpret_cast<const float4 *>(&hbuf[p][0]);
-#pragma unroll
-    for (int kk = 0; kk < 32; ++kk) {
-      const float4 ha = hp[kk * 8 + ks];
-      const float4 hb = hp[(32 + kk) * 8 + ks];
+    // ---- W_hh slice into registers: 4 gate rows of my unit x my 32 k -------------------------------------
+    float Wr[4][32];
+    {
+      const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * kH * kH;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float w = Wr[g][kk];
-        acc[g][0] = fmaf(w, ha.x, acc[g][0]); acc[g][1] = fmaf(w, ha.y, acc[g][1]);
-        acc[g][2] = fmaf(w, ha.z, acc[g][2]); acc[g][3] = fmaf(w, ha.w, acc[g][3]);
-        acc[g][4] = fmaf(w, hb.x, acc[g][4]); acc[g][5] = fmaf(w, hb.y, acc[g][5]);
-        acc[g][6] = fmaf(w, hb.z, acc[g][6]); acc[g][7] = fmaf(w, hb.w, acc[g][7]);
+        const float4 *src = reinterpret_cast<const float4 *>(W + (size_t)(g * kH + unit) * kH + ks * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = __ldg(src + q);
+          Wr[g][4 * q + 0] = v.x; Wr[g][4 * q + 1] = v.y; Wr[g][4 * q + 2] = v.z; Wr[g][4 * q + 3] = v.w;
+        }
       }
     }
-    // ---- reduce over the 8 k-slices by recursive halving; lane ks ends with episode slot ks ---------------
-    float r1[4][4], r2[4][2], pre[4];
-    const bool b2 = ks & 4, b1 = ks & 2, b0 = ks & 1;
+
+    // ---- my cells: (unit, episode slot ks) of each tile ----------------------------------------------------
+    int bq[NT], len[NT];
+    int nsteps = 0;
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float keep = b2 ? acc[g][4 + e] : acc[g][e];
-        const float send = b2 ? acc[g][e] : acc[g][4 + e];
-        r1[g][e] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float keep = b1 ? r1[g][2 + e] : r1[g][e];
-        const float send = b1 ? r1[g][e] : r1[g][2 + e];
-        r2[g][e] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-      }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float keep = b0 ? r2[g][1] : r2[g][0];
-      const float send = b0 ? r2[g][0] : r2[g][1];
-      pre[g] = keep + __shfl_xor_sync(0xffffffffu, send, 1) + gxc[g];
+    for (int j = 0; j < NT; ++j) {
+      const int tile = grp * NT + j;
+      const int slot = tile * kBT + ks;
+      bq[j] = (tile < n_tiles && slot < B) ? (order ? order[slot] : slot) : -1;
+      len[j] = (bq[j] >= 0) ? min(max(lengths[bq[j]], 0), T) : 0;
+      nsteps = max(nsteps, len[j]);
     }
-    // ---- gates, cell, output ------------------------------------------------------------------------------
-    float hn = 0.0f;
-    if (active) {
-      const float ig = sigmoidf_acc(pre[0]), fg = sigmoidf_acc(pre[1]);
-      const float gg = tanhf(pre[2]), og = sigmoidf_acc(pre[3]);
-      c = fmaf(fg, c, ig * gg);
-      hn = og * tanhf(c);
-      const int t = dir ? len - 1 - s : s;
-      y_cell[(size_t)t * ycols] = hn;
-      if (SAVE) {
-        float *gs = g_cell + (size_t)t * 5 * kH;
-        gs[0] = ig; gs[kH] = fg; gs[2 * kH] = gg; gs[3 * kH] = og; gs[4 * kH] = c;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
+
+    for (int i = tid; i < NT * 2 * kHBufFloats; i += kThreads) (&hbuf[0][0][0])[i] = 0.0f;
+    if (tid == 0) {
+#pragma unroll
+      for (int j = 0; j < NT * 2; ++j) mbar_init(smem_u32(&full_bar[0][0] + j), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster.sync();  // every CTA's barriers and zeroed buffers exist before any remote store
+
+    const size_t gx_enc = (size_t)enc * B * T * 8 * kH;
+    const int gcol = dir * 4 * kH + unit;
+    const size_t ycol = (size_t)enc * 2 * kH + dir * kH + unit;
+    const size_t gate_base = ((size_t)enc * 2 + dir) * B;
+
+    float c[NT], gxn[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      c[j] = 0.0f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gxn[j][g] = 0.0f;
+      if (len[j] > 0) {
+        const int t0 = dir ? len[j] - 1 : 0;
+        const float *g_row = gx + gx_enc + ((size_t)bq[j] * T + t0) * 8 * kH + gcol;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gxn[j][g] = __ldg(g_row + g * kH);
       }
     }
-    if (s + 1 < nsteps) {  // broadcast h_s: assemble the 4 episodes of my group, 2 remote stores per lane
-      const int base = lane & ~3;
-      float4 v;
-      v.x = __shfl_sync(0xffffffffu, hn, base + 0);
-      v.y = __shfl_sync(0xffffffffu, hn, base + 1);
-      v.z = __shfl_sync(0xffffffffu, hn, base + 2);
-      v.w = __shfl_sync(0xffffffffu, hn, base + 3);
-      const uint32_t boff = (uint32_t)(p ^ 1) * (kHBufFloats * 4), moff = (uint32_t)(p ^ 1) * 8;
-      st_async_v4(raddr0 + boff, v, rbar0 + moff);
-      st_async_v4(raddr1 + boff, v, rbar1 + moff);
+
+    for (int s = 0; s < nsteps; ++s) {
+      const int p = s & 1;  // buffer holding h_{s-1}
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (tid == 0 && s + 1 < nsteps) mbar_arrive_expect_tx(smem_u32(&full_bar[j][p ^ 1]), kHBufFloats * 4);
+        if (s > 0) mbar_wait(smem_u32(&full_bar[j][p]), ((s - 1) >> 1) & 1);
+
+        const bool active = s < len[j];
+        float gxc[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gxc[g] = gxn[j][g];
+        if (s + 1 < len[j]) {  // prefetch the next step's input projection
+          const int tn = dir ? len[j] - 2 - s : s + 1;
+          const float *g_row = gx + gx_enc + ((size_t)bq[j] * T + tn) * 8 * kH + gcol;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) gxn[j][g] = __ldg(g_row + g * kH);
+        }
+
+        // ---- 4 gate rows x 8 episodes x my 32 k ------------------------------------------------------------
+        float acc[4][8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[g][e] = 0.0f;
+        const float4 *hp = reinterpret_cast<const float4 *>(&hbuf[j][p][0]);
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+          const float4 ha = hp[kk * 8 + ks];
+          const float4 hb = hp[(32 + kk) * 8 + ks];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float w = Wr[g][kk];
+            acc[g][0] = fmaf(w, ha.x, acc[g][0]); acc[g][1] = fmaf(w, ha.y, acc[g][1]);
+            acc[g][2] = fmaf(w, ha.z, acc[g][2]); acc[g][3] = fmaf(w, ha.w, acc[g][3]);
+            acc[g][4] = fmaf(w, hb.x, acc[g][4]); acc[g][5] = fmaf(w, hb.y, acc[g][5]);
+            acc[g][6] = fmaf(w, hb.z, acc[g][6]); acc[g][7] = fmaf(w, hb.w, acc[g][7]);
+          }
+        }
+        // ---- reduce over the 8 k-slices by recursive halving; lane ks ends with episode slot ks -------------
+        float r1[4][4], r2[4][2], pre[4];
+        const bool b2 = ks & 4, b1 = ks & 2, b0 = ks & 1;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float keep = b2 ? acc[g][4 + e] : acc[g][e];
+            const float send = b2 ? acc[g][e] : acc[g][4 + e];
+            r1[g][e] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float keep = b1 ? r1[g][2 + e] : r1[g][e];
+            const float send = b1 ? r1[g][e] : r1[g][2 + e];
+            r2[g][e] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float keep = b0 ? r2[g][1] : r2[g][0];
+          const float send = b0 ? r2[g][0] : r2[g][1];
+          pre[g] = keep + __shfl_xor_sync(0xffffffffu, send, 1) + gxc[g];
+        }
+        // ---- gates, cell, output ----------------------------------------------------------------------------
+        float hn = 0.0f;
+        if (active) {
+          const float ig = sigmoidf_acc(pre[0]), fg = sigmoidf_acc(pre[1]);
+          const float gg = tanhf(pre[2]), og = sigmoidf_acc(pre[3]);
+          c[j] = fmaf(fg, c[j], ig * gg);
+          hn = og * tanhf(c[j]);
+          const int t = dir ? len[j] - 1 - s : s;
+          y[((size_t)bq[j] * T + t) * ycols + ycol] = hn;
+          if (SAVE) {
+            float *gs = gates + ((gate_base + bq[j]) * T + t) * 5 * kH + unit;
+            gs[0] = ig; gs[kH] = fg; gs[2 * kH] = gg; gs[3 * kH] = og; gs[4 * kH] = c[j];
+          }
+        }
+        if (s + 1 < nsteps) {  // broadcast h_s: assemble the 4 episodes of my group, 2 remote stores per lane
+          const int base = lane & ~3;
+          float4 v;
+          v.x = __shfl_sync(0xffffffffu, hn, base + 0);
+          v.y = __shfl_sync(0xffffffffu, hn, base + 1);
+          v.z = __shfl_sync(0xffffffffu, hn, base + 2);
+          v.w = __shfl_sync(0xffffffffu, hn, base + 3);
+          const uint32_t boff = (uint32_t)(j * 2 + (p ^ 1)) * (kHBufFloats * 4), moff = (uint32_t)(j * 2 + (p ^ 1)) * 8;
+          st_async_v4(raddr0 + boff, v, rbar0 + moff);
+          st_async_v4(raddr1 + boff, v, rbar1 + moff);
+        }
+      }
     }
+    // zero the padded tail of my (episode, unit) columns
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      if (bq[j] >= 0)
+        for (int t = len[j]; t < T; ++t) y[((size_t)bq[j] * T + t) * ycols + ycol] = 0.0f;
+    cluster.sync();  // nobody moves on (or exits) while a peer may still address its shared memory
   }
-  // zero the padded tail of my (episode, unit) column
-  if (b >= 0)
-    for (int t = len; t < T; ++t) y_cell[(size_t)t * ycols] = 0.0f;
-  cluster.sync();  // nobody exits while a peer may still address its shared memory
+}
+
+// number of 8-CTA clusters of this kernel the device can hold at once (GPC granularity: ~14 on a B200)
+template <typename K>
+static int max_active_clusters(K kernel) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCluster * 64);
+  cfg.blockDim = dim3(kThreads);
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = kCluster;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 14;
+  }
+  return n;
 }
 
 }  // namespace mts
@@ -248,12 +293,21 @@ extern "C" int mts_lstm_rec_fwd(const float *gx, const float *w_hh, const int32_
   MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0 && H > 0, MTS_E_BADARG, "lstm_rec_fwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (H == kH) {
+    static int cap = 0;
+    if (!cap) cap = max_active_clusters(lstm_fwd_cluster_kernel<false, 1>);
     const int n_tiles = (B + kBT - 1) / kBT;
-    const unsigned grid = (unsigned)(n_tiles * 2 * n_enc * kCluster);
-    if (gates)
-      lstm_fwd_cluster_kernel<true><<<grid, kThreads, 0, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
-    else
-      lstm_fwd_cluster_kernel<false><<<grid, kThreads, 0, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+    const int items1 = n_tiles * 2 * n_enc;
+    // one tile per cluster while everything fits in a single wave; otherwise two interleaved tiles per cluster
+    if (items1 <= cap) {
+      const unsigned grid = (unsigned)(items1 * kCluster);
+      if (gates) lstm_fwd_cluster_kernel<true, 1><<<grid, kThreads, 0, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+      else lstm_fwd_cluster_kernel<false, 1><<<grid, kThreads, 0, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+    } else {
+      const int items2 = ((n_tiles + 1) / 2) * 2 * n_enc;
+      const unsigned grid = (unsigned)((items2 < cap ? items2 : cap) * kCluster);
+      if (gates) lstm_fwd_cluster_kernel<true, 2><<<grid, kThreads, 0, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+      else lstm_fwd_cluster_kernel<false, 2><<<grid, kThreads, 0, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+    }
   } else {
     MTS_REQUIRE(H <= 2048, MTS_E_UNSUPPORTED, "lstm_rec_fwd: H > 2048 not supported by the generic kernel");
     const size_t smem = (size_t)6 * H * sizeof(float);

@@ -19,9 +19,9 @@ __global__ void __launch_bounds__(256) pack_rows_split_kernel(const float *__res
     float v = 0.0f;
     if (k < D1) v = __ldg(src1 + (int64_t)b * bstride1 + (int64_t)t * D1 + k);
     else if (k < D1 + D2) v = __ldg(src2 + (int64_t)b * bstride2 + (int64_t)t * D2 + (k - D1));
-    const float h = tf32_hi(v);
+    const float h = tf32_rn(v);
     hi[idx] = h;
-    lo[idx] = v - h;  // exact: the remainder has at most 13 significant bits
+    lo[idx] = tf32_rn(v - h);  // v - h is exact in fp32; rounding it to TF32 leaves an O(2^-23 |v|) residue
   }
 }
 
@@ -33,9 +33,9 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
     const int k = (int)(idx % Kp);
     const int64_t r = idx / Kp;
     const float v = (k < cols) ? __ldg(src + r * ld + k) : 0.0f;
-    const float h = tf32_hi(v);
+    const float h = tf32_rn(v);
     hi[idx] = h;
-    lo[idx] = v - h;
+    lo[idx] = tf32_rn(v - h);
   }
 }
 

@@ -269,7 +269,7 @@ class BiLstmStackFn(torch.autograd.Function):
     def forward(ctx, x1, x2, xs2, lens, packed, n_enc, *flat):
         rnn0 = packed.rnns[0]
         H, L = rnn0.hidden_size, rnn0.num_layers
-        need = any(p.requires_grad for p in flat) and torch.is_grad_enabled()
+        need = any(ctx.needs_input_grad)  # grad mode is off inside forward(); this reflects the caller's mode
         y, saved = _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save=need)
         if need:
             ctx.x1, ctx.x2, ctx.xs2, ctx.lens, ctx.packed, ctx.n_enc = x1, x2, xs2, lens, packed, n_enc
@@ -456,5 +456,5 @@ class CrfNllFn(torch.autograd.Function):
         de = torch.empty_like(emis)
         dt = torch.empty_like(trans)
         _call("mts_crf_nll_bwd", _ptr(emis), _ptr(tags), tags.stride(0), _ptr(ctx.lens.dev), _ptr(trans), _ptr(alphas),
-              _ptr(stats[0]), B, L, C, _ptr(scale), _ptr(de), _ptr(dt), _stream())
+              B, L, C, _ptr(scale), _ptr(de), _ptr(dt), _stream())
         return de, dt, None, None
