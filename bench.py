@@ -138,6 +138,82 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_CFG = dict(B=10, D1=384, D2=512, H=256, L=2, Tmin=84, Tmax=2437)
+TRAIN_WORKLOAD = ("configs[1]: early-fusion BiLSTM focal-loss training step (fwd + BPTT + Adam), NonNews-shaped batch of 10 "
+                  "episodes, 84..2437 sentences, 896-d inputs, H256 x 2 layers")
+
+
+def train_batch(seed):
+    c = TRAIN_CFG
+    g = torch.Generator().manual_seed(4321 + seed)
+    lengths = torch.randint(c["Tmin"], c["Tmax"] + 1, (c["B"],), generator=g)
+    T = int(lengths.max())
+    x = torch.randn(c["B"], T, c["D1"] + c["D2"], generator=g)
+    y = (torch.rand(c["B"], T, generator=g) < 0.07).float()
+    for b, n in enumerate(lengths.tolist()):
+        x[b, n:] = 0
+        y[b, n - 1] = 0
+        y[b, n:] = -1
+    return {"src_tokens": x, "src_tokens2": None, "src_lengths": lengths, "tgt_tokens": y, "id": torch.arange(c["B"]),
+            "domain": None}
+
+
+def train_bench(m, dev, rank, world, steps, barrier):
+    """Training episodes/s: each rank owns a batch of 10 episodes (weak scaling); one flat-bucket NCCL all-reduce
+    of the gradients per step, loss normalised by the global sentence count (dist.train_step)."""
+    from multimodaltopicsegmentation_b200 import dist as mdist, ops
+
+    c = TRAIN_CFG
+    torch.manual_seed(0)
+    seg = m.TextSegmenter(2, c["D1"] + c["D2"], c["H"], num_layers=c["L"], architecture="BiLSTM", loss_fn="FocalLoss",
+                          optimizer="Adam", lr=1e-3).to(dev)
+    opt = seg.configure_optimizers()["optimizer"]
+    bucket = mdist.GradBucket(seg.parameters())
+    batches = [m.to_device(train_batch(10 * rank + i), dev) for i in range(2)]
+    n_sent = sum(int(b["src_lengths"].sum()) for b in batches) / len(batches)
+    for i in range(2):
+        mdist.train_step(seg, batches[i % 2], opt, bucket)
+    barrier()
+    ops.reset_launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(steps):
+        loss = mdist.train_step(seg, batches[i % 2], opt, bucket)
+    end.record()
+    barrier()
+    t = torch.tensor([start.elapsed_time(end)], device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"metric": "training episodes/sec", "value": c["B"] * world / (ms / 1e3), "unit": "episodes/s",
+            "ms_per_step": ms, "steps": steps, "workload": TRAIN_WORKLOAD, "sentences_per_step_per_gpu": n_sent,
+            "gpu_launches_per_step": ops.launch_count() / steps, "grad_bucket_bytes": bucket.nbytes,
+            "last_loss": float(loss)}
+
+
+def cpu_train_reference():
+    from oracle import ref_torch as rt
+
+    c = TRAIN_CFG
+    torch.manual_seed(0)
+    model = rt.Segmenter(2, c["D1"] + c["D2"], c["H"], num_layers=c["L"], loss_fn="FocalLoss")
+    opt = torch.optim.Adam(model.parameters(), eps=1e-7, lr=1e-3)
+    batch = train_batch(0)
+    times = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = model.loss(batch["src_tokens"], batch["src_lengths"], batch["tgt_tokens"])
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    best = min(times[1:])
+    return {"value": c["B"] / best, "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "best of 2 steps (after 1 warm-up) on one batch of 10 episodes, oracle/ref_torch.py on host cores"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
@@ -225,8 +301,12 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
 
+    train = train_bench(m, dev, rank, world, max(3, args.steps // 2), barrier)
+
     if rank != 0:
         return
+    if world == 1:
+        train["cpu_baseline"] = cpu_train_reference()
     total_sent = n_sent_step * args.steps * world
     value = total_sent / (ms / 1e3)
     hbm_peak, peak_src = peaks()
@@ -255,6 +335,7 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": {"value": cpu_val, "unit": "sentences/s", "cores": cores, "kind": "port",
                          "sample": "5 full batches of 64x300 sentences through oracle/ref_torch.py (torch CPU, all threads)"},
         "clocks": clk.summary(),
+        "train": train,
     }
     print(json.dumps(line), flush=True)
 

@@ -87,13 +87,15 @@ int mts_lstm_rec_fwd(const float *gx, const float *w_hh, const int32_t *lengths,
 
 /* Backward through time of the same layer.
  *   dy      [B, T, n_enc*2H]    gradient w.r.t. y (ignored at t >= len_b)
- *   gates   as saved by the forward call;  y as produced by the forward call (h_{t-1} source)
+ *   gates   as saved by the forward call
+ *   w_hh_t  [n_enc, 2, H, 4H]   transposed copy of w_hh (row pairs adjacent: feeds the packed-fp32 FMA pipe)
  *   dgx     [n_enc, B*T, 2*4H]  gradient w.r.t. gx (zero at padded steps).  The weight gradients are GEMMs
  *                               over dgx issued by the caller: dW_ih = dgx^T X, dW_hh = dgx^T H_prev
  *                               (mts_gemm_f32 layout 3 with a row shift), db = mts_colsum(dgx).
  */
-int mts_lstm_rec_bwd(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
-                     const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream);
+int mts_lstm_rec_bwd(const float *dy, const float *gates, const float *w_hh, const float *w_hh_t,
+                     const int32_t *lengths, const int32_t *order, int n_enc, int B, int T, int H, float *dgx,
+                     void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Head + decode  (models/CRF.py:340,361-369: Linear then sigmoid/softmax threshold)

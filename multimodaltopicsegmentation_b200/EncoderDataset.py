@@ -98,6 +98,14 @@ class AudioPortionDatasetInference(Dataset):
                 "src_lengths": torch.LongTensor(lengths)}
 
 
-def to_device(batch, device, non_blocking=True):
-    """What pl.Trainer does with a batch dict: move every tensor, leave the rest."""
-    return {k: (v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v) for k, v in batch.items()}
+def to_device(batch, device, non_blocking=True, lengths_on_host=True):
+    """What pl.Trainer does with a batch dict: move every tensor, leave the rest.  `src_lengths` is consumed on the
+    host by the reference (lengths.data.tolist(), NeuralArchitectures.py:98) and by our launch planning, so by default
+    it stays there and no device->host sync is needed per step; the modules accept it on either side."""
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v) and not (lengths_on_host and k == "src_lengths"):
+            out[k] = v.to(device, non_blocking=non_blocking)
+        else:
+            out[k] = v
+    return out

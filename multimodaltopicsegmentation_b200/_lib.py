@@ -29,7 +29,7 @@ SIGNATURES = {
     "mts_colsum_ws_bytes": (c_int64, [c_int, c_int]),
     "mts_colsum": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, _P]),
     "mts_lstm_rec_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
-    "mts_lstm_rec_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "mts_lstm_rec_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "mts_head_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
     "mts_head_bwd_ws_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "mts_head_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),

@@ -86,14 +86,20 @@ __global__ void __launch_bounds__(256) lstm_bwd_generic_kernel(const float *__re
 // ---------------------------------------------------------------------------------------------------------
 // H = 256 cluster kernel (persistent over work items; NT tiles of 8 episodes interleaved per item, as forward)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kDpStride = 8;             // floats per dp row (8 episodes)
-constexpr int kDpFloats = 128 * 8 + 4 * 8;  // 128 rows + 8 floats of padding per 32-row slice (bank spread)
-__device__ __forceinline__ int dp_row_base(int lr) { return lr * kDpStride + (lr >> 5) * 8; }
+// dp buffer layout (float4 granules): [gate rs][row pair r2 = u>>1][episode pair xp = e>>1] ->
+// (dp[u even][e even], dp[u odd][e even], dp[u even][e odd], dp[u odd][e odd]); one granule of padding per gate
+// so that the 4 gate slices read by a quarter-warp fall into different banks.  Row pairs arrive as aligned
+// register pairs for FFMA2.
+constexpr int kDpGateStride4 = 16 * 4 + 1;          // granules per gate slice (16 row pairs x 4 episode pairs + pad)
+constexpr int kDpFloats = 4 * kDpGateStride4 * 4;   // floats per buffer
+__device__ __forceinline__ int dp_index(int gate, int u, int e) {
+  return ((gate * kDpGateStride4 + (u >> 1) * 4 + (e >> 1)) << 2) + ((e & 1) << 1) + (u & 1);
+}
 
 template <int NT>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     lstm_bwd_cluster_kernel(const float *__restrict__ dy, const float *__restrict__ gates,
-                            const float *__restrict__ w_hh, const int32_t *__restrict__ lengths,
+                            const float *__restrict__ w_hh_t, const int32_t *__restrict__ lengths,
                             const int32_t *__restrict__ order, int B, int T, int n_enc, int n_tiles,
                             float *__restrict__ dgx) {
   // dynamic shared memory (NT = 2 needs 49.7 KB, above the 48 KB static limit):
@@ -129,13 +135,20 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     const int dir = (item / groups) & 1;
     const int enc = item / (2 * groups);
 
-    float Wb[32][4];
+    // (W[row 2 r2][k], W[row 2 r2 + 1][k]) for my gate slice rs and my 4 k, read from the TRANSPOSED copy
+    // W_hh^T [k][row] so that row pairs are adjacent in memory and land in aligned register pairs for FFMA2.
+    float2 Wp[16][4];
     {
-      const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * kH * kH;
+      const float *Wt = w_hh_t + ((size_t)enc * 2 + dir) * 4 * kH * kH;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(rs * kH + rank * kUnits + j) * kH + kg * 4));
-        Wb[j][0] = v.x; Wb[j][1] = v.y; Wb[j][2] = v.z; Wb[j][3] = v.w;
+      for (int q = 0; q < 4; ++q) {
+        const float4 *col = reinterpret_cast<const float4 *>(Wt + (size_t)(kg * 4 + q) * 4 * kH + rs * kH + rank * kUnits);
+#pragma unroll
+        for (int r4 = 0; r4 < 8; ++r4) {
+          const float4 v = __ldg(col + r4);
+          Wp[2 * r4][q] = make_float2(v.x, v.y);
+          Wp[2 * r4 + 1][q] = make_float2(v.z, v.w);
+        }
       }
     }
 
@@ -208,10 +221,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           o[0] = g.dpi; o[kH] = g.dpf; o[2 * kH] = g.dpg; o[3 * kH] = g.dpo;
         }
         float *dpb = &dpbuf[j][p][0];
-        dpb[dp_row_base(0 * 32 + u) + e] = g.dpi;
-        dpb[dp_row_base(1 * 32 + u) + e] = g.dpf;
-        dpb[dp_row_base(2 * 32 + u) + e] = g.dpg;
-        dpb[dp_row_base(3 * 32 + u) + e] = g.dpo;
+        dpb[dp_index(0, u, e)] = g.dpi;
+        dpb[dp_index(1, u, e)] = g.dpf;
+        dpb[dp_index(2, u, e)] = g.dpg;
+        dpb[dp_index(3, u, e)] = g.dpo;
         if (s + 1 < len[j]) {  // prefetch the next step's activations (and the cell state two steps ahead)
           const int tn = dir ? s + 1 : len[j] - 2 - s;
           const float *gs = gates + ((gate_base + bq[j]) * T + tn) * 5 * kH + unit;
@@ -226,24 +239,32 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         __syncthreads();
         if (s + 1 >= nsteps) continue;  // the last step's dh_prev has no consumer
 
-        // ---- matvec phase: 32 rows (gate rs) x 4 k x 8 episodes ----------------------------------------------
+        // ---- matvec phase: 32 rows (gate rs) x 4 k x 8 episodes, FFMA2 over row pairs ------------------------
         float acc[4][8];
+        const float4 *dp4 = reinterpret_cast<const float4 *>(dpb) + rs * kDpGateStride4;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int pass = 0; pass < 2; ++pass) {
+          float2 a2[4][4];
 #pragma unroll
-          for (int x = 0; x < 8; ++x) acc[q][x] = 0.0f;
+          for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float4 da = *reinterpret_cast<const float4 *>(&dpb[dp_row_base(rs * 32 + r)]);
-          const float4 db = *reinterpret_cast<const float4 *>(&dpb[dp_row_base(rs * 32 + r) + 4]);
+            for (int x = 0; x < 4; ++x) a2[q][x] = make_float2(0.0f, 0.0f);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float w = Wb[r][q];
-            acc[q][0] = fmaf(w, da.x, acc[q][0]); acc[q][1] = fmaf(w, da.y, acc[q][1]);
-            acc[q][2] = fmaf(w, da.z, acc[q][2]); acc[q][3] = fmaf(w, da.w, acc[q][3]);
-            acc[q][4] = fmaf(w, db.x, acc[q][4]); acc[q][5] = fmaf(w, db.y, acc[q][5]);
-            acc[q][6] = fmaf(w, db.z, acc[q][6]); acc[q][7] = fmaf(w, db.w, acc[q][7]);
+          for (int r2 = 0; r2 < 16; ++r2) {
+            const float4 da = dp4[r2 * 4 + pass * 2];      // episodes 4 pass + {0,1}, rows 2 r2 + {0,1}
+            const float4 db = dp4[r2 * 4 + pass * 2 + 1];  // episodes 4 pass + {2,3}
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              a2[q][0] = __ffma2_rn(Wp[r2][q], make_float2(da.x, da.y), a2[q][0]);
+              a2[q][1] = __ffma2_rn(Wp[r2][q], make_float2(da.z, da.w), a2[q][1]);
+              a2[q][2] = __ffma2_rn(Wp[r2][q], make_float2(db.x, db.y), a2[q][2]);
+              a2[q][3] = __ffma2_rn(Wp[r2][q], make_float2(db.z, db.w), a2[q][3]);
+            }
           }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) acc[q][pass * 4 + x] = a2[q][x].x + a2[q][x].y;
         }
         // reduce over the 4 row slices (gates); lane rs keeps k = 4 kg + rs
         float r1[2][8], out[8];
@@ -308,9 +329,10 @@ static int max_active_clusters_bwd(K kernel, size_t smem) {
 
 using namespace mts;
 
-extern "C" int mts_lstm_rec_bwd(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
-                                const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream) {
-  MTS_REQUIRE(dy && gates && w_hh && lengths && dgx, MTS_E_BADARG, "lstm_rec_bwd: null pointer");
+extern "C" int mts_lstm_rec_bwd(const float *dy, const float *gates, const float *w_hh, const float *w_hh_t,
+                                const int32_t *lengths, const int32_t *order, int n_enc, int B, int T, int H, float *dgx,
+                                void *stream) {
+  MTS_REQUIRE(dy && gates && w_hh && w_hh_t && lengths && dgx, MTS_E_BADARG, "lstm_rec_bwd: null pointer");
   MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0 && H > 0, MTS_E_BADARG, "lstm_rec_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (H == kH) {
@@ -323,12 +345,12 @@ extern "C" int mts_lstm_rec_bwd(const float *dy, const float *gates, const float
     const int n_tiles = (B + kBT - 1) / kBT;
     const int items1 = n_tiles * 2 * n_enc;
     if (items1 <= cap) {
-      lstm_bwd_cluster_kernel<1><<<(unsigned)(items1 * kCluster), kThreads, smem1, st>>>(dy, gates, w_hh, lengths, order, B,
-                                                                                         T, n_enc, n_tiles, dgx);
+      lstm_bwd_cluster_kernel<1><<<(unsigned)(items1 * kCluster), kThreads, smem1, st>>>(dy, gates, w_hh_t, lengths, order,
+                                                                                         B, T, n_enc, n_tiles, dgx);
     } else {
       const int items2 = ((n_tiles + 1) / 2) * 2 * n_enc;
       lstm_bwd_cluster_kernel<2><<<(unsigned)((items2 < cap ? items2 : cap) * kCluster), kThreads, smem2, st>>>(
-          dy, gates, w_hh, lengths, order, B, T, n_enc, n_tiles, dgx);
+          dy, gates, w_hh_t, lengths, order, B, T, n_enc, n_tiles, dgx);
     }
   } else {
     MTS_REQUIRE(H <= 2048, MTS_E_UNSUPPORTED, "lstm_rec_bwd: H > 2048 not supported by the generic kernel");

@@ -92,11 +92,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   const int unit = rank * kUnits + u;       // hidden unit inside the layer, 0..255
   const int ycols = n_enc * 2 * kH;
 
-  // remote addresses: lane writes the assembled float4 of its 4-episode group to CTAs {2*(ks&3), 2*(ks&3)+1}
-  // (the mapped shared::cluster window is linear in the CTA-local offset, so tile / buffer offsets just add)
-  const int half = ks >> 2;
-  const uint32_t dst0 = 2 * (ks & 3), dst1 = dst0 + 1;
-  const uint32_t la = smem_u32(&hbuf[0][0][((half * 32 + u) * 8 + rank) * 4]);
+  // h buffer layout (float4 granules): [half = e>>2][epair = (e>>1)&1][k2 = (k&31)>>1][ks = k>>5] ->
+  // (h[k even][e even], h[k odd][e even], h[k even][e odd], h[k odd][e odd]).  A quarter-warp (8 k-slices) reads
+  // 128 contiguous bytes per LDS.128: conflict-free, and k-pairs arrive as aligned register pairs for FFMA2.
+  // Remote stores: the 4 lanes holding (unit pair) x (episode pair) share one granule; lane gi of the group
+  // sends it to CTAs {2 gi, 2 gi + 1}.  (The mapped shared::cluster window is linear in the CTA-local offset,
+  // so tile / buffer offsets just add.)
+  const int gi = ((lane >> 3) & 1) * 2 + (lane & 1);
+  const uint32_t dst0 = 2 * gi, dst1 = dst0 + 1;
+  const uint32_t la = smem_u32(&hbuf[0][0][((((ks >> 2) * 2 + ((ks >> 1) & 1)) * 16 + (u >> 1)) * 8 + rank) * 4]);
   const uint32_t lb = smem_u32(&full_bar[0][0]);
   const uint32_t raddr0 = mapa(la, dst0), raddr1 = mapa(la, dst1);
   const uint32_t rbar0 = mapa(lb, dst0), rbar1 = mapa(lb, dst1);
@@ -181,25 +185,36 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           for (int g = 0; g < 4; ++g) gxn[j][g] = __ldg(g_row + g * kH);
         }
 
-        // ---- 4 gate rows x 8 episodes x my 32 k ------------------------------------------------------------
+        // ---- 4 gate rows x 8 episodes x my 32 k, on the packed fp32 pipe ------------------------------------
+        // Blackwell issues scalar FFMA at half rate; FFMA2 (fma.rn.f32x2) restores the full fp32 rate.  Pairs
+        // run over consecutive k: (W[g][k], W[g][k+1]) * (h[k][e], h[k+1][e]) -> (even-k sum, odd-k sum), added
+        // at the end; two passes of 4 episodes keep the accumulators at 32 registers.
         float acc[4][8];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[g][e] = 0.0f;
         const float4 *hp = reinterpret_cast<const float4 *>(&hbuf[j][p][0]);
 #pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          const float4 ha = hp[kk * 8 + ks];
-          const float4 hb = hp[(32 + kk) * 8 + ks];
+        for (int pass = 0; pass < 2; ++pass) {
+          float2 a2[4][4];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float w = Wr[g][kk];
-            acc[g][0] = fmaf(w, ha.x, acc[g][0]); acc[g][1] = fmaf(w, ha.y, acc[g][1]);
-            acc[g][2] = fmaf(w, ha.z, acc[g][2]); acc[g][3] = fmaf(w, ha.w, acc[g][3]);
-            acc[g][4] = fmaf(w, hb.x, acc[g][4]); acc[g][5] = fmaf(w, hb.y, acc[g][5]);
-            acc[g][6] = fmaf(w, hb.z, acc[g][6]); acc[g][7] = fmaf(w, hb.w, acc[g][7]);
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a2[g][e] = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int k2 = 0; k2 < 16; ++k2) {
+            const float4 ha = hp[((pass * 2 + 0) * 16 + k2) * 8 + ks];  // episodes 4 pass + {0,1}, k = 2 k2 + {0,1}
+            const float4 hb = hp[((pass * 2 + 1) * 16 + k2) * 8 + ks];  // episodes 4 pass + {2,3}
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float2 w2 = make_float2(Wr[g][2 * k2], Wr[g][2 * k2 + 1]);
+              a2[g][0] = __ffma2_rn(w2, make_float2(ha.x, ha.y), a2[g][0]);
+              a2[g][1] = __ffma2_rn(w2, make_float2(ha.z, ha.w), a2[g][1]);
+              a2[g][2] = __ffma2_rn(w2, make_float2(hb.x, hb.y), a2[g][2]);
+              a2[g][3] = __ffma2_rn(w2, make_float2(hb.z, hb.w), a2[g][3]);
+            }
           }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[g][pass * 4 + e] = a2[g][e].x + a2[g][e].y;
         }
         // ---- reduce over the 8 k-slices by recursive halving; lane ks ends with episode slot ks -------------
         float r1[4][4], r2[4][2], pre[4];
@@ -229,10 +244,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         // ---- gates, cell, output ----------------------------------------------------------------------------
         float hn = 0.0f;
         if (active) {
-          const float ig = sigmoidf_acc(pre[0]), fg = sigmoidf_acc(pre[1]);
-          const float gg = tanhf(pre[2]), og = sigmoidf_acc(pre[3]);
+          const float ig = sigmoid_fast(pre[0]), fg = sigmoid_fast(pre[1]);
+          const float gg = tanh_fast(pre[2]), og = sigmoid_fast(pre[3]);
           c[j] = fmaf(fg, c[j], ig * gg);
-          hn = og * tanhf(c[j]);
+          hn = og * tanh_fast(c[j]);
           const int t = dir ? len[j] - 1 - s : s;
           y[((size_t)bq[j] * T + t) * ycols + ycol] = hn;
           if (SAVE) {
@@ -240,13 +255,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
             gs[0] = ig; gs[kH] = fg; gs[2 * kH] = gg; gs[3 * kH] = og; gs[4 * kH] = c[j];
           }
         }
-        if (s + 1 < nsteps) {  // broadcast h_s: assemble the 4 episodes of my group, 2 remote stores per lane
-          const int base = lane & ~3;
+        if (s + 1 < nsteps) {  // broadcast h_s: 2 units x 2 episodes per 16-byte remote store, 2 stores per lane
+          const int l0 = lane & ~9;  // group = lanes {l0, l0+8, l0+1, l0+9}: (even unit, odd unit) x (even ep, odd ep)
           float4 v;
-          v.x = __shfl_sync(0xffffffffu, hn, base + 0);
-          v.y = __shfl_sync(0xffffffffu, hn, base + 1);
-          v.z = __shfl_sync(0xffffffffu, hn, base + 2);
-          v.w = __shfl_sync(0xffffffffu, hn, base + 3);
+          v.x = __shfl_sync(0xffffffffu, hn, l0);
+          v.y = __shfl_sync(0xffffffffu, hn, l0 + 8);
+          v.z = __shfl_sync(0xffffffffu, hn, l0 + 1);
+          v.w = __shfl_sync(0xffffffffu, hn, l0 + 9);
           const uint32_t boff = (uint32_t)(j * 2 + (p ^ 1)) * (kHBufFloats * 4), moff = (uint32_t)(j * 2 + (p ^ 1)) * 8;
           st_async_v4(raddr0 + boff, v, rbar0 + moff);
           st_async_v4(raddr1 + boff, v, rbar1 + moff);

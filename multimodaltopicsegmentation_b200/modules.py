@@ -221,13 +221,15 @@ class CRF(nn.Module):
             best, paths = ops.crf_viterbi(self.emissions(features), lens, self.transitions)
         return best, _tags_to_lists(paths, lens, as_bool=False)
 
-    def loss(self, features, ys, masks):
-        """negative log likelihood, mean over the batch (CRF.py:130-146)"""
+    def loss(self, features, ys, masks, global_count=None):
+        """negative log likelihood, mean over the batch (CRF.py:130-146).  `global_count`: number of episodes over
+        all data-parallel ranks (defaults to this batch's)."""
         lens = self._lens_from_masks(masks, features)
         emis = self.emissions(features)
         ys = ops._check(ys.to(features.device).float(), "tags")
         stats = ops.CrfNllFn.apply(emis, self.transitions, ys, lens)
-        return (stats[0] - stats[1]).mean()
+        nll = stats[0] - stats[1]
+        return nll.mean() if global_count is None else nll.sum() / float(global_count)
 
 
 class BiRnnCrf(nn.Module):
@@ -243,10 +245,10 @@ class BiRnnCrf(nn.Module):
         self.crf = CRF(hidden_dim * 2, self.tagset_size)
         self.th = None  # test_step assigns it on every model (lightning_model.py:587); unused by Viterbi
 
-    def loss(self, xs, lengths, tags, segments=None):
+    def loss(self, xs, lengths, tags, segments=None, global_count=None):
         x0 = xs[0] if isinstance(xs, (tuple, list)) else xs
         lens = _lens(lengths, x0)
-        return self.crf.loss(self.model(xs, lens), tags[:, : lens.T], lens)
+        return self.crf.loss(self.model(xs, lens), tags[:, : lens.T], lens, global_count=global_count)
 
     def forward(self, xs, lenghts, threshold=None):
         x0 = xs[0] if isinstance(xs, (tuple, list)) else xs

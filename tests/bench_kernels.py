@@ -58,8 +58,9 @@ def bench_rec():
     rec_call(gx, whh, lens, y, gates, B, T)
     dy = torch.randn_like(y)
     dgx = torch.empty_like(gx)
-    ms = timeit(lambda: ops._call("mts_lstm_rec_bwd", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
-                                  lens.order.data_ptr(), 1, B, T, H, dgx.data_ptr(), ops._stream()))
+    whh_t = whh.transpose(2, 3).contiguous()
+    ms = timeit(lambda: ops._call("mts_lstm_rec_bwd", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), whh_t.data_ptr(),
+                                  lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H, dgx.data_ptr(), ops._stream()))
     print(f"backward B=64 T=300: {ms:.3f} ms  ({ms * 1e3 / T:.2f} us/step)")
 
 
