@@ -88,6 +88,14 @@ if __name__ == "__main__":
         bench_rec()
     elif what == "gemm":
         bench_gemm()
+    elif what == "gemm_one":
+        M, N, K = 19200, 2048, 896
+        a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)
+        c = torch.empty(M, N, device=dev)
+        a_hi, a_lo = ops.split_tf32(a); b_hi, b_lo = ops.split_tf32(b)
+        for _ in range(3):
+            ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, c, M, N, epilogue=1)
+        torch.cuda.synchronize()
     elif what == "rec_one":
         B, T = int(sys.argv[2]), int(sys.argv[3])
         args = rec_setup(B, T)
