@@ -148,6 +148,35 @@ int mts_crf_nll_bwd(const float *emis, const float *tags, int64_t ldt, const int
                     const float *alphas, int B, int L, int C, const float *scale_dev, float *d_emis,
                     float *d_trans, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pyramidal windowed-attention encoder (HF LongformerModel as driven by
+ * models/RestrictedTransformerLayer.py:65-133 and models/CRF.py:521-536; d_model = input width, all-local
+ * attention, LayerNorm eps 1e-12, GELU(erf)).  The dense layers are mts_gemm_tf32x3; these are the fused
+ * kernels around them.  Every kernel takes `lengths` -- the reference's host-built mask tensors
+ * (create_masks_huggingface, RestrictedTransformerLayer.py:101-116) are never materialised.
+ * ---------------------------------------------------------------------------------------------- */
+/* LongformerEmbeddings (HF modeling_longformer.py:401-442): y[b,t,:] = LN(x[b,t,:] + pos[t+2,:] + typ[:]).
+ *   x [B,S,d] with batch stride x_bstride (elements); pos = the full position table [>= S+2, d]; d % 4 == 0.
+ *   y [B*S,d]; optional y_hi/y_lo [B*S,Kp] = TF32 halves of y for the next GEMM (both or neither);
+ *   optional sum_out [B*S,d] (pre-LN values) and stats [B*S,2] = (mean, rstd), saved for the backward pass. */
+int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *pos, const float *typ, const float *gamma,
+                     const float *beta, int B, int S, int d, float eps, float *y, float *y_hi, float *y_lo, int Kp,
+                     float *sum_out, float *stats, void *stream);
+/* LongformerSelfOutput / LongformerOutput (:1060-1071, :1119-1130): y = LN(a + res); a is the dense output
+ *   (bias already added by the GEMM epilogue).  sum_out may alias a. */
+int mts_add_ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, int M, int d, float eps,
+                   float *y, float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats, void *stream);
+/* LongformerIntermediate (:1103-1116) activation fused with the operand split: hi/lo [rows,Kp] of GELU(src). */
+int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, float *hi, float *lo, void *stream);
+/* LongformerSelfAttention (:481-639; sliding chunks :758-867) for all-local attention:
+ *   qkv [B*S, ld] rows = [q | k | v] (each nheads*hd wide, head-major), q NOT yet scaled (the kernel divides by
+ *   sqrt(hd) as HF does at :513); token i attends to j with |i-j| <= w and j < len_b; softmax in fp32;
+ *   rows i >= len_b give exact zeros (:578).  hd % 4 == 0, hd <= 128.
+ *   out [B*S, nheads*hd] and/or its TF32 halves out_hi/out_lo [B*S,Kp] (Kp == nheads*hd);
+ *   lse [B,nheads,S] or NULL: log-sum-exp of every query row, saved for the backward pass. */
+int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads, int hd, int w,
+                      float *out, float *out_hi, float *out_lo, int Kp, float *lse, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,399 @@
+// Pyramidal windowed-attention encoder, forward kernels.  Restates what the reference obtains from HF
+// `LongformerModel(inputs_embeds=...)` (models/RestrictedTransformerLayer.py:65-133 -> HF modeling_longformer.py):
+//   * LongformerEmbeddings (:401-442): LN_{eps}(x + P[2 + t] + E_type[0])            -> mts_embed_ln_fwd
+//   * LongformerSelfOutput / LongformerOutput (:1060-1071, :1119-1130): LN(dense + x) -> mts_add_ln_fwd
+//   * LongformerSelfAttention (:481-639, sliding chunks :758-867): softmax over |i-j| <= w, j < len_b,
+//     q scaled by 1/sqrt(hd), masked queries output exact zeros                    -> mts_band_attn_fwd
+//   * LongformerIntermediate (:1103-1116): GELU(erf); fused here with the hi/lo split that feeds the
+//     next 3xTF32 GEMM                                                              -> mts_gelu_split
+// No mask tensor is ever built (create_masks_huggingface, RestrictedTransformerLayer.py:101-116, is a host
+// double loop in the reference): every kernel takes `lengths`.
+//
+// The dense layers themselves are mts_gemm_tf32x3 (tcgen05).  The kernels here are the HBM-bound glue:
+// LN kernels move 4d in + 4d (+ 8 Kp for the GEMM operand halves) out per token; the attention kernel reads
+// q,k,v (12d) and writes o (4d, or the two operand halves) per token and only ever touches in-window keys.
+#include "common.cuh"
+
+namespace mts {
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm forward, one warp per token row, values held in registers (two-pass mean / variance).
+//   MODE 0: v = x[b, t, :] + pos[t + 2, :] + typ[:]       (embeddings; position ids start at pad_token_id + 1 = 2)
+//   MODE 1: v = a[row, :] + res[row, :]                    (dense output + residual)
+// outputs: y fp32, optional (hi, lo) TF32 halves [M, Kp] for the next GEMM, optional pre-LN sum and
+// (mean, rstd) for the backward pass.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 16;  // float4 per lane -> d <= 2048
+
+template <int MODE>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a, int64_t a_bstride,
+                                                     const float *__restrict__ b, const float *__restrict__ typ,
+                                                     const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                     int M, int S, int d, float eps, float *__restrict__ y,
+                                                     float *__restrict__ y_hi, float *__restrict__ y_lo, int Kp,
+                                                     float *__restrict__ sum_out, float *__restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int nv = d >> 2;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+    const float4 *pa, *pb;
+    if (MODE == 0) {
+      const int bi = row / S, t = row % S;
+      pa = reinterpret_cast<const float4 *>(a + (int64_t)bi * a_bstride + (int64_t)t * d);
+      pb = reinterpret_cast<const float4 *>(b + (int64_t)(t + 2) * d);
+    } else {
+      pa = reinterpret_cast<const float4 *>(a + (int64_t)row * d);
+      pb = reinterpret_cast<const float4 *>(b + (int64_t)row * d);
+    }
+    float4 v[LN_MAXV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float4 x = __ldg(pa + c);
+        const float4 r = __ldg(pb + c);
+        x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+        if (MODE == 0) {
+          const float4 e = __ldg(reinterpret_cast<const float4 *>(typ) + c);
+          x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
+        }
+        v[i] = x;
+        s += (x.x + x.y) + (x.z + x.w);
+      }
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      if (lane + 32 * i < nv) {
+        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + eps);
+    if (stats && lane == 0) { stats[2 * (int64_t)row] = mean; stats[2 * (int64_t)row + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        if (sum_out) reinterpret_cast<float4 *>(sum_out + (int64_t)row * d)[c] = v[i];
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + c);
+        const float4 be = __ldg(reinterpret_cast<const float4 *>(beta) + c);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + be.x;
+        o.y = (v[i].y - mean) * rstd * g.y + be.y;
+        o.z = (v[i].z - mean) * rstd * g.z + be.z;
+        o.w = (v[i].w - mean) * rstd * g.w + be.w;
+        reinterpret_cast<float4 *>(y + (int64_t)row * d)[c] = o;
+        if (y_hi) {
+          float4 h, l;
+          h.x = tf32_rn(o.x); l.x = tf32_rn(o.x - h.x);
+          h.y = tf32_rn(o.y); l.y = tf32_rn(o.y - h.y);
+          h.z = tf32_rn(o.z); l.z = tf32_rn(o.z - h.z);
+          h.w = tf32_rn(o.w); l.w = tf32_rn(o.w - h.w);
+          reinterpret_cast<float4 *>(y_hi + (int64_t)row * Kp)[c] = h;
+          reinterpret_cast<float4 *>(y_lo + (int64_t)row * Kp)[c] = l;
+        }
+      }
+    }
+    if (y_hi)
+      for (int c = d + lane; c < Kp; c += 32) { y_hi[(int64_t)row * Kp + c] = 0.0f; y_lo[(int64_t)row * Kp + c] = 0.0f; }
+  }
+}
+
+// GELU(erf) + hi/lo split: src [rows, cols] (row stride ld) -> hi/lo [rows, Kp]
+__global__ void __launch_bounds__(256) gelu_split_kernel(const float *__restrict__ src, int64_t ld, int rows, int cols,
+                                                         int Kp, float *__restrict__ hi, float *__restrict__ lo) {
+  const int64_t total = (int64_t)rows * Kp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Kp);
+    const int64_t r = idx / Kp;
+    const float v = (k < cols) ? gelu_erf(__ldg(src + r * ld + k)) : 0.0f;
+    const float h = tf32_rn(v);
+    hi[idx] = h;
+    lo[idx] = tf32_rn(v - h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Banded attention, forward.  One CTA per (32-query block, head, episode); key/value tiles of 64 rows are
+// staged in shared memory and ONLY the tiles intersecting [q0 - w, q0 + 32 + w) x [0, len_b) are read
+// (HF's sliding chunks compute 2w x 2w blocks and mask half of them away).  Running-max softmax in fp32
+// (HF: softmax in fp32, modeling_longformer.py:573), exact zeros for padded queries (:578).
+//   phase 1  S = Q K^T   thread = 2 queries x 4 keys, float4 along the head dimension
+//   phase 2  row max / exp / sum by warp shuffles (4 rows per warp), rescale factors to shared memory
+//   phase 3  O = alpha O + P V   thread = 4 queries x 4 head columns
+// Shared rows are padded to a stride = 4 (mod 8) words so that 8 consecutive rows read as float4 hit
+// 8 distinct bank groups.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BA_BQ = 32, BA_TK = 64, BA_THREADS = 256, BA_PS = BA_TK + 4;
+
+__host__ __device__ inline int ba_row_stride(int hd) { return (hd % 8 == 0) ? hd + 4 : hd; }
+static size_t ba_smem_bytes(int hd) {
+  return sizeof(float) * ((size_t)(BA_BQ + 2 * BA_TK) * ba_row_stride(hd) + BA_BQ * BA_PS + 3 * BA_BQ);
+}
+
+__global__ void __launch_bounds__(BA_THREADS, 2)
+    band_attn_fwd_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths, int S,
+                         int nheads, int hd, int w, float *__restrict__ out, float *__restrict__ out_hi,
+                         float *__restrict__ out_lo, int Kp, float *__restrict__ lse) {
+  extern __shared__ __align__(16) float sm[];
+  const int RS = ba_row_stride(hd);
+  float *Qs = sm;
+  float *Ks = Qs + BA_BQ * RS;
+  float *Vs = Ks + BA_TK * RS;
+  float *Ps = Vs + BA_TK * RS;
+  float *m_s = Ps + BA_BQ * BA_PS;
+  float *l_s = m_s + BA_BQ;
+  float *al_s = l_s + BA_BQ;
+
+  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * BA_BQ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = nheads * hd, nv = hd >> 2;
+  const int len = min(max(lengths[b], 0), S);
+  const int64_t row0 = (int64_t)b * S;
+  const int cg = tid % nv, rg = tid / nv;  // phase-3 mapping: 4 head columns x 4 queries
+  const bool pv_thread = rg < BA_BQ / 4;
+
+  if (q0 >= len) {  // whole block is padding: exact zeros
+    if (pv_thread) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = q0 + rg * 4 + r;
+        if (i < S) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (out) reinterpret_cast<float4 *>(out + (row0 + i) * d + head * hd)[cg] = z;
+          if (out_hi) {
+            reinterpret_cast<float4 *>(out_hi + (row0 + i) * Kp + head * hd)[cg] = z;
+            reinterpret_cast<float4 *>(out_lo + (row0 + i) * Kp + head * hd)[cg] = z;
+          }
+        }
+      }
+    }
+    if (lse && tid < BA_BQ && q0 + tid < S) lse[((int64_t)b * nheads + head) * S + q0 + tid] = 0.0f;
+    return;
+  }
+
+  const float scale = sqrtf((float)hd);
+  for (int idx = tid; idx < BA_BQ * nv; idx += BA_THREADS) {
+    const int r = idx / nv, c = idx % nv;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < S) {
+      v = __ldg(reinterpret_cast<const float4 *>(qkv + (row0 + q0 + r) * ld + head * hd) + c);
+      v.x /= scale; v.y /= scale; v.z /= scale; v.w /= scale;  // query_vectors /= sqrt(head_dim) (HF :513)
+    }
+    reinterpret_cast<float4 *>(Qs + r * RS)[c] = v;
+  }
+  if (tid < BA_BQ) { m_s[tid] = -INFINITY; l_s[tid] = 0.0f; al_s[tid] = 0.0f; }
+
+  float o[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[r][c] = 0.0f;
+
+  const int kbeg = max(0, q0 - w), kend = min(len, q0 + BA_BQ + w);
+  const int qg = tid >> 4, kg = tid & 15;  // phase-1 mapping
+
+  for (int k0 = kbeg; k0 < kend; k0 += BA_TK) {
+    for (int idx = tid; idx < BA_TK * nv; idx += BA_THREADS) {
+      const int r = idx / nv, c = idx % nv;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + r < kend) {
+        const float *base = qkv + (row0 + k0 + r) * ld + head * hd;
+        kv = __ldg(reinterpret_cast<const float4 *>(base + d) + c);
+        vv = __ldg(reinterpret_cast<const float4 *>(base + 2 * d) + c);
+      }
+      reinterpret_cast<float4 *>(Ks + r * RS)[c] = kv;
+      reinterpret_cast<float4 *>(Vs + r * RS)[c] = vv;
+    }
+    __syncthreads();
+    // ---- phase 1: scores --------------------------------------------------------------------------------
+    {
+      float acc[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][j] = 0.0f;
+      const float4 *qa = reinterpret_cast<const float4 *>(Qs + qg * RS);
+      const float4 *qb = reinterpret_cast<const float4 *>(Qs + (qg + 16) * RS);
+      for (int c = 0; c < nv; ++c) {
+        const float4 x0 = qa[c], x1 = qb[c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 kk = reinterpret_cast<const float4 *>(Ks + (kg + 16 * j) * RS)[c];
+          acc[0][j] = fmaf(x0.x, kk.x, fmaf(x0.y, kk.y, fmaf(x0.z, kk.z, fmaf(x0.w, kk.w, acc[0][j]))));
+          acc[1][j] = fmaf(x1.x, kk.x, fmaf(x1.y, kk.y, fmaf(x1.z, kk.z, fmaf(x1.w, kk.w, acc[1][j]))));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int i = q0 + qg + 16 * a;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kj = k0 + kg + 16 * j;
+          const bool ok = (i < len) && (kj < kend) && (kj >= i - w) && (kj <= i + w);
+          Ps[(qg + 16 * a) * BA_PS + kg + 16 * j] = ok ? acc[a][j] : -INFINITY;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: running softmax -----------------------------------------------------------------------
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = warp * 4 + rr;
+      const float s0 = Ps[r * BA_PS + lane], s1 = Ps[r * BA_PS + lane + 32];
+      const float mx = warp_max(fmaxf(s0, s1));
+      const float m_old = m_s[r];
+      const float m_new = fmaxf(m_old, mx);
+      const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+      const float p0 = expf(s0 - m_use), p1 = expf(s1 - m_use);
+      const float sum = warp_sum(p0 + p1);
+      Ps[r * BA_PS + lane] = p0;
+      Ps[r * BA_PS + lane + 32] = p1;
+      __syncwarp();
+      if (lane == 0) {
+        const float alpha = expf(m_old - m_use);
+        m_s[r] = m_new;
+        l_s[r] = l_s[r] * alpha + sum;
+        al_s[r] = alpha;
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: O = alpha O + P V ----------------------------------------------------------------------
+    if (pv_thread) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float al = al_s[rg * 4 + r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[r][c] *= al;
+      }
+#pragma unroll 4
+      for (int k4 = 0; k4 < BA_TK / 4; ++k4) {
+        float4 p[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) p[r] = reinterpret_cast<const float4 *>(Ps + (rg * 4 + r) * BA_PS)[k4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 vv = reinterpret_cast<const float4 *>(Vs + (4 * k4 + kk) * RS)[cg];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float pk = kk == 0 ? p[r].x : kk == 1 ? p[r].y : kk == 2 ? p[r].z : p[r].w;
+            o[r][0] = fmaf(pk, vv.x, o[r][0]);
+            o[r][1] = fmaf(pk, vv.y, o[r][1]);
+            o[r][2] = fmaf(pk, vv.z, o[r][2]);
+            o[r][3] = fmaf(pk, vv.w, o[r][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (pv_thread) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = q0 + rg * 4 + r;
+      if (i >= S) continue;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < len) {
+        const float inv = 1.0f / l_s[rg * 4 + r];
+        v = make_float4(o[r][0] * inv, o[r][1] * inv, o[r][2] * inv, o[r][3] * inv);
+      }
+      if (out) reinterpret_cast<float4 *>(out + (row0 + i) * d + head * hd)[cg] = v;
+      if (out_hi) {
+        float4 h, l;
+        h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
+        h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
+        h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
+        h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
+        reinterpret_cast<float4 *>(out_hi + (row0 + i) * Kp + head * hd)[cg] = h;
+        reinterpret_cast<float4 *>(out_lo + (row0 + i) * Kp + head * hd)[cg] = l;
+      }
+    }
+  }
+  if (lse && tid < BA_BQ && q0 + tid < S)
+    lse[((int64_t)b * nheads + head) * S + q0 + tid] = (q0 + tid < len) ? m_s[tid] + logf(l_s[tid]) : 0.0f;
+}
+
+static unsigned ew_grid(int64_t total) {
+  int64_t g = (total + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace mts
+
+using namespace mts;
+
+static int ln_args_ok(const char *who, int M, int d, const float *y_hi, const float *y_lo, int Kp) {
+  (void)who;
+  if (M <= 0 || d <= 0) { set_error("layer norm: empty shape"); return MTS_E_BADARG; }
+  if (d % 4 != 0 || d > 128 * LN_MAXV) { set_error("layer norm: width must be a multiple of 4 and <= 2048"); return MTS_E_UNSUPPORTED; }
+  if ((y_hi == nullptr) != (y_lo == nullptr)) { set_error("layer norm: hi and lo go together"); return MTS_E_BADARG; }
+  if (y_hi && (Kp % 32 != 0 || Kp < d)) { set_error("layer norm: Kp must be a multiple of 32 and >= d"); return MTS_E_BADARG; }
+  return 0;
+}
+
+extern "C" int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *pos, const float *typ,
+                                const float *gamma, const float *beta, int B, int S, int d, float eps, float *y,
+                                float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats, void *stream) {
+  MTS_REQUIRE(x && pos && typ && gamma && beta && y, MTS_E_BADARG, "embed_ln_fwd: null pointer");
+  MTS_REQUIRE(B > 0 && S > 0, MTS_E_BADARG, "embed_ln_fwd: empty shape");
+  int rc = ln_args_ok("embed_ln_fwd", B * S, d, y_hi, y_lo, Kp);
+  if (rc) return rc;
+  const int M = B * S;
+  const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);
+  ln_fwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bstride, pos, typ, gamma, beta, M, S, d, eps, y, y_hi,
+                                                            y_lo, Kp, sum_out, stats);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mts_add_ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, int M, int d,
+                              float eps, float *y, float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats,
+                              void *stream) {
+  MTS_REQUIRE(a && res && gamma && beta && y, MTS_E_BADARG, "add_ln_fwd: null pointer");
+  int rc = ln_args_ok("add_ln_fwd", M, d, y_hi, y_lo, Kp);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);
+  ln_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, 0, res, nullptr, gamma, beta, M, 0, d, eps, y, y_hi, y_lo,
+                                                            Kp, sum_out, stats);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, float *hi, float *lo,
+                              void *stream) {
+  MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "gelu_split: null pointer");
+  MTS_REQUIRE(rows > 0 && cols > 0 && Kp % 32 == 0 && Kp >= cols, MTS_E_BADARG, "gelu_split: bad shape");
+  gelu_split_kernel<<<ew_grid((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, hi, lo);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads,
+                                 int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
+                                 void *stream) {
+  MTS_REQUIRE(qkv && lengths && (out || out_hi), MTS_E_BADARG, "band_attn_fwd: null pointer");
+  MTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), MTS_E_BADARG, "band_attn_fwd: hi and lo go together");
+  MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_fwd: bad shape");
+  MTS_REQUIRE(hd % 4 == 0 && hd <= 128, MTS_E_UNSUPPORTED, "band_attn_fwd: head dim must be a multiple of 4 and <= 128");
+  MTS_REQUIRE(ld % 4 == 0 && ld >= 3 * nheads * hd, MTS_E_BADARG, "band_attn_fwd: qkv row stride");
+  MTS_REQUIRE(!out_hi || (Kp % 32 == 0 && Kp >= nheads * hd), MTS_E_BADARG, "band_attn_fwd: Kp");
+  MTS_REQUIRE(!out_hi || Kp == nheads * hd, MTS_E_UNSUPPORTED,
+              "band_attn_fwd: the split output needs a model width that is a multiple of 32");
+  const size_t smem = ba_smem_bytes(hd);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    MTS_CUDA(cudaFuncSetAttribute(band_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const dim3 grid((S + BA_BQ - 1) / BA_BQ, nheads, B);
+  band_attn_fwd_kernel<<<grid, BA_THREADS, smem, (cudaStream_t)stream>>>(qkv, ld, lengths, S, nheads, hd, w, out, out_hi,
+                                                                        out_lo, Kp, lse);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,333 @@
+"""Pyramidal windowed-attention segmenter -- host-side mirror of
+
+    Transformer_segmenter        <- models/CRF.py:508-610
+    Longformer_Local_Attention   <- models/RestrictedTransformerLayer.py:65-133
+
+The reference builds an HF `LongformerModel` and feeds it `inputs_embeds`; what runs is: embeddings
+(+position ids starting at 2, +token-type row 0, LayerNorm eps 1e-12), then per layer q/k/v projections, banded
+softmax attention with one-sided reach `attention_window // 2`, output projection + residual + LayerNorm,
+GELU feed-forward + residual + LayerNorm (HF modeling_longformer.py:401-442, 481-639, 1060-1171).  Here the same
+arithmetic runs in libmts_b200.so: tcgen05 3xTF32 GEMMs (ops.gemm_tf32x3) and the fused kernels of csrc/xfmr.cu.
+
+The module tree below only carries PARAMETERS, with the HF names and shapes, so that a reference checkpoint
+(`model.model.model.encoder.layer.N.attention.self.query.weight`, ...) loads key for key -- including the
+tensors HF allocates but this path never reads (`word_embeddings`, `*_global` projections, `pooler`).
+
+Superset note: HF's sliding-chunk implementation only accepts sequence lengths that are multiples of every
+layer's window; the kernels here accept any S <= 4094 and agree with HF wherever HF runs.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import _build_head, _head_decode, _head_loss, _lens
+
+_ptr, _call, _stream, _pad32 = ops._ptr, ops._call, ops._stream, ops._pad32
+
+LN_EPS = 1e-12  # the wrapper's layer_norm_eps argument never reaches the HF config (RestrictedTransformerLayer.py:72,82-92)
+
+
+# --------------------------------------------------------------------------------------------------------
+# parameter containers with HF's names
+# --------------------------------------------------------------------------------------------------------
+def _linear(i, o, std=0.02):
+    lin = nn.Linear(i, o)
+    nn.init.normal_(lin.weight, mean=0.0, std=std)  # HF _init_weights: normal(0, initializer_range), zero bias
+    nn.init.zeros_(lin.bias)
+    return lin
+
+
+def _embedding(n, d, padding_idx=None):
+    emb = nn.Embedding(n, d, padding_idx=padding_idx)
+    nn.init.normal_(emb.weight, mean=0.0, std=0.02)
+    if padding_idx is not None:
+        with torch.no_grad():
+            emb.weight[padding_idx].zero_()
+    return emb
+
+
+class _Embeddings(nn.Module):
+    def __init__(self, d, vocab=30522, max_pos=4096, type_vocab=2, pad_token_id=1):
+        super().__init__()
+        self.word_embeddings = _embedding(vocab, d, pad_token_id)  # unused: the reference feeds inputs_embeds
+        self.token_type_embeddings = _embedding(type_vocab, d)
+        self.LayerNorm = nn.LayerNorm(d, eps=LN_EPS)
+        self.position_embeddings = _embedding(max_pos, d, pad_token_id)
+
+
+class _SelfAttention(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.query, self.key, self.value = _linear(d, d), _linear(d, d), _linear(d, d)
+        # allocated by HF for global attention; the reference passes an all-zero global mask, so never read
+        self.query_global, self.key_global, self.value_global = _linear(d, d), _linear(d, d), _linear(d, d)
+
+
+class _DenseLN(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.dense = _linear(i, o)
+        self.LayerNorm = nn.LayerNorm(o, eps=LN_EPS)
+
+
+class _Dense(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.dense = _linear(i, o)
+
+
+class _Attention(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.self = _SelfAttention(d)
+        self.output = _DenseLN(d, d)
+
+
+class _Layer(nn.Module):
+    def __init__(self, d, f):
+        super().__init__()
+        self.attention = _Attention(d)
+        self.intermediate = _Dense(d, f)
+        self.output = _DenseLN(f, d)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, d, f, n_layers):
+        super().__init__()
+        self.layer = nn.ModuleList([_Layer(d, f) for _ in range(n_layers)])
+
+
+class _LongformerParams(nn.Module):
+    """Parameter tree of HF LongformerModel (add_pooling_layer=True)."""
+
+    def __init__(self, d, f, n_layers):
+        super().__init__()
+        self.embeddings = _Embeddings(d)
+        self.encoder = _Encoder(d, f, n_layers)
+        self.pooler = _Dense(d, d)  # HF computes the pooled output and the reference discards it
+
+
+# --------------------------------------------------------------------------------------------------------
+# GEMM-ready shadow copies of the weights (rebuilt only when a parameter changes)
+# --------------------------------------------------------------------------------------------------------
+class PackedEncoder:
+    def __init__(self, params: _LongformerParams):
+        self.params = params
+        self.key = None
+        self.layers = None
+
+    def used_parameters(self):
+        """Parameters that take part in the forward pass, in a fixed order (= the gradient order of EncoderFn)."""
+        m = self.params
+        out = [m.embeddings.token_type_embeddings.weight, m.embeddings.position_embeddings.weight,
+               m.embeddings.LayerNorm.weight, m.embeddings.LayerNorm.bias]
+        for lyr in m.encoder.layer:
+            sa = lyr.attention.self
+            out += [sa.query.weight, sa.query.bias, sa.key.weight, sa.key.bias, sa.value.weight, sa.value.bias,
+                    lyr.attention.output.dense.weight, lyr.attention.output.dense.bias,
+                    lyr.attention.output.LayerNorm.weight, lyr.attention.output.LayerNorm.bias,
+                    lyr.intermediate.dense.weight, lyr.intermediate.dense.bias,
+                    lyr.output.dense.weight, lyr.output.dense.bias,
+                    lyr.output.LayerNorm.weight, lyr.output.LayerNorm.bias]
+        return out
+
+    PER_LAYER = 16
+
+    def get(self):
+        ps = self.used_parameters()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key == self.key:
+            return self.layers
+        layers = []
+        with torch.no_grad():
+            for lyr in self.params.encoder.layer:
+                sa = lyr.attention.self
+                wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], dim=0).contiguous()
+                bqkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias]).contiguous()
+                ent = {"wqkv": ops.split_tf32(wqkv), "bqkv": bqkv,
+                       "wo": ops.split_tf32(lyr.attention.output.dense.weight.detach().contiguous()),
+                       "bo": lyr.attention.output.dense.bias.detach().contiguous(),
+                       "w1": ops.split_tf32(lyr.intermediate.dense.weight.detach().contiguous()),
+                       "b1": lyr.intermediate.dense.bias.detach().contiguous(),
+                       "w2": ops.split_tf32(lyr.output.dense.weight.detach().contiguous()),
+                       "b2": lyr.output.dense.bias.detach().contiguous()}
+                layers.append(ent)
+        self.key, self.layers = key, layers
+        return layers
+
+    def transposed(self, l):
+        """hi/lo of W^T for the dX GEMMs of the backward pass (made on first use per weight version)."""
+        ent = self.get()[l]
+        if "wqkv_t" not in ent:
+            lyr = self.params.encoder.layer[l]
+            sa = lyr.attention.self
+            with torch.no_grad():
+                wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], dim=0)
+                ent["wqkv_t"] = ops.split_tf32(wqkv.t().contiguous())
+                ent["wo_t"] = ops.split_tf32(lyr.attention.output.dense.weight.detach().t().contiguous())
+                ent["w1_t"] = ops.split_tf32(lyr.intermediate.dense.weight.detach().t().contiguous())
+                ent["w2_t"] = ops.split_tf32(lyr.output.dense.weight.detach().t().contiguous())
+        return ent
+
+
+def _ln(mode, a, b, typ, gamma, beta, B, S, d, want_split, save):
+    """mode 0: embeddings LN over x=a [B,S,d] with position table b; mode 1: LN(a + b) over [M,d] rows."""
+    M = B * S
+    dev = a.device
+    y = torch.empty((M, d), device=dev, dtype=torch.float32)
+    kp = _pad32(d)
+    hl = torch.empty((2, M, kp), device=dev, dtype=torch.float32) if want_split else None
+    pre = torch.empty((M, d), device=dev, dtype=torch.float32) if save else None
+    stats = torch.empty((M, 2), device=dev, dtype=torch.float32) if save else None
+    hi, lo = (hl[0], hl[1]) if want_split else (None, None)
+    if mode == 0:
+        _call("mts_embed_ln_fwd", _ptr(a), a.stride(0), _ptr(b), _ptr(typ), _ptr(gamma), _ptr(beta), B, S, d, LN_EPS,
+              _ptr(y), _ptr(hi), _ptr(lo), kp, _ptr(pre), _ptr(stats), _stream())
+    else:
+        _call("mts_add_ln_fwd", _ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), M, d, LN_EPS, _ptr(y), _ptr(hi), _ptr(lo), kp,
+              _ptr(pre), _ptr(stats), _stream())
+    return y, hi, lo, pre, stats
+
+
+def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
+    """x [B,S,d] -> last hidden state [B,S,d].  `reaches[l]` = one-sided window of layer l.
+    With save=True also returns what the backward pass needs."""
+    B, S, d = x.shape
+    M = B * S
+    dev = x.device
+    hd = d // nheads
+    m = packed.params
+    layers = packed.get()
+    emb = m.embeddings
+    h, h_hi, h_lo, pre0, st0 = _ln(0, x, emb.position_embeddings.weight.detach(), emb.token_type_embeddings.weight.detach()[0],
+                                   emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), B, S, d, True, save)
+    saved = {"emb": (pre0, st0), "layers": []}
+    for l, ent in enumerate(layers):
+        lyr = m.encoder.layer[l]
+        F = lyr.intermediate.dense.out_features
+        qkv = torch.empty((M, 3 * d), device=dev, dtype=torch.float32)
+        ops.gemm_tf32x3(h_hi, h_lo, ent["wqkv"][0], ent["wqkv"][1], ent["bqkv"], qkv, M, 3 * d, epilogue=1)
+        kp = _pad32(d)
+        a_hl = torch.empty((2, M, kp), device=dev, dtype=torch.float32)
+        lse = torch.empty((B, nheads, S), device=dev, dtype=torch.float32) if save else None
+        if kp == d:
+            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), B, S, nheads, hd, reaches[l], 0, _ptr(a_hl[0]),
+                  _ptr(a_hl[1]), kp, _ptr(lse), _stream())
+        else:  # widths that are not a multiple of 32: plain output, then the generic (zero-padding) split
+            a = torch.empty((M, d), device=dev, dtype=torch.float32)
+            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), B, S, nheads, hd, reaches[l], _ptr(a), 0, 0, 0,
+                  _ptr(lse), _stream())
+            _call("mts_split_tf32", _ptr(a), d, M, d, kp, _ptr(a_hl[0]), _ptr(a_hl[1]), _stream())
+        t = torch.empty((M, d), device=dev, dtype=torch.float32)
+        ops.gemm_tf32x3(a_hl[0], a_hl[1], ent["wo"][0], ent["wo"][1], ent["bo"], t, M, d, epilogue=1)
+        ln1 = lyr.attention.output.LayerNorm
+        y, y_hi, y_lo, pre1, st1 = _ln(1, t, h, None, ln1.weight.detach(), ln1.bias.detach(), M, 1, d, True, save)
+        zp = torch.empty((M, F), device=dev, dtype=torch.float32)
+        ops.gemm_tf32x3(y_hi, y_lo, ent["w1"][0], ent["w1"][1], ent["b1"], zp, M, F, epilogue=1)
+        kf = _pad32(F)
+        z_hl = torch.empty((2, M, kf), device=dev, dtype=torch.float32)
+        _call("mts_gelu_split", _ptr(zp), F, M, F, kf, _ptr(z_hl[0]), _ptr(z_hl[1]), _stream())
+        u = torch.empty((M, d), device=dev, dtype=torch.float32)
+        ops.gemm_tf32x3(z_hl[0], z_hl[1], ent["w2"][0], ent["w2"][1], ent["b2"], u, M, d, epilogue=1)
+        ln2 = lyr.output.LayerNorm
+        h_in = h
+        last = l == len(layers) - 1
+        h, h_hi, h_lo, pre2, st2 = _ln(1, u, y, None, ln2.weight.detach(), ln2.bias.detach(), M, 1, d, not last, save)
+        if save:
+            saved["layers"].append({"h_in": h_in, "qkv": qkv, "lse": lse, "a_hl": a_hl, "pre1": pre1, "st1": st1,
+                                    "y": y, "zp": zp, "z_hl": z_hl, "pre2": pre2, "st2": st2})
+    return h.view(B, S, d), saved
+
+
+class EncoderFn(torch.autograd.Function):
+    """Differentiable w.r.t. the encoder parameters (the input embeddings are data)."""
+
+    @staticmethod
+    def forward(ctx, x, lens, packed, nheads, reaches, *params):
+        need = any(ctx.needs_input_grad)
+        out, saved = encoder_forward(x, lens, packed, nheads, reaches, save=need)
+        if need:
+            ctx.saved, ctx.lens, ctx.packed, ctx.nheads, ctx.reaches = saved, lens, packed, nheads, reaches
+            ctx.shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .transformer_bwd import encoder_backward
+
+        grads = encoder_backward(ctx, dout.contiguous())
+        ctx.saved = None
+        return (None, None, None, None, None, *grads)
+
+
+class Longformer_Local_Attention(nn.Module):
+    def __init__(self, d_model: int, nhead: int, n_layers: int, dim_feedforward: int = 2048, window_size=3,
+                 dropout: float = 0.1, dropout_attention: float = 0.1, layer_norm_eps: float = 1e-5, tagset_size=2,
+                 device=None, max_position_embedding=4096) -> None:
+        super().__init__()
+        if d_model % nhead != 0:
+            raise ValueError(f"The hidden size ({d_model}) is not a multiple of the number of attention heads ({nhead})")
+        windows = list(window_size) if isinstance(window_size, (list, tuple)) else [window_size] * n_layers
+        assert len(windows) == n_layers, "`len(config.attention_window)` should equal `config.num_hidden_layers`"
+        for i, wdw in enumerate(windows):  # HF LongformerSelfAttention.__init__ asserts
+            assert wdw % 2 == 0, f"`attention_window` for layer {i} has to be an even value. Given {wdw}"
+            assert wdw > 0, f"`attention_window` for layer {i} has to be positive. Given {wdw}"
+        self.d_model, self.nhead, self.windows = d_model, nhead, windows
+        self.reaches = [wdw // 2 for wdw in windows]
+        self.hidden_dropout, self.attention_dropout = float(dropout), float(dropout_attention)
+        self.max_positions = max_position_embedding
+        self.model = _LongformerParams(d_model, dim_feedforward, n_layers)
+        self._packed = None
+
+    def packed(self):
+        if self._packed is None:
+            self._packed = PackedEncoder(self.model)
+        return self._packed
+
+    def forward(self, src, lengths):
+        x = ops._check(src, "src")
+        if x.dim() != 3 or x.shape[2] != self.d_model:
+            raise ValueError(f"expected [B, S, {self.d_model}] embeddings, got {tuple(x.shape)}")
+        if x.shape[1] + 2 > self.max_positions:
+            raise IndexError(f"sequence length {x.shape[1]} exceeds the position table ({self.max_positions} rows, "
+                             "position ids start at 2)")
+        if self.training and (self.hidden_dropout > 0 or self.attention_dropout > 0):
+            raise NotImplementedError("dropout inside the windowed encoder is not implemented on the B200 path; "
+                                      "train with dropout_in = dropout_out = 0")
+        if x.stride(2) != 1 or x.stride(1) != x.shape[2]:
+            x = x.contiguous()
+        lens = lengths if isinstance(lengths, ops.Lengths) else ops.Lengths(lengths, x.device, x.shape[1])
+        packed = self.packed()
+        return EncoderFn.apply(x, lens, packed, self.nhead, self.reaches, *packed.used_parameters())
+
+
+class Transformer_segmenter(nn.Module):
+    def __init__(self, tagset_size, embedding_dim, hidden_dim, num_layers=6, nheads=8, dropout_in=0.0, dropout_out=0.0,
+                 batch_first=True, loss_fn="CrossEntropy", positional_encoding=True, threshold=None, restricted=True,
+                 window_size=127, alpha=0.9, gamma=2):
+        super().__init__()
+        if not restricted:
+            raise NotImplementedError("only the windowed (restricted) encoder is on the B200 hot path")
+        self.embedding_dim, self.hidden_dim, self.tagset_size = embedding_dim, hidden_dim, tagset_size
+        self.device = "cuda"
+        self.no_mask = True
+        windows = [win * window_size for win in range(num_layers, 0, -1)]  # pyramidal, models/CRF.py:529
+        self.model = Longformer_Local_Attention(embedding_dim, nheads, num_layers, hidden_dim, window_size=windows,
+                                                dropout=dropout_in, dropout_attention=dropout_out, layer_norm_eps=1e-5,
+                                                tagset_size=tagset_size, device=None, max_position_embedding=4096)
+        _build_head(self, embedding_dim, tagset_size, loss_fn, threshold, alpha, gamma)
+
+    def loss(self, xs, lengths, tags, segments=None, global_count=None):
+        if segments is not None:
+            raise NotImplementedError("the auxiliary cosine loss (segments=...) is outside the B200 hot path")
+        lens = ops.Lengths(lengths, xs.device, xs.shape[1]) if not isinstance(lengths, ops.Lengths) else lengths
+        return _head_loss(self, self.model(xs, lens), lens, tags, global_count)
+
+    def forward(self, xs, lenghts, threshold=0.4):
+        lens = ops.Lengths(lenghts, xs.device, xs.shape[1]) if not isinstance(lenghts, ops.Lengths) else lenghts
+        with torch.no_grad():
+            return _head_decode(self, self.model(xs, lens), lens, threshold)

@@ -412,3 +412,101 @@ def test_text_segmenter_steps(dev):
     assert [len(t) for t in tags] == [30, 12, 21, 7]
     with pytest.raises(ValueError):
         TextSegmenter(2, 20, 256, architecture="nope")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# pyramidal windowed-attention segmenter (HF LongformerModel in the reference)
+# ----------------------------------------------------------------------------------------------------------
+def load_params_allow_unused(module, fx, dev):
+    """The transformer fixtures omit the tensors HF allocates but never reads (word_embeddings, *_global, pooler)."""
+    sd = {k[2:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("p:")}
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(("word_embeddings" in k or "_global" in k or "pooler" in k) for k in missing), missing
+    return module.to(dev)
+
+
+@pytest.mark.parametrize("B,S,h,hd,w,lens", [
+    (2, 24, 4, 8, 4, [24, 13]),
+    (3, 200, 2, 112, 48, [200, 77, 1]),
+    (2, 130, 3, 64, 8, [130, 31]),
+    (2, 96, 2, 32, 100, [96, 50]),      # window wider than the episode: dense attention
+    (1, 700, 1, 16, 360, [650]),        # default-config reach (window 120 x 6 layers)
+])
+def test_band_attention_forward(dev, B, S, h, hd, w, lens):
+    from multimodaltopicsegmentation_b200 import ops
+    from oracle import ref_numpy as rn
+
+    g = torch.Generator().manual_seed(S + hd + w)
+    d = h * hd
+    qkv = torch.randn(B * S, 3 * d, generator=g)
+    L = ops.Lengths(lens, dev, S)
+    qkv_d = qkv.to(dev)
+    out = torch.empty(B * S, d, device=dev)
+    lse = torch.empty(B, h, S, device=dev)
+    ops._call("mts_band_attn_fwd", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
+              lse.data_ptr(), ops._stream())
+    split = lambda t: t.view(B, S, h, hd).permute(0, 2, 1, 3).numpy()
+    q = split(qkv[:, :d]) / np.float32(np.sqrt(hd))
+    ref = rn.banded_attention(q.astype(np.float32), split(qkv[:, d:2 * d]), split(qkv[:, 2 * d:]), lens, w)
+    got = out.view(B, S, h, hd).permute(0, 2, 1, 3)
+    close(got, ref, rtol=1e-4, atol=1e-5)
+    for b, n in enumerate(lens):  # padded queries: exact zeros (HF modeling_longformer.py:578)
+        assert float(out.view(B, S, d)[b, n:].abs().max() if n < S else 0.0) == 0.0
+    if d % 32 == 0:  # fused operand split
+        hl = torch.empty(2, B * S, d, device=dev)
+        ops._call("mts_band_attn_fwd", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, 0, hl[0].data_ptr(),
+                  hl[1].data_ptr(), d, 0, ops._stream())
+        assert float(((hl[0] + hl[1]) - out).abs().max()) <= 2.0 ** -21 * float(out.abs().max())
+        assert int((hl.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+def test_transformer_golden_forward(dev, golden):
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+
+    fx = golden("transformer_focal")
+    nh, w = int(fx["i:nheads"]), int(fx["i:window"])
+    m = load_params_allow_unused(Transformer_segmenter(2, 32, 16, num_layers=2, nheads=nh, loss_fn="FocalLoss",
+                                                        window_size=w), fx, dev).eval()
+    x = torch.from_numpy(fx["i:x"]).to(dev)
+    lengths = torch.from_numpy(fx["i:lengths"])
+    m.th = float(fx["i:th"])
+    hidden = m.model(x, lengths)
+    close(hidden, fx["o:hidden"])
+    scores, tags = m(x, lengths)
+    assert tuple(scores.shape) == fx["o:scores"].shape  # time axis = S for the transformer
+    close(scores, fx["o:scores"], atol=1e-4)  # classification weights were scaled x20 in the fixture
+    tags_equal(tags, fx["o:tags"])
+    with torch.no_grad():
+        loss = m.loss(x, lengths, torch.from_numpy(fx["i:y"]).to(dev))
+    close(loss, fx["o:loss"])
+
+
+def test_transformer_vs_hf_twin(dev):
+    """Medium shapes against the HF LongformerModel twin (oracle/ref_torch.py), ragged lengths."""
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(11)
+    g = torch.Generator().manual_seed(12)
+    B, S, d, F, nl, nh, w = 3, 96, 64, 48, 3, 4, 8   # windows [24, 16, 8]; S is a multiple of all of them
+    ref = rt.WindowedSegmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="BinaryCrossEntropy", window_size=w).eval()
+    ours = Transformer_segmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="BinaryCrossEntropy", window_size=w)
+    sd = {k: v for k, v in ref.state_dict().items()}
+    missing, unexpected = ours.load_state_dict(sd, strict=False)
+    assert not missing, missing
+    assert all("position_ids" in k for k in unexpected), unexpected   # HF buffers, if any
+    ours = ours.to(dev).eval()
+    x = torch.randn(B, S, d, generator=g)
+    lengths = torch.tensor([96, 40, 7])
+    y = (torch.rand(B, S, generator=g) < 0.2).float()
+    ref.th = ours.th = 0.5
+    with torch.no_grad():
+        s_ref, t_ref = ref(x, lengths)
+        l_ref = ref.loss(x, lengths, y)
+        s, t = ours(x.to(dev), lengths)
+        l = ours.loss(x.to(dev), lengths, y.to(dev))
+    for b, n in enumerate(lengths.tolist()):
+        close(s[b, :n], s_ref[b, :n], atol=2e-5)
+    assert t == t_ref
+    close(l, l_ref)
