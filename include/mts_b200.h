@@ -166,8 +166,10 @@ int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *pos, const 
  *   (bias already added by the GEMM epilogue).  sum_out may alias a. */
 int mts_add_ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, int M, int d, float eps,
                    float *y, float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats, void *stream);
-/* LongformerIntermediate (:1103-1116) activation fused with the operand split: hi/lo [rows,Kp] of GELU(src). */
-int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, float *hi, float *lo, void *stream);
+/* LongformerIntermediate (:1103-1116) activation fused with the operand split: hi/lo [rows,Kp] of GELU(src);
+ * act [rows,cols] or NULL: GELU(src) in fp32, kept for the weight gradient of the next dense layer. */
+int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, float *act, float *hi, float *lo,
+                   void *stream);
 /* LongformerSelfAttention (:481-639; sliding chunks :758-867) for all-local attention:
  *   qkv [B*S, ld] rows = [q | k | v] (each nheads*hd wide, head-major), q NOT yet scaled (the kernel divides by
  *   sqrt(hd) as HF does at :513); token i attends to j with |i-j| <= w and j < len_b; softmax in fp32;
@@ -176,6 +178,25 @@ int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, flo
  *   lse [B,nheads,S] or NULL: log-sum-exp of every query row, saved for the backward pass. */
 int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads, int hd, int w,
                       float *out, float *out_hi, float *out_lo, int Kp, float *lse, void *stream);
+
+/* Backward of the encoder pieces (the reference: autograd through HF LongformerModel).
+ * mts_ln_bwd: dy, pre (pre-LN values), stats (mean, rstd) as saved by the forward calls -> dx [M,d] (+ its TF32
+ *   halves dx_hi/dx_lo [M,Kp], both or neither), dgamma [d], dbeta [d] (overwritten); ws >= mts_ln_bwd_ws_bytes. */
+int64_t mts_ln_bwd_ws_bytes(int M, int d);
+int mts_ln_bwd(const float *dy, const float *pre, const float *stats, const float *gamma, int M, int d, float *dx,
+               float *dx_hi, float *dx_lo, int Kp, float *dgamma, float *dbeta, void *ws, void *stream);
+/* dzp = dz * GELU'(zp) [rows,cols] and its TF32 halves hi/lo [rows,Kp]. */
+int mts_gelu_bwd(const float *dz, const float *zp, int rows, int cols, int Kp, float *dzp, float *hi, float *lo,
+                 void *stream);
+/* dpos[t,:] = sum_b dpre[b,t,:]  (gradient rows 2..S+1 of the position table; the token-type gradient is the
+ * column sum of dpos, mts_colsum). */
+int mts_embed_bwd(const float *dpre, int B, int S, int d, float *dpos, void *stream);
+/* Banded attention backward: qkv, lse as in the forward call, o = forward output [B*S, nheads*hd], d_o its
+ * gradient -> dqkv [B*S, ld] = [dq | dk | dv] (dq already includes the 1/sqrt(hd) factor), zero at padded rows.
+ * delta_ws: B*nheads*S floats of scratch. */
+int mts_band_attn_bwd(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
+                      const int32_t *lengths, int B, int S, int nheads, int hd, int w, float *dqkv, float *delta_ws,
+                      void *stream);
 
 #ifdef __cplusplus
 }

@@ -104,13 +104,15 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
 
 // GELU(erf) + hi/lo split: src [rows, cols] (row stride ld) -> hi/lo [rows, Kp]
 __global__ void __launch_bounds__(256) gelu_split_kernel(const float *__restrict__ src, int64_t ld, int rows, int cols,
-                                                         int Kp, float *__restrict__ hi, float *__restrict__ lo) {
+                                                         int Kp, float *__restrict__ act, float *__restrict__ hi,
+                                                         float *__restrict__ lo) {
   const int64_t total = (int64_t)rows * Kp;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(idx % Kp);
     const int64_t r = idx / Kp;
     const float v = (k < cols) ? gelu_erf(__ldg(src + r * ld + k)) : 0.0f;
+    if (act && k < cols) act[r * cols + k] = v;
     const float h = tf32_rn(v);
     hi[idx] = h;
     lo[idx] = tf32_rn(v - h);
@@ -365,11 +367,11 @@ extern "C" int mts_add_ln_fwd(const float *a, const float *res, const float *gam
   return 0;
 }
 
-extern "C" int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, float *hi, float *lo,
-                              void *stream) {
+extern "C" int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, float *act, float *hi,
+                              float *lo, void *stream) {
   MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "gelu_split: null pointer");
   MTS_REQUIRE(rows > 0 && cols > 0 && Kp % 32 == 0 && Kp >= cols, MTS_E_BADARG, "gelu_split: bad shape");
-  gelu_split_kernel<<<ew_grid((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, hi, lo);
+  gelu_split_kernel<<<ew_grid((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, act, hi, lo);
   MTS_LAUNCH_CHECK();
   return 0;
 }

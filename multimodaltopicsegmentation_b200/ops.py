@@ -13,7 +13,7 @@ from . import _lib
 _LAUNCHES = 0
 # kernels launched per ABI call (for the bench's gpu_launches claim)
 _KERNELS_PER_CALL = {
-    "mts_seg_loss_fwd": 2, "mts_head_bwd": 3, "mts_colsum": 2,
+    "mts_seg_loss_fwd": 2, "mts_head_bwd": 3, "mts_colsum": 2, "mts_ln_bwd": 3, "mts_band_attn_bwd": 2,
 }
 
 

@@ -18,13 +18,11 @@ layer's window; the kernels here accept any S <= 4094 and agr
 """
 from __future__ import annotations
 
-import math
-
 import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import _build_head, _head_decode, _head_loss, _lens
+from .modules import _build_head, _head_decode, _head_loss
 
 _ptr, _call, _stream, _pad32 = ops._ptr, ops._call, ops._stream, ops._pad32
 
@@ -214,11 +212,11 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
         kp = _pad32(d)
         a_hl = torch.empty((2, M, kp), device=dev, dtype=torch.float32)
         lse = torch.empty((B, nheads, S), device=dev, dtype=torch.float32) if save else None
+        a = torch.empty((M, d), device=dev, dtype=torch.float32) if (save or kp != d) else None
         if kp == d:
-            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), B, S, nheads, hd, reaches[l], 0, _ptr(a_hl[0]),
-                  _ptr(a_hl[1]), kp, _ptr(lse), _stream())
+            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), B, S, nheads, hd, reaches[l], _ptr(a),
+                  _ptr(a_hl[0]), _ptr(a_hl[1]), kp, _ptr(lse), _stream())
         else:  # widths that are not a multiple of 32: plain output, then the generic (zero-padding) split
-            a = torch.empty((M, d), device=dev, dtype=torch.float32)
             _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), B, S, nheads, hd, reaches[l], _ptr(a), 0, 0, 0,
                   _ptr(lse), _stream())
             _call("mts_split_tf32", _ptr(a), d, M, d, kp, _ptr(a_hl[0]), _ptr(a_hl[1]), _stream())
@@ -230,7 +228,8 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
         ops.gemm_tf32x3(y_hi, y_lo, ent["w1"][0], ent["w1"][1], ent["b1"], zp, M, F, epilogue=1)
         kf = _pad32(F)
         z_hl = torch.empty((2, M, kf), device=dev, dtype=torch.float32)
-        _call("mts_gelu_split", _ptr(zp), F, M, F, kf, _ptr(z_hl[0]), _ptr(z_hl[1]), _stream())
+        z = torch.empty((M, F), device=dev, dtype=torch.float32) if save else None
+        _call("mts_gelu_split", _ptr(zp), F, M, F, kf, _ptr(z), _ptr(z_hl[0]), _ptr(z_hl[1]), _stream())
         u = torch.empty((M, d), device=dev, dtype=torch.float32)
         ops.gemm_tf32x3(z_hl[0], z_hl[1], ent["w2"][0], ent["w2"][1], ent["b2"], u, M, d, epilogue=1)
         ln2 = lyr.output.LayerNorm
@@ -238,8 +237,8 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
         last = l == len(layers) - 1
         h, h_hi, h_lo, pre2, st2 = _ln(1, u, y, None, ln2.weight.detach(), ln2.bias.detach(), M, 1, d, not last, save)
         if save:
-            saved["layers"].append({"h_in": h_in, "qkv": qkv, "lse": lse, "a_hl": a_hl, "pre1": pre1, "st1": st1,
-                                    "y": y, "zp": zp, "z_hl": z_hl, "pre2": pre2, "st2": st2})
+            saved["layers"].append({"h_in": h_in, "qkv": qkv, "lse": lse, "a": a, "pre1": pre1, "st1": st1,
+                                    "y": y, "zp": zp, "z": z, "pre2": pre2, "st2": st2})
     return h.view(B, S, d), saved
 
 

@@ -510,3 +510,141 @@ def test_transformer_vs_hf_twin(dev):
         close(s[b, :n], s_ref[b, :n], atol=2e-5)
     assert t == t_ref
     close(l, l_ref)
+
+
+def _dense_band_attention_torch(qkv, lens, B, S, h, hd, w):
+    """float64 autograd reference: dense scores with the band / length mask, zero rows for padded queries."""
+    d = h * hd
+    q, k, v = [t.view(B, S, h, hd).permute(0, 2, 1, 3) for t in (qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:])]
+    s = (q / np.sqrt(hd)) @ k.transpose(-1, -2)
+    idx = torch.arange(S)
+    band = (idx[:, None] - idx[None, :]).abs() <= w
+    outs = []
+    for b in range(B):
+        n = lens[b]
+        allowed = band & (idx[None, :] < n)
+        sb = s[b].masked_fill(~allowed, float("-inf"))
+        sb = torch.where(allowed.any(-1, keepdim=True), sb, torch.zeros_like(sb))
+        p = torch.softmax(sb, dim=-1) * (idx < n)[None, :, None]
+        outs.append(p @ v[b])
+    return torch.stack(outs).permute(0, 2, 1, 3).reshape(B * S, d)
+
+
+@pytest.mark.parametrize("B,S,h,hd,w,lens", [
+    (2, 24, 4, 8, 4, [24, 13]),
+    (2, 150, 2, 112, 48, [150, 61]),
+    (2, 130, 3, 64, 8, [130, 31]),
+    (1, 300, 1, 16, 120, [280]),
+])
+def test_band_attention_backward(dev, B, S, h, hd, w, lens):
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator().manual_seed(S + hd + w + 1)
+    d = h * hd
+    qkv = torch.randn(B * S, 3 * d, generator=g, dtype=torch.float64).requires_grad_(True)
+    do = torch.randn(B * S, d, generator=g, dtype=torch.float64)
+    ref = _dense_band_attention_torch(qkv, lens, B, S, h, hd, w)
+    ref.backward(do)
+    L = ops.Lengths(lens, dev, S)
+    qkv_d = qkv.detach().float().to(dev)
+    out = torch.empty(B * S, d, device=dev)
+    lse = torch.empty(B, h, S, device=dev)
+    ops._call("mts_band_attn_fwd", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
+              lse.data_ptr(), ops._stream())
+    close(out, ref.detach().float(), rtol=1e-4, atol=1e-5)
+    dqkv = torch.full((B * S, 3 * d), float("nan"), device=dev)
+    delta = torch.empty(B, h, S, device=dev)
+    do_d = do.float().to(dev)
+    ops._call("mts_band_attn_bwd", qkv_d.data_ptr(), 3 * d, out.data_ptr(), do_d.data_ptr(), lse.data_ptr(),
+              L.dev.data_ptr(), B, S, h, hd, w, dqkv.data_ptr(), delta.data_ptr(), ops._stream())
+    scale = float(qkv.grad.abs().max())
+    close(dqkv, qkv.grad.float(), rtol=1e-4, atol=2e-5 * scale)
+
+
+@pytest.mark.parametrize("M,d", [(37, 32), (1000, 896), (300, 1024), (64, 100)])
+def test_layer_norm_forward_backward(dev, M, d):
+    from multimodaltopicsegmentation_b200 import _lib, ops
+
+    g = torch.Generator().manual_seed(M + d)
+    a = torch.randn(M, d, generator=g, dtype=torch.float64)
+    r = torch.randn(M, d, generator=g, dtype=torch.float64)
+    gamma = torch.randn(d, generator=g, dtype=torch.float64).requires_grad_(True)
+    beta = torch.randn(d, generator=g, dtype=torch.float64).requires_grad_(True)
+    pre = (a + r).requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(pre, (d,), gamma, beta, eps=1e-12)
+    dy = torch.randn(M, d, generator=g, dtype=torch.float64)
+    ref.backward(dy)
+    f = lambda t: t.detach().float().to(dev).contiguous()
+    kp = (d + 31) // 32 * 32
+    y, hl = torch.empty(M, d, device=dev), torch.empty(2, M, kp, device=dev)
+    pre_d, stats = torch.empty(M, d, device=dev), torch.empty(M, 2, device=dev)
+    ops._call("mts_add_ln_fwd", f(a).data_ptr(), f(r).data_ptr(), f(gamma).data_ptr(), f(beta).data_ptr(), M, d, 1e-12,
+              y.data_ptr(), hl[0].data_ptr(), hl[1].data_ptr(), kp, pre_d.data_ptr(), stats.data_ptr(), ops._stream())
+    close(y, ref.detach().float(), rtol=1e-4, atol=1e-5)
+    assert float(((hl[0] + hl[1])[:, :d] - y).abs().max()) <= 2.0 ** -21 * float(y.abs().max())
+    assert float(hl[:, :, d:].abs().max() if kp > d else 0.0) == 0.0
+    dx, dhl = torch.empty(M, d, device=dev), torch.empty(2, M, kp, device=dev)
+    dgb = torch.empty(2, d, device=dev)
+    ws = torch.empty(_lib.load().mts_ln_bwd_ws_bytes(M, d) // 4, device=dev)
+    ops._call("mts_ln_bwd", f(dy).data_ptr(), pre_d.data_ptr(), stats.data_ptr(), f(gamma).data_ptr(), M, d,
+              dx.data_ptr(), dhl[0].data_ptr(), dhl[1].data_ptr(), kp, dgb[0].data_ptr(), dgb[1].data_ptr(),
+              ws.data_ptr(), ops._stream())
+    close(dx, pre.grad.float(), rtol=1e-4, atol=1e-5 * float(pre.grad.abs().max()))
+    close(dgb[0], gamma.grad.float(), rtol=1e-4, atol=1e-5 * float(gamma.grad.abs().max()))
+    close(dgb[1], beta.grad.float(), rtol=1e-4, atol=1e-5 * float(beta.grad.abs().max()))
+    assert float(((dhl[0] + dhl[1])[:, :d] - dx).abs().max()) <= 2.0 ** -21 * float(dx.abs().max())
+
+
+def test_transformer_golden_backward(dev, golden):
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+
+    fx = golden("transformer_focal")
+    nh, w = int(fx["i:nheads"]), int(fx["i:window"])
+    m = load_params_allow_unused(Transformer_segmenter(2, 32, 16, num_layers=2, nheads=nh, loss_fn="FocalLoss",
+                                                        window_size=w), fx, dev)
+    x = torch.from_numpy(fx["i:x"]).to(dev)
+    loss = m.loss(x, torch.from_numpy(fx["i:lengths"]), torch.from_numpy(fx["i:y"]).to(dev))
+    loss.backward()
+    close(loss, fx["o:loss"])
+    named = dict(m.named_parameters())
+    for k in fx.files:
+        if not k.startswith("g:"):
+            continue
+        ref = fx[k]
+        got = named[k[2:]].grad
+        assert got is not None, k
+        close(got, ref, rtol=2e-4, atol=2e-6 + 1e-4 * float(np.abs(ref).max()), msg=k)
+    for k, p in named.items():  # tensors HF never reads receive no gradient
+        if "word_embeddings" in k or "_global" in k or "pooler" in k:
+            assert p.grad is None, k
+
+
+def test_transformer_training_vs_hf_twin(dev):
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(21)
+    g = torch.Generator().manual_seed(22)
+    B, S, d, F, nl, nh, w = 3, 96, 64, 48, 3, 4, 8
+    ref = rt.WindowedSegmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="FocalLoss", window_size=w).train()
+    ours = Transformer_segmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="FocalLoss", window_size=w)
+    missing, unexpected = ours.load_state_dict(ref.state_dict(), strict=False)
+    assert not missing, missing
+    ours = ours.to(dev).train()
+    x = torch.randn(B, S, d, generator=g)
+    lengths = torch.tensor([96, 40, 7])
+    y = (torch.rand(B, S, generator=g) < 0.2).float()
+    l_ref = ref.loss(x, lengths, y)
+    l_ref.backward()
+    l = ours.loss(x.to(dev), lengths, y.to(dev))
+    l.backward()
+    close(l, l_ref)
+    ref_named = dict(ref.named_parameters())
+    checked = 0
+    for k, p in ours.named_parameters():
+        r = ref_named[k].grad
+        if r is None or float(r.abs().max()) == 0.0:
+            continue
+        close(p.grad, r, rtol=2e-4, atol=1e-4 * float(r.abs().max()), msg=k)
+        checked += 1
+    assert checked >= 4 + 16 * nl + 2
