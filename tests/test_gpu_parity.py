@@ -578,7 +578,8 @@ def test_layer_norm_forward_backward(dev, M, d):
     kp = (d + 31) // 32 * 32
     y, hl = torch.empty(M, d, device=dev), torch.empty(2, M, kp, device=dev)
     pre_d, stats = torch.empty(M, d, device=dev), torch.empty(M, 2, device=dev)
-    ops._call("mts_add_ln_fwd", f(a).data_ptr(), f(r).data_ptr(), f(gamma).data_ptr(), f(beta).data_ptr(), M, d, 1e-12,
+    a_d, r_d, g_d, b_d, dy_d = f(a), f(r), f(gamma), f(beta), f(dy)  # keep the device copies alive across the calls
+    ops._call("mts_add_ln_fwd", a_d.data_ptr(), r_d.data_ptr(), g_d.data_ptr(), b_d.data_ptr(), M, d, 1e-12,
               y.data_ptr(), hl[0].data_ptr(), hl[1].data_ptr(), kp, pre_d.data_ptr(), stats.data_ptr(), ops._stream())
     close(y, ref.detach().float(), rtol=1e-4, atol=1e-5)
     assert float(((hl[0] + hl[1])[:, :d] - y).abs().max()) <= 2.0 ** -21 * float(y.abs().max())
@@ -586,7 +587,7 @@ def test_layer_norm_forward_backward(dev, M, d):
     dx, dhl = torch.empty(M, d, device=dev), torch.empty(2, M, kp, device=dev)
     dgb = torch.empty(2, d, device=dev)
     ws = torch.empty(_lib.load().mts_ln_bwd_ws_bytes(M, d) // 4, device=dev)
-    ops._call("mts_ln_bwd", f(dy).data_ptr(), pre_d.data_ptr(), stats.data_ptr(), f(gamma).data_ptr(), M, d,
+    ops._call("mts_ln_bwd", dy_d.data_ptr(), pre_d.data_ptr(), stats.data_ptr(), g_d.data_ptr(), M, d,
               dx.data_ptr(), dhl[0].data_ptr(), dhl[1].data_ptr(), kp, dgb[0].data_ptr(), dgb[1].data_ptr(),
               ws.data_ptr(), ops._stream())
     close(dx, pre.grad.float(), rtol=1e-4, atol=1e-5 * float(pre.grad.abs().max()))
@@ -645,6 +646,11 @@ def test_transformer_training_vs_hf_twin(dev):
         r = ref_named[k].grad
         if r is None or float(r.abs().max()) == 0.0:
             continue
+        if k.endswith("attention.self.key.bias"):
+            # softmax is invariant to a per-query constant, so d loss / d b_k is exactly 0 in exact arithmetic:
+            # both sides hold rounding noise only
+            assert float(p.grad.abs().max()) < 1e-9 and float(r.abs().max()) < 1e-9
+            continue
         close(p.grad, r, rtol=2e-4, atol=1e-4 * float(r.abs().max()), msg=k)
         checked += 1
-    assert checked >= 4 + 16 * nl + 2
+    assert checked >= 4 + 15 * nl + 2
