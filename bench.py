@@ -214,6 +214,124 @@ def cpu_train_reference():
             "sample": "best of 2 steps (after 1 warm-up) on one batch of 10 episodes, oracle/ref_torch.py on host cores"}
 
 
+XF_CFG = dict(B=256, S=960, D=896, F=256, L=6, heads=8, window=16)
+XF_WORKLOAD = ("configs[2]: RestrictedTransformer (pyramidal windowed attention, 6 layers, window 16 -> reaches 48..8, 8 heads, "
+               "d 896, FFN 256) inference, 256 episodes x 960 sentences (960 not 1000: HF needs S % lcm(windows) == 0), "
+               "lengths 100..960")
+XF_ATTN_BYTES_PER_TOKEN = 16 * 896   # read q,k,v + write o, fp32
+XF_GEMM_FLOPS_PER_TOKEN = 2 * 896 * (3 * 896 + 896 + 256 + 256)  # qkv + out-proj + FFN1 + FFN2 per layer
+
+
+def xf_batch(seed, B):
+    c = XF_CFG
+    g = torch.Generator().manual_seed(777 + seed)
+    lengths = torch.randint(100, c["S"] + 1, (B,), generator=g)
+    lengths[0] = c["S"]
+    return lengths
+
+
+def transformer_bench(m, dev, rank, world, steps, barrier):
+    """cfg3: windowed-attention segmenter inference.  Device-resident value, e2e from pinned host memory, per-kernel
+    CUDA-event times, roofline fractions of the banded-attention kernel (HBM) and the dense layers (tensor)."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    c = XF_CFG
+    torch.manual_seed(0)
+    seg = m.TextSegmenter(2, c["D"], c["F"], num_layers=c["L"], architecture="Transformer", loss_fn="FocalLoss",
+                          nheads=c["heads"], attention_window=c["window"], threshold=0.5).to(dev).eval()
+    seg.model.th = 0.5
+    model = seg.model
+    lengths = xf_batch(rank, c["B"])
+    n_sent = int(lengths.sum())
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    xs = [torch.randn(c["B"], c["S"], c["D"], device=dev, generator=g) for _ in range(2)]  # 2 x 881 MB >> L2
+    lens = ops.Lengths(lengths, dev, c["S"])
+
+    def step(i):
+        with torch.no_grad():
+            return model(xs[i % 2], lens)
+
+    for i in range(2):
+        step(i)
+    barrier()
+    ops.reset_launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(steps):
+        step(i)
+    end.record()
+    barrier()
+    launches = ops.launch_count()
+    t = torch.tensor([start.elapsed_time(end)], device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    ops.PROFILE = {}
+    step(0)
+    torch.cuda.synchronize()
+    prof = {k: [s.elapsed_time(e) for s, e in v] for k, v in ops.PROFILE.items()}
+    ops.PROFILE = None
+    # e2e: host (pinned) embeddings in, host tag lists out
+    host = xs[0].cpu().pin_memory()
+    def e2e(i):
+        batch = {"src_tokens": host.to(dev, non_blocking=True), "src_lengths": lengths}
+        return seg.predict_step(batch, i)
+    e2e(0)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, steps // 2)
+    for i in range(n_e2e):
+        e2e(i)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    hbm_peak, _ = peaks()
+    tokens = c["B"] * c["S"]
+    attn = prof.get("mts_band_attn_fwd", [])
+    gemm = prof.get("mts_gemm_tf32x3", [])
+    out = {"metric": "segmented sentences/sec", "value": n_sent * world / (ms / 1e3), "unit": "sentences/s",
+           "ms_per_step": ms, "steps": steps, "workload": XF_WORKLOAD, "valid_sentences_per_step_per_gpu": n_sent,
+           "tokens_per_step_per_gpu": tokens, "gpu_launches_per_step": launches / steps,
+           "e2e": {"value": n_sent * world / e2e_s, "unit": "sentences/s", "h2d_bytes_per_step": host.numel() * 4,
+                   "d2h_bytes_per_step": tokens, "api": "TextSegmenter.predict_step on pinned host tensors"},
+           "kernel_ms_per_step": {k: sum(v) for k, v in prof.items()}}
+    if attn:
+        per_layer = [n_sent * XF_ATTN_BYTES_PER_TOKEN / (x / 1e3) / 1e9 for x in attn]
+        out["roofline_attention"] = {"kernel": "band_attn_fwd_kernel, per layer (reach 48,40,32,24,16,8)", "bound": "hbm",
+                                     "achieved_gbs_per_layer": per_layer, "peak": hbm_peak,
+                                     "frac_per_layer": [a / hbm_peak for a in per_layer],
+                                     "algorithmic_bytes_per_launch": n_sent * XF_ATTN_BYTES_PER_TOKEN,
+                                     "ms_per_layer": attn}
+    if gemm:
+        tf = tokens * XF_GEMM_FLOPS_PER_TOKEN * c["L"] / (sum(gemm) / 1e3) / 1e12
+        out["roofline_dense"] = {"kernel": "gemm_tf32x3_kernel (24 launches)", "bound": "tensor",
+                                 "achieved_tflops_fp32_equiv": tf, "achieved_tflops_tf32_issued": 3 * tf,
+                                 "note": "3xTF32: three tensor-core products per fp32-grade product; TF32 dense peak is "
+                                         "half the bf16 figure in MEASURED_PEAKS.json"}
+    return out
+
+
+def cpu_transformer_reference():
+    from oracle import ref_torch as rt
+
+    c = XF_CFG
+    torch.manual_seed(0)
+    model = rt.WindowedSegmenter(2, c["D"], c["F"], num_layers=c["L"], nheads=c["heads"], loss_fn="FocalLoss",
+                                 threshold=0.5, window_size=c["window"]).eval()
+    B = 4
+    lengths = xf_batch(0, B)
+    x = torch.randn(B, c["S"], c["D"])
+    with torch.no_grad():
+        model(x, lengths)
+        t0 = time.perf_counter()
+        model(x, lengths)
+        dt = time.perf_counter() - t0
+    return {"value": int(lengths.sum()) / dt, "unit": "sentences/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "1 batch of 4 episodes x 960 sentences (after 1 warm-up) through oracle/ref_torch.py "
+                      "(HF LongformerModel on host cores; the reference's host mask loop not included)"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
@@ -302,11 +420,18 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = float(t.item())
 
     train = train_bench(m, dev, rank, world, max(3, args.steps // 2), barrier)
+    xf = None
+    if not args.skip_transformer:
+        del dev_sets, pinned
+        torch.cuda.empty_cache()
+        xf = transformer_bench(m, dev, rank, world, max(3, args.steps // 4), barrier)
 
     if rank != 0:
         return
     if world == 1:
         train["cpu_baseline"] = cpu_train_reference()
+        if xf is not None:
+            xf["cpu_baseline"] = cpu_transformer_reference()
     total_sent = n_sent_step * args.steps * world
     value = total_sent / (ms / 1e3)
     hbm_peak, peak_src = peaks()
@@ -336,6 +461,7 @@ def run_ours(args, rank, world, local_rank):
                          "sample": "5 full batches of 64x300 sentences through oracle/ref_torch.py (torch CPU, all threads)"},
         "clocks": clk.summary(),
         "train": train,
+        "transformer": xf,
     }
     print(json.dumps(line), flush=True)
 
@@ -346,6 +472,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-transformer", action="store_true", help="skip the configs[2] windowed-attention leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
