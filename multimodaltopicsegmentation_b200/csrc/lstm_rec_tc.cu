@@ -1,0 +1,368 @@
+// LSTM recurrence, forward, on the 5th-generation tensor cores (H == 256).
+// Same contract as lstm_rec.cu (torch.nn.LSTM as called at models/NeuralArchitectures.py:113-115: packed
+// variable-length, bidirectional, zero initial state, gate rows i,f,g,o; gx = X W_ih^T + b_ih + b_hh hoisted).
+//
+// One cluster of 8 CTAs advances a tile of 16 episodes of one (direction, encoder).  CTA r owns hidden units
+// [32r, 32r+32) = 128 gate rows of W_hh and keeps them ON CHIP for the whole sequence, split for 3xTF32:
+//     W = W_hi + W_lo,  W_hi = what kind::tf32 reads of the fp32 word (top 19 bits), W_lo = tf32(W - W_hi)
+//     W_hi : shared memory, 128 x 256 fp32, K-major SWIZZLE_128B (the A operand through a descriptor)  128 KB
+//     W_lo : TENSOR MEMORY, 128 lanes x 256 columns (the A operand of the .ts form of tcgen05.mma)       128 KB
+// (2 MB of split weights per direction do not fit the shared memory of 8 SMs; TMEM holds the other half.)
+// Per step, per CTA:
+//     pre[128 x 16] = W_hi h + W_lo h + W_hi h_lo          96 tcgen05.mma 128x16x8, accumulator in TMEM
+//     epilogue warps: tcgen05.ld -> + gx -> sigmoid/tanh -> shared-memory transpose -> cell update (c in
+//     registers) -> h_t to HBM and, as raw fp32, straight into the B-operand buffers (K-block r) of all 8 CTAs
+//     with st.async (DSMEM) completing on the receivers' mbarriers; the receivers only derive h_lo.
+// The only per-step synchronisation is mbarrier-based (no cluster barrier).
+#include <cooperative_groups.h>
+
+#include "cluster_utils.cuh"
+#include "tcgen05_utils.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mts {
+
+constexpr int TR_NB = 16;                 // episodes per tile (= MMA N)
+constexpr int TR_THREADS = 160;           // warp 0: MMA issuer / TMEM owner; warps 1..4: epilogue
+constexpr int TR_EPI = 128;
+constexpr int TR_WHI_BYTES = 8 * 128 * 128;        // 8 k-blocks x 128 rows x 128 B
+constexpr int TR_B_BYTES = 8 * TR_NB * 128;        // one h buffer: 8 k-blocks x 16 rows x 128 B = 16 KB
+constexpr int TR_ACT_FLOATS = 4 * TR_NB * 32;
+constexpr int TR_TMEM_COLS = 512;
+constexpr int TR_ACC_COL = 256;                    // accumulator columns [256, 272); W_lo in [0, 256)
+constexpr int TR_SMEM = TR_WHI_BYTES + 3 * TR_B_BYTES + TR_ACT_FLOATS * 4 + 256 + 1024;
+
+// Optional in-kernel timeline (profiling hook, off unless mts_debug_rec_profile() installs a buffer): CTA 0 writes
+// clock64() stamps of the phases of steps [8, 8 + TR_PROF_STEPS) -- slots 0..4 by the MMA thread, 5..11 by epilogue
+// thread 0 -- so that the per-step critical path can be read without a profiler.
+constexpr int TR_PROF_STEPS = 4, TR_PROF_SLOTS = 12;
+__device__ long long *g_tr_prof = nullptr;
+#define TR_STAMP(slot)                                                                     \
+  do {                                                                                     \
+    if (prof && s >= 8 && s < 8 + TR_PROF_STEPS) prof[(s - 8) * TR_PROF_SLOTS + (slot)] = clock64(); \
+  } while (0)
+
+template <bool SAVE>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1)
+    lstm_fwd_tc_kernel(const float *__restrict__ gx, const float *__restrict__ w_hh,
+                       const int32_t *__restrict__ lengths, const int32_t *__restrict__ order, int B, int T, int n_enc,
+                       int n_tiles, float *__restrict__ y, float *__restrict__ gates) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *whi = smem;
+  uint8_t *bhi = whi + TR_WHI_BYTES;       // [2][TR_B_BYTES]
+  uint8_t *blo = bhi + 2 * TR_B_BYTES;     // [TR_B_BYTES]
+  float *act = reinterpret_cast<float *>(blo + TR_B_BYTES);  // [4][NB][32]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(act + TR_ACT_FLOATS);
+  uint64_t *h_full = bars;        // [2]  h_{s-1} landed in bhi[s & 1] (tx bytes from all 8 CTAs)
+  uint64_t *lo_ready = bars + 2;  //      blo derived from bhi[s & 1]
+  uint64_t *acc_full = bars + 3;  //      the step's MMAs have completed
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+  int *len_s = reinterpret_cast<int *>(bars + 5);  // [NB]
+  int *bq_s = len_s + TR_NB;                       // [NB]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t rank = cluster.block_rank();
+  const int n_clusters = gridDim.x / kCluster;
+  const int n_items = n_tiles * 2 * n_enc;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ycols = n_enc * 2 * kH;
+
+  if (tid == 0) {
+    tc::bar_init(tc::s_u32(&h_full[0]), 1);
+    tc::bar_init(tc::s_u32(&h_full[1]), 1);
+    tc::bar_init(tc::s_u32(lo_ready), TR_EPI);
+    tc::bar_init(tc::s_u32(acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tc::tmem_alloc<TR_TMEM_COLS>(tc::s_u32(tmem_slot));
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // running mbarrier phases (the barriers are initialised once and live across work items)
+  uint32_t ph_h[2] = {0, 0}, ph_lo = 0, ph_acc = 0;
+
+  // epilogue-thread identities
+  const int et = tid - 32;              // 0..127 for warps 1..4
+  const int q = warp & 3;               // TMEM lane quarter = gate index (i,f,g,o) this warp reads
+  const int cj = et & 7, ce = et >> 3;  // cell mapping: units 4 cj .. 4 cj + 3 of episode slot ce
+
+  int cur_dir = -1, cur_enc = -1;
+  long long *prof = (blockIdx.x == 0 && (tid == 0 || tid == 32)) ? g_tr_prof : nullptr;
+
+  for (int item = blockIdx.x / kCluster; item < n_items; item += n_clusters) {
+    const int tile = item % n_tiles;
+    const int dir = (item / n_tiles) & 1;
+    const int enc = item / (2 * n_tiles);
+    const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * kH * kH;
+
+    // ---- weights on chip (only when the (direction, encoder) changes) ----------------------------------------
+    if (dir != cur_dir || enc != cur_enc) {
+      for (int idx = tid; idx < 128 * 64; idx += TR_THREADS) {
+        const int r = idx >> 6, c = idx & 63;  // tile row (gate r>>5, unit r&31), 16-byte chunk along K
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)((r >> 5) * kH + rank * kUnits + (r & 31)) * kH) + c);
+        *reinterpret_cast<float4 *>(whi + (c >> 3) * 16384 + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
+      }
+      if (warp >= 1) {
+        const int r = q * 32 + lane;
+        const float *wrow = W + (size_t)(q * kH + rank * kUnits + lane) * kH;
+        (void)r;
+#pragma unroll 1
+        for (int kk = 0; kk < 8; ++kk) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(wrow + kk * 32) + i);
+            v[4 * i + 0] = tc::tf32_rest(x.x); v[4 * i + 1] = tc::tf32_rest(x.y);
+            v[4 * i + 2] = tc::tf32_rest(x.z); v[4 * i + 3] = tc::tf32_rest(x.w);
+          }
+          tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kk * 32), v);
+        }
+        tc::tmem_wait_st();
+      }
+      cur_dir = dir;
+      cur_enc = enc;
+    }
+    // ---- tile bookkeeping, zero initial state ---------------------------------------------------------------
+    if (tid < TR_NB) {
+      const int slot = tile * TR_NB + tid;
+      const int bq = (slot < B) ? (order ? order[slot] : slot) : -1;
+      bq_s[tid] = bq;
+      len_s[tid] = (bq >= 0) ? min(max(lengths[bq], 0), T) : 0;
+    }
+    for (int idx = tid; idx < TR_B_BYTES / 16; idx += TR_THREADS) {
+      reinterpret_cast<float4 *>(bhi)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // h_{-1} = 0 (buffer 0)
+      reinterpret_cast<float4 *>(blo)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    int nsteps = 0;
+#pragma unroll
+    for (int e = 0; e < TR_NB; ++e) nsteps = max(nsteps, len_s[e]);
+    cluster.sync();  // every CTA of the cluster is ready to receive
+
+    const size_t gx_enc = (size_t)enc * B * T * 8 * kH;
+
+    if (warp == 0) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        constexpr uint32_t idesc = tc::idesc_tf32(128, TR_NB);
+        const uint32_t d_tmem = tmem_base + TR_ACC_COL;
+        const uint32_t whi_a = tc::s_u32(whi), blo_a = tc::s_u32(blo);
+        for (int s = 0; s < nsteps; ++s) {
+          const int p = s & 1;
+          TR_STAMP(0);
+          if (s + 1 < nsteps) tc::bar_expect_tx(tc::s_u32(&h_full[p ^ 1]), TR_B_BYTES);
+          if (s > 0) { tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]); ph_h[p] ^= 1; }
+          TR_STAMP(1);
+          tc::fence_proxy_async();
+          tc::tc_fence_after();
+          const uint32_t bhi_a = tc::s_u32(bhi + p * TR_B_BYTES);
+#pragma unroll 1
+          for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a = tc::desc_sw128(whi_a + kb * 16384 + k * 32);
+              const uint64_t b = tc::desc_sw128(bhi_a + kb * (TR_NB * 128) + k * 32);
+              tc::umma_tf32_ss(d_tmem, a, b, idesc, (kb | k) != 0);
+              tc::umma_tf32_ts(d_tmem, tmem_base + (uint32_t)(kb * 32 + k * 8), b, idesc, 1);
+            }
+          }
+          TR_STAMP(2);
+          tc::bar_wait_wd(tc::s_u32(lo_ready), ph_lo); ph_lo ^= 1;
+          TR_STAMP(3);
+          tc::fence_proxy_async();
+          tc::tc_fence_after();
+#pragma unroll 1
+          for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a = tc::desc_sw128(whi_a + kb * 16384 + k * 32);
+              const uint64_t b = tc::desc_sw128(blo_a + kb * (TR_NB * 128) + k * 32);
+              tc::umma_tf32_ss(d_tmem, a, b, idesc, 1);
+            }
+          }
+          tc::umma_commit(tc::s_u32(acc_full));
+          TR_STAMP(4);
+          // the next step's first MMA overwrites the accumulator: it is issued only after h_full[p ^ 1] completes,
+          // i.e. after every epilogue thread of this CTA has read its accumulator rows and sent h_s.
+        }
+      }
+      __syncwarp();
+    } else {
+      // ===================== epilogue warps =====================
+      const int gcol = dir * 4 * kH + q * kH + (int)rank * kUnits + lane;   // my gate row inside a gx row
+      float gxn[TR_NB];
+#pragma unroll
+      for (int e = 0; e < TR_NB; ++e) {
+        const int len = len_s[e];
+        gxn[e] = 0.0f;
+        if (len > 0) {
+          const int t0 = dir ? len - 1 : 0;
+          gxn[e] = __ldg(gx + gx_enc + ((size_t)bq_s[e] * T + t0) * 8 * kH + gcol);
+        }
+      }
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      const int my_len = len_s[ce], my_b = bq_s[ce];
+      const size_t ycol = (size_t)enc * 2 * kH + dir * kH + rank * kUnits + 4 * cj;
+      const size_t gate_base = ((size_t)enc * 2 + dir) * B;
+      // remote addresses of my 16-byte granule in every CTA's bhi[0] and of their h_full[0]
+      const uint32_t my_off = (uint32_t)(rank * (TR_NB * 128)) + tc::sw128_offset(ce, 4 * cj);
+      uint32_t raddr[kCluster], rbar[kCluster];
+#pragma unroll
+      for (int r = 0; r < kCluster; ++r) {
+        raddr[r] = mapa(tc::s_u32(bhi) + my_off, r);
+        rbar[r] = mapa(tc::s_u32(&h_full[0]), r);
+      }
+
+      for (int s = 0; s < nsteps; ++s) {
+        const int p = s & 1;
+        TR_STAMP(5);
+        // ---- derive h_lo from the freshly landed h_{s-1} ---------------------------------------------------
+        if (s > 0) {
+          tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]); ph_h[p] ^= 1;
+          TR_STAMP(6);
+          const float4 *src = reinterpret_cast<const float4 *>(bhi + p * TR_B_BYTES);
+          float4 *dst = reinterpret_cast<float4 *>(blo);
+#pragma unroll
+          for (int i = 0; i < TR_B_BYTES / 16 / TR_EPI; ++i) {
+            const float4 v = src[et + TR_EPI * i];
+            dst[et + TR_EPI * i] = make_float4(tc::tf32_rest(v.x), tc::tf32_rest(v.y), tc::tf32_rest(v.z), tc::tf32_rest(v.w));
+          }
+          tc::fence_proxy_async();
+        }
+        tc::bar_arrive(tc::s_u32(lo_ready));
+        TR_STAMP(7);
+        // ---- next step's input projection (independent of h) ---------------------------------------------------
+        float gxc[TR_NB];
+#pragma unroll
+        for (int e = 0; e < TR_NB; ++e) {
+          gxc[e] = gxn[e];
+          const int len = len_s[e];
+          if (s + 1 < len) {
+            const int tn = dir ? len - 2 - s : s + 1;
+            gxn[e] = __ldg(gx + gx_enc + ((size_t)bq_s[e] * T + tn) * 8 * kH + gcol);
+          }
+        }
+        // ---- accumulator -> gate activations -> shared memory ---------------------------------------------------
+        tc::bar_wait_wd(tc::s_u32(acc_full), ph_acc); ph_acc ^= 1;
+        TR_STAMP(8);
+        tc::tc_fence_after();
+        float pre[TR_NB];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + TR_ACC_COL, pre);
+        tc::tc_fence_before();
+#pragma unroll
+        for (int e = 0; e < TR_NB; ++e) {
+          const float z = pre[e] + gxc[e];
+          act[(q * TR_NB + e) * 32 + lane] = (q == 2) ? tanh_fast(z) : sigmoid_fast(z);
+        }
+        TR_STAMP(9);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        TR_STAMP(10);
+        // ---- cell update: 4 units x 1 episode per thread -----------------------------------------------------
+        const float4 ig = *reinterpret_cast<const float4 *>(act + (0 * TR_NB + ce) * 32 + 4 * cj);
+        const float4 fg = *reinterpret_cast<const float4 *>(act + (1 * TR_NB + ce) * 32 + 4 * cj);
+        const float4 gg = *reinterpret_cast<const float4 *>(act + (2 * TR_NB + ce) * 32 + 4 * cj);
+        const float4 og = *reinterpret_cast<const float4 *>(act + (3 * TR_NB + ce) * 32 + 4 * cj);
+        float4 hn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < my_len) {
+          c[0] = fmaf(fg.x, c[0], ig.x * gg.x); c[1] = fmaf(fg.y, c[1], ig.y * gg.y);
+          c[2] = fmaf(fg.z, c[2], ig.z * gg.z); c[3] = fmaf(fg.w, c[3], ig.w * gg.w);
+          hn = make_float4(og.x * tanh_fast(c[0]), og.y * tanh_fast(c[1]), og.z * tanh_fast(c[2]), og.w * tanh_fast(c[3]));
+        }
+        if (s + 1 < nsteps) {  // h_s, raw fp32, into K-block `rank` of every CTA's next B buffer
+          const uint32_t boff = (uint32_t)((p ^ 1) * TR_B_BYTES), moff = (uint32_t)((p ^ 1) * 8);
+#pragma unroll
+          for (int r = 0; r < kCluster; ++r) st_async_v4(raddr[r] + boff, hn, rbar[r] + moff);
+        }
+        TR_STAMP(11);
+        if (s < my_len) {
+          const int t = dir ? my_len - 1 - s : s;
+          *reinterpret_cast<float4 *>(y + ((size_t)my_b * T + t) * ycols + ycol) = hn;
+          if (SAVE) {
+            float *gs = gates + ((gate_base + my_b) * T + t) * 5 * kH + rank * kUnits + 4 * cj;
+            *reinterpret_cast<float4 *>(gs) = ig;
+            *reinterpret_cast<float4 *>(gs + kH) = fg;
+            *reinterpret_cast<float4 *>(gs + 2 * kH) = gg;
+            *reinterpret_cast<float4 *>(gs + 3 * kH) = og;
+            *reinterpret_cast<float4 *>(gs + 4 * kH) = make_float4(c[0], c[1], c[2], c[3]);
+          }
+        }
+      }
+      // zero the padded tail of my (episode, 4 units) columns
+      if (my_b >= 0)
+        for (int t = my_len; t < T; ++t)
+          *reinterpret_cast<float4 *>(y + ((size_t)my_b * T + t) * ycols + ycol) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // the MMA thread's phase counters must follow the epilogue's view of h_full (it skips nothing), and vice versa
+    tc::tc_fence_before();
+    __syncthreads();
+    cluster.sync();  // nobody re-zeroes buffers (or exits) while a peer may still address its shared memory
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<TR_TMEM_COLS>(tmem_base);
+  }
+}
+
+template <typename K>
+static int tc_max_active_clusters(K kernel) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCluster * 64);
+  cfg.blockDim = dim3(TR_THREADS);
+  cfg.dynamicSmemBytes = TR_SMEM;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = kCluster;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 8;
+  }
+  return n;
+}
+
+}  // namespace mts
+
+using namespace mts;
+
+// profiling hook: buf = device buffer of TR_PROF_STEPS * TR_PROF_SLOTS int64 (or NULL to switch the timeline off)
+extern "C" int mts_debug_rec_profile(long long *buf) {
+  MTS_CUDA(cudaMemcpyToSymbol(g_tr_prof, &buf, sizeof(buf)));
+  return 0;
+}
+
+// tensor-core forward recurrence; same arguments as mts_lstm_rec_fwd, H must be 256
+extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order,
+                                   int n_enc, int B, int T, int H, float *y, float *gates, void *stream) {
+  MTS_REQUIRE(gx && w_hh && lengths && y, MTS_E_BADARG, "lstm_rec_fwd_tc: null pointer");
+  MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0, MTS_E_BADARG, "lstm_rec_fwd_tc: bad shape");
+  MTS_REQUIRE(H == kH, MTS_E_UNSUPPORTED, "lstm_rec_fwd_tc: the tensor-core recurrence serves H == 256");
+  MTS_REQUIRE((n_enc * 2 * kH) % 4 == 0 && (((uintptr_t)y | (uintptr_t)gx | (uintptr_t)w_hh) & 15) == 0, MTS_E_BADARG,
+              "lstm_rec_fwd_tc: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  static int cap = 0;
+  if (!cap) {
+    MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+    MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+    cap = tc_max_active_clusters(lstm_fwd_tc_kernel<false>);
+  }
+  const int n_tiles = (B + TR_NB - 1) / TR_NB;
+  const int items = n_tiles * 2 * n_enc;
+  const unsigned grid = (unsigned)((items < cap ? items : cap) * kCluster);
+  if (gates) lstm_fwd_tc_kernel<true><<<grid, TR_THREADS, TR_SMEM, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+  else lstm_fwd_tc_kernel<false><<<grid, TR_THREADS, TR_SMEM, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}

@@ -29,6 +29,8 @@ def reset_launch_count():
 PROFILE = None  # bench.py sets this to a dict to collect CUDA-event timings per ABI entry point
 # debugging aid for tests only: MTS_GEMM_IMPL=simt routes the input projections through mts_gemm_f32
 GEMM_IMPL = __import__("os").environ.get("MTS_GEMM_IMPL", "tcgen05")
+# recurrence for H == 256: "tc" = tcgen05 tensor-core kernel (default), "fma" = exact-fp32 packed-FMA cluster kernel
+REC_IMPL = __import__("os").environ.get("MTS_REC_IMPL", "tc")
 
 
 def _call(name, *args):
@@ -254,8 +256,8 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
                             ldc=8 * H)
         y = torch.empty((B, T, n_enc * 2 * H), device=dev, dtype=torch.float32)
         gates = torch.empty((n_enc, 2, B, T, 5, H), device=dev, dtype=torch.float32) if save else None
-        _call("mts_lstm_rec_fwd", _ptr(gx), _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order), n_enc, B, T, H,
-              _ptr(y), _ptr(gates), _stream())
+        _call("mts_lstm_rec_fwd_tc" if (H == 256 and REC_IMPL == "tc") else "mts_lstm_rec_fwd", _ptr(gx),
+              _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order), n_enc, B, T, H, _ptr(y), _ptr(gates), _stream())
         saved.append((y_prev, y, gates))
         y_prev = y
     return y_prev, saved
