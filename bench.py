@@ -435,7 +435,8 @@ def run_ours(args, rank, world, local_rank):
     total_sent = n_sent_step * args.steps * world
     value = total_sent / (ms / 1e3)
     hbm_peak, peak_src = peaks()
-    rec_ms = prof.get("mts_lstm_rec_fwd", float("nan"))
+    rec_name = "mts_lstm_rec_fwd_tc" if "mts_lstm_rec_fwd_tc" in prof else "mts_lstm_rec_fwd"
+    rec_ms = prof.get(rec_name, float("nan"))
     rec_bytes = n_sent_step * ALGO_BYTES_PER_SENTENCE_REC
     achieved = rec_bytes / (rec_ms / 1e3) / 1e9
     cpu_val, cpu_ms, cores = cpu_reference(5, 1) if world == 1 or rank == 0 else (None, None, None)
@@ -447,15 +448,18 @@ def run_ours(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": c["B"], "global_batch": c["B"] * world,
                    "l2": "4 rotating input sets (275 MB) exceed the 126 MB L2", "gemm": "tcgen05 3xTF32",
+                   "recurrence": "tcgen05 3xTF32, W_hh resident in TMEM" if rec_name.endswith("_tc") else "packed-fp32 FMA",
                    "parallelism": f"dp{world} (episodes sharded, final all_gather of tags)" if world > 1 else "single GPU"},
         "e2e": {"value": total_sent / e2e_s, "unit": "sentences/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "TextSegmenter.predict_step on pinned host tensors"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "lstm_fwd_cluster_kernel (one launch per layer, both directions)", "bound": "hbm",
+        "roofline": {"kernel": ("lstm_fwd_tc_kernel" if rec_name.endswith("_tc") else "lstm_fwd_cluster_kernel") +
+                               " (one launch per layer, both directions)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": rec_bytes,
                      "avg_launch_ms": rec_ms,
-                     "note": "latency/FMA-bound at 64 episodes per GPU: fp32-exact recurrence, see DESIGN.md section 4"},
+                     "note": "latency-bound at 64 episodes per GPU (T serial steps; per step: tcgen05 MMAs, DSMEM all-gather of "
+                             "h, gate epilogue): see DESIGN.md section 4 and profiles/ for the B sweep"},
         "kernel_ms_per_call": prof, "kernel_calls_per_step": calls,
         "cpu_baseline": {"value": cpu_val, "unit": "sentences/s", "cores": cores, "kind": "port",
                          "sample": "5 full batches of 64x300 sentences through oracle/ref_torch.py (torch CPU, all threads)"},

@@ -5,9 +5,11 @@
 // One cluster of 8 CTAs advances a tile of 16 episodes of one (direction, encoder).  CTA r owns hidden units
 // [32r, 32r+32) = 128 gate rows of W_hh and keeps them ON CHIP for the whole sequence, split for 3xTF32:
 //     W = W_hi + W_lo,  W_hi = what kind::tf32 reads of the fp32 word (top 19 bits), W_lo = tf32(W - W_hi)
-//     W_hi : shared memory, 128 x 256 fp32, K-major SWIZZLE_128B (the A operand through a descriptor)  128 KB
-//     W_lo : TENSOR MEMORY, 128 lanes x 256 columns (the A operand of the .ts form of tcgen05.mma)       128 KB
-// (2 MB of split weights per direction do not fit the shared memory of 8 SMs; TMEM holds the other half.)
+//     W_hi : TENSOR MEMORY, 128 lanes x 256 columns   } the A operand of the .ts form of tcgen05.mma: measured
+//     W_lo : TENSOR MEMORY, 128 lanes x 224 columns   } ~14 cycles per 128x16x8 MMA against ~38 when A is read from
+//     W_lo tail (k >= 224): shared memory, 16 KB      } shared memory (4 KB of A per instruction at 128 B/clk)
+// (2 MB of split weights per direction do not fit the shared memory of 8 SMs; TMEM holds all but 16 KB per CTA,
+//  the last 32 TMEM columns hold the accumulator.)
 // Per step, per CTA:
 //     pre[128 x 16] = W_hi h + W_lo h + W_hi h_lo          96 tcgen05.mma 128x16x8, accumulator in TMEM
 //     epilogue warps: tcgen05.ld -> + gx -> sigmoid/tanh -> shared-memory transpose -> cell update (c in
@@ -26,12 +28,15 @@ namespace mts {
 constexpr int TR_NB = 16;                 // episodes per tile (= MMA N)
 constexpr int TR_THREADS = 160;           // warp 0: MMA issuer / TMEM owner; warps 1..4: epilogue
 constexpr int TR_EPI = 128;
-constexpr int TR_WHI_BYTES = 8 * 128 * 128;        // 8 k-blocks x 128 rows x 128 B
+constexpr int TR_TAIL_BYTES = 128 * 128;           // W_lo, k-block 7: 128 rows x 128 B, K-major SWIZZLE_128B
 constexpr int TR_B_BYTES = 8 * TR_NB * 128;        // one h buffer: 8 k-blocks x 16 rows x 128 B = 16 KB
 constexpr int TR_ACT_FLOATS = 4 * TR_NB * 32;
 constexpr int TR_TMEM_COLS = 512;
-constexpr int TR_ACC_COL = 256;                    // accumulator columns [256, 272); W_lo in [0, 256)
-constexpr int TR_SMEM = TR_WHI_BYTES + 3 * TR_B_BYTES + TR_ACT_FLOATS * 4 + 256 + 1024;
+constexpr int TR_WLO_COL = 256;                    // W_hi in columns [0, 256), W_lo (k < 224) in [256, 480)
+constexpr int TR_ACC_COL = 480;                    // accumulator columns [480, 496)
+constexpr int TR_SMEM_USED = TR_TAIL_BYTES + 3 * TR_B_BYTES + TR_ACT_FLOATS * 4 + 512 + 1024;
+// every CTA allocates all 512 TMEM columns, so two CTAs must never share an SM: ask for more than half its shared memory
+constexpr int TR_SMEM = TR_SMEM_USED > 120 * 1024 ? TR_SMEM_USED : 120 * 1024;
 
 // Optional in-kernel timeline (profiling hook, off unless mts_debug_rec_profile() installs a buffer): CTA 0 writes
 // clock64() stamps of the phases of steps [8, 8 + TR_PROF_STEPS) -- slots 0..4 by the MMA thread, 5..11 by epilogue
@@ -50,29 +55,30 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
                        int n_tiles, float *__restrict__ y, float *__restrict__ gates) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *whi = smem;
-  uint8_t *bhi = whi + TR_WHI_BYTES;       // [2][TR_B_BYTES]
+  uint8_t *wtail = smem;
+  uint8_t *bhi = wtail + TR_TAIL_BYTES;    // [2][TR_B_BYTES]
   uint8_t *blo = bhi + 2 * TR_B_BYTES;     // [TR_B_BYTES]
   float *act = reinterpret_cast<float *>(blo + TR_B_BYTES);  // [4][NB][32]
   uint64_t *bars = reinterpret_cast<uint64_t *>(act + TR_ACT_FLOATS);
-  uint64_t *h_full = bars;        // [2]  h_{s-1} landed in bhi[s & 1] (tx bytes from all 8 CTAs)
-  uint64_t *lo_ready = bars + 2;  //      blo derived from bhi[s & 1]
-  uint64_t *acc_full = bars + 3;  //      the step's MMAs have completed
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
-  int *len_s = reinterpret_cast<int *>(bars + 5);  // [NB]
-  int *bq_s = len_s + TR_NB;                       // [NB]
+  uint64_t *h_full = bars;         // [2]  h_{s-1} landed in bhi[s & 1] (16 KB: 2 KB from each of the 8 CTAs)
+  uint64_t *lo_ready = bars + 16;  //      blo derived from it (16 KB of st.async from this CTA to itself)
+  uint64_t *acc_full = bars + 24;  //         the step's MMAs have completed
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 25);
+  int *len_s = reinterpret_cast<int *>(bars + 26);  // [NB]
+  int *bq_s = len_s + TR_NB;                        // [NB]
 
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
   const int n_clusters = gridDim.x / kCluster;
   const int n_items = n_tiles * 2 * n_enc;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
   const int ycols = n_enc * 2 * kH;
 
   if (tid == 0) {
     tc::bar_init(tc::s_u32(&h_full[0]), 1);
     tc::bar_init(tc::s_u32(&h_full[1]), 1);
-    tc::bar_init(tc::s_u32(lo_ready), TR_EPI);
+    tc::bar_init(tc::s_u32(lo_ready), 1);
     tc::bar_init(tc::s_u32(acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -101,25 +107,33 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
 
     // ---- weights on chip (only when the (direction, encoder) changes) ----------------------------------------
     if (dir != cur_dir || enc != cur_enc) {
-      for (int idx = tid; idx < 128 * 64; idx += TR_THREADS) {
-        const int r = idx >> 6, c = idx & 63;  // tile row (gate r>>5, unit r&31), 16-byte chunk along K
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(W + (size_t)((r >> 5) * kH + rank * kUnits + (r & 31)) * kH) + c);
-        *reinterpret_cast<float4 *>(whi + (c >> 3) * 16384 + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
-      }
-      if (warp >= 1) {
+      if (warp >= 1) {  // thread = one gate row of the tile: (gate q, unit lane)
         const int r = q * 32 + lane;
         const float *wrow = W + (size_t)(q * kH + rank * kUnits + lane) * kH;
-        (void)r;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        // K-blocks are stored in ARRIVAL order: slot kk holds the columns of hidden units [32 src, 32 src + 32) with
+        // src = (rank - kk) % 8, the CTA whose h slice lands kk-th in this CTA's operand buffer (see the sends below),
+        // so that every tensor-memory / shared-memory offset of the step loop is a compile-time constant.
 #pragma unroll 1
         for (int kk = 0; kk < 8; ++kk) {
-          float v[32];
+          const int src_blk = ((int)rank - kk) & 7;
+          float hi[32], lo[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 x = __ldg(reinterpret_cast<const float4 *>(wrow + kk * 32) + i);
-            v[4 * i + 0] = tc::tf32_rest(x.x); v[4 * i + 1] = tc::tf32_rest(x.y);
-            v[4 * i + 2] = tc::tf32_rest(x.z); v[4 * i + 3] = tc::tf32_rest(x.w);
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(wrow + src_blk * 32) + i);
+            hi[4 * i + 0] = x.x; hi[4 * i + 1] = x.y; hi[4 * i + 2] = x.z; hi[4 * i + 3] = x.w;
+            lo[4 * i + 0] = tc::tf32_rest(x.x); lo[4 * i + 1] = tc::tf32_rest(x.y);
+            lo[4 * i + 2] = tc::tf32_rest(x.z); lo[4 * i + 3] = tc::tf32_rest(x.w);
           }
-          tc::tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kk * 32), v);
+          tc::tmem_st32(trow + (uint32_t)(kk * 32), hi);  // raw fp32 words: the tensor core reads their top 19 bits
+          if (kk < 7) {
+            tc::tmem_st32(trow + (uint32_t)(TR_WLO_COL + kk * 32), lo);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4 *>(wtail + r * 128 + ((i ^ (r & 7)) << 4)) =
+                  make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
         }
         tc::tmem_wait_st();
       }
@@ -149,51 +163,59 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
     const size_t gx_enc = (size_t)enc * B * T * 8 * kH;
 
     if (warp == 0) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        constexpr uint32_t idesc = tc::idesc_tf32(128, TR_NB);
-        const uint32_t d_tmem = tmem_base + TR_ACC_COL;
-        const uint32_t whi_a = tc::s_u32(whi), blo_a = tc::s_u32(blo);
-        for (int s = 0; s < nsteps; ++s) {
-          const int p = s & 1;
-          TR_STAMP(0);
+      // ===================== MMA issuer: warp-uniform control flow, one elected lane issues =====================
+      constexpr uint32_t idesc = tc::idesc_tf32(128, TR_NB);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t d_tmem = tb + TR_ACC_COL;
+      const uint32_t tail_a = tc::s_u32(wtail), blo_a = tc::s_u32(blo);
+      const bool leader = tc::elect_one();
+      // Every CTA sends its h slice to CTA (rank + i) % 8 at slot i, into K-block slot i of the receiver's buffer.
+      // No proxy fence in the loop: both operand buffers are written through the async proxy (st.async from the
+      // peers for h, st.async-to-self for h_lo), and the mbarrier wait orders them before the MMAs.
+      for (int s = 0; s < nsteps; ++s) {
+        const int p = s & 1;
+        TR_STAMP(0);
+        if (leader) {
           if (s + 1 < nsteps) tc::bar_expect_tx(tc::s_u32(&h_full[p ^ 1]), TR_B_BYTES);
-          if (s > 0) { tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]); ph_h[p] ^= 1; }
-          TR_STAMP(1);
-          tc::fence_proxy_async();
-          tc::tc_fence_after();
-          const uint32_t bhi_a = tc::s_u32(bhi + p * TR_B_BYTES);
-#pragma unroll 1
-          for (int kb = 0; kb < 8; ++kb) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t a = tc::desc_sw128(whi_a + kb * 16384 + k * 32);
-              const uint64_t b = tc::desc_sw128(bhi_a + kb * (TR_NB * 128) + k * 32);
-              tc::umma_tf32_ss(d_tmem, a, b, idesc, (kb | k) != 0);
-              tc::umma_tf32_ts(d_tmem, tmem_base + (uint32_t)(kb * 32 + k * 8), b, idesc, 1);
-            }
-          }
-          TR_STAMP(2);
-          tc::bar_wait_wd(tc::s_u32(lo_ready), ph_lo); ph_lo ^= 1;
-          TR_STAMP(3);
-          tc::fence_proxy_async();
-          tc::tc_fence_after();
-#pragma unroll 1
-          for (int kb = 0; kb < 8; ++kb) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t a = tc::desc_sw128(whi_a + kb * 16384 + k * 32);
-              const uint64_t b = tc::desc_sw128(blo_a + kb * (TR_NB * 128) + k * 32);
-              tc::umma_tf32_ss(d_tmem, a, b, idesc, 1);
-            }
-          }
-          tc::umma_commit(tc::s_u32(acc_full));
-          TR_STAMP(4);
-          // the next step's first MMA overwrites the accumulator: it is issued only after h_full[p ^ 1] completes,
-          // i.e. after every epilogue thread of this CTA has read its accumulator rows and sent h_s.
+          if (s > 0) tc::bar_expect_tx(tc::s_u32(lo_ready), TR_B_BYTES);
         }
+        const uint32_t bhi_a = tc::s_u32(bhi + p * TR_B_BYTES);
+        if (s > 0) tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]);
+        TR_STAMP(1);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = tc::desc_sw128(bhi_a + kb * (TR_NB * 128) + k * 32);
+            if (leader) {
+              tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, (kb | k) != 0);
+              if (kb < 7) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(TR_WLO_COL + kb * 32 + k * 8), bd, idesc, 1);
+              else tc::umma_tf32_ss(d_tmem, tc::desc_sw128(tail_a + k * 32), bd, idesc, 1);
+            }
+          }
+        }
+        TR_STAMP(2);
+        if (s > 0) {  // at s == 0 both h and h_lo are the zero-filled buffers: the h_lo product contributes nothing
+          tc::bar_wait_wd(tc::s_u32(lo_ready), ph_lo);
+          TR_STAMP(3);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t bd = tc::desc_sw128(blo_a + kb * (TR_NB * 128) + k * 32);
+              if (leader) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, 1);
+            }
+          }
+        }
+        if (s > 0) { ph_h[p] ^= 1; ph_lo ^= 1; }
+        if (leader) tc::umma_commit(tc::s_u32(acc_full));
+        __syncwarp();
+        TR_STAMP(4);
+        // the next step's first MMA overwrites the accumulator: it is issued only after h_full[p ^ 1] completes,
+        // i.e. after every epilogue thread of this CTA has read its accumulator rows and sent h_s.
       }
-      __syncwarp();
     } else {
       // ===================== epilogue warps =====================
       const int gcol = dir * 4 * kH + q * kH + (int)rank * kUnits + lane;   // my gate row inside a gx row
@@ -212,31 +234,32 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
       const size_t ycol = (size_t)enc * 2 * kH + dir * kH + rank * kUnits + 4 * cj;
       const size_t gate_base = ((size_t)enc * 2 + dir) * B;
       // remote addresses of my 16-byte granule in every CTA's bhi[0] and of their h_full[0]
-      const uint32_t my_off = (uint32_t)(rank * (TR_NB * 128)) + tc::sw128_offset(ce, 4 * cj);
+      const uint32_t my_off = tc::sw128_offset(ce, 4 * cj);
       uint32_t raddr[kCluster], rbar[kCluster];
 #pragma unroll
-      for (int r = 0; r < kCluster; ++r) {
-        raddr[r] = mapa(tc::s_u32(bhi) + my_off, r);
-        rbar[r] = mapa(tc::s_u32(&h_full[0]), r);
+      for (int i = 0; i < kCluster; ++i) {  // slot i goes to CTA (rank + i) % 8: self first, then round the ring
+        const uint32_t r = (rank + i) & 7;
+        raddr[i] = mapa(tc::s_u32(bhi) + (uint32_t)(i * (TR_NB * 128)) + my_off, r);  // K-block slot i of that CTA
+        rbar[i] = mapa(tc::s_u32(&h_full[0]), r);                                    // its h_full[0]
       }
+      const uint32_t blo_self = mapa(tc::s_u32(blo), rank), lo_bar_self = mapa(tc::s_u32(lo_ready), rank);
 
       for (int s = 0; s < nsteps; ++s) {
         const int p = s & 1;
         TR_STAMP(5);
-        // ---- derive h_lo from the freshly landed h_{s-1} ---------------------------------------------------
+        // ---- derive h_lo (8 float4 per thread); written with st.async to this CTA (async proxy: no proxy fence) ------
         if (s > 0) {
           tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]); ph_h[p] ^= 1;
           TR_STAMP(6);
           const float4 *src = reinterpret_cast<const float4 *>(bhi + p * TR_B_BYTES);
-          float4 *dst = reinterpret_cast<float4 *>(blo);
 #pragma unroll
           for (int i = 0; i < TR_B_BYTES / 16 / TR_EPI; ++i) {
-            const float4 v = src[et + TR_EPI * i];
-            dst[et + TR_EPI * i] = make_float4(tc::tf32_rest(v.x), tc::tf32_rest(v.y), tc::tf32_rest(v.z), tc::tf32_rest(v.w));
+            const int f4 = et + TR_EPI * i;
+            const float4 v = src[f4];
+            st_async_v4(blo_self + (uint32_t)f4 * 16,
+                        make_float4(tc::tf32_rest(v.x), tc::tf32_rest(v.y), tc::tf32_rest(v.z), tc::tf32_rest(v.w)), lo_bar_self);
           }
-          tc::fence_proxy_async();
         }
-        tc::bar_arrive(tc::s_u32(lo_ready));
         TR_STAMP(7);
         // ---- next step's input projection (independent of h) ---------------------------------------------------
         float gxc[TR_NB];
@@ -256,12 +279,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
         float pre[TR_NB];
         tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + TR_ACC_COL, pre);
         tc::tc_fence_before();
+        TR_STAMP(9);
+        // one exponential + one reciprocal per element for every gate: tanh(z) = 2 sigmoid(2 z) - 1  (the MUFU
+        // pipe, 4 lanes/clk per sub-partition, bounds this phase: each epilogue warp has a sub-partition to itself)
+        const float zs = (q == 2) ? -2.0f * 1.4426950408889634f : -1.4426950408889634f;
+        const float oa = (q == 2) ? 2.0f : 1.0f, ob = (q == 2) ? -1.0f : 0.0f;
 #pragma unroll
         for (int e = 0; e < TR_NB; ++e) {
           const float z = pre[e] + gxc[e];
-          act[(q * TR_NB + e) * 32 + lane] = (q == 2) ? tanh_fast(z) : sigmoid_fast(z);
+          const float sg = __fdividef(1.0f, 1.0f + exp2f(z * zs));
+          act[(q * TR_NB + e) * 32 + lane] = fmaf(sg, oa, ob);
         }
-        TR_STAMP(9);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         TR_STAMP(10);
         // ---- cell update: 4 units x 1 episode per thread -----------------------------------------------------

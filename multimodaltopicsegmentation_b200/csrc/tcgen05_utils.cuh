@@ -87,6 +87,20 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// Warp-collective issue forms: the WHOLE warp executes these with warp-uniform operands and one elected lane
+// issues.  (Issuing from inside `if (lane == 0)` makes ptxas build an ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+// around every UTCHMMA -- ~70 cycles per instruction; with uniform control flow the operands stay in uniform
+// registers.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(COLS) : "memory");

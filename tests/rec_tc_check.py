@@ -136,7 +136,7 @@ def timeline(B=16, T=40):
     ops._call("mts_debug_rec_profile", 0)
     st = buf.cpu().view(4, 12)
     names = ["mma:start", "mma:h_full", "mma:hi issued", "mma:lo_ready", "mma:commit", "epi:start", "epi:h_full",
-             "epi:lo done", "epi:acc_full", "epi:act stored", "epi:bar", "epi:sent"]
+             "epi:lo done", "epi:acc_full", "epi:tmem ld", "epi:act+bar", "epi:sent"]
     t0 = int(st[0, 0])
     for i in range(4):
         print(f"step {8 + i}: " + "  ".join(f"{n}={int(st[i, k]) - t0}" for k, n in enumerate(names)))

@@ -654,3 +654,38 @@ def test_transformer_training_vs_hf_twin(dev):
         close(p.grad, r, rtol=2e-4, atol=1e-4 * float(r.abs().max()), msg=k)
         checked += 1
     assert checked >= 4 + 15 * nl + 2
+
+
+# ----------------------------------------------------------------------------------------------------------
+# tensor-core recurrence (tcgen05, W_hh in tensor memory) against the exact-fp32 FMA kernel and float64
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,n_enc,save", [(3, 5, 1, False), (16, 40, 1, True), (37, 61, 1, True), (20, 33, 2, True),
+                                            (300, 50, 1, False)])
+def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save):
+    from multimodaltopicsegmentation_b200 import ops
+
+    H = 256
+    g = torch.Generator(device=dev).manual_seed(B * 1000 + T)
+    gx = torch.randn((n_enc, B * T, 8 * H), device=dev, generator=g)
+    whh = torch.randn((n_enc, 2, 4 * H, H), device=dev, generator=g) * 0.06
+    hg = torch.Generator().manual_seed(B + T)
+    lengths = [T] + [int(v) for v in torch.randint(1, T + 1, (B - 1,), generator=hg)]
+    lens = ops.Lengths(lengths, dev, T)
+
+    def run(name):
+        y = torch.full((B, T, n_enc * 2 * H), float("nan"), device=dev)
+        gates = torch.full((n_enc, 2, B, T, 5, H), float("nan"), device=dev) if save else None
+        ops._call(name, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T, H,
+                  y.data_ptr(), 0 if gates is None else gates.data_ptr(), ops._stream())
+        return y, gates
+
+    y_f, g_f = run("mts_lstm_rec_fwd")
+    y_t, g_t = run("mts_lstm_rec_fwd_tc")
+    assert not bool(torch.isnan(y_t).any())          # every position written (zeros beyond len_b)
+    for b, n in enumerate(lengths):
+        assert float(y_t[b, n:].abs().max() if n < T else 0.0) == 0.0
+    close(y_t, y_f, rtol=1e-4, atol=1e-5)
+    if save:
+        assert bool((torch.isnan(g_t) == torch.isnan(g_f)).all())   # same (valid-step) coverage of the saved gates
+        ok = ~torch.isnan(g_f)
+        close(g_t[ok], g_f[ok], rtol=1e-4, atol=2e-5)
