@@ -109,3 +109,56 @@ def to_device(batch, device, non_blocking=True, lengths_on_host=True):
         else:
             out[k] = v
     return out
+
+
+class DevicePrefetcher:
+    """Loader -> device pipeline: iterate over the batch dicts of a DataLoader (or any
+    iterable of collater outputs) with the host->device copy of batch i+1 running on a side CUDA stream while batch
+    i computes.  The reference leaves this to pl.Trainer, which copies on the compute stream; here the copy of the
+    next [B,T,D] embedding block (the only large transfer of the path) hides behind the kernels of the current one.
+    Host tensors should be pinned (DataLoader(pin_memory=True)); `src_lengths` stays on the host (see to_device).
+    `src_tokens` may be a (text, audio) pair of tensors: the early-fusion concat then happens inside the operand
+    packing kernel instead of on the host."""
+
+    def __init__(self, loader, device, lengths_on_host=True):
+        self.loader, self.device, self.lengths_on_host = loader, torch.device(device), lengths_on_host
+        self.stream = torch.cuda.Stream(self.device)
+
+    def _stage(self, batch):
+        moved = []
+
+        def mv(v):
+            if torch.is_tensor(v):
+                t = v.to(self.device, non_blocking=True)
+                moved.append(t)
+                return t
+            if isinstance(v, (tuple, list)) and v and all(torch.is_tensor(x) for x in v):
+                return type(v)(mv(x) for x in v)
+            return v
+
+        with torch.cuda.stream(self.stream):
+            out = {k: (v if (self.lengths_on_host and k == "src_lengths") else mv(v)) for k, v in batch.items()}
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return out, ev, moved
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev, moved = nxt
+            try:
+                nxt = self._stage(next(it))
+            except StopIteration:
+                nxt = None
+            compute = torch.cuda.current_stream(self.device)
+            compute.wait_event(ev)
+            for t in moved:  # allocated on the side stream, consumed on the compute stream
+                t.record_stream(compute)
+            yield cur
+
+    def __len__(self):
+        return len(self.loader)

@@ -5,7 +5,7 @@ The package mirrors the reference's Python interface for the segmentation-model 
 its arithmetic in hand-written CUDA kernels behind the C ABI of include/mts_b200.h.
 """
 from . import _lib, ops  # noqa: F401
-from .EncoderDataset import AudioPortionDataset, AudioPortionDatasetInference, to_device  # noqa: F401
+from .EncoderDataset import AudioPortionDataset, AudioPortionDatasetInference, DevicePrefetcher, to_device  # noqa: F401
 from .lightning_model import TextSegmenter  # noqa: F401
 from .metrics import compute_Pk, compute_window_diff, get_boundaries  # noqa: F401
 from .modules import CRF, RNN, BiLSTM, BiLSTMLateFusion, BiRnnCrf  # noqa: F401

@@ -37,8 +37,11 @@ def rec_setup(B, T, H=256, save=False, n_enc=1):
     return gx, whh, lens, y, gates
 
 
+REC_NAME = "mts_lstm_rec_fwd" if os.environ.get("MTS_REC_IMPL", "tc") == "fma" else "mts_lstm_rec_fwd_tc"
+
+
 def rec_call(gx, whh, lens, y, gates, B, T, H=256, n_enc=1):
-    ops._call("mts_lstm_rec_fwd", gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T,
+    ops._call(REC_NAME, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T,
               H, y.data_ptr(), 0 if gates is None else gates.data_ptr(), ops._stream())
 
 
@@ -96,6 +99,24 @@ if __name__ == "__main__":
         for _ in range(3):
             ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, c, M, N, epilogue=1)
         torch.cuda.synchronize()
+    elif what == "attn_one":  # cfg3-shaped banded attention, one layer (reach w), for ncu
+        w = int(sys.argv[2]) if len(sys.argv) > 2 else 48
+        B, S, h, hd = 256, 960, 8, 112
+        d = h * hd
+        g = torch.Generator(device=dev).manual_seed(0)
+        qkv = torch.randn(B * S, 3 * d, device=dev, generator=g)
+        lengths = torch.randint(100, S + 1, (B,))
+        lengths[0] = S
+        lens = ops.Lengths(lengths, dev, S)
+        hl = torch.empty(2, B * S, d, device=dev)
+        for _ in range(3):
+            ops._call("mts_band_attn_fwd", qkv.data_ptr(), 3 * d, lens.dev.data_ptr(), B, S, h, hd, w, 0, hl[0].data_ptr(),
+                      hl[1].data_ptr(), d, 0, ops._stream())
+        torch.cuda.synchronize()
+        ms = timeit(lambda: ops._call("mts_band_attn_fwd", qkv.data_ptr(), 3 * d, lens.dev.data_ptr(), B, S, h, hd, w, 0,
+                                      hl[0].data_ptr(), hl[1].data_ptr(), d, 0, ops._stream()), iters=3, warmup=0)
+        n = int(lengths.sum())
+        print(f"band_attn_fwd w={w}: {ms:.3f} ms, {n * 16 * d / ms / 1e6:.1f} GB/s algorithmic ({n} valid tokens)")
     elif what == "rec_one":
         B, T = int(sys.argv[2]), int(sys.argv[3])
         args = rec_setup(B, T)
