@@ -17,6 +17,7 @@
 //     with st.async (DSMEM) completing on the receivers' mbarriers; the receivers only derive h_lo.
 // The only per-step synchronisation is mbarrier-based (no cluster barrier).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "cluster_utils.cuh"
 #include "tcgen05_utils.cuh"
@@ -26,17 +27,21 @@ namespace cg = cooperative_groups;
 namespace mts {
 
 constexpr int TR_NB = 16;                 // episodes per tile (= MMA N)
-constexpr int TR_THREADS = 160;           // warp 0: MMA issuer / TMEM owner; warps 1..4: epilogue
+constexpr int TR_SUB_THREADS = 160;       // one tile pipeline: warp 0 MMA issuer, warps 1..4 epilogue
 constexpr int TR_EPI = 128;
 constexpr int TR_TAIL_BYTES = 128 * 128;           // W_lo, k-block 7: 128 rows x 128 B, K-major SWIZZLE_128B
 constexpr int TR_B_BYTES = 8 * TR_NB * 128;        // one h buffer: 8 k-blocks x 16 rows x 128 B = 16 KB
 constexpr int TR_ACT_FLOATS = 4 * TR_NB * 32;
 constexpr int TR_TMEM_COLS = 512;
 constexpr int TR_WLO_COL = 256;                    // W_hi in columns [0, 256), W_lo (k < 224) in [256, 480)
-constexpr int TR_ACC_COL = 480;                    // accumulator columns [480, 496)
-constexpr int TR_SMEM_USED = TR_TAIL_BYTES + 3 * TR_B_BYTES + TR_ACT_FLOATS * 4 + 512 + 1024;
+constexpr int TR_ACC_COL = 480;                    // accumulator columns [480, 496) (+16 for the second pipeline)
+constexpr int TR_SUB_BYTES = 3 * TR_B_BYTES + TR_ACT_FLOATS * 4 + 1024;  // per tile pipeline: bhi[2], blo, act, barriers
+static_assert(TR_SUB_BYTES % 1024 == 0 && TR_TAIL_BYTES % 1024 == 0, "SWIZZLE_128B operand buffers need 1024-byte alignment");
 // every CTA allocates all 512 TMEM columns, so two CTAs must never share an SM: ask for more than half its shared memory
-constexpr int TR_SMEM = TR_SMEM_USED > 120 * 1024 ? TR_SMEM_USED : 120 * 1024;
+template <int NT>
+constexpr int tr_smem() {
+  return (TR_TAIL_BYTES + NT * TR_SUB_BYTES + 1024) > 120 * 1024 ? (TR_TAIL_BYTES + NT * TR_SUB_BYTES + 1024) : 120 * 1024;
+}
 
 // Optional in-kernel timeline (profiling hook, off unless mts_debug_rec_profile() installs a buffer): CTA 0 writes
 // clock64() stamps of the phases of steps [8, 8 + TR_PROF_STEPS) -- slots 0..4 by the MMA thread, 5..11 by epilogue
@@ -48,34 +53,44 @@ __device__ long long *g_tr_prof = nullptr;
     if (prof && s >= 8 && s < 8 + TR_PROF_STEPS) prof[(s - 8) * TR_PROF_SLOTS + (slot)] = clock64(); \
   } while (0)
 
-template <bool SAVE>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1)
+// NT = tile pipelines per CTA.  NT == 2 runs two independent tiles of 16 episodes of the same (direction, encoder)
+// side by side -- each with its own MMA-issuing warp, 4 epilogue warps, operand buffers, barriers and accumulator
+// columns -- against ONE resident copy of the weights: while one tile waits for its h exchange, the tensor pipe,
+// the MUFU pipe and the DSMEM ports work for the other.  Used when there are more tiles than clusters.
+template <bool SAVE, int NT>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREADS * NT, 1)
     lstm_fwd_tc_kernel(const float *__restrict__ gx, const float *__restrict__ w_hh,
                        const int32_t *__restrict__ lengths, const int32_t *__restrict__ order, int B, int T, int n_enc,
                        int n_tiles, float *__restrict__ y, float *__restrict__ gates) {
+  constexpr int THREADS = TR_SUB_THREADS * NT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *wtail = smem;
-  uint8_t *bhi = wtail + TR_TAIL_BYTES;    // [2][TR_B_BYTES]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+  const int sub = (NT == 2 && warp >= 5) ? 1 : 0;         // tile pipeline this warp belongs to
+  const int wr = warp - 5 * sub;                           // role inside the pipeline: 0 = MMA issuer, 1..4 = epilogue
+
+  uint8_t *wtail = smem;                                   // shared by both pipelines
+  uint8_t *sub_base = wtail + TR_TAIL_BYTES + sub * TR_SUB_BYTES;
+  uint8_t *bhi = sub_base;                 // [2][TR_B_BYTES]
   uint8_t *blo = bhi + 2 * TR_B_BYTES;     // [TR_B_BYTES]
   float *act = reinterpret_cast<float *>(blo + TR_B_BYTES);  // [4][NB][32]
   uint64_t *bars = reinterpret_cast<uint64_t *>(act + TR_ACT_FLOATS);
   uint64_t *h_full = bars;         // [2]  h_{s-1} landed in bhi[s & 1] (16 KB: 2 KB from each of the 8 CTAs)
-  uint64_t *lo_ready = bars + 16;  //      blo derived from it (16 KB of st.async from this CTA to itself)
-  uint64_t *acc_full = bars + 24;  //         the step's MMAs have completed
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 25);
-  int *len_s = reinterpret_cast<int *>(bars + 26);  // [NB]
+  uint64_t *lo_ready = bars + 2;   //      blo derived from it (16 KB of st.async from this CTA to itself)
+  uint64_t *acc_full = bars + 3;   //      the step's MMAs have completed
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TR_TAIL_BYTES + TR_ACT_FLOATS * 4 + 3 * TR_B_BYTES) + 8;  // pipeline 0's bars + 4
+  int *len_s = reinterpret_cast<int *>(bars + 6);   // [NB]
   int *bq_s = len_s + TR_NB;                        // [NB]
 
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank();
   const int n_clusters = gridDim.x / kCluster;
-  const int n_items = n_tiles * 2 * n_enc;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+  const int groups = (n_tiles + NT - 1) / NT;              // tile groups per (direction, encoder)
+  const int n_items = groups * 2 * n_enc;
   const int ycols = n_enc * 2 * kH;
 
-  if (tid == 0) {
+  if (wr == 0 && lane == 0) {
     tc::bar_init(tc::s_u32(&h_full[0]), 1);
     tc::bar_init(tc::s_u32(&h_full[1]), 1);
     tc::bar_init(tc::s_u32(lo_ready), 1);
@@ -87,12 +102,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_col = TR_ACC_COL + 16 * sub;
 
   // running mbarrier phases (the barriers are initialised once and live across work items)
   uint32_t ph_h[2] = {0, 0}, ph_lo = 0, ph_acc = 0;
 
   // epilogue-thread identities
-  const int et = tid - 32;              // 0..127 for warps 1..4
+  const int et = (wr - 1) * 32 + lane;  // 0..127 over the pipeline's epilogue warps
   const int q = warp & 3;               // TMEM lane quarter = gate index (i,f,g,o) this warp reads
   const int cj = et & 7, ce = et >> 3;  // cell mapping: units 4 cj .. 4 cj + 3 of episode slot ce
 
@@ -100,14 +116,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
   long long *prof = (blockIdx.x == 0 && (tid == 0 || tid == 32)) ? g_tr_prof : nullptr;
 
   for (int item = blockIdx.x / kCluster; item < n_items; item += n_clusters) {
-    const int tile = item % n_tiles;
-    const int dir = (item / n_tiles) & 1;
-    const int enc = item / (2 * n_tiles);
+    const int tile = (item % groups) * NT + sub;   // may be >= n_tiles for the second pipeline of the last group
+    const int dir = (item / groups) & 1;
+    const int enc = item / (2 * groups);
     const float *W = w_hh + ((size_t)enc * 2 + dir) * 4 * kH * kH;
 
     // ---- weights on chip (only when the (direction, encoder) changes) ----------------------------------------
     if (dir != cur_dir || enc != cur_enc) {
-      if (warp >= 1) {  // thread = one gate row of the tile: (gate q, unit lane)
+      if (sub == 0 && wr >= 1) {  // thread = one gate row of the tile: (gate q, unit lane)
         const int r = q * 32 + lane;
         const float *wrow = W + (size_t)(q * kH + rank * kUnits + lane) * kH;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -141,13 +157,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
       cur_enc = enc;
     }
     // ---- tile bookkeeping, zero initial state ---------------------------------------------------------------
-    if (tid < TR_NB) {
-      const int slot = tile * TR_NB + tid;
-      const int bq = (slot < B) ? (order ? order[slot] : slot) : -1;
-      bq_s[tid] = bq;
-      len_s[tid] = (bq >= 0) ? min(max(lengths[bq], 0), T) : 0;
+    const int st = tid - sub * TR_SUB_THREADS;  // thread index inside the pipeline
+    if (st < TR_NB) {
+      const int slot = tile * TR_NB + st;
+      const int bq = (tile < n_tiles && slot < B) ? (order ? order[slot] : slot) : -1;
+      bq_s[st] = bq;
+      len_s[st] = (bq >= 0) ? min(max(lengths[bq], 0), T) : 0;
     }
-    for (int idx = tid; idx < TR_B_BYTES / 16; idx += TR_THREADS) {
+    for (int idx = st; idx < TR_B_BYTES / 16; idx += TR_SUB_THREADS) {
       reinterpret_cast<float4 *>(bhi)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // h_{-1} = 0 (buffer 0)
       reinterpret_cast<float4 *>(blo)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -162,11 +179,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
 
     const size_t gx_enc = (size_t)enc * B * T * 8 * kH;
 
-    if (warp == 0) {
+    if (wr == 0) {
       // ===================== MMA issuer: warp-uniform control flow, one elected lane issues =====================
       constexpr uint32_t idesc = tc::idesc_tf32(128, TR_NB);
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t d_tmem = tb + TR_ACC_COL;
+      const uint32_t d_tmem = tb + acc_col;
       const uint32_t tail_a = tc::s_u32(wtail), blo_a = tc::s_u32(blo);
       const bool leader = tc::elect_one();
       // Every CTA sends its h slice to CTA (rank + i) % 8 at slot i, into K-block slot i of the receiver's buffer.
@@ -277,7 +294,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
         TR_STAMP(8);
         tc::tc_fence_after();
         float pre[TR_NB];
-        tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + TR_ACC_COL, pre);
+        tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col, pre);
         tc::tc_fence_before();
         TR_STAMP(9);
         // one exponential + one reciprocal per element for every gate: tanh(z) = 2 sigmoid(2 z) - 1  (the MUFU
@@ -290,7 +307,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
           const float sg = __fdividef(1.0f, 1.0f + exp2f(z * zs));
           act[(q * TR_NB + e) * 32 + lane] = fmaf(sg, oa, ob);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (sub == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         TR_STAMP(10);
         // ---- cell update: 4 units x 1 episode per thread -----------------------------------------------------
         const float4 ig = *reinterpret_cast<const float4 *>(act + (0 * TR_NB + ce) * 32 + 4 * cj);
@@ -338,14 +356,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_THREADS, 1
     tc::tc_fence_after();
     tc::tmem_dealloc<TR_TMEM_COLS>(tmem_base);
   }
+  (void)THREADS;
 }
 
 template <typename K>
-static int tc_max_active_clusters(K kernel) {
+static int tc_max_active_clusters(K kernel, int threads, int smem) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kCluster * 64);
-  cfg.blockDim = dim3(TR_THREADS);
-  cfg.dynamicSmemBytes = TR_SMEM;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = kCluster;
@@ -382,15 +401,27 @@ extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int
   cudaStream_t st = (cudaStream_t)stream;
   static int cap = 0;
   if (!cap) {
-    MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
-    MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
-    cap = tc_max_active_clusters(lstm_fwd_tc_kernel<false>);
+    MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<1>()));
+    MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<1>()));
+    MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<2>()));
+    MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<2>()));
+    cap = tc_max_active_clusters(lstm_fwd_tc_kernel<false, 2>, 2 * TR_SUB_THREADS, tr_smem<2>());
   }
   const int n_tiles = (B + TR_NB - 1) / TR_NB;
-  const int items = n_tiles * 2 * n_enc;
-  const unsigned grid = (unsigned)((items < cap ? items : cap) * kCluster);
-  if (gates) lstm_fwd_tc_kernel<true><<<grid, TR_THREADS, TR_SMEM, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
-  else lstm_fwd_tc_kernel<false><<<grid, TR_THREADS, TR_SMEM, st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+  const int items1 = n_tiles * 2 * n_enc;
+  // one tile per cluster while everything fits in a single wave; otherwise two tile pipelines per cluster
+  static const char *force = getenv("MTS_REC_NT");
+  const bool two = force ? (force[0] == '2') : (items1 > cap);
+  if (!two) {
+    const unsigned grid = (unsigned)((items1 < cap ? items1 : cap) * kCluster);
+    if (gates) lstm_fwd_tc_kernel<true, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+    else lstm_fwd_tc_kernel<false, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+  } else {
+    const int items2 = ((n_tiles + 1) / 2) * 2 * n_enc;
+    const unsigned grid = (unsigned)((items2 < cap ? items2 : cap) * kCluster);
+    if (gates) lstm_fwd_tc_kernel<true, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+    else lstm_fwd_tc_kernel<false, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+  }
   MTS_LAUNCH_CHECK();
   return 0;
 }
