@@ -689,3 +689,92 @@ def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save):
         assert bool((torch.isnan(g_t) == torch.isnan(g_f)).all())   # same (valid-step) coverage of the saved gates
         ok = ~torch.isnan(g_f)
         close(g_t[ok], g_f[ok], rtol=1e-4, atol=2e-5)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# full-size configurations: size-independent properties (the CPU oracle would take minutes at these sizes)
+# ----------------------------------------------------------------------------------------------------------
+def test_cfg3_full_size_properties(dev):
+    """BASELINE configs[2] shape at reduced batch (32 of 256 episodes x 960 sentences x 896, 6 layers, window 16):
+    episode independence (an episode alone == inside the batch), invariance to whatever sits in the padded rows, and
+    a spot check of 2 episodes against the HF twin on the CPU."""
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(3)
+    g = torch.Generator().manual_seed(33)
+    B, S, d, F, nl, nh, w = 32, 960, 896, 256, 6, 8, 16
+    ours = Transformer_segmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="FocalLoss", window_size=w).to(dev).eval()
+    ours.th = 0.5
+    lengths = torch.randint(100, S + 1, (B,), generator=g)
+    lengths[0], lengths[1] = S, 333
+    x = torch.randn(B, S, d, generator=g).to(dev)
+    s_all, t_all = ours(x, lengths)
+    assert tuple(s_all.shape) == (B, S, 1) and [len(t) for t in t_all] == lengths.tolist()
+    # (1) padded rows of the INPUT never influence valid outputs
+    x2 = x.clone()
+    for b, n in enumerate(lengths.tolist()):
+        x2[b, n:] = 1e3
+    s_pad, t_pad = ours(x2, lengths)
+    for b, n in enumerate(lengths.tolist()):
+        assert torch.equal(s_pad[b, :n], s_all[b, :n])
+    assert t_pad == t_all
+    # (2) an episode alone gives the same scores as inside the batch (same kernels, same arithmetic per row)
+    for b in (1, 7):
+        s_one, t_one = ours(x[b:b + 1].contiguous(), lengths[b:b + 1])
+        n = int(lengths[b])
+        close(s_one[0, :n], s_all[b, :n], rtol=1e-5, atol=1e-6)
+    # (3) spot check against the HF LongformerModel twin on the host (2 episodes)
+    ref = rt.WindowedSegmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="FocalLoss", window_size=w).eval()
+    missing, unexpected = ref.load_state_dict({k: v.cpu() for k, v in ours.state_dict().items()}, strict=False)
+    assert not unexpected, unexpected
+    ref.th = 0.5
+    with torch.no_grad():
+        s_ref, t_ref = ref(x[:2].cpu(), lengths[:2])
+    for b in range(2):
+        n = int(lengths[b])
+        close(s_all[b, :n], s_ref[b, :n], rtol=1e-4, atol=3e-5)
+    assert sum(int(a != r) for ta, tr in zip(t_all[:2], t_ref) for a, r in zip(ta, tr)) == 0
+
+
+def test_cfg5_long_episode_properties(dev):
+    """BASELINE configs[4] shape: 8 episodes x 8192 sentences x 1024-d, BiLSTM(+CRF) inference.  Permutation
+    equivariance over episodes, padding invariance, Viterbi path score == gold score of the returned path."""
+    from multimodaltopicsegmentation_b200 import BiLSTM, BiRnnCrf, ops
+
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(55)
+    B, T, D, H = 8, 8192, 1024, 256
+    lengths = torch.randint(3000, T + 1, (B,), generator=g)
+    lengths[3] = T
+    x = torch.randn(B, T, D, generator=g).to(dev)
+    m = BiLSTM(2, D, H, num_layers=2, loss_fn="FocalLoss").to(dev)
+    m.th = 0.5
+    s, tags = m(x, lengths)
+    assert tuple(s.shape) == (B, T, 1) and [len(t) for t in tags] == lengths.tolist()
+    perm = torch.tensor([5, 2, 7, 0, 3, 6, 1, 4])
+    s_p, tags_p = m(x[perm].contiguous(), lengths[perm])
+    for i, b in enumerate(perm.tolist()):
+        n = int(lengths[b])
+        assert torch.equal(s_p[i, :n], s[b, :n])   # same tile arithmetic whatever the batch order
+        assert tags_p[i] == tags[b]
+    x2 = x.clone()
+    for b, n in enumerate(lengths.tolist()):
+        x2[b, n:] = -77.0
+    s2, _ = m(x2, lengths)
+    for b, n in enumerate(lengths.tolist()):
+        assert torch.equal(s2[b, :n], s[b, :n])
+    # CRF over the same encoder: the decoded path must score exactly what Viterbi reported
+    c = BiRnnCrf(2, D, H, num_layers=2).to(dev)
+    c.model.load_state_dict(m.model.state_dict())
+    best, paths = c(x, lengths)
+    assert [len(p) for p in paths] == lengths.tolist() and all(v in (0, 1) for v in paths[0][:100])
+    feats = c.model(x, lengths)
+    lens = ops.Lengths(lengths, dev, T)
+    emis = c.crf.emissions(feats)
+    tag_t = torch.zeros(B, T, device=dev)
+    for b, p in enumerate(paths):
+        tag_t[b, :len(p)] = torch.tensor(p, dtype=torch.float32)
+    stats = ops.CrfNllFn.apply(emis.detach(), c.crf.transitions.detach(), tag_t, lens)
+    close(stats[1], best, rtol=2e-5, atol=1e-2)          # gold score of the Viterbi path (summed in another order)
+    assert bool((stats[0] >= stats[1] - 1e-2).all())     # log Z >= score of any single path
