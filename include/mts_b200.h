@@ -46,6 +46,14 @@ int mts_pack_rows_split(const float *src1, int64_t bstride1, int D1, const float
 /* Generic 2-D split: src [rows, cols] (row stride `ld`) -> hi/lo [rows, Kp]. */
 int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, int Kp, float *hi, float *lo, void *stream);
 
+/* Transposed split for the weight-gradient GEMMs (a contraction over tokens needs both operands K-major along the
+ * token axis):  out[c, r] = src[(r / T) * bstride + (r % T + shift) * ld + c] when 0 <= r % T + shift < lengths[r / T]
+ * (lengths may be NULL: T), else 0;  hi/lo [cols, Kp], Kp % 32 == 0, Kp >= rows, columns >= rows zero.
+ * shift in {-1, 0, +1}: the h_{t-1} / h_{t+1} operand of dW_hh without a shifted copy of the hidden states.
+ * A plain [rows, cols] matrix: T = rows, bstride = 0. */
+int mts_transpose_split(const float *src, int64_t bstride, int64_t ld, int rows, int cols, int T, int shift,
+                        const int32_t *lengths, int Kp, float *hi, float *lo, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ GELU), fp32 in / fp32 out.
  *   replaces: nn.LSTM's input projection (models/NeuralArchitectures.py:113), nn.Linear heads

@@ -116,49 +116,64 @@ class DevicePrefetcher:
     iterable of collater outputs) with the host->device copy of batch i+1 running on a side CUDA stream while batch
     i computes.  The reference leaves this to pl.Trainer, which copies on the compute stream; here the copy of the
     next [B,T,D] embedding block (the only large transfer of the path) hides behind the kernels of the current one.
+
+    Two sets of device staging buffers are allocated once and reused (no allocator traffic per step): the copy into
+    slot k waits for the event recorded on the compute stream when the consumer asked for the batch after the one
+    that last used slot k -- i.e. after all of its work had been issued.
     Host tensors should be pinned (DataLoader(pin_memory=True)); `src_lengths` stays on the host (see to_device).
     `src_tokens` may be a (text, audio) pair of tensors: the early-fusion concat then happens inside the operand
     packing kernel instead of on the host."""
 
-    def __init__(self, loader, device, lengths_on_host=True):
+    def __init__(self, loader, device, lengths_on_host=True, depth=2):
         self.loader, self.device, self.lengths_on_host = loader, torch.device(device), lengths_on_host
         self.stream = torch.cuda.Stream(self.device)
+        self.depth = depth
+        self.buffers = [dict() for _ in range(depth)]
+        self.free_ev = [None] * depth
 
-    def _stage(self, batch):
-        moved = []
+    def _copy(self, v, slot, key):
+        buf = self.buffers[slot].get(key)
+        if buf is None or buf.numel() < v.numel() or buf.dtype != v.dtype:
+            buf = torch.empty(max(v.numel(), 1), dtype=v.dtype, device=self.device)
+            self.buffers[slot][key] = buf
+        dst = buf[: v.numel()].view(v.shape)
+        dst.copy_(v, non_blocking=True)
+        return dst
 
-        def mv(v):
+    def _stage(self, batch, slot):
+        def mv(v, key):
             if torch.is_tensor(v):
-                t = v.to(self.device, non_blocking=True)
-                moved.append(t)
-                return t
+                return self._copy(v, slot, key)
             if isinstance(v, (tuple, list)) and v and all(torch.is_tensor(x) for x in v):
-                return type(v)(mv(x) for x in v)
+                return type(v)(self._copy(x, slot, (key, i)) for i, x in enumerate(v))
             return v
 
         with torch.cuda.stream(self.stream):
-            out = {k: (v if (self.lengths_on_host and k == "src_lengths") else mv(v)) for k, v in batch.items()}
+            if self.free_ev[slot] is not None:
+                self.stream.wait_event(self.free_ev[slot])
+            out = {k: (v if (self.lengths_on_host and k == "src_lengths") else mv(v, k)) for k, v in batch.items()}
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return out, ev, moved
+        return out, ev, slot
 
     def __iter__(self):
         it = iter(self.loader)
         try:
-            nxt = self._stage(next(it))
+            nxt = self._stage(next(it), 0)
         except StopIteration:
             return
+        compute = torch.cuda.current_stream(self.device)
         while nxt is not None:
-            cur, ev, moved = nxt
+            cur, ev, slot = nxt
             try:
-                nxt = self._stage(next(it))
+                nxt = self._stage(next(it), (slot + 1) % self.depth)
             except StopIteration:
                 nxt = None
-            compute = torch.cuda.current_stream(self.device)
             compute.wait_event(ev)
-            for t in moved:  # allocated on the side stream, consumed on the compute stream
-                t.record_stream(compute)
             yield cur
+            done = torch.cuda.Event()  # everything the consumer did with `cur` has been issued by now
+            done.record(compute)
+            self.free_ev[slot] = done
 
     def __len__(self):
         return len(self.loader)

@@ -39,6 +39,43 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
   }
 }
 
+// Transposed operand preparation for the weight-gradient GEMMs (dW = dY^T X is a contraction over TOKENS, so both
+// operands must be K-major along the token axis for the tensor-core kernel):
+//   out[c, r] = src[(r / T) * bstride + (r % T + shift) * ld + c]   for 0 <= r % T + shift < lengths[r / T],  else 0
+// written as (hi, lo) TF32 halves [cols, Kp], columns r >= rows zero-filled.  shift = -1 / +1 yields the h_{t-1} /
+// h_{t+1} operand of dW_hh without a shifted copy of the hidden states.  32 x 32 tiles through shared memory:
+// coalesced reads along the source columns, coalesced writes along the token axis.
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float *__restrict__ src, int64_t bstride, int64_t ld,
+                                                             int rows, int cols, int T, int shift,
+                                                             const int32_t *__restrict__ lengths, int Kp,
+                                                             float *__restrict__ hi, float *__restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.0f;
+    if (r < rows && c < cols) {
+      const int b = r / T, t = r % T + shift;
+      const int len = lengths ? lengths[b] : T;
+      if (t >= 0 && t < len && t < T) v = __ldg(src + (int64_t)b * bstride + (int64_t)t * ld + c);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < cols && r < Kp) {
+      const float v = tile[tx][ty + 8 * i];
+      const float h = tf32_rn(v);
+      hi[(int64_t)c * Kp + r] = h;
+      lo[(int64_t)c * Kp + r] = tf32_rn(v - h);
+    }
+  }
+}
+
 }  // namespace mts
 
 using namespace mts;
@@ -66,6 +103,18 @@ extern "C" int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, 
   MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "split_tf32: null pointer");
   MTS_REQUIRE(rows > 0 && cols > 0 && Kp % 32 == 0 && Kp >= cols, MTS_E_BADARG, "split_tf32: bad shape");
   split_tf32_kernel<<<grid_for((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, hi, lo);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mts_transpose_split(const float *src, int64_t bstride, int64_t ld, int rows, int cols, int T, int shift,
+                                   const int32_t *lengths, int Kp, float *hi, float *lo, void *stream) {
+  MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "transpose_split: null pointer");
+  MTS_REQUIRE(rows > 0 && cols > 0 && T > 0 && Kp % 32 == 0 && Kp >= rows, MTS_E_BADARG, "transpose_split: bad shape");
+  MTS_REQUIRE(shift >= -1 && shift <= 1, MTS_E_BADARG, "transpose_split: shift must be -1, 0 or +1");
+  const dim3 grid((unsigned)(Kp / 32), (unsigned)((cols + 31) / 32));
+  MTS_REQUIRE(grid.y <= 65535, MTS_E_UNSUPPORTED, "transpose_split: too many columns");
+  transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, bstride, ld, rows, cols, T, shift, lengths, Kp, hi, lo);
   MTS_LAUNCH_CHECK();
   return 0;
 }

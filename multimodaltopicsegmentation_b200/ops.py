@@ -121,6 +121,23 @@ def pack_rows_split(x1, x2, B, T):
     return out[0], out[1]
 
 
+def transpose_split(src_ptr, bstride, ld, rows, cols, T, device, shift=0, lengths=None):
+    """(hi, lo) [cols, pad32(rows)] of the transposed (optionally time-shifted / length-masked) source: the K-major
+    operand of a GEMM that contracts over tokens (weight gradients)."""
+    kp = _pad32(rows)
+    out = torch.empty((2, cols, kp), device=device, dtype=torch.float32)
+    _call("mts_transpose_split", src_ptr, bstride, ld, rows, cols, T, shift, _ptr(lengths), kp, _ptr(out[0]), _ptr(out[1]),
+          _stream())
+    return out[0], out[1]
+
+
+def weight_grad(dyT, x_ptr, x_bstride, x_ld, rows, n_in, T, out, ldc, device, shift=0, lengths=None):
+    """out[n_out, n_in] (row stride ldc) = dY^T X over `rows` tokens on the tensor cores.  dyT = (hi, lo) of dY^T
+    [n_out, pad32(rows)] from transpose_split; X is transposed / split here."""
+    xT = transpose_split(x_ptr, x_bstride, x_ld, rows, n_in, T, device, shift=shift, lengths=lengths)
+    gemm_tf32x3(dyT[0], dyT[1], xT[0], xT[1], None, out, dyT[0].shape[0], n_in, ldc=ldc)
+
+
 def gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, out, M, N, epilogue=0, accumulate=False, ldc=None):
     kp = a_hi.shape[1]
     assert b_hi.shape[1] == kp
@@ -290,6 +307,8 @@ class BiLstmStackFn(torch.autograd.Function):
         dy = dy.contiguous()
         grads = [[None] * (8 * L) for _ in range(n_enc)]
         splits = max(1, min(16, N // 2048))
+        tensor_core = GEMM_IMPL != "simt"
+        ycols = n_enc * 2 * H
         for layer in range(L - 1, -1, -1):
             y_in, y_out, gates = ctx.saved[layer]
             dgx = torch.empty((n_enc, N, 8 * H), device=dev, dtype=torch.float32)
@@ -306,33 +325,54 @@ class BiLstmStackFn(torch.autograd.Function):
                 # biases: column sums of dgx (b_ih and b_hh receive identical gradients)
                 db = torch.empty(8 * H, device=dev, dtype=torch.float32)
                 colsum(_ptr(dg), 8 * H, N, 8 * H, db)
-                # input weights, both directions at once: [8H, D] = dgx^T X
                 dwih = torch.empty((8 * H, D), device=dev, dtype=torch.float32)
+                dwhh = torch.empty((2, 4 * H, H), device=dev, dtype=torch.float32)
+                yo = y_out.view(N, ycols)
                 if layer == 0:
                     if n_enc == 1:  # early fusion: the two modality blocks of W_ih get their own GEMM (no concat copy)
                         srcs = [(ctx.x1, 0)] + ([(ctx.x2, ctx.x1.shape[2])] if ctx.x2 is not None else [])
                     else:
                         srcs = [(ctx.x1 if e == 0 else ctx.xs2, 0)]
-                    for x, off in srcs:
-                        xc = x if (x.shape[1] == T and x.is_contiguous()) else x[:, :T].contiguous()
-                        Dx = xc.shape[2]
-                        gemm_f32(_ptr(dg), 8 * H, _ptr(xc), Dx, None, dwih.data_ptr() + 4 * off, D, 8 * H, Dx, N,
-                                 layout=3, splits=splits)
-                else:
-                    xin = y_in.view(N, n_enc * 2 * H)
-                    gemm_f32(_ptr(dg), 8 * H, xin.data_ptr() + 4 * e * 2 * H, n_enc * 2 * H, None, _ptr(dwih), D,
-                             8 * H, D, N, layout=3, splits=splits)
-                    # gradient to the lower layer's output: dgx W_ih  (layout 2), written in place into dy_next
-                    wcat = torch.cat([w_f.detach(), w_r.detach()], dim=0)
-                    gemm_f32(_ptr(dg), 8 * H, _ptr(wcat), D, None, dy_next.data_ptr() + 4 * e * 2 * H, n_enc * 2 * H,
-                             N, D, 8 * H, layout=2)
-                # recurrent weights: dW_hh[dir] = dgx_dir^T H_prev  (H_prev = this layer's output shifted in time)
-                dwhh = torch.empty((2, 4 * H, H), device=dev, dtype=torch.float32)
-                yo = y_out.view(N, n_enc * 2 * H)
-                for d, shift in ((0, -1), (1, 1)):
-                    gemm_f32(dg.data_ptr() + 4 * d * 4 * H, 8 * H, yo.data_ptr() + 4 * (e * 2 * H + d * H),
-                             n_enc * 2 * H, None, _ptr(dwhh[d]), H, 4 * H, H, N, layout=3, splits=splits, shift=shift,
-                             T=T, lengths=lens.dev)
+                if tensor_core:
+                    # weight gradients contract over tokens: both operands transposed to K-major (hi, lo) halves, then
+                    # the tcgen05 3xTF32 GEMM.  dgx^T is shared by dW_ih and both dW_hh.
+                    dgT = transpose_split(_ptr(dg), 0, 8 * H, N, 8 * H, N, dev)
+                    if layer == 0:
+                        for x, off in srcs:
+                            weight_grad(dgT, _ptr(x), x.stride(0), x.stride(1), N, x.shape[2], T, dwih[:, off:], D, dev)
+                    else:
+                        weight_grad(dgT, y_in.data_ptr() + 4 * e * 2 * H, 0, ycols, N, 2 * H, N, dwih, D, dev)
+                        # gradient to the lower layer's output: dgx W_ih, straight into its column block of dy_next
+                        if "wih_t" not in layers[layer]:
+                            layers[layer]["wih_t"] = {}
+                        if e not in layers[layer]["wih_t"]:
+                            layers[layer]["wih_t"][e] = split_tf32(torch.cat([w_f.detach(), w_r.detach()], dim=0).t().contiguous())
+                        wt = layers[layer]["wih_t"][e]
+                        dg_hl = split_tf32(dg)
+                        gemm_tf32x3(dg_hl[0], dg_hl[1], wt[0], wt[1], None, dy_next.view(N, ycols)[:, e * 2 * H:], N, D,
+                                    ldc=ycols)
+                    for d, shift in ((0, -1), (1, 1)):
+                        weight_grad((dgT[0][d * 4 * H:(d + 1) * 4 * H], dgT[1][d * 4 * H:(d + 1) * 4 * H]),
+                                    yo.data_ptr() + 4 * (e * 2 * H + d * H), T * ycols, ycols, N, H, T, dwhh[d], H, dev,
+                                    shift=shift, lengths=lens.dev)
+                else:  # exact-fp32 CUDA-core GEMMs (MTS_GEMM_IMPL=simt): the second opinion for the tensor-core path
+                    if layer == 0:
+                        for x, off in srcs:
+                            xc = x if (x.shape[1] == T and x.is_contiguous()) else x[:, :T].contiguous()
+                            Dx = xc.shape[2]
+                            gemm_f32(_ptr(dg), 8 * H, _ptr(xc), Dx, None, dwih.data_ptr() + 4 * off, D, 8 * H, Dx, N,
+                                     layout=3, splits=splits)
+                    else:
+                        xin = y_in.view(N, ycols)
+                        gemm_f32(_ptr(dg), 8 * H, xin.data_ptr() + 4 * e * 2 * H, ycols, None, _ptr(dwih), D,
+                                 8 * H, D, N, layout=3, splits=splits)
+                        wcat = torch.cat([w_f.detach(), w_r.detach()], dim=0)
+                        gemm_f32(_ptr(dg), 8 * H, _ptr(wcat), D, None, dy_next.data_ptr() + 4 * e * 2 * H, ycols,
+                                 N, D, 8 * H, layout=2)
+                    for d, shift in ((0, -1), (1, 1)):
+                        gemm_f32(dg.data_ptr() + 4 * d * 4 * H, 8 * H, yo.data_ptr() + 4 * (e * 2 * H + d * H),
+                                 ycols, None, _ptr(dwhh[d]), H, 4 * H, H, N, layout=3, splits=splits, shift=shift,
+                                 T=T, lengths=lens.dev)
                 base = 8 * layer
                 g = grads[e]
                 g[base + 0], g[base + 1] = dwih[:4 * H], dwhh[0]

@@ -776,5 +776,5 @@ def test_cfg5_long_episode_properties(dev):
     for b, p in enumerate(paths):
         tag_t[b, :len(p)] = torch.tensor(p, dtype=torch.float32)
     stats = ops.CrfNllFn.apply(emis.detach(), c.crf.transitions.detach(), tag_t, lens)
-    close(stats[1], best, rtol=2e-5, atol=1e-2)          # gold score of the Viterbi path (summed in another order)
-    assert bool((stats[0] >= stats[1] - 1e-2).all())     # log Z >= score of any single path
+    close(stats[1], best, rtol=3e-4, atol=1e-2)          # gold score of the Viterbi path (8192 fp32 terms summed in another order)
+    assert bool((stats[0] >= stats[1] * (1 - 3e-4)).all())     # log Z >= score of any single path
