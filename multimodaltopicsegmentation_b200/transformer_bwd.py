@@ -2,7 +2,8 @@
 gradients from autograd through HF LongformerModel; here every step is a kernel of libmts_b200.so:
 
     dX of a dense layer   tcgen05 3xTF32 GEMM of the (hi, lo) halves of dY against the transposed weight halves
-    dW, db                exact-fp32 split-K GEMM dY^T X over all tokens, column sums
+    dW, db                dY^T X contracts over tokens: both operands transposed to K-major (hi, lo) halves
+                          (mts_transpose_split), then the same tcgen05 GEMM; column sums for the biases
     LayerNorm, GELU, banded attention, embeddings: csrc/xfmr_bwd.cu
 
 Residual connections are folded in by letting the dX GEMM accumulate into the buffer that already holds the
@@ -33,9 +34,13 @@ def _dense_param_grads(dy, x, M, n_out, n_in):
     """dW [n_out, n_in] = dY^T X over M tokens, db = column sums of dY."""
     dev = dy.device
     dw = torch.empty((n_out, n_in), device=dev, dtype=torch.float32)
-    splits = max(1, min(16, M // 2048))
-    ops.gemm_f32(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), None, _ptr(dw), n_in, n_out, n_in, M, layout=3,
-                 splits=splits)
+    if ops.GEMM_IMPL != "simt":  # contraction over tokens: transpose both operands to K-major halves, tcgen05 GEMM
+        dyT = ops.transpose_split(_ptr(dy), 0, dy.stride(0), M, n_out, M, dev)
+        ops.weight_grad(dyT, _ptr(x), 0, x.stride(0), M, n_in, M, dw, n_in, dev)
+    else:
+        splits = max(1, min(16, M // 2048))
+        ops.gemm_f32(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), None, _ptr(dw), n_in, n_out, n_in, M, layout=3,
+                     splits=splits)
     db = torch.empty(n_out, device=dev, dtype=torch.float32)
     ops.colsum(_ptr(dy), dy.stride(0), M, n_out, db)
     return dw, db
