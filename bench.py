@@ -378,11 +378,13 @@ def run_ours(args, rank, world, local_rank):
             a, b, l = pinned[i % n_sets]
             yield {"src_tokens": (a, b), "src_lengths": l}
 
+    prefetcher = m.DevicePrefetcher(None, dev)
+
     def e2e_run(n):
         # public API: DevicePrefetcher (H2D of batch i+1 on a side stream) + TextSegmenter.predict_step, which returns
         # host lists -- so every step includes its H2D copies and the D2H of its tags
         out = None
-        for i, batch in enumerate(m.DevicePrefetcher(host_batches(n), dev)):
+        for i, batch in enumerate(prefetcher.iterate(host_batches(n))):
             out = seg.predict_step(batch, i)
         return out
 

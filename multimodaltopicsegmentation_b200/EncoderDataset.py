@@ -157,7 +157,11 @@ class DevicePrefetcher:
         return out, ev, slot
 
     def __iter__(self):
-        it = iter(self.loader)
+        return self.iterate(self.loader)
+
+    def iterate(self, loader):
+        """Iterate over another loader with the same staging buffers (e.g. one prefetcher for all epochs)."""
+        it = iter(loader)
         try:
             nxt = self._stage(next(it), 0)
         except StopIteration:

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
-                       int epilogue, int accumulate) {
+                       int epilogue, int accumulate, int splits) {
   using Cfg = TcCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -130,8 +130,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = Kp / TC_BK;
+  // work item = (output tile, K split).  splits > 1 (long-K, few-tile products such as weight gradients, which would
+  // otherwise leave most SMs idle): every item reduces its K range and adds its partial tile into C with fp32 atomics
+  // (C holds zeros or the running sum; the bias rides on split 0).
+  const int num_tiles = tiles_m * tiles_n * splits;
+  const int total_kb = Kp / TC_BK;
+  const int kb_per = (total_kb + splits - 1) / splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { bar_init(s_u32(&full_bar[s]), 1); bar_init(s_u32(&empty_bar[s]), 1); }
@@ -158,9 +162,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / splits, sp = item % splits;
         const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = sp * kb_per, kb1 = min(total_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           bar_wait(s_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = s_u32(&full_bar[stage]);
           bar_expect_tx(fb, Cfg::kStageBytes);
@@ -181,11 +187,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int sp = item % splits;
+        const int kb0 = sp * kb_per, kb1 = min(total_kb, kb0 + kb_per);
+        if (kb0 >= kb1) continue;  // empty trailing split: nothing to add (the epilogue skips it too)
         bar_wait(s_u32(&tempty_bar[acc_stage]), acc_phase ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           bar_wait(s_u32(&full_bar[stage]), phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
@@ -195,12 +204,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);  // +32 B per k-step inside the swizzle row
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));
             umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
             umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
           }
           umma_commit(s_u32(&empty_bar[stage]));  // smem slot free once these MMAs have read it
-          if (kb == num_kb - 1) umma_commit(s_u32(&tfull_bar[acc_stage]));
+          if (kb == kb1 - 1) umma_commit(s_u32(&tfull_bar[acc_stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
@@ -211,7 +220,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int tile = item / splits, sp = item % splits;
+      if (sp * kb_per >= total_kb) continue;
       const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
       bar_wait(s_u32(&tfull_bar[acc_stage]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -226,10 +237,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c0 + j;
-            if (epilogue >= 1 && n < N) v[j] += __ldg(bias + n);
+            if (epilogue >= 1 && sp == 0 && n < N) v[j] += __ldg(bias + n);
             if (epilogue == 2) v[j] = gelu_erf(v[j]);
           }
-          if (full) {
+          if (splits > 1) {
+            if (full && ((reinterpret_cast<uintptr_t>(c_row + c0) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c_row + c0 + 4 * j), "f"(v[4 * j]),
+                             "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c0 + j < N) atomicAdd(c_row + c0 + j, v[j]);
+            }
+          } else if (full) {
             float4 *dst = reinterpret_cast<float4 *>(c_row + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -291,6 +314,12 @@ static int make_map(CUtensorMap *map, const float *ptr, int rows, int Kp, int bo
   return 0;
 }
 
+__global__ void __launch_bounds__(256) zero_matrix_kernel(float *__restrict__ C, int M, int N, int64_t ldc) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    C[(i / N) * ldc + (i % N)] = 0.0f;
+}
+
 template <int BN>
 static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
                      float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, cudaStream_t st) {
@@ -307,9 +336,29 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
     attr_set = true;
   }
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  // Split K (a) when the output has too few tiles to fill the device and K is long (weight gradients: K = all tokens)
+  // and (b) ALWAYS beyond 3072 elements of K: the tensor core truncates when it aligns addends to its fp32
+  // accumulator, a drift that grows linearly with K (measured 9e-6 of the output scale at K = 896); chunks of <= 2048
+  // summed with round-to-nearest atomics keep the product inside the 2e-5 contract at any K.
+  int splits = 1;
+  const int num_kb = Kp / TC_BK;
+  if (epilogue != 2) {
+    if (tiles * 2 <= kNumSMs && num_kb >= 32) {
+      splits = kNumSMs / tiles;
+      if (splits > num_kb / 8) splits = num_kb / 8;
+    }
+    if (num_kb > 96 && splits < (num_kb + 63) / 64) splits = (num_kb + 63) / 64;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1 && !accumulate) {
+    const int64_t total = (int64_t)M * N;
+    const unsigned zg = (unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    zero_matrix_kernel<<<zg, 256, 0, st>>>(C, M, N, ldc);
+  }
+  const int items = tiles * splits;
+  const int grid = items < kNumSMs ? items : kNumSMs;
   gemm_tf32x3_kernel<BN><<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc,
-                                                                   epilogue, accumulate);
+                                                                   epilogue, accumulate, splits);
   MTS_LAUNCH_CHECK();
   return 0;
 }

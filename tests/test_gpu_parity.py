@@ -64,7 +64,8 @@ def test_gemm_f32_nt(dev, M, N, K):
     close(c, ref, rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 256, 96), (1000, 2048, 896), (129, 136, 40), (4096, 1024, 512), (19200, 2048, 896)])
+@pytest.mark.parametrize("M,N,K", [(300, 256, 96), (1000, 2048, 896), (129, 136, 40), (4096, 1024, 512), (19200, 2048, 896),
+                                   (256, 256, 8192), (200, 100, 5000), (1024, 256, 22920)])  # the last three: split-K
 def test_gemm_tf32x3(dev, M, N, K):
     """tcgen05 3xTF32 vs float64: error must be fp32-grade (no worse than 4x a plain fp32 matmul's)."""
     from multimodaltopicsegmentation_b200 import ops
@@ -92,9 +93,36 @@ def test_gemm_tf32x3(dev, M, N, K):
     c2 = c.clone()
     ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, None, c2, M, N, epilogue=0, accumulate=True)
     close(c2, (2 * ref - biasd.double()).float(), rtol=1e-5, atol=4e-5 * scale)
-    c3 = torch.empty(M, N, device=dev)
-    ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, biasd, c3, M, N, epilogue=2)
-    close(c3, torch.nn.functional.gelu(ref).float(), rtol=1e-5, atol=2e-5 * scale)
+    if K <= 3072:  # the GELU epilogue cannot be split over K; the encoder's GELU GEMM has K = d_model
+        c3 = torch.empty(M, N, device=dev)
+        ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, biasd, c3, M, N, epilogue=2)
+        close(c3, torch.nn.functional.gelu(ref).float(), rtol=1e-5, atol=2e-5 * scale)
+
+
+@pytest.mark.parametrize("rows,cols,T,shift", [(100, 40, 100, 0), (3 * 37, 65, 37, -1), (3 * 37, 65, 37, 1), (2048, 896, 2048, 0)])
+def test_transpose_split(dev, rows, cols, T, shift):
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator().manual_seed(rows + cols)
+    B = rows // T
+    src = torch.randn(B, T + 3, cols + 5, generator=g).to(dev)   # padded batch / row strides
+    lengths = torch.randint(1, T + 1, (B,), generator=g)
+    lens_dev = lengths.to(torch.int32).to(dev) if shift else None
+    hi, lo = ops.transpose_split(src.data_ptr(), src.stride(0), src.stride(1), rows, cols, T, dev, shift=shift,
+                                 lengths=lens_dev)
+    kp = (rows + 31) // 32 * 32
+    assert tuple(hi.shape) == (cols, kp)
+    ref = torch.zeros(rows, cols)
+    sc = src.cpu()
+    for b in range(B):
+        n = int(lengths[b]) if shift else T
+        for t in range(T):
+            if 0 <= t + shift < n:
+                ref[b * T + t] = sc[b, t + shift, :cols]
+    got = (hi + lo)[:, :rows].T.cpu()
+    assert float((got - ref).abs().max()) <= 2.0 ** -21 * float(ref.abs().max())
+    assert float(hi[:, rows:].abs().max() if kp > rows else 0.0) == 0.0
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
 
 
 def test_gemm_tn_shift(dev):
