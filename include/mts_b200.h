@@ -116,6 +116,12 @@ int mts_lstm_rec_bwd(const float *dy, const float *gates, const float *w_hh, con
                      const int32_t *lengths, const int32_t *order, int n_enc, int B, int T, int H, float *dgx,
                      void *stream);
 
+/* The same backward recurrence on the tensor cores (H == 256 only): the transposed weight slice of every CTA
+ * resident in tensor memory, tcgen05.mma per step, partial products reduce-scattered through distributed shared
+ * memory.  Same results (to fp32 rounding) as mts_lstm_rec_bwd; needs no transposed copy of w_hh. */
+int mts_lstm_rec_bwd_tc(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
+                        const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Head + decode  (models/CRF.py:340,361-369: Linear then sigmoid/softmax threshold)
  *   feats [B,T,F] (row stride F), w [n_out,F], bias [n_out] -> scores [B,T,n_out];

@@ -312,10 +312,14 @@ class BiLstmStackFn(torch.autograd.Function):
         for layer in range(L - 1, -1, -1):
             y_in, y_out, gates = ctx.saved[layer]
             dgx = torch.empty((n_enc, N, 8 * H), device=dev, dtype=torch.float32)
-            if "whh_t" not in layers[layer]:  # transposed copy, made once per weight version and only when training
-                layers[layer]["whh_t"] = layers[layer]["whh"].transpose(2, 3).contiguous()
-            _call("mts_lstm_rec_bwd", _ptr(dy), _ptr(gates), _ptr(layers[layer]["whh"]), _ptr(layers[layer]["whh_t"]),
-                  _ptr(lens.dev), _ptr(lens.order), n_enc, B, T, H, _ptr(dgx), _stream())
+            if H == 256 and REC_IMPL == "tc":
+                _call("mts_lstm_rec_bwd_tc", _ptr(dy), _ptr(gates), _ptr(layers[layer]["whh"]), _ptr(lens.dev),
+                      _ptr(lens.order), n_enc, B, T, H, _ptr(dgx), _stream())
+            else:
+                if "whh_t" not in layers[layer]:  # transposed copy, made once per weight version, only when training
+                    layers[layer]["whh_t"] = layers[layer]["whh"].transpose(2, 3).contiguous()
+                _call("mts_lstm_rec_bwd", _ptr(dy), _ptr(gates), _ptr(layers[layer]["whh"]), _ptr(layers[layer]["whh_t"]),
+                      _ptr(lens.dev), _ptr(lens.order), n_enc, B, T, H, _ptr(dgx), _stream())
             dy_next = torch.empty((B, T, n_enc * 2 * H), device=dev, dtype=torch.float32) if layer > 0 else None
             for e in range(n_enc):
                 rnn = packed.rnns[e]

@@ -89,6 +89,50 @@ def compare(B, T, lengths, n_enc=1, save=False, check64=False):
     return ok
 
 
+def compare_bwd(B, T, lengths, n_enc=1):
+    """backward: tensor-core kernel vs the packed-FMA cluster kernel on the same saved gates and dy."""
+    H = 256
+    g = torch.Generator(device=dev).manual_seed(B * 77 + T)
+    gx = torch.randn((n_enc, B * T, 8 * H), device=dev, generator=g)
+    whh = torch.randn((n_enc, 2, 4 * H, H), device=dev, generator=g) * 0.06
+    lens = ops.Lengths(lengths, dev, T)
+    y, gates = run("mts_lstm_rec_fwd", gx, whh, lens, B, T, H, n_enc, True)
+    dy = torch.randn((B, T, n_enc * 2 * H), device=dev, generator=g)
+    whh_t = whh.transpose(2, 3).contiguous()
+    d_f = torch.full((n_enc, B * T, 8 * H), float("nan"), device=dev)
+    d_t = torch.full((n_enc, B * T, 8 * H), float("nan"), device=dev)
+    ops._call("mts_lstm_rec_bwd", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), whh_t.data_ptr(), lens.dev.data_ptr(),
+              lens.order.data_ptr(), n_enc, B, T, H, d_f.data_ptr(), ops._stream())
+    ops._call("mts_lstm_rec_bwd_tc", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
+              lens.order.data_ptr(), n_enc, B, T, H, d_t.data_ptr(), ops._stream())
+    torch.cuda.synchronize()
+    nan = bool(torch.isnan(d_t).any())
+    err = float((d_f - d_t).abs().max())
+    scale = float(d_f.abs().max())
+    ok = (not nan) and err < 2e-5 * max(scale, 1.0)
+    print(("ok   " if ok else "FAIL ") + f"bwd B={B} T={T} n_enc={n_enc}: max |fma - tc| = {err:.3e} (scale {scale:.3e}, nan {nan})", flush=True)
+    return ok
+
+
+def sweep_bwd():
+    H, T = 256, 300
+    print("B     bwd fma ms (us/step)   bwd tc ms (us/step)")
+    for B in (10, 16, 64, 128, 256):
+        g = torch.Generator(device=dev).manual_seed(0)
+        gx = torch.randn((1, B * T, 8 * H), device=dev, generator=g) * 0.5
+        whh = torch.randn((1, 2, 4 * H, H), device=dev, generator=g) * 0.05
+        lens = ops.Lengths([T] * B, dev, T)
+        y, gates = run("mts_lstm_rec_fwd_tc", gx, whh, lens, B, T, H, 1, True)
+        dy = torch.randn_like(y)
+        whh_t = whh.transpose(2, 3).contiguous()
+        dgx = torch.empty_like(gx)
+        a = timeit(lambda: ops._call("mts_lstm_rec_bwd", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), whh_t.data_ptr(),
+                                     lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H, dgx.data_ptr(), ops._stream()))
+        b = timeit(lambda: ops._call("mts_lstm_rec_bwd_tc", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(),
+                                     lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H, dgx.data_ptr(), ops._stream()))
+        print(f"{B:5d} {a:9.3f} ({a * 1e3 / T:6.2f}) {b:9.3f} ({b * 1e3 / T:6.2f})", flush=True)
+
+
 def timeit(fn, iters=5, warmup=2):
     for _ in range(warmup):
         fn()
@@ -153,6 +197,14 @@ if __name__ == "__main__":
         ok = compare(37, 61, [61] + [int(x) for x in torch.randint(1, 62, (36,))], save=True) and ok
         ok = compare(20, 33, [33] + [int(x) for x in torch.randint(1, 34, (19,))], n_enc=2, save=True) and ok
         ok = compare(300, 50, [50] * 300) and ok
+    if what in ("all", "bwd"):
+        ok = compare_bwd(3, 5, [5, 3, 1]) and ok
+        ok = compare_bwd(16, 40, [40] * 16) and ok
+        ok = compare_bwd(37, 61, [61] + [int(x) for x in torch.randint(1, 62, (36,))]) and ok
+        ok = compare_bwd(20, 33, [33] + [int(x) for x in torch.randint(1, 34, (19,))], n_enc=2) and ok
+        ok = compare_bwd(300, 50, [50] * 300) and ok
+        if ok:
+            sweep_bwd()
     if what in ("all", "timeline"):
         timeline()
     if what in ("all", "sweep") and ok:

@@ -806,3 +806,33 @@ def test_cfg5_long_episode_properties(dev):
     stats = ops.CrfNllFn.apply(emis.detach(), c.crf.transitions.detach(), tag_t, lens)
     close(stats[1], best, rtol=3e-4, atol=1e-2)          # gold score of the Viterbi path (8192 fp32 terms summed in another order)
     assert bool((stats[0] >= stats[1] * (1 - 3e-4)).all())     # log Z >= score of any single path
+
+
+@pytest.mark.parametrize("B,T,n_enc", [(3, 5, 1), (37, 61, 1), (20, 33, 2), (300, 50, 1)])
+def test_recurrence_backward_tensor_core_vs_fma(dev, B, T, n_enc):
+    """lstm_bwd_tc_kernel (tcgen05, transposed W_hh slice in tensor memory) against the packed-FMA BPTT kernel."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    H = 256
+    g = torch.Generator(device=dev).manual_seed(B * 77 + T)
+    gx = torch.randn((n_enc, B * T, 8 * H), device=dev, generator=g)
+    whh = torch.randn((n_enc, 2, 4 * H, H), device=dev, generator=g) * 0.06
+    hg = torch.Generator().manual_seed(B + T)
+    lengths = [T] + [int(v) for v in torch.randint(1, T + 1, (B - 1,), generator=hg)]
+    lens = ops.Lengths(lengths, dev, T)
+    y = torch.empty((B, T, n_enc * 2 * H), device=dev)
+    gates = torch.zeros((n_enc, 2, B, T, 5, H), device=dev)
+    ops._call("mts_lstm_rec_fwd_tc", gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T,
+              H, y.data_ptr(), gates.data_ptr(), ops._stream())
+    dy = torch.randn((B, T, n_enc * 2 * H), device=dev, generator=g)
+    whh_t = whh.transpose(2, 3).contiguous()
+    d_f = torch.full((n_enc, B * T, 8 * H), float("nan"), device=dev)
+    d_t = torch.full((n_enc, B * T, 8 * H), float("nan"), device=dev)
+    ops._call("mts_lstm_rec_bwd", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), whh_t.data_ptr(), lens.dev.data_ptr(),
+              lens.order.data_ptr(), n_enc, B, T, H, d_f.data_ptr(), ops._stream())
+    ops._call("mts_lstm_rec_bwd_tc", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
+              lens.order.data_ptr(), n_enc, B, T, H, d_t.data_ptr(), ops._stream())
+    assert not bool(torch.isnan(d_t).any())       # every row written, zeros at padded steps
+    for b, n in enumerate(lengths):
+        assert float(d_t[:, b * T + n:(b + 1) * T].abs().max() if n < T else 0.0) == 0.0
+    close(d_t, d_f, rtol=1e-4, atol=2e-5 * float(d_f.abs().max()))
