@@ -238,10 +238,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
           *reinterpret_cast<float *>(bhi + 1 * (TB_NB * 128) + off) = dpf;
           *reinterpret_cast<float *>(bhi + 2 * (TB_NB * 128) + off) = dpg;
           *reinterpret_cast<float *>(bhi + 3 * (TB_NB * 128) + off) = dpo;
-          *reinterpret_cast<float *>(blo + 0 * (TB_NB * 128) + off) = tc::tf32_rest(dpi);
-          *reinterpret_cast<float *>(blo + 1 * (TB_NB * 128) + off) = tc::tf32_rest(dpf);
-          *reinterpret_cast<float *>(blo + 2 * (TB_NB * 128) + off) = tc::tf32_rest(dpg);
-          *reinterpret_cast<float *>(blo + 3 * (TB_NB * 128) + off) = tc::tf32_rest(dpo);
+          *reinterpret_cast<float *>(blo + 0 * (TB_NB * 128) + off) = tc::tf32_rest_raw(dpi);
+          *reinterpret_cast<float *>(blo + 1 * (TB_NB * 128) + off) = tc::tf32_rest_raw(dpf);
+          *reinterpret_cast<float *>(blo + 2 * (TB_NB * 128) + off) = tc::tf32_rest_raw(dpg);
+          *reinterpret_cast<float *>(blo + 3 * (TB_NB * 128) + off) = tc::tf32_rest_raw(dpo);
         }
         if (s + 1 < nsteps) {
           tc::fence_proxy_async();   // generic-proxy writes of the operand -> visible to tcgen05.mma

@@ -93,7 +93,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
   if (wr == 0 && lane == 0) {
     tc::bar_init(tc::s_u32(&h_full[0]), 1);
     tc::bar_init(tc::s_u32(&h_full[1]), 1);
-    tc::bar_init(tc::s_u32(lo_ready), 1);
+    tc::bar_init(tc::s_u32(lo_ready), TR_EPI);
     tc::bar_init(tc::s_u32(acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -187,15 +187,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
       const uint32_t tail_a = tc::s_u32(wtail), blo_a = tc::s_u32(blo);
       const bool leader = tc::elect_one();
       // Every CTA sends its h slice to CTA (rank + i) % 8 at slot i, into K-block slot i of the receiver's buffer.
-      // No proxy fence in the loop: both operand buffers are written through the async proxy (st.async from the
-      // peers for h, st.async-to-self for h_lo), and the mbarrier wait orders them before the MMAs.
+      // h arrives through the async proxy (st.async from the peers): the mbarrier wait alone orders it before the MMAs.
+      // h_lo is derived with ordinary stores + a writer-side fence.proxy.async (measured faster than st.async-to-self,
+      // whose delivery adds ~440 cycles).
       for (int s = 0; s < nsteps; ++s) {
         const int p = s & 1;
         TR_STAMP(0);
-        if (leader) {
-          if (s + 1 < nsteps) tc::bar_expect_tx(tc::s_u32(&h_full[p ^ 1]), TR_B_BYTES);
-          if (s > 0) tc::bar_expect_tx(tc::s_u32(lo_ready), TR_B_BYTES);
-        }
+        if (leader && s + 1 < nsteps) tc::bar_expect_tx(tc::s_u32(&h_full[p ^ 1]), TR_B_BYTES);
         const uint32_t bhi_a = tc::s_u32(bhi + p * TR_B_BYTES);
         if (s > 0) tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]);
         TR_STAMP(1);
@@ -259,7 +257,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
         raddr[i] = mapa(tc::s_u32(bhi) + (uint32_t)(i * (TR_NB * 128)) + my_off, r);  // K-block slot i of that CTA
         rbar[i] = mapa(tc::s_u32(&h_full[0]), r);                                    // its h_full[0]
       }
-      const uint32_t blo_self = mapa(tc::s_u32(blo), rank), lo_bar_self = mapa(tc::s_u32(lo_ready), rank);
 
       for (int s = 0; s < nsteps; ++s) {
         const int p = s & 1;
@@ -269,13 +266,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
           tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]); ph_h[p] ^= 1;
           TR_STAMP(6);
           const float4 *src = reinterpret_cast<const float4 *>(bhi + p * TR_B_BYTES);
+          float4 *dst = reinterpret_cast<float4 *>(blo);
 #pragma unroll
           for (int i = 0; i < TR_B_BYTES / 16 / TR_EPI; ++i) {
             const int f4 = et + TR_EPI * i;
             const float4 v = src[f4];
-            st_async_v4(blo_self + (uint32_t)f4 * 16,
-                        make_float4(tc::tf32_rest(v.x), tc::tf32_rest(v.y), tc::tf32_rest(v.z), tc::tf32_rest(v.w)), lo_bar_self);
+            dst[f4] = make_float4(tc::tf32_rest_raw(v.x), tc::tf32_rest_raw(v.y), tc::tf32_rest_raw(v.z), tc::tf32_rest_raw(v.w));
           }
+          tc::fence_proxy_async();   // generic-proxy writes of h_lo -> visible to tcgen05.mma
+          tc::bar_arrive(tc::s_u32(lo_ready));
         }
         TR_STAMP(7);
         // ---- next step's input projection (independent of h) ---------------------------------------------------

@@ -146,6 +146,10 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // the part the tensor core drops, itself rounded to TF32: x = tf32_trunc(x) + tf32_rest(x) + O(2^-22 |x|)
 __device__ __forceinline__ float tf32_rest(float x) { return tf32_rn(x - tf32_trunc(x)); }
+// the same without the final rounding (exact fp32 remainder, <= 13 significant bits): as an MMA operand it is
+// truncated to 11 bits by the tensor core, i.e. x = tf32_trunc(x) + [tf32_rest_raw(x)]_tf32 + O(2^-21 |x|).
+// Used on the per-step critical paths, where cvt.rna.tf32 (XU pipe) would cost more than the last bit is worth.
+__device__ __forceinline__ float tf32_rest_raw(float x) { return x - tf32_trunc(x); }
 
 }  // namespace tc
 }  // namespace mts
