@@ -76,11 +76,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
   uint8_t *blo = bhi + 2 * TR_B_BYTES;     // [TR_B_BYTES]
   float *act = reinterpret_cast<float *>(blo + TR_B_BYTES);  // [4][NB][32]
   uint64_t *bars = reinterpret_cast<uint64_t *>(act + TR_ACT_FLOATS);
-  uint64_t *h_full = bars;         // [2]  h_{s-1} landed in bhi[s & 1] (16 KB: 2 KB from each of the 8 CTAs)
-  uint64_t *lo_ready = bars + 2;   //      blo derived from it (16 KB of st.async from this CTA to itself)
-  uint64_t *acc_full = bars + 3;   //      the step's MMAs have completed
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TR_TAIL_BYTES + TR_ACT_FLOATS * 4 + 3 * TR_B_BYTES) + 8;  // pipeline 0's bars + 4
-  int *len_s = reinterpret_cast<int *>(bars + 6);   // [NB]
+  uint64_t *h_full = bars;         // [2][2]  half g (K-block slots 4g..4g+3, 8 KB) of h_{s-1} landed in bhi[s & 1]
+  uint64_t *lo_ready = bars + 4;   // [2]     the same half of blo derived
+  uint64_t *acc_full = bars + 6;   //         the step's MMAs have completed
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TR_TAIL_BYTES + TR_ACT_FLOATS * 4 + 3 * TR_B_BYTES) + 14;  // pipeline 0's bars + 7
+  int *len_s = reinterpret_cast<int *>(bars + 8);   // [NB]
   int *bq_s = len_s + TR_NB;                        // [NB]
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -91,9 +91,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
   const int ycols = n_enc * 2 * kH;
 
   if (wr == 0 && lane == 0) {
-    tc::bar_init(tc::s_u32(&h_full[0]), 1);
-    tc::bar_init(tc::s_u32(&h_full[1]), 1);
-    tc::bar_init(tc::s_u32(lo_ready), TR_EPI);
+    for (int i = 0; i < 4; ++i) tc::bar_init(tc::s_u32(&h_full[i]), 1);
+    tc::bar_init(tc::s_u32(&lo_ready[0]), TR_EPI);
+    tc::bar_init(tc::s_u32(&lo_ready[1]), TR_EPI);
     tc::bar_init(tc::s_u32(acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -186,41 +186,51 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
       const uint32_t d_tmem = tb + acc_col;
       const uint32_t tail_a = tc::s_u32(wtail), blo_a = tc::s_u32(blo);
       const bool leader = tc::elect_one();
-      // Every CTA sends its h slice to CTA (rank + i) % 8 at slot i, into K-block slot i of the receiver's buffer.
-      // h arrives through the async proxy (st.async from the peers): the mbarrier wait alone orders it before the MMAs.
-      // h_lo is derived with ordinary stores + a writer-side fence.proxy.async (measured faster than st.async-to-self,
-      // whose delivery adds ~440 cycles).
+      // Every CTA sends its h slice to CTA (rank + i) % 8 at slot i, into K-block slot i of the receiver's buffer, so
+      // the slots fill in order; they are tracked as two halves (slots 0-3, 4-7) with one mbarrier each, and the MMAs /
+      // the h_lo derivation of the first half overlap the arrival of the second.  h arrives through the async proxy
+      // (st.async from the peers): the mbarrier wait alone orders it before the MMAs.  h_lo is derived with ordinary
+      // stores + a writer-side fence.proxy.async (measured faster than st.async-to-self: delivery adds ~440 cycles).
       for (int s = 0; s < nsteps; ++s) {
         const int p = s & 1;
         TR_STAMP(0);
-        if (leader && s + 1 < nsteps) tc::bar_expect_tx(tc::s_u32(&h_full[p ^ 1]), TR_B_BYTES);
+        if (leader && s + 1 < nsteps) {
+          tc::bar_expect_tx(tc::s_u32(&h_full[(p ^ 1) * 2 + 0]), TR_B_BYTES / 2);
+          tc::bar_expect_tx(tc::s_u32(&h_full[(p ^ 1) * 2 + 1]), TR_B_BYTES / 2);
+        }
         const uint32_t bhi_a = tc::s_u32(bhi + p * TR_B_BYTES);
-        if (s > 0) tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]);
-        TR_STAMP(1);
-        tc::tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {
+        for (int g = 0; g < 2; ++g) {
+          if (s > 0) tc::bar_wait_wd(tc::s_u32(&h_full[p * 2 + g]), ph_h[p]);
+          if (g == 0) TR_STAMP(1);
+          tc::tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t bd = tc::desc_sw128(bhi_a + kb * (TR_NB * 128) + k * 32);
-            if (leader) {
-              tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, (kb | k) != 0);
-              if (kb < 7) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(TR_WLO_COL + kb * 32 + k * 8), bd, idesc, 1);
-              else tc::umma_tf32_ss(d_tmem, tc::desc_sw128(tail_a + k * 32), bd, idesc, 1);
+          for (int kb = 4 * g; kb < 4 * g + 4; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t bd = tc::desc_sw128(bhi_a + kb * (TR_NB * 128) + k * 32);
+              if (leader) {
+                tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, (kb | k) != 0);
+                if (kb < 7) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(TR_WLO_COL + kb * 32 + k * 8), bd, idesc, 1);
+                else tc::umma_tf32_ss(d_tmem, tc::desc_sw128(tail_a + k * 32), bd, idesc, 1);
+              }
             }
           }
         }
         TR_STAMP(2);
         if (s > 0) {  // at s == 0 both h and h_lo are the zero-filled buffers: the h_lo product contributes nothing
-          tc::bar_wait_wd(tc::s_u32(lo_ready), ph_lo);
-          TR_STAMP(3);
-          tc::tc_fence_after();
 #pragma unroll
-          for (int kb = 0; kb < 8; ++kb) {
+          for (int g = 0; g < 2; ++g) {
+            tc::bar_wait_wd(tc::s_u32(&lo_ready[g]), ph_lo);
+            if (g == 1) TR_STAMP(3);
+            tc::tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t bd = tc::desc_sw128(blo_a + kb * (TR_NB * 128) + k * 32);
-              if (leader) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, 1);
+            for (int kb = 4 * g; kb < 4 * g + 4; ++kb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t bd = tc::desc_sw128(blo_a + kb * (TR_NB * 128) + k * 32);
+                if (leader) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, 1);
+              }
             }
           }
         }
@@ -255,26 +265,30 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
       for (int i = 0; i < kCluster; ++i) {  // slot i goes to CTA (rank + i) % 8: self first, then round the ring
         const uint32_t r = (rank + i) & 7;
         raddr[i] = mapa(tc::s_u32(bhi) + (uint32_t)(i * (TR_NB * 128)) + my_off, r);  // K-block slot i of that CTA
-        rbar[i] = mapa(tc::s_u32(&h_full[0]), r);                                    // its h_full[0]
+        rbar[i] = mapa(tc::s_u32(&h_full[i >> 2]), r);                               // half i / 4 of its buffer 0
       }
 
       for (int s = 0; s < nsteps; ++s) {
         const int p = s & 1;
         TR_STAMP(5);
-        // ---- derive h_lo (8 float4 per thread); written with st.async to this CTA (async proxy: no proxy fence) ------
+        // ---- derive h_lo, half by half as the halves land (4 float4 per thread per half) ----------------------------
         if (s > 0) {
-          tc::bar_wait_wd(tc::s_u32(&h_full[p]), ph_h[p]); ph_h[p] ^= 1;
-          TR_STAMP(6);
           const float4 *src = reinterpret_cast<const float4 *>(bhi + p * TR_B_BYTES);
           float4 *dst = reinterpret_cast<float4 *>(blo);
 #pragma unroll
-          for (int i = 0; i < TR_B_BYTES / 16 / TR_EPI; ++i) {
-            const int f4 = et + TR_EPI * i;
-            const float4 v = src[f4];
-            dst[f4] = make_float4(tc::tf32_rest_raw(v.x), tc::tf32_rest_raw(v.y), tc::tf32_rest_raw(v.z), tc::tf32_rest_raw(v.w));
+          for (int g = 0; g < 2; ++g) {
+            tc::bar_wait_wd(tc::s_u32(&h_full[p * 2 + g]), ph_h[p]);
+            if (g == 0) TR_STAMP(6);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int f4 = g * 512 + et + TR_EPI * i;
+              const float4 v = src[f4];
+              dst[f4] = make_float4(tc::tf32_rest_raw(v.x), tc::tf32_rest_raw(v.y), tc::tf32_rest_raw(v.z), tc::tf32_rest_raw(v.w));
+            }
+            tc::fence_proxy_async();   // generic-proxy writes of h_lo -> visible to tcgen05.mma
+            tc::bar_arrive(tc::s_u32(&lo_ready[g]));
           }
-          tc::fence_proxy_async();   // generic-proxy writes of h_lo -> visible to tcgen05.mma
-          tc::bar_arrive(tc::s_u32(lo_ready));
+          ph_h[p] ^= 1;
         }
         TR_STAMP(7);
         // ---- next step's input projection (independent of h) ---------------------------------------------------
@@ -321,7 +335,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
           hn = make_float4(og.x * tanh_fast(c[0]), og.y * tanh_fast(c[1]), og.z * tanh_fast(c[2]), og.w * tanh_fast(c[3]));
         }
         if (s + 1 < nsteps) {  // h_s, raw fp32, into K-block `rank` of every CTA's next B buffer
-          const uint32_t boff = (uint32_t)((p ^ 1) * TR_B_BYTES), moff = (uint32_t)((p ^ 1) * 8);
+          const uint32_t boff = (uint32_t)((p ^ 1) * TR_B_BYTES), moff = (uint32_t)((p ^ 1) * 16);
 #pragma unroll
           for (int r = 0; r < kCluster; ++r) st_async_v4(raddr[r] + boff, hn, rbar[r] + moff);
         }
