@@ -203,6 +203,11 @@ int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, flo
  *   lse [B,nheads,S] or NULL: log-sum-exp of every query row, saved for the backward pass. */
 int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads, int hd, int w,
                       float *out, float *out_hi, float *out_lo, int Kp, float *lse, void *stream);
+/* The same on the tensor cores: warp-level mma.sync m16n8k8 TF32 with 3xTF32 compensation for Q K^T and P V, S kept in
+ * registers (hd in {8,16,32,64,112,128}).  Same contract and results; on B200 it runs at the speed of the CUDA-core
+ * kernel (measured), so mts_band_attn_fwd stays the default; MTS_ATTN_IMPL=mma switches the default entry over. */
+int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads, int hd, int w,
+                          float *out, float *out_hi, float *out_lo, int Kp, float *lse, void *stream);
 
 /* Backward of the encoder pieces (the reference: autograd through HF LongformerModel).
  * mts_ln_bwd: dy, pre (pre-LN values), stats (mean, rstd) as saved by the forward calls -> dx [M,d] (+ its TF32

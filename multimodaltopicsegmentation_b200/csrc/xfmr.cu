@@ -12,6 +12,8 @@
 // The dense layers themselves are mts_gemm_tf32x3 (tcgen05).  The kernels here are the HBM-bound glue:
 // LN kernels move 4d in + 4d (+ 8 Kp for the GEMM operand halves) out per token; the attention kernel reads
 // q,k,v (12d) and writes o (4d, or the two operand halves) per token and only ever touches in-window keys.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mts {
@@ -320,6 +322,232 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
     lse[((int64_t)b * nheads + head) * S + q0 + tid] = (q0 + tid < len) ? m_s[tid] + logf(l_s[tid]) : 0.0f;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Banded attention, forward, on the tensor cores: warp-level mma.sync m16n8k8 TF32 with 3xTF32 error compensation
+// (x = hi + lo, hi = the 19 bits the tensor core keeps, products hi*hi + hi*lo + lo*hi: fp32-grade scores and outputs).
+// One CTA = 64 queries of one head (4 warps x 16 rows); K/V tiles of 64 keys in shared memory; every warp only
+// multiplies the 8-key column tiles that intersect ITS 16-row band, so small windows do proportionally less work.
+// Q fragments stay in registers for the whole CTA; S never leaves registers: the accumulator fragment of S
+// (rows g, g+8; keys 2t, 2t+1) is re-used directly as the A fragment of P V by pairing MMA k-index t with key 2t and
+// t+4 with key 2t+1 on the V side (no shuffles, no shared-memory round trip).  Shared rows have stride hd + 4 words
+// (= 4 mod 8), which makes both the K-fragment reads (8 keys x 4 k) and the V-fragment reads (4 key pairs x 8
+// columns) bank-conflict free.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BM_BQ = 64, BM_TK = 64, BM_THREADS = 128;
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                                const uint32_t a3, const uint32_t b0, const uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_hi_bits(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+__device__ __forceinline__ uint32_t tf32_lo_bits(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
+
+template <int NHD>  // head dim / 8
+__global__ void __launch_bounds__(BM_THREADS, 2)
+    band_attn_fwd_mma_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths, int S,
+                             int nheads, int w, float *__restrict__ out, float *__restrict__ out_hi,
+                             float *__restrict__ out_lo, int Kp, float *__restrict__ lse) {
+  constexpr int HD = NHD * 8, RS = HD + 4, NV = HD / 4;
+  extern __shared__ __align__(16) float sm[];
+  float *Ks = sm;                 // [64][RS]  (first holds the scaled Q tile)
+  float *Vs = Ks + BM_TK * RS;    // [64][RS]
+
+  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * BM_BQ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int d = nheads * HD;
+  const int len = min(max(lengths[b], 0), S);
+  const int64_t row0 = (int64_t)b * S;
+  const int r0 = q0 + 16 * warp;             // first query row of this warp
+  const int ia = r0 + g, ib = r0 + g + 8;    // the two rows this thread holds
+
+  if (q0 >= len) {  // whole block is padding: exact zeros
+    for (int idx = tid; idx < BM_BQ * NV; idx += BM_THREADS) {
+      const int r = idx / NV, c = idx % NV;
+      if (q0 + r < S) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (out) reinterpret_cast<float4 *>(out + (row0 + q0 + r) * d + head * HD)[c] = z;
+        if (out_hi) {
+          reinterpret_cast<float4 *>(out_hi + (row0 + q0 + r) * Kp + head * HD)[c] = z;
+          reinterpret_cast<float4 *>(out_lo + (row0 + q0 + r) * Kp + head * HD)[c] = z;
+        }
+      }
+    }
+    if (lse && tid < BM_BQ && q0 + tid < S) lse[((int64_t)b * nheads + head) * S + q0 + tid] = 0.0f;
+    return;
+  }
+
+  // ---- Q tile -> shared (scaled as HF does, :513) -> A fragments in registers ------------------------------------
+  const float scale = sqrtf((float)HD);
+  for (int idx = tid; idx < BM_BQ * NV; idx += BM_THREADS) {
+    const int r = idx / NV, c = idx % NV;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < S) {
+      v = __ldg(reinterpret_cast<const float4 *>(qkv + (row0 + q0 + r) * ld + head * HD) + c);
+      v.x /= scale; v.y /= scale; v.z /= scale; v.w /= scale;
+    }
+    reinterpret_cast<float4 *>(Ks + r * RS)[c] = v;
+  }
+  __syncthreads();
+  float aq[NHD][4];
+#pragma unroll
+  for (int ks = 0; ks < NHD; ++ks) {
+    const float *qa = Ks + (16 * warp + g) * RS + 8 * ks + t;
+    aq[ks][0] = qa[0]; aq[ks][1] = qa[8 * RS]; aq[ks][2] = qa[4]; aq[ks][3] = qa[8 * RS + 4];
+  }
+  __syncthreads();
+
+  float oacc[NHD][4];
+#pragma unroll
+  for (int n = 0; n < NHD; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.0f; }
+  float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.0f, l_b = 0.0f;
+
+  const int kbeg = max(0, q0 - w), kend = min(len, q0 + BM_BQ + w);
+  for (int k0 = kbeg; k0 < kend; k0 += BM_TK) {
+    for (int idx = tid; idx < BM_TK * NV; idx += BM_THREADS) {
+      const int r = idx / NV, c = idx % NV;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + r < kend) {
+        const float *base = qkv + (row0 + k0 + r) * ld + head * HD;
+        kv = __ldg(reinterpret_cast<const float4 *>(base + d) + c);
+        vv = __ldg(reinterpret_cast<const float4 *>(base + 2 * d) + c);
+      }
+      reinterpret_cast<float4 *>(Ks + r * RS)[c] = kv;
+      reinterpret_cast<float4 *>(Vs + r * RS)[c] = vv;
+    }
+    __syncthreads();
+    // 8-key column tiles of this K tile that intersect the band of my 16 rows (warp-uniform)
+    int jlo = (r0 - w - k0) >> 3, jhi = (r0 + 15 + w - k0) >> 3;
+    jlo = max(jlo, 0);
+    jhi = min(jhi, min(BM_TK / 8 - 1, (kend - 1 - k0) >> 3));
+    if (r0 < len && jlo <= jhi) {
+      // ---- S = Q K^T on the active column tiles ------------------------------------------------------------------
+      float sacc[BM_TK / 8][4];
+#pragma unroll
+      for (int j = 0; j < BM_TK / 8; ++j) { sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f; }
+#pragma unroll
+      for (int ks = 0; ks < NHD; ++ks) {
+        const uint32_t h0 = tf32_hi_bits(aq[ks][0]), h1 = tf32_hi_bits(aq[ks][1]);
+        const uint32_t h2 = tf32_hi_bits(aq[ks][2]), h3 = tf32_hi_bits(aq[ks][3]);
+        const uint32_t l0 = tf32_lo_bits(aq[ks][0], h0), l1 = tf32_lo_bits(aq[ks][1], h1);
+        const uint32_t l2 = tf32_lo_bits(aq[ks][2], h2), l3 = tf32_lo_bits(aq[ks][3], h3);
+#pragma unroll
+        for (int j = 0; j < BM_TK / 8; ++j) {
+          if (j >= jlo && j <= jhi) {
+            const float *kp = Ks + (8 * j + g) * RS + 8 * ks + t;
+            const float kb0 = kp[0], kb1 = kp[4];
+            const uint32_t bh0 = tf32_hi_bits(kb0), bh1 = tf32_hi_bits(kb1);
+            const uint32_t bl0 = tf32_lo_bits(kb0, bh0), bl1 = tf32_lo_bits(kb1, bh1);
+            mma_tf32_16x8x8(sacc[j], h0, h1, h2, h3, bh0, bh1);
+            mma_tf32_16x8x8(sacc[j], h0, h1, h2, h3, bl0, bl1);
+            mma_tf32_16x8x8(sacc[j], l0, l1, l2, l3, bh0, bh1);
+          }
+        }
+      }
+      // ---- band / length mask, running softmax (rows ia and ib) ---------------------------------------------------
+      float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < BM_TK / 8; ++j) {
+        const bool act = (j >= jlo && j <= jhi);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int key = k0 + 8 * j + 2 * t + c;
+          const bool oka = act && ia < len && key < kend && key >= ia - w && key <= ia + w;
+          const bool okb = act && ib < len && key < kend && key >= ib - w && key <= ib + w;
+          sacc[j][c] = oka ? sacc[j][c] : -INFINITY;
+          sacc[j][2 + c] = okb ? sacc[j][2 + c] : -INFINITY;
+          mx_a = fmaxf(mx_a, sacc[j][c]);
+          mx_b = fmaxf(mx_b, sacc[j][2 + c]);
+        }
+      }
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1)); mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1)); mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+      const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+      const float mu_a = (mn_a == -INFINITY) ? 0.0f : mn_a, mu_b = (mn_b == -INFINITY) ? 0.0f : mn_b;
+      const float al_a = expf(m_a - mu_a), al_b = expf(m_b - mu_b);
+      m_a = mn_a; m_b = mn_b;
+      float ps_a = 0.0f, ps_b = 0.0f;
+#pragma unroll
+      for (int j = 0; j < BM_TK / 8; ++j) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          sacc[j][c] = expf(sacc[j][c] - mu_a);
+          sacc[j][2 + c] = expf(sacc[j][2 + c] - mu_b);
+          ps_a += sacc[j][c];
+          ps_b += sacc[j][2 + c];
+        }
+      }
+      l_a = l_a * al_a + ps_a;   // per-thread partial row sums; reduced over the quad at the end
+      l_b = l_b * al_b + ps_b;
+#pragma unroll
+      for (int n = 0; n < NHD; ++n) { oacc[n][0] *= al_a; oacc[n][1] *= al_a; oacc[n][2] *= al_b; oacc[n][3] *= al_b; }
+      // ---- O += P V: the S accumulator fragment is the A fragment (k-index t <-> key 2t, t+4 <-> key 2t+1) ----------
+#pragma unroll
+      for (int j = 0; j < BM_TK / 8; ++j) {
+        if (j >= jlo && j <= jhi) {
+          const uint32_t h0 = tf32_hi_bits(sacc[j][0]), h1 = tf32_hi_bits(sacc[j][2]);
+          const uint32_t h2 = tf32_hi_bits(sacc[j][1]), h3 = tf32_hi_bits(sacc[j][3]);
+          const uint32_t l0 = tf32_lo_bits(sacc[j][0], h0), l1 = tf32_lo_bits(sacc[j][2], h1);
+          const uint32_t l2 = tf32_lo_bits(sacc[j][1], h2), l3 = tf32_lo_bits(sacc[j][3], h3);
+          const float *vp = Vs + (8 * j + 2 * t) * RS + g;
+#pragma unroll
+          for (int n = 0; n < NHD; ++n) {
+            const float vb0 = vp[8 * n], vb1 = vp[RS + 8 * n];
+            const uint32_t bh0 = tf32_hi_bits(vb0), bh1 = tf32_hi_bits(vb1);
+            const uint32_t bl0 = tf32_lo_bits(vb0, bh0), bl1 = tf32_lo_bits(vb1, bh1);
+            mma_tf32_16x8x8(oacc[n], h0, h1, h2, h3, bh0, bh1);
+            mma_tf32_16x8x8(oacc[n], h0, h1, h2, h3, bl0, bl1);
+            mma_tf32_16x8x8(oacc[n], l0, l1, l2, l3, bh0, bh1);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 1); l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 1); l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+  const float inv_a = (ia < len) ? 1.0f / l_a : 0.0f, inv_b = (ib < len) ? 1.0f / l_b : 0.0f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int i = half ? ib : ia;
+    if (i >= S) continue;
+    const float inv = half ? inv_b : inv_a;
+#pragma unroll
+    for (int n = 0; n < NHD; ++n) {
+      const float2 v = make_float2(oacc[n][2 * half] * inv, oacc[n][2 * half + 1] * inv);
+      const int col = head * HD + 8 * n + 2 * t;
+      if (out) *reinterpret_cast<float2 *>(out + (row0 + i) * d + col) = v;
+      if (out_hi) {
+        const float hx = tf32_rn(v.x), hy = tf32_rn(v.y);
+        *reinterpret_cast<float2 *>(out_hi + (row0 + i) * Kp + col) = make_float2(hx, hy);
+        *reinterpret_cast<float2 *>(out_lo + (row0 + i) * Kp + col) = make_float2(tf32_rn(v.x - hx), tf32_rn(v.y - hy));
+      }
+    }
+    if (lse && t == 0)
+      lse[((int64_t)b * nheads + head) * S + i] = (i < len) ? (half ? m_b + logf(l_b) : m_a + logf(l_a)) : 0.0f;
+  }
+}
+
+template <int NHD>
+static int launch_band_mma(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads, int w, float *out,
+                           float *out_hi, float *out_lo, int Kp, float *lse, cudaStream_t st) {
+  constexpr int HD = NHD * 8;
+  const size_t smem = sizeof(float) * 2 * BM_TK * (HD + 4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTS_CUDA(cudaFuncSetAttribute(band_attn_fwd_mma_kernel<NHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const dim3 grid((S + BM_BQ - 1) / BM_BQ, nheads, B);
+  band_attn_fwd_mma_kernel<NHD><<<grid, BM_THREADS, smem, st>>>(qkv, ld, lengths, S, nheads, w, out, out_hi, out_lo, Kp, lse);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
 static unsigned ew_grid(int64_t total) {
   int64_t g = (total + 255) / 256;
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -376,6 +604,28 @@ extern "C" int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, 
   return 0;
 }
 
+extern "C" int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads,
+                                     int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
+                                     void *stream) {
+  MTS_REQUIRE(qkv && lengths && (out || out_hi), MTS_E_BADARG, "band_attn_fwd_mma: null pointer");
+  MTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), MTS_E_BADARG, "band_attn_fwd_mma: hi and lo go together");
+  MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_fwd_mma: bad shape");
+  MTS_REQUIRE(ld % 4 == 0 && ld >= 3 * nheads * hd, MTS_E_BADARG, "band_attn_fwd_mma: qkv row stride");
+  MTS_REQUIRE(!out_hi || Kp == nheads * hd, MTS_E_UNSUPPORTED, "band_attn_fwd_mma: the split output needs Kp == model width");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (hd) {
+    case 8: return launch_band_mma<1>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 16: return launch_band_mma<2>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 32: return launch_band_mma<4>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 64: return launch_band_mma<8>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 112: return launch_band_mma<14>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 128: return launch_band_mma<16>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    default: break;
+  }
+  set_error("band_attn_fwd_mma: head dim must be one of 8, 16, 32, 64, 112, 128");
+  return MTS_E_UNSUPPORTED;
+}
+
 extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads,
                                  int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
                                  void *stream) {
@@ -387,6 +637,10 @@ extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *le
   MTS_REQUIRE(!out_hi || (Kp % 32 == 0 && Kp >= nheads * hd), MTS_E_BADARG, "band_attn_fwd: Kp");
   MTS_REQUIRE(!out_hi || Kp == nheads * hd, MTS_E_UNSUPPORTED,
               "band_attn_fwd: the split output needs a model width that is a multiple of 32");
+  // MTS_ATTN_IMPL=mma routes to the tensor-core kernel (same results; measured the same speed on B200)
+  static const char *impl = getenv("MTS_ATTN_IMPL");
+  if (impl && impl[0] == 'm' && (hd == 8 || hd == 16 || hd == 32 || hd == 64 || hd == 112 || hd == 128))
+    return mts_band_attn_fwd_mma(qkv, ld, lengths, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, stream);
   const size_t smem = ba_smem_bytes(hd);
   static size_t smem_set = 0;
   if (smem > smem_set) {

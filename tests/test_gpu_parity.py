@@ -454,6 +454,7 @@ def load_params_allow_unused(module, fx, dev):
     return module.to(dev)
 
 
+@pytest.mark.parametrize("entry", ["mts_band_attn_fwd", "mts_band_attn_fwd_mma"])
 @pytest.mark.parametrize("B,S,h,hd,w,lens", [
     (2, 24, 4, 8, 4, [24, 13]),
     (3, 200, 2, 112, 48, [200, 77, 1]),
@@ -461,7 +462,8 @@ def load_params_allow_unused(module, fx, dev):
     (2, 96, 2, 32, 100, [96, 50]),      # window wider than the episode: dense attention
     (1, 700, 1, 16, 360, [650]),        # default-config reach (window 120 x 6 layers)
 ])
-def test_band_attention_forward(dev, B, S, h, hd, w, lens):
+def test_band_attention_forward(dev, B, S, h, hd, w, lens, entry):
+    """CUDA-core kernel and mma.sync tensor-core kernel against the numpy restatement of HF's banded attention."""
     from multimodaltopicsegmentation_b200 import ops
     from oracle import ref_numpy as rn
 
@@ -472,7 +474,7 @@ def test_band_attention_forward(dev, B, S, h, hd, w, lens):
     qkv_d = qkv.to(dev)
     out = torch.empty(B * S, d, device=dev)
     lse = torch.empty(B, h, S, device=dev)
-    ops._call("mts_band_attn_fwd", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
+    ops._call(entry, qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
               lse.data_ptr(), ops._stream())
     split = lambda t: t.view(B, S, h, hd).permute(0, 2, 1, 3).numpy()
     q = split(qkv[:, :d]) / np.float32(np.sqrt(hd))
@@ -483,7 +485,7 @@ def test_band_attention_forward(dev, B, S, h, hd, w, lens):
         assert float(out.view(B, S, d)[b, n:].abs().max() if n < S else 0.0) == 0.0
     if d % 32 == 0:  # fused operand split
         hl = torch.empty(2, B * S, d, device=dev)
-        ops._call("mts_band_attn_fwd", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, 0, hl[0].data_ptr(),
+        ops._call(entry, qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, 0, hl[0].data_ptr(),
                   hl[1].data_ptr(), d, 0, ops._stream())
         assert float(((hl[0] + hl[1]) - out).abs().max()) <= 2.0 ** -21 * float(out.abs().max())
         assert int((hl.view(torch.int32) & 0x1FFF).abs().max()) == 0
