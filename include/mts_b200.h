@@ -54,6 +54,12 @@ int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, int Kp, flo
 int mts_transpose_split(const float *src, int64_t bstride, int64_t ld, int rows, int cols, int T, int shift,
                         const int32_t *lengths, int Kp, float *hi, float *lo, void *stream);
 
+/* Device-side collater (the reference pads every batch on the host, EncoderDataset.py:91-152): episodes packed back
+ * to back in src [sum(len), D] with offsets[E+1] (int64) and lengths[E] (int32); for the B episode ids of a batch
+ *   out[b, t, :] = t < lengths[ids[b]] ? src[offsets[ids[b]] + t, :] : pad      (out [B,T,D]) */
+int mts_gather_pad(const float *src, const int64_t *offsets, const int32_t *lengths, const int32_t *ids, int B, int T,
+                   int D, float pad, float *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ GELU), fp32 in / fp32 out.
  *   replaces: nn.LSTM's input projection (models/NeuralArchitectures.py:113), nn.Linear heads

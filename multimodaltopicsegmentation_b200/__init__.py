@@ -7,6 +7,8 @@ its arithmetic in hand-written CUDA kernels behind the C ABI of include/mts_b200
 from . import _lib, ops  # noqa: F401
 from .EncoderDataset import AudioPortionDataset, AudioPortionDatasetInference, DevicePrefetcher, to_device  # noqa: F401
 from .lightning_model import TextSegmenter  # noqa: F401
+from .load_datasets_precomputed import (ResidentDataset, cross_validation_split, load_dataset_for_inference,  # noqa: F401
+                                        load_dataset_from_precomputed)
 from .metrics import compute_Pk, compute_window_diff, get_boundaries  # noqa: F401
 from .modules import CRF, RNN, BiLSTM, BiLSTMLateFusion, BiRnnCrf  # noqa: F401
 

@@ -76,6 +76,23 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float *__res
   }
 }
 
+// Device-side collater (EncoderDataset.py:91-152 builds the padded batch on the host, every step): episodes live
+// packed back to back in HBM; out[b, t, :] = t < lengths[ids[b]] ? src[offsets[ids[b]] + t, :] : pad.
+__global__ void __launch_bounds__(256) gather_pad_kernel(const float *__restrict__ src, const int64_t *__restrict__ offsets,
+                                                        const int32_t *__restrict__ lengths,
+                                                        const int32_t *__restrict__ ids, int B, int T, int D, float pad,
+                                                        float *__restrict__ out) {
+  const int64_t total = (int64_t)B * T * D;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % D);
+    const int64_t row = idx / D;
+    const int b = (int)(row / T), t = (int)(row % T);
+    const int e = ids[b];
+    out[idx] = (t < lengths[e]) ? __ldg(src + (offsets[e] + t) * D + c) : pad;
+  }
+}
+
 }  // namespace mts
 
 using namespace mts;
@@ -115,6 +132,15 @@ extern "C" int mts_transpose_split(const float *src, int64_t bstride, int64_t ld
   const dim3 grid((unsigned)(Kp / 32), (unsigned)((cols + 31) / 32));
   MTS_REQUIRE(grid.y <= 65535, MTS_E_UNSUPPORTED, "transpose_split: too many columns");
   transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, bstride, ld, rows, cols, T, shift, lengths, Kp, hi, lo);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mts_gather_pad(const float *src, const int64_t *offsets, const int32_t *lengths, const int32_t *ids, int B,
+                              int T, int D, float pad, float *out, void *stream) {
+  MTS_REQUIRE(src && offsets && lengths && ids && out, MTS_E_BADARG, "gather_pad: null pointer");
+  MTS_REQUIRE(B > 0 && T > 0 && D > 0, MTS_E_BADARG, "gather_pad: bad shape");
+  gather_pad_kernel<<<grid_for((int64_t)B * T * D), 256, 0, (cudaStream_t)stream>>>(src, offsets, lengths, ids, B, T, D, pad, out);
   MTS_LAUNCH_CHECK();
   return 0;
 }
