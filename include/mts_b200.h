@@ -161,6 +161,15 @@ int mts_seg_loss_bwd(const float *scores, const float *target, int64_t ldt, cons
                      int kind, float alpha, float gamma, float inv_count, const float *count_dev,
                      const float *grad_out, float *d_scores, void *stream);
 
+/* On-device evaluation counts (models/lightning_model.py:16-55, 607-637 walk every episode on the host through
+ * segeval).  tags [B, ld_tags] uint8 predictions (mts_head_fwd / Viterbi paths cast to uint8), target [B, ldt] float
+ * (the collater's tgt_tokens), lengths int32.  Both sides get their last unit forced to a boundary (as compute_Pk
+ * does); `zero_last` first clears it (the end_boundary option).  out [B, 8] int32 =
+ *   {Pk mismatches, WindowDiff mismatches, n - k (number of windows), k, tp, fp, fn, reference segments},
+ * k = segeval's default window round-half-even(n / (2 segments)), min 2.  The host forms Pk = out0/out2 etc. */
+int mts_seg_metrics(const uint8_t *tags, int64_t ld_tags, const float *target, int64_t ldt, const int32_t *lengths,
+                    int B, int T, int zero_last, int32_t *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Linear-chain CRF (models/CRF.py:98-240) on emissions [B,L,C], C = tags + 2 (START = C-2, STOP = C-1),
  * trans[i*C + j] = score of j -> i, lengths int32.  3 <= C <= 8.

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mts_head_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "mts_seg_loss_fwd": (c_int, [_P, _P, c_int64, _P, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P, _P]),
     "mts_seg_loss_bwd": (c_int, [_P, _P, c_int64, _P, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P]),
+    "mts_seg_metrics": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, _P, _P]),
     "mts_crf_viterbi": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mts_crf_nll_fwd": (c_int, [_P, _P, c_int64, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mts_crf_nll_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),

@@ -319,3 +319,109 @@ extern "C" int mts_seg_loss_bwd(const float *scores, const float *target, int64_
   return 0;
 }
 
+
+
+// ---------------------------------------------------------------------------------------------------------
+// On-device evaluation counts.  The reference's test_step walks every episode on the
+// host through segeval (models/lightning_model.py:16-55, 607-637: Decimal arithmetic over Python lists).  Pk and
+// WindowDiff are integer counts over prefix sums of the boundary flags; the host only forms the final ratios.
+//   per episode b (n = len_b), after forcing the last unit to close a segment on both sides (:27-30):
+//     seg_r[i], seg_h[i] = number of boundaries before position i   (exclusive prefix sums)
+//     k = round-half-even(n / (2 * #reference segments)), at least 2                  (segeval's default window)
+//     pk  = #{ i < n-k : (seg_r[i] == seg_r[i+k]) != (seg_h[i] == seg_h[i+k]) }
+//     wd  = #{ i < n-k : seg_r[i+k] - seg_r[i] != seg_h[i+k] - seg_h[i] }
+//   and tp / fp / fn of the raw boundary flags (F1 of the boundary class); `zero_last` first clears the last unit
+//   of both sides (the end_boundary option, :609-611).
+//   out[b][8] = {pk, wd, n - k, k, tp, fp, fn, #reference segments}
+// One CTA per episode; prefix sums by warp 0 (shuffle scan, 32 per iteration), counting by all threads.
+// ---------------------------------------------------------------------------------------------------------
+namespace mts {
+
+__global__ void __launch_bounds__(128) seg_metrics_kernel(const uint8_t *__restrict__ tags, int64_t ld_tags,
+                                                          const float *__restrict__ target, int64_t ldt,
+                                                          const int32_t *__restrict__ lengths, int T, int zero_last,
+                                                          int32_t *__restrict__ out) {
+  extern __shared__ int32_t seg[];  // seg_r[T + 1], seg_h[T + 1]
+  __shared__ int32_t cnt[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int n = min(max(lengths[b], 0), T);
+  int32_t *seg_r = seg, *seg_h = seg + (T + 1);
+  const uint8_t *hb = tags + (int64_t)b * ld_tags;
+  const float *rb = target + (int64_t)b * ldt;
+  if (tid < 8) cnt[tid] = 0;
+  __syncthreads();
+  if (n == 0) {
+    if (tid < 8) out[b * 8 + tid] = 0;
+    return;
+  }
+  // raw-flag confusion counts
+  int tp = 0, fp = 0, fn = 0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const bool last = (i == n - 1);
+    const bool r = !(zero_last && last) && rb[i] != 0.0f;
+    const bool h = !(zero_last && last) && hb[i] != 0;
+    tp += r && h; fp += !r && h; fn += r && !h;
+  }
+  atomicAdd(&cnt[4], tp); atomicAdd(&cnt[5], fp); atomicAdd(&cnt[6], fn);
+  // exclusive prefix sums of the flags with the last unit forced to 1
+  if (tid < 32) {
+    int carry_r = 0, carry_h = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      int r = 0, h = 0;
+      if (i < n) {
+        r = (i == n - 1) ? 1 : (rb[i] != 0.0f);
+        h = (i == n - 1) ? 1 : (hb[i] != 0);
+      }
+      int sr = r, sh = h;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ur = __shfl_up_sync(0xffffffffu, sr, o), uh = __shfl_up_sync(0xffffffffu, sh, o);
+        if (lane >= o) { sr += ur; sh += uh; }
+      }
+      if (i < n) { seg_r[i] = carry_r + sr - r; seg_h[i] = carry_h + sh - h; }
+      carry_r += __shfl_sync(0xffffffffu, sr, 31);
+      carry_h += __shfl_sync(0xffffffffu, sh, 31);
+    }
+    if (lane == 0) {
+      seg_r[n] = carry_r; seg_h[n] = carry_h;
+      const int den = 2 * carry_r;  // carry_r = number of reference segments (>= 1)
+      int q = n / den;
+      const int r2 = 2 * (n % den);
+      if (r2 > den || (r2 == den && (q & 1))) ++q;
+      cnt[3] = q > 1 ? q : 2;
+      cnt[7] = carry_r;
+    }
+  }
+  __syncthreads();
+  const int k = cnt[3];
+  int pk = 0, wd = 0;
+  for (int i = tid; i + k < n; i += blockDim.x) {
+    const int dr = seg_r[i + k] - seg_r[i], dh = seg_h[i + k] - seg_h[i];
+    pk += (dr == 0) != (dh == 0);
+    wd += dr != dh;
+  }
+  atomicAdd(&cnt[0], pk); atomicAdd(&cnt[1], wd);
+  __syncthreads();
+  if (tid == 0) cnt[2] = n - k;
+  __syncthreads();
+  if (tid < 8) out[b * 8 + tid] = cnt[tid];
+}
+
+}  // namespace mts
+
+extern "C" int mts_seg_metrics(const uint8_t *tags, int64_t ld_tags, const float *target, int64_t ldt,
+                               const int32_t *lengths, int B, int T, int zero_last, int32_t *out, void *stream) {
+  MTS_REQUIRE(tags && target && lengths && out, MTS_E_BADARG, "seg_metrics: null pointer");
+  MTS_REQUIRE(B > 0 && T > 0, MTS_E_BADARG, "seg_metrics: bad shape");
+  const size_t smem = (size_t)2 * (T + 1) * sizeof(int32_t);
+  MTS_REQUIRE(smem <= 200 * 1024, MTS_E_UNSUPPORTED, "seg_metrics: episodes longer than 25 000 sentences are not supported");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    MTS_CUDA(cudaFuncSetAttribute(mts::seg_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  mts::seg_metrics_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(tags, ld_tags, target, ldt, lengths, T, zero_last, out);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}

@@ -97,6 +97,8 @@ class TextSegmenter(_Base):
         self.results = []
         self.all_scores = bool(all_scores)
         self.scores = []
+        # additive switch: evaluation counts on the device; False = the reference's host walk
+        self.device_metrics = True
 
     def forward(self, x):
         return self.model(x)
@@ -140,6 +142,8 @@ class TextSegmenter(_Base):
         if self.metric.lower() in ("b", "scaiano"):
             raise NotImplementedError("B / WinPR evaluation is outside the hot path (SURVEY.md section 2 row 9)")
         lens_host = [int(v) for v in lengths]
+        if self.device_metrics and not self.zero_base and torch.is_tensor(target) and target.is_cuda:
+            return self._test_step_on_device(xs, lengths, target, lens_host)
         if self.zero_base:
             threshold = 0.4
             tags = [np.zeros(n) for n in lens_host]
@@ -164,6 +168,35 @@ class TextSegmenter(_Base):
             except AssertionError:
                 loss_wd += float(compute_Pk(np.array(tag), tgt))
         n = len(target)
+        results = {"Pk_loss": loss_pk / n, "F1_loss": loss_f1 / n, "WD_loss": loss_wd / n, "threshold": threshold}
+        key = {"F1": "F1_loss", "WD": "WD_loss"}.get(self.metric, "Pk_loss")
+        results["test_loss"] = results.pop(key)
+        if self.all:
+            self.results.append(results)
+        if self.all_scores and score is not None:
+            self.scores.extend([s.detach().cpu().numpy() for s in score])
+        self.log_dict(results, on_epoch=True, prog_bar=True)
+        return results
+
+    def _test_step_on_device(self, xs, lengths, target, lens_host):
+        """Same results as the host walk below, from per-episode integer counts made on the device
+        (mts_seg_metrics): one [B, 8] int32 copy instead of a tag matrix + a Python/Decimal loop per episode."""
+        from decimal import Decimal
+
+        threshold = self.threshold if self.threshold is not None else 0.4
+        if not threshold:
+            threshold = 0.5
+        self.model.th = threshold
+        score, tags_dev, lens = self.model.decode_device(*xs, lengths)
+        counts = ops.seg_metrics(tags_dev, target, lens, zero_last=self.eb).cpu().tolist()
+        loss_pk = loss_f1 = loss_wd = 0.0
+        for pk, wd, windows, _k, tp, fp, fn, _segs in counts:
+            pk_val = float(Decimal(pk) / Decimal(windows)) if windows > 0 else 0.0
+            loss_pk += pk_val
+            loss_wd += float(Decimal(wd) / Decimal(windows)) if windows > 0 else pk_val  # segeval asserts -> Pk (:634-637)
+            denom = 2 * tp + fp + fn
+            loss_f1 += 2.0 * tp / denom if denom else 0.0
+        n = len(counts)
         results = {"Pk_loss": loss_pk / n, "F1_loss": loss_f1 / n, "WD_loss": loss_wd / n, "threshold": threshold}
         key = {"F1": "F1_loss", "WD": "WD_loss"}.get(self.metric, "Pk_loss")
         results["test_loss"] = results.pop(key)

@@ -120,11 +120,15 @@ def _head_loss(mod, feats, lens, tags, global_count=None):
     return ops.SegLossFn.apply(scores, tags, lens, kind, mod.alpha, mod.gamma, inv)
 
 
-def _head_decode(mod, feats, lens, threshold):
+def _head_decode_device(mod, feats, lens, threshold):
+    """scores [B,T,n_out] and uint8 tags [B,T] (0xFF beyond len_b), both left on the device."""
     if mod.th is not None:
         threshold = mod.th
-    scores, tags = ops.head_decode(feats, mod.classification.weight.detach(), mod.classification.bias.detach(), lens,
-                                   threshold)
+    return ops.head_decode(feats, mod.classification.weight.detach(), mod.classification.bias.detach(), lens, threshold)
+
+
+def _head_decode(mod, feats, lens, threshold):
+    scores, tags = _head_decode_device(mod, feats, lens, threshold)
     return scores, _tags_to_lists(tags, lens, as_bool=True)
 
 
@@ -151,6 +155,13 @@ class BiLSTM(nn.Module):
         lens = _lens(lenghts, x0)
         with torch.no_grad():
             return _head_decode(self, self.model(xs, lens), lens, threshold)
+
+    def decode_device(self, xs, lenghts, threshold=0.4):
+        """forward() without the device->host hop: (scores, uint8 tags [B,T] on the device, Lengths)."""
+        x0 = xs[0] if isinstance(xs, (tuple, list)) else xs
+        lens = _lens(lenghts, x0)
+        with torch.no_grad():
+            return (*_head_decode_device(self, self.model(xs, lens), lens, threshold), lens)
 
 
 class BiLSTMLateFusion(nn.Module):
@@ -191,6 +202,11 @@ class BiLSTMLateFusion(nn.Module):
         lens = _lens(lenghts, x1)
         with torch.no_grad():
             return _head_decode(self, self._features(x1, x2, lens), lens, threshold)
+
+    def decode_device(self, x1, x2, lenghts, threshold=0.4):
+        lens = _lens(lenghts, x1)
+        with torch.no_grad():
+            return (*_head_decode_device(self, self._features(x1, x2, lens), lens, threshold), lens)
 
 
 class CRF(nn.Module):
@@ -255,3 +271,11 @@ class BiRnnCrf(nn.Module):
         lens = _lens(lenghts, x0)
         with torch.no_grad():
             return self.crf(self.model(xs, lens), lens)
+
+    def decode_device(self, xs, lenghts, threshold=None):
+        """(best_score [B], uint8 Viterbi tags [B,T] on the device (0xFF beyond len_b), Lengths)."""
+        x0 = xs[0] if isinstance(xs, (tuple, list)) else xs
+        lens = _lens(lenghts, x0)
+        with torch.no_grad():
+            best, paths = ops.crf_viterbi(self.crf.emissions(self.model(xs, lens)), lens, self.crf.transitions)
+        return best, paths.to(torch.uint8), lens  # -1 (padding) wraps to 0xFF

@@ -432,6 +432,22 @@ def head_decode(feats, w, b, lens, th):
     return scores, tags
 
 
+def seg_metrics(tags_u8, target, lens, zero_last=False):
+    """Per-episode evaluation counts on the device: int32 [B, 8] = {Pk mismatches, WindowDiff mismatches, windows,
+    k, tp, fp, fn, reference segments} (see mts_seg_metrics)."""
+    tags_u8 = _check(tags_u8, "tags", torch.uint8)
+    target = _check(target, "target")
+    if target.stride(-1) != 1:
+        target = target.contiguous()
+    if tags_u8.stride(-1) != 1:
+        tags_u8 = tags_u8.contiguous()
+    B, T = tags_u8.shape
+    out = torch.empty((B, 8), device=tags_u8.device, dtype=torch.int32)
+    _call("mts_seg_metrics", _ptr(tags_u8), tags_u8.stride(0), _ptr(target), target.stride(0), _ptr(lens.dev), B, T,
+          int(bool(zero_last)), _ptr(out), _stream())
+    return out
+
+
 LOSS_KINDS = {"FocalLoss": 0, "BinaryCrossEntropy": 1, "CrossEntropy": 2}
 
 

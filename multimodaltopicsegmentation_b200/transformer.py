@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import _build_head, _head_decode, _head_loss
+from .modules import _build_head, _head_decode, _head_decode_device, _head_loss
 
 _ptr, _call, _stream, _pad32 = ops._ptr, ops._call, ops._stream, ops._pad32
 
@@ -330,3 +330,8 @@ class Transformer_segmenter(nn.Module):
         lens = ops.Lengths(lenghts, xs.device, xs.shape[1]) if not isinstance(lenghts, ops.Lengths) else lenghts
         with torch.no_grad():
             return _head_decode(self, self.model(xs, lens), lens, threshold)
+
+    def decode_device(self, xs, lenghts, threshold=0.4):
+        lens = ops.Lengths(lenghts, xs.device, xs.shape[1]) if not isinstance(lenghts, ops.Lengths) else lenghts
+        with torch.no_grad():
+            return (*_head_decode_device(self, self.model(xs, lens), lens, threshold), lens)

@@ -838,3 +838,67 @@ def test_recurrence_backward_tensor_core_vs_fma(dev, B, T, n_enc):
     for b, n in enumerate(lengths):
         assert float(d_t[:, b * T + n:(b + 1) * T].abs().max() if n < T else 0.0) == 0.0
     close(d_t, d_f, rtol=1e-4, atol=2e-5 * float(d_f.abs().max()))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# on-device evaluation counts (Pk / WindowDiff / F1) against the host metrics (integer work: bit-exact)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("zero_last", [False, True])
+def test_seg_metrics_counts_bit_exact(dev, zero_last):
+    from decimal import Decimal
+
+    from multimodaltopicsegmentation_b200 import ops
+    from multimodaltopicsegmentation_b200.metrics import compute_Pk, compute_window_diff, f1_boundary
+
+    g = torch.Generator().manual_seed(17 + int(zero_last))
+    lengths = [1, 2, 3, 5, 17, 64, 65, 300, 1000, 8192, 40, 40]
+    B, T = len(lengths), max(lengths)
+    hyp = (torch.rand(B, T, generator=g) < 0.1).to(torch.uint8)
+    ref = (torch.rand(B, T, generator=g) < 0.08).float()
+    hyp[10] = 0; ref[10] = 0          # no boundaries at all
+    hyp[11] = 1; ref[11] = 1          # every sentence a boundary
+    for b, n in enumerate(lengths):
+        hyp[b, n:] = 255
+        ref[b, n:] = -1.0
+    lens = ops.Lengths(lengths, dev, T)
+    counts = ops.seg_metrics(hyp.to(dev), ref.to(dev), lens, zero_last=zero_last).cpu().tolist()
+    for b, n in enumerate(lengths):
+        h = hyp[b, :n].numpy().astype(int).copy()
+        r = ref[b, :n].numpy().astype(int).copy()
+        if zero_last:
+            h[-1] = 0; r[-1] = 0
+        pk, wd, windows, k, tp, fp, fn, segs = counts[b]
+        pk_host = compute_Pk(h, r)
+        assert (Decimal(pk) / Decimal(windows) if windows > 0 else Decimal(0)) == pk_host, (b, n)
+        try:
+            wd_host = compute_window_diff(h, r)
+            assert windows > 0 and Decimal(wd) / Decimal(windows) == wd_host, (b, n)
+        except AssertionError as e:
+            if windows > 0:
+                raise e
+        denom = 2 * tp + fp + fn
+        assert (2.0 * tp / denom if denom else 0.0) == f1_boundary(r, h)
+
+
+@pytest.mark.parametrize("arch,eb", [("BiLSTM", False), ("BiLSTM", True), ("biLSTMCRF", False)])
+def test_test_step_device_metrics_equal_host_walk(dev, arch, eb):
+    from multimodaltopicsegmentation_b200 import AudioPortionDataset, TextSegmenter, to_device
+
+    g = torch.Generator().manual_seed(23)
+    lines = []
+    for n in (30, 12, 21, 7, 55):
+        lab = (torch.rand(n, generator=g) < 0.2).long().tolist()
+        lab[-1] = 0
+        lines.append((torch.randn(n, 20, generator=g), lab, "ep"))
+    ds = AudioPortionDataset(lines, {"0": 0, "1": 1}, CRF=arch.lower().endswith("crf"), truncate=False)
+    batch = to_device(ds.collater([ds[i] for i in range(len(lines))]), dev)
+    torch.manual_seed(1)
+    seg = TextSegmenter(2, 20, 256, num_layers=1, architecture=arch, loss_fn="FocalLoss", threshold=0.45,
+                        end_boundary=eb, metric="Pk").to(dev)
+    seg.device_metrics = True
+    on_device = seg.test_step(batch, 0)
+    seg.device_metrics = False
+    on_host = seg.test_step(batch, 0)
+    assert set(on_device) == set(on_host)
+    for k in on_host:
+        assert on_device[k] == on_host[k], (k, on_device[k], on_host[k])
