@@ -32,8 +32,12 @@ const char *mts_last_error(void);      /* static string describing the last nega
 int mts_device_ok(void);               /* 0 when the current device is compute capability 10.x */
 
 /* ------------------------------------------------------------------------------------------------
- * Operand preparation.  3xTF32 GEMMs take every fp32 operand as a (hi, lo) pair of TF32-representable
- * fp32 matrices, K padded with zeros to a multiple of 32.
+ * Operand preparation.  The tensor-core GEMM (mts_gemm_tf32x3) takes every fp32 operand X [rows, K] as a pair
+ *   hi : fp32 [rows, Kp]  the values themselves, zero beyond K (kind::tf32 reads the top 19 bits of each word)
+ *   lo : the SAME byte size, holding bf16 [rows, 2 Kp]: per 32-wide K block 64 values, for an A operand
+ *        [ bf16(x_k), k = 0..31 | bf16(x_k - trunc_tf32(x_k)), k = 0..31 ], for a B operand the halves swapped
+ * with Kp = K rounded up to a multiple of 32.  Every kernel below that has (hi, lo) outputs writes this format
+ * (A side unless it takes a `side` argument).
  * ---------------------------------------------------------------------------------------------- */
 
 /* Early fusion (utils/load_datasets_precomputed.py:158-161 `torch.cat(embs, axis=-1)`) fused with the
@@ -43,8 +47,10 @@ int mts_device_ok(void);               /* 0 when the current device is compute c
 int mts_pack_rows_split(const float *src1, int64_t bstride1, int D1, const float *src2, int64_t bstride2, int D2,
                         int B, int T, int Kp, float *hi, float *lo, void *stream);
 
-/* Generic 2-D split: src [rows, cols] (row stride `ld`) -> hi/lo [rows, Kp]. */
-int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, int Kp, float *hi, float *lo, void *stream);
+/* Generic 2-D split: src [rows, cols] (row stride `ld`) -> hi/lo [rows, Kp].  side: 0 = the matrix will be the A
+ * operand of mts_gemm_tf32x3, 1 = the B operand (the two halves of the correction blocks are swapped, see below). */
+int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, int Kp, int side, float *hi, float *lo,
+                   void *stream);
 
 /* Transposed split for the weight-gradient GEMMs (a contraction over tokens needs both operands K-major along the
  * token axis):  out[c, r] = src[(r / T) * bstride + (r % T + shift) * ld + c] when 0 <= r % T + shift < lengths[r / T]
@@ -52,7 +58,7 @@ int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, int Kp, flo
  * shift in {-1, 0, +1}: the h_{t-1} / h_{t+1} operand of dW_hh without a shifted copy of the hidden states.
  * A plain [rows, cols] matrix: T = rows, bstride = 0. */
 int mts_transpose_split(const float *src, int64_t bstride, int64_t ld, int rows, int cols, int T, int shift,
-                        const int32_t *lengths, int Kp, float *hi, float *lo, void *stream);
+                        const int32_t *lengths, int Kp, int side, float *hi, float *lo, void *stream);
 
 /* Device-side collater (the reference pads every batch on the host, EncoderDataset.py:91-152): episodes packed back
  * to back in src [sum(len), D] with offsets[E+1] (int64) and lengths[E] (int32); for the B episode ids of a batch
@@ -64,9 +70,13 @@ int mts_gather_pad(const float *src, const int64_t *offsets, const int32_t *leng
  * GEMM:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ GELU), fp32 in / fp32 out.
  *   replaces: nn.LSTM's input projection (models/NeuralArchitectures.py:113), nn.Linear heads
  *   (models/CRF.py:299-310) and HF Longformer's dense layers (modeling_longformer.py:513-515,1067,1112,1126).
- * mts_gemm_tf32x3: tcgen05 + TMA, error-compensated 3xTF32 (fp32-grade accuracy).  A_hi/A_lo [M,Kp],
- *   B_hi/B_lo [N,Kp] as produced above; ldc in elements; epilogue: 0 none, 1 +bias, 2 +bias then GELU(erf).
- *   accumulate != 0 adds into C (used for split weight-gradient sums).
+ * mts_gemm_tf32x3: tcgen05 + TMA, error-compensated TF32 (fp32-grade accuracy): hi(A) hi(B)^T on kind::tf32 plus
+ *   the two 2^-11-sized correction terms as ONE bf16 product over the packed `lo` operands (the entry keeps its
+ *   historical name; it issues 2, not 3, instruction streams per product).  A_hi/A_lo [M,Kp], B_hi/B_lo [N,Kp] as
+ *   produced above (A side / B side); ldc in elements; epilogue: 0 none, 1 +bias, 2 +bias then GELU(erf).
+ *   accumulate != 0 adds into C.  K is split automatically (few output tiles with long K; always beyond K = 3072:
+ *   the tensor core truncates when aligning addends, a drift linear in K) and the partial tiles meet in C through
+ *   fp32 atomics.
  * mts_gemm_f32: exact-fp32 CUDA-core GEMM, C[M,N] (+)= op(A) op(B), used for the gradient products whose
  *   reduction runs over sentences and to validate the tensor-core kernel.  layout 0: A[M,K] B[N,K]^T;
  *   2: A[M,K] B[K,N]; 3: A[K,M]^T B[K,N].  splits > 1 = split-K with atomics.  shift != 0 (layouts 2,3) reads

@@ -22,8 +22,8 @@ SIGNATURES = {
     "mts_last_error": (ctypes.c_char_p, []),
     "mts_device_ok": (c_int, []),
     "mts_pack_rows_split": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
-    "mts_split_tf32": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
-    "mts_transpose_split": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "mts_split_tf32": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "mts_transpose_split": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P]),
     "mts_gather_pad": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P]),
     "mts_gemm_tf32x3": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, c_int, _P]),
     "mts_gemm_f32": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -61,6 +61,43 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(r);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Operand format of mts_gemm_tf32x3 (error-compensated TF32 GEMM: one TF32 product + one BF16 correction product).
+//   x = hi + rest,  hi = tf32_trunc(x) = what kind::tf32 reads of the raw fp32 word,  rest = x - hi (exact, <= 13 bits)
+//   A B^T ~= hi(A) hi(B)^T  [kind::tf32 on the RAW fp32 operands]
+//          + bf16(A) bf16(rest B)^T + bf16(rest A) bf16(B)^T   [kind::f16/bf16: the correction terms carry 2^-11 of the
+//            magnitude, so 8-bit mantissas leave a relative error of ~2^-19; bf16 runs K = 16 per MMA: 2 instead of 3
+//            instruction streams per product]
+//   "hi" array : fp32 [rows, Kp], the values themselves, zero beyond the logical width
+//   "lo" array : same byte size, holding bf16 [rows, 2 Kp]: per 32-wide K block 64 values --
+//                A operand (side 0): [ bf16(x_k), k = 0..31 | bf16(rest x_k), k = 0..31 ],  B operand (side 1): halves swapped,
+//                so that one K = 64 bf16 block of A times the same block of B sums both correction terms.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rest_exact(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ uint32_t bf16x2_bits(float first, float second) {  // `first` at the lower address
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+  return r;
+}
+__device__ __forceinline__ uint16_t bf16_bits(float x) { return (uint16_t)(bf16x2_bits(x, 0.0f) & 0xFFFFu); }
+// row = start of one operand row of the "lo" array (Kp floats = 2 Kp bf16); k = logical K index
+__device__ __forceinline__ void corr_store1(float *row, int k, float x, int side) {
+  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 5) * 64 + (k & 31);
+  b[side ? 32 : 0] = bf16_bits(x);
+  b[side ? 0 : 32] = bf16_bits(tf32_rest_exact(x));
+}
+__device__ __forceinline__ void corr_store2(float *row, int k, float2 v, int side) {  // k even
+  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 5) * 64 + (k & 31);
+  *reinterpret_cast<uint32_t *>(b + (side ? 32 : 0)) = bf16x2_bits(v.x, v.y);
+  *reinterpret_cast<uint32_t *>(b + (side ? 0 : 32)) = bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y));
+}
+__device__ __forceinline__ void corr_store4(float *row, int k, float4 v, int side) {  // k a multiple of 4
+  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 5) * 64 + (k & 31);
+  *reinterpret_cast<uint2 *>(b + (side ? 32 : 0)) = make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
+  *reinterpret_cast<uint2 *>(b + (side ? 0 : 32)) =
+      make_uint2(bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y)), bf16x2_bits(tf32_rest_exact(v.z), tf32_rest_exact(v.w)));
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 }  // namespace mts

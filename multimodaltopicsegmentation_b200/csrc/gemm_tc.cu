@@ -1,13 +1,19 @@
-// tcgen05 + TMA GEMM with error-compensated 3xTF32 accumulation (fp32-grade accuracy on the 5th-gen tensor
-// cores, which have no fp32-input mode).   C[M,N] = A[M,K] * B[N,K]^T (+bias) (+GELU)
+// tcgen05 + TMA GEMM with error-compensated TF32 accumulation (fp32-grade accuracy on the 5th-gen tensor cores,
+// which have no fp32-input mode).   C[M,N] = A[M,K] * B[N,K]^T (+bias) (+GELU)
 //
-//   A = A_hi + A_lo, B = B_hi + B_lo with *_hi the top 19 bits (what kind::tf32 reads) and *_lo the exact
-//   fp32 remainder (<= 13 significant bits).  D += A_hi B_hi + A_hi B_lo + A_lo B_hi ; the dropped
-//   A_lo B_lo term is ~2^-22 relative.  Operands come pre-split from pack.cu, K padded to 32.
+//   x = hi + rest with hi = the top 19 bits of the fp32 word (exactly what kind::tf32 reads: the tensor core
+//   truncates, measured) and rest = x - hi (exact, <= 13 bits, ~2^-11 of the magnitude).
+//       D += hi(A) hi(B)^T                                  4 MMAs kind::tf32 (K = 8) on the RAW fp32 operands
+//          + bf16(A) bf16(rest B)^T + bf16(rest A) bf16(B)^T   4 MMAs kind::f16 (bf16, K = 16) on the packed correction
+//                                                              operand: 64 bf16 per 32-wide K block, halves ordered
+//                                                              (x | rest) for A and (rest | x) for B  (common.cuh)
+//   The correction terms are 2^-11 of the product, so bf16's 8-bit mantissa leaves ~2^-19 relative error -- and the
+//   correction costs ONE instruction stream instead of the two of a 3xTF32 scheme (8 instead of 12 MMAs per k-block).
+//   The dropped rest*rest term is ~2^-22.  Operands come from pack.cu / the producing kernels, K padded to 32.
 //
 // Structure (one CTA per SM, persistent over output tiles, warp-specialised):
 //   warp 0   : TMA producer  -- 4 tiled tensor maps (SWIZZLE_128B, 32 fp32 = 128 B inner box) per k-block
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs of 128 x BN x 8 per k-block)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (4 tf32 + 4 bf16 MMAs of 128 x BN per k-block)
 //   warps 2-5: epilogue -- tcgen05.ld 32x32b from the 2-deep TMEM accumulator ring, bias / GELU, global store
 // Pipelines: smem full/empty mbarrier ring (TMA <-> MMA), TMEM full/empty ring (MMA <-> epilogue).
 #include <cuda.h>
@@ -81,12 +87,24 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with bf16 inputs (a_format = b_format = 1), fp32 accumulate, K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
@@ -172,9 +190,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           bar_expect_tx(fb, Cfg::kStageBytes);
           const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
           tma_load_2d(base, &map_a_hi, kb * TC_BK, m0, fb);
-          tma_load_2d(base + Cfg::kABytes, &map_a_lo, kb * TC_BK, m0, fb);
+          tma_load_2d(base + Cfg::kABytes, &map_a_lo, kb * 2 * TC_BK, m0, fb);  // bf16 elements: 64 per k-block
           tma_load_2d(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
-          tma_load_2d(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * TC_BK, n0, fb);
+          tma_load_2d(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * 2 * TC_BK, n0, fb);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -182,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN), idesc_c = make_idesc_bf16(TC_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc_stage = 0;
@@ -204,9 +222,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);  // +32 B per k-step inside the swizzle row
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));  // K = 8 fp32 = 32 B
+            umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_c, 1);                     // K = 16 bf16 = 32 B
           }
           umma_commit(s_u32(&empty_bar[stage]));  // smem slot free once these MMAs have read it
           if (kb == kb1 - 1) umma_commit(s_u32(&tfull_bar[acc_stage]));
@@ -300,14 +317,16 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap *map, const float *ptr, int rows, int Kp, int box_rows) {
+// corr = false: fp32 [rows, Kp], box 32 x box_rows;  corr = true: the packed bf16 correction operand, [rows, 2 Kp] bf16
+// in the same bytes, box 64 x box_rows.  Either way one box row is one 128-byte swizzle row.
+static int make_map(CUtensorMap *map, const float *ptr, int rows, int Kp, int box_rows, bool corr = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled not available"); return MTS_E_NODEVICE; }
-  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)(corr ? 2 * Kp : Kp), (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(corr ? 2 * TC_BK : TC_BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+  CUresult r = fn(map, corr ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled failed"); return MTS_E_BADARG; }
@@ -327,9 +346,9 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if ((rc = make_map(&ma_hi, A_hi, M, Kp, TC_BM))) return rc;
-  if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM))) return rc;
+  if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM, true))) return rc;
   if ((rc = make_map(&mb_hi, B_hi, N, Kp, BN))) return rc;
-  if ((rc = make_map(&mb_lo, B_lo, N, Kp, BN))) return rc;
+  if ((rc = make_map(&mb_lo, B_lo, N, Kp, BN, true))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -19,23 +19,21 @@ __global__ void __launch_bounds__(256) pack_rows_split_kernel(const float *__res
     float v = 0.0f;
     if (k < D1) v = __ldg(src1 + (int64_t)b * bstride1 + (int64_t)t * D1 + k);
     else if (k < D1 + D2) v = __ldg(src2 + (int64_t)b * bstride2 + (int64_t)t * D2 + (k - D1));
-    const float h = tf32_rn(v);
-    hi[idx] = h;
-    lo[idx] = tf32_rn(v - h);  // v - h is exact in fp32; rounding it to TF32 leaves an O(2^-23 |v|) residue
+    hi[idx] = v;                                // the tensor core reads the top 19 bits of the raw word
+    corr_store1(lo + row * Kp, k, v, 0);        // bf16 correction operand (A side), see common.cuh
   }
 }
 
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ src, int64_t ld, int rows, int cols,
-                                                         int Kp, float *__restrict__ hi, float *__restrict__ lo) {
+                                                         int Kp, int side, float *__restrict__ hi, float *__restrict__ lo) {
   const int64_t total = (int64_t)rows * Kp;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(idx % Kp);
     const int64_t r = idx / Kp;
     const float v = (k < cols) ? __ldg(src + r * ld + k) : 0.0f;
-    const float h = tf32_rn(v);
-    hi[idx] = h;
-    lo[idx] = tf32_rn(v - h);
+    hi[idx] = v;
+    corr_store1(lo + r * Kp, k, v, side);
   }
 }
 
@@ -47,7 +45,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
 // coalesced reads along the source columns, coalesced writes along the token axis.
 __global__ void __launch_bounds__(256) transpose_split_kernel(const float *__restrict__ src, int64_t bstride, int64_t ld,
                                                              int rows, int cols, int T, int shift,
-                                                             const int32_t *__restrict__ lengths, int Kp,
+                                                             const int32_t *__restrict__ lengths, int Kp, int side,
                                                              float *__restrict__ hi, float *__restrict__ lo) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -69,9 +67,8 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float *__res
     const int c = c0 + ty + 8 * i, r = r0 + tx;
     if (c < cols && r < Kp) {
       const float v = tile[tx][ty + 8 * i];
-      const float h = tf32_rn(v);
-      hi[(int64_t)c * Kp + r] = h;
-      lo[(int64_t)c * Kp + r] = tf32_rn(v - h);
+      hi[(int64_t)c * Kp + r] = v;
+      corr_store1(lo + (int64_t)c * Kp, r, v, side);
     }
   }
 }
@@ -115,23 +112,24 @@ extern "C" int mts_pack_rows_split(const float *src1, int64_t bstride1, int D1, 
   return 0;
 }
 
-extern "C" int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, int Kp, float *hi, float *lo,
+extern "C" int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, int Kp, int side, float *hi, float *lo,
                               void *stream) {
   MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "split_tf32: null pointer");
   MTS_REQUIRE(rows > 0 && cols > 0 && Kp % 32 == 0 && Kp >= cols, MTS_E_BADARG, "split_tf32: bad shape");
-  split_tf32_kernel<<<grid_for((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, hi, lo);
+  MTS_REQUIRE(side == 0 || side == 1, MTS_E_BADARG, "split_tf32: side must be 0 (A operand) or 1 (B operand)");
+  split_tf32_kernel<<<grid_for((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, side, hi, lo);
   MTS_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int mts_transpose_split(const float *src, int64_t bstride, int64_t ld, int rows, int cols, int T, int shift,
-                                   const int32_t *lengths, int Kp, float *hi, float *lo, void *stream) {
+                                   const int32_t *lengths, int Kp, int side, float *hi, float *lo, void *stream) {
   MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "transpose_split: null pointer");
   MTS_REQUIRE(rows > 0 && cols > 0 && T > 0 && Kp % 32 == 0 && Kp >= rows, MTS_E_BADARG, "transpose_split: bad shape");
   MTS_REQUIRE(shift >= -1 && shift <= 1, MTS_E_BADARG, "transpose_split: shift must be -1, 0 or +1");
   const dim3 grid((unsigned)(Kp / 32), (unsigned)((cols + 31) / 32));
   MTS_REQUIRE(grid.y <= 65535, MTS_E_UNSUPPORTED, "transpose_split: too many columns");
-  transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, bstride, ld, rows, cols, T, shift, lengths, Kp, hi, lo);
+  transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, bstride, ld, rows, cols, T, shift, lengths, Kp, side, hi, lo);
   MTS_LAUNCH_CHECK();
   return 0;
 }

@@ -89,18 +89,13 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
         o.w = (v[i].w - mean) * rstd * g.w + be.w;
         reinterpret_cast<float4 *>(y + (int64_t)row * d)[c] = o;
         if (y_hi) {
-          float4 h, l;
-          h.x = tf32_rn(o.x); l.x = tf32_rn(o.x - h.x);
-          h.y = tf32_rn(o.y); l.y = tf32_rn(o.y - h.y);
-          h.z = tf32_rn(o.z); l.z = tf32_rn(o.z - h.z);
-          h.w = tf32_rn(o.w); l.w = tf32_rn(o.w - h.w);
-          reinterpret_cast<float4 *>(y_hi + (int64_t)row * Kp)[c] = h;
-          reinterpret_cast<float4 *>(y_lo + (int64_t)row * Kp)[c] = l;
+          reinterpret_cast<float4 *>(y_hi + (int64_t)row * Kp)[c] = o;
+          corr_store4(y_lo + (int64_t)row * Kp, 4 * c, o, 0);
         }
       }
     }
     if (y_hi)
-      for (int c = d + lane; c < Kp; c += 32) { y_hi[(int64_t)row * Kp + c] = 0.0f; y_lo[(int64_t)row * Kp + c] = 0.0f; }
+      for (int c = d + lane; c < Kp; c += 32) { y_hi[(int64_t)row * Kp + c] = 0.0f; corr_store1(y_lo + (int64_t)row * Kp, c, 0.0f, 0); }
   }
 }
 
@@ -115,9 +110,8 @@ __global__ void __launch_bounds__(256) gelu_split_kernel(const float *__restrict
     const int64_t r = idx / Kp;
     const float v = (k < cols) ? gelu_erf(__ldg(src + r * ld + k)) : 0.0f;
     if (act && k < cols) act[r * cols + k] = v;
-    const float h = tf32_rn(v);
-    hi[idx] = h;
-    lo[idx] = tf32_rn(v - h);
+    hi[idx] = v;
+    corr_store1(lo + r * Kp, k, v, 0);
   }
 }
 
@@ -171,7 +165,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
           if (out) reinterpret_cast<float4 *>(out + (row0 + i) * d + head * hd)[cg] = z;
           if (out_hi) {
             reinterpret_cast<float4 *>(out_hi + (row0 + i) * Kp + head * hd)[cg] = z;
-            reinterpret_cast<float4 *>(out_lo + (row0 + i) * Kp + head * hd)[cg] = z;
+            corr_store4(out_lo + (row0 + i) * Kp, head * hd + 4 * cg, z, 0);
           }
         }
       }
@@ -308,13 +302,8 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
       }
       if (out) reinterpret_cast<float4 *>(out + (row0 + i) * d + head * hd)[cg] = v;
       if (out_hi) {
-        float4 h, l;
-        h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
-        h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
-        h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
-        h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
-        reinterpret_cast<float4 *>(out_hi + (row0 + i) * Kp + head * hd)[cg] = h;
-        reinterpret_cast<float4 *>(out_lo + (row0 + i) * Kp + head * hd)[cg] = l;
+        reinterpret_cast<float4 *>(out_hi + (row0 + i) * Kp + head * hd)[cg] = v;
+        corr_store4(out_lo + (row0 + i) * Kp, head * hd + 4 * cg, v, 0);
       }
     }
   }
@@ -372,7 +361,7 @@ __global__ void __launch_bounds__(BM_THREADS, 2)
         if (out) reinterpret_cast<float4 *>(out + (row0 + q0 + r) * d + head * HD)[c] = z;
         if (out_hi) {
           reinterpret_cast<float4 *>(out_hi + (row0 + q0 + r) * Kp + head * HD)[c] = z;
-          reinterpret_cast<float4 *>(out_lo + (row0 + q0 + r) * Kp + head * HD)[c] = z;
+          corr_store4(out_lo + (row0 + q0 + r) * Kp, head * HD + 4 * c, z, 0);
         }
       }
     }
@@ -522,9 +511,8 @@ __global__ void __launch_bounds__(BM_THREADS, 2)
       const int col = head * HD + 8 * n + 2 * t;
       if (out) *reinterpret_cast<float2 *>(out + (row0 + i) * d + col) = v;
       if (out_hi) {
-        const float hx = tf32_rn(v.x), hy = tf32_rn(v.y);
-        *reinterpret_cast<float2 *>(out_hi + (row0 + i) * Kp + col) = make_float2(hx, hy);
-        *reinterpret_cast<float2 *>(out_lo + (row0 + i) * Kp + col) = make_float2(tf32_rn(v.x - hx), tf32_rn(v.y - hy));
+        *reinterpret_cast<float2 *>(out_hi + (row0 + i) * Kp + col) = v;
+        corr_store2(out_lo + (row0 + i) * Kp, col, v, 0);
       }
     }
     if (lse && t == 0)

@@ -6,19 +6,13 @@
 //   banded softmax  dV = P^T dO, dP = dO V^T, dS = P (dP - rowsum(dO O)), dQ = dS K / sqrt(hd), dK = dS^T Q / sqrt(hd)
 //                   restricted to |i-j| <= w, j < len_b, i < len_b, with P recomputed from the saved log-sum-exp
 //   embeddings      dP[2 + t] = sum_b dpre[b, t], dE_type[0] = sum_{b,t} dpre[b, t]
-// Every dX that feeds a 3xTF32 GEMM is also written as its (hi, lo) TF32 halves in the same pass.
+// Every dX that feeds a tensor-core GEMM is also written as its operand pair (raw fp32 + bf16 correction, common.cuh)
+// in the same pass.
 #include "common.cuh"
 
 namespace mts {
 
 constexpr int LNB_MAXV = 16;
-
-__device__ __forceinline__ void split4(const float4 v, float4 &h, float4 &l) {
-  h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
-  h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
-  h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
-  h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
-}
 
 // one warp per row: dx (and its TF32 halves)
 __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const float *__restrict__ dy, const float *__restrict__ pre,
@@ -58,15 +52,13 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const float *__restrict_
         o.w = rstd * (g[i].w - m1 - xh[i].w * m2);
         reinterpret_cast<float4 *>(dx + (int64_t)row * d)[c] = o;
         if (dx_hi) {
-          float4 h, l;
-          split4(o, h, l);
-          reinterpret_cast<float4 *>(dx_hi + (int64_t)row * Kp)[c] = h;
-          reinterpret_cast<float4 *>(dx_lo + (int64_t)row * Kp)[c] = l;
+          reinterpret_cast<float4 *>(dx_hi + (int64_t)row * Kp)[c] = o;
+          corr_store4(dx_lo + (int64_t)row * Kp, 4 * c, o, 0);
         }
       }
     }
     if (dx_hi)
-      for (int c = d + lane; c < Kp; c += 32) { dx_hi[(int64_t)row * Kp + c] = 0.0f; dx_lo[(int64_t)row * Kp + c] = 0.0f; }
+      for (int c = d + lane; c < Kp; c += 32) { dx_hi[(int64_t)row * Kp + c] = 0.0f; corr_store1(dx_lo + (int64_t)row * Kp, c, 0.0f, 0); }
   }
 }
 
@@ -119,9 +111,8 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float *__restrict__
       v = __ldg(dz + r * cols + k) * (cdf + x * pdf);
       dzp[r * cols + k] = v;
     }
-    const float h = tf32_rn(v);
-    hi[idx] = h;
-    lo[idx] = tf32_rn(v - h);
+    hi[idx] = v;
+    corr_store1(lo + r * Kp, k, v, 0);
   }
 }
 

@@ -99,14 +99,18 @@ class Lengths:
 # --------------------------------------------------------------------------------------------------------
 # GEMMs
 # --------------------------------------------------------------------------------------------------------
-def split_tf32(src2d, cols=None, ld=None, rows=None):
-    """src [rows, cols] (row stride ld) -> (hi, lo) [rows, pad32(cols)]"""
+A_SIDE, B_SIDE = 0, 1  # which GEMM operand a split matrix will be (the correction halves are ordered per side)
+
+
+def split_tf32(src2d, cols=None, ld=None, rows=None, side=A_SIDE):
+    """src [rows, cols] (row stride ld) -> (hi, lo) [rows, pad32(cols)]: hi = the fp32 values (zero padded), lo = the
+    packed bf16 correction operand of the same byte size (include/mts_b200.h, "Operand preparation")."""
     rows = src2d.shape[0] if rows is None else rows
     cols = src2d.shape[1] if cols is None else cols
     ld = src2d.stride(0) if ld is None else ld
     kp = _pad32(cols)
     out = torch.empty((2, rows, kp), device=src2d.device, dtype=torch.float32)
-    _call("mts_split_tf32", _ptr(src2d), ld, rows, cols, kp, _ptr(out[0]), _ptr(out[1]), _stream())
+    _call("mts_split_tf32", _ptr(src2d), ld, rows, cols, kp, side, _ptr(out[0]), _ptr(out[1]), _stream())
     return out[0], out[1]
 
 
@@ -121,20 +125,20 @@ def pack_rows_split(x1, x2, B, T):
     return out[0], out[1]
 
 
-def transpose_split(src_ptr, bstride, ld, rows, cols, T, device, shift=0, lengths=None):
+def transpose_split(src_ptr, bstride, ld, rows, cols, T, device, shift=0, lengths=None, side=A_SIDE):
     """(hi, lo) [cols, pad32(rows)] of the transposed (optionally time-shifted / length-masked) source: the K-major
     operand of a GEMM that contracts over tokens (weight gradients)."""
     kp = _pad32(rows)
     out = torch.empty((2, cols, kp), device=device, dtype=torch.float32)
-    _call("mts_transpose_split", src_ptr, bstride, ld, rows, cols, T, shift, _ptr(lengths), kp, _ptr(out[0]), _ptr(out[1]),
-          _stream())
+    _call("mts_transpose_split", src_ptr, bstride, ld, rows, cols, T, shift, _ptr(lengths), kp, side, _ptr(out[0]),
+          _ptr(out[1]), _stream())
     return out[0], out[1]
 
 
 def weight_grad(dyT, x_ptr, x_bstride, x_ld, rows, n_in, T, out, ldc, device, shift=0, lengths=None):
     """out[n_out, n_in] (row stride ldc) = dY^T X over `rows` tokens on the tensor cores.  dyT = (hi, lo) of dY^T
     [n_out, pad32(rows)] from transpose_split; X is transposed / split here."""
-    xT = transpose_split(x_ptr, x_bstride, x_ld, rows, n_in, T, device, shift=shift, lengths=lengths)
+    xT = transpose_split(x_ptr, x_bstride, x_ld, rows, n_in, T, device, shift=shift, lengths=lengths, side=B_SIDE)
     gemm_tf32x3(dyT[0], dyT[1], xT[0], xT[1], None, out, dyT[0].shape[0], n_in, ldc=ldc)
 
 
@@ -233,7 +237,7 @@ class PackedLstm:
                     pair = torch.empty((2, 8 * H, kp), device=dev, dtype=torch.float32)
                     for d, w in enumerate((w_f, w_r)):
                         wc = w.detach().contiguous()
-                        _call("mts_split_tf32", _ptr(wc), D, 4 * H, D, kp, _ptr(pair[0, d * 4 * H:]),
+                        _call("mts_split_tf32", _ptr(wc), D, 4 * H, D, kp, B_SIDE, _ptr(pair[0, d * 4 * H:]),
                               _ptr(pair[1, d * 4 * H:]), _stream())
                     wih.append((pair[0], pair[1]))
                     bias.append(torch.cat([bi_f.detach() + bh_f.detach(), bi_r.detach() + bh_r.detach()]))
@@ -265,7 +269,7 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
                 a_hi, a_lo = split_tf32(src, cols=2 * H, ld=n_enc * 2 * H, rows=B * T)
             w_hi, w_lo = layers[layer]["wih"][e]
             if GEMM_IMPL == "simt":
-                a, w = a_hi + a_lo, w_hi + w_lo
+                a, w = a_hi, w_hi  # the hi arrays are the fp32 values themselves
                 gemm_f32(_ptr(a), a.shape[1], _ptr(w), w.shape[1], layers[layer]["bias"][e], _ptr(gx[e]), 8 * H, B * T,
                          8 * H, a.shape[1], layout=0, epilogue=1)
             else:
@@ -350,7 +354,8 @@ class BiLstmStackFn(torch.autograd.Function):
                         if "wih_t" not in layers[layer]:
                             layers[layer]["wih_t"] = {}
                         if e not in layers[layer]["wih_t"]:
-                            layers[layer]["wih_t"][e] = split_tf32(torch.cat([w_f.detach(), w_r.detach()], dim=0).t().contiguous())
+                            layers[layer]["wih_t"][e] = split_tf32(torch.cat([w_f.detach(), w_r.detach()], dim=0).t().contiguous(),
+                                                                   side=B_SIDE)
                         wt = layers[layer]["wih_t"][e]
                         dg_hl = split_tf32(dg)
                         gemm_tf32x3(dg_hl[0], dg_hl[1], wt[0], wt[1], None, dy_next.view(N, ycols)[:, e * 2 * H:], N, D,

@@ -146,12 +146,13 @@ class PackedEncoder:
                 sa = lyr.attention.self
                 wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], dim=0).contiguous()
                 bqkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias]).contiguous()
-                ent = {"wqkv": ops.split_tf32(wqkv), "bqkv": bqkv,
-                       "wo": ops.split_tf32(lyr.attention.output.dense.weight.detach().contiguous()),
+                B_ = ops.B_SIDE
+                ent = {"wqkv": ops.split_tf32(wqkv, side=B_), "bqkv": bqkv,
+                       "wo": ops.split_tf32(lyr.attention.output.dense.weight.detach().contiguous(), side=B_),
                        "bo": lyr.attention.output.dense.bias.detach().contiguous(),
-                       "w1": ops.split_tf32(lyr.intermediate.dense.weight.detach().contiguous()),
+                       "w1": ops.split_tf32(lyr.intermediate.dense.weight.detach().contiguous(), side=B_),
                        "b1": lyr.intermediate.dense.bias.detach().contiguous(),
-                       "w2": ops.split_tf32(lyr.output.dense.weight.detach().contiguous()),
+                       "w2": ops.split_tf32(lyr.output.dense.weight.detach().contiguous(), side=B_),
                        "b2": lyr.output.dense.bias.detach().contiguous()}
                 layers.append(ent)
         self.key, self.layers = key, layers
@@ -165,10 +166,11 @@ class PackedEncoder:
             sa = lyr.attention.self
             with torch.no_grad():
                 wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], dim=0)
-                ent["wqkv_t"] = ops.split_tf32(wqkv.t().contiguous())
-                ent["wo_t"] = ops.split_tf32(lyr.attention.output.dense.weight.detach().t().contiguous())
-                ent["w1_t"] = ops.split_tf32(lyr.intermediate.dense.weight.detach().t().contiguous())
-                ent["w2_t"] = ops.split_tf32(lyr.output.dense.weight.detach().t().contiguous())
+                B_ = ops.B_SIDE
+                ent["wqkv_t"] = ops.split_tf32(wqkv.t().contiguous(), side=B_)
+                ent["wo_t"] = ops.split_tf32(lyr.attention.output.dense.weight.detach().t().contiguous(), side=B_)
+                ent["w1_t"] = ops.split_tf32(lyr.intermediate.dense.weight.detach().t().contiguous(), side=B_)
+                ent["w2_t"] = ops.split_tf32(lyr.output.dense.weight.detach().t().contiguous(), side=B_)
         return ent
 
 
@@ -219,7 +221,7 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
         else:  # widths that are not a multiple of 32: plain output, then the generic (zero-padding) split
             _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), B, S, nheads, hd, reaches[l], _ptr(a), 0, 0, 0,
                   _ptr(lse), _stream())
-            _call("mts_split_tf32", _ptr(a), d, M, d, kp, _ptr(a_hl[0]), _ptr(a_hl[1]), _stream())
+            _call("mts_split_tf32", _ptr(a), d, M, d, kp, ops.A_SIDE, _ptr(a_hl[0]), _ptr(a_hl[1]), _stream())
         t = torch.empty((M, d), device=dev, dtype=torch.float32)
         ops.gemm_tf32x3(a_hl[0], a_hl[1], ent["wo"][0], ent["wo"][1], ent["bo"], t, M, d, epilogue=1)
         ln1 = lyr.attention.output.LayerNorm

@@ -75,7 +75,7 @@ def bench_gemm():
         bias = torch.randn(N, device=dev)
         c = torch.empty(M, N, device=dev)
         a_hi, a_lo = ops.split_tf32(a)
-        b_hi, b_lo = ops.split_tf32(b)
+        b_hi, b_lo = ops.split_tf32(b, side=ops.B_SIDE)
         ms = timeit(lambda: ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, c, M, N, epilogue=1))
         ms2 = timeit(lambda: ops.gemm_f32(a.data_ptr(), K, b.data_ptr(), K, bias, c.data_ptr(), N, M, N, K, layout=0,
                                           epilogue=1), iters=3, warmup=1)
@@ -95,7 +95,7 @@ if __name__ == "__main__":
         M, N, K = 19200, 2048, 896
         a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)
         c = torch.empty(M, N, device=dev)
-        a_hi, a_lo = ops.split_tf32(a); b_hi, b_lo = ops.split_tf32(b)
+        a_hi, a_lo = ops.split_tf32(a); b_hi, b_lo = ops.split_tf32(b, side=ops.B_SIDE)
         for _ in range(3):
             ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, c, M, N, epilogue=1)
         torch.cuda.synchronize()

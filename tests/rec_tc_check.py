@@ -19,12 +19,12 @@ def trunc_check():
     M, N, K = 256, 128, 64
     a = torch.randn(M, K, generator=g).to(dev)
     b = torch.randn(N, K, generator=g).to(dev)
-    b_hi, _ = ops.split_tf32(b)
+    b_hi = (b.view(torch.int32) & ~0x1FFF).view(torch.float32).contiguous()   # TF32-representable B
     zeros_a, zeros_b = torch.zeros_like(a), torch.zeros_like(b_hi)
     c = torch.empty(M, N, device=dev)
-    ops.gemm_tf32x3(a.contiguous(), zeros_a, b_hi, zeros_b, None, c, M, N)
+    ops.gemm_tf32x3(a.contiguous(), zeros_a, b_hi, zeros_b, None, c, M, N)     # zero correction operands: hi x hi only
     a_tr = (a.view(torch.int32) & ~0x1FFF).view(torch.float32)
-    a_rn, _ = ops.split_tf32(a)
+    a_rn = ((a.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)      # round-to-nearest TF32 (ties away)
     ref_tr = a_tr.double() @ b_hi.double().T
     ref_rn = a_rn.double() @ b_hi.double().T
     e_tr = float((c.double() - ref_tr).abs().max())

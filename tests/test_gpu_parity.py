@@ -42,6 +42,22 @@ def tags_equal(tags, arr):
         assert [int(v) for v in t] == arr[b, :n].tolist()
 
 
+def check_operand_pair(hi, lo, x, side):
+    """(hi, lo) as the tensor-core GEMM wants them (include/mts_b200.h "Operand preparation"): hi = x zero-padded to Kp;
+    lo = bf16 [rows, 2 Kp], per 32-wide K block [bf16(x) | bf16(x - trunc_tf32(x))] for an A operand, swapped for B."""
+    rows, K = x.shape
+    kp = hi.shape[1]
+    assert kp % 32 == 0 and kp >= K and tuple(lo.shape) == (rows, kp)
+    assert torch.equal(hi[:, :K], x) and float(hi[:, K:].abs().max() if kp > K else 0.0) == 0.0
+    xp = torch.zeros(rows, kp, device=x.device)
+    xp[:, :K] = x
+    rest = xp - (xp.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    blocks = lo.contiguous().view(torch.bfloat16).view(rows, kp // 32, 2, 32)
+    first, second = (rest, xp) if side else (xp, rest)
+    assert torch.equal(blocks[:, :, 0], first.to(torch.bfloat16).view(rows, kp // 32, 32))
+    assert torch.equal(blocks[:, :, 1], second.to(torch.bfloat16).view(rows, kp // 32, 32))
+
+
 def close(a, b, rtol=RTOL, atol=ATOL, msg=""):
     a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
     b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
@@ -74,11 +90,10 @@ def test_gemm_tf32x3(dev, M, N, K):
     a, b, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
     ad, bd, biasd = a.to(dev), b.to(dev), bias.to(dev)
     ref = (ad.double() @ bd.double().T + biasd.double())
-    a_hi, a_lo = ops.split_tf32(ad)
-    b_hi, b_lo = ops.split_tf32(bd)
-    # the split loses at most ~2^-23 relative, and both halves are TF32-representable (low 13 bits clear)
-    assert ((a_hi[:, :K] + a_lo[:, :K]) - ad).abs().max().item() <= 2.0 ** -22 * ad.abs().max().item()
-    assert int((a_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((a_lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    a_hi, a_lo = ops.split_tf32(ad, side=ops.A_SIDE)
+    b_hi, b_lo = ops.split_tf32(bd, side=ops.B_SIDE)
+    check_operand_pair(a_hi, a_lo, ad, side=0)
+    check_operand_pair(b_hi, b_lo, bd, side=1)
     c = torch.empty(M, N, device=dev)
     ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, biasd, c, M, N, epilogue=1)
     err = (c.double() - ref).abs().max().item()
@@ -109,7 +124,7 @@ def test_transpose_split(dev, rows, cols, T, shift):
     lengths = torch.randint(1, T + 1, (B,), generator=g)
     lens_dev = lengths.to(torch.int32).to(dev) if shift else None
     hi, lo = ops.transpose_split(src.data_ptr(), src.stride(0), src.stride(1), rows, cols, T, dev, shift=shift,
-                                 lengths=lens_dev)
+                                 lengths=lens_dev, side=ops.B_SIDE)
     kp = (rows + 31) // 32 * 32
     assert tuple(hi.shape) == (cols, kp)
     ref = torch.zeros(rows, cols)
@@ -119,10 +134,7 @@ def test_transpose_split(dev, rows, cols, T, shift):
         for t in range(T):
             if 0 <= t + shift < n:
                 ref[b * T + t] = sc[b, t + shift, :cols]
-    got = (hi + lo)[:, :rows].T.cpu()
-    assert float((got - ref).abs().max()) <= 2.0 ** -21 * float(ref.abs().max())
-    assert float(hi[:, rows:].abs().max() if kp > rows else 0.0) == 0.0
-    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    check_operand_pair(hi, lo, ref.T.contiguous().to(dev), side=1)
 
 
 def test_gemm_tn_shift(dev):
@@ -487,8 +499,7 @@ def test_band_attention_forward(dev, B, S, h, hd, w, lens, entry):
         hl = torch.empty(2, B * S, d, device=dev)
         ops._call(entry, qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, 0, hl[0].data_ptr(),
                   hl[1].data_ptr(), d, 0, ops._stream())
-        assert float(((hl[0] + hl[1]) - out).abs().max()) <= 2.0 ** -21 * float(out.abs().max())
-        assert int((hl.view(torch.int32) & 0x1FFF).abs().max()) == 0
+        check_operand_pair(hl[0], hl[1], out, side=0)
 
 
 def test_transformer_golden_forward(dev, golden):
@@ -612,8 +623,7 @@ def test_layer_norm_forward_backward(dev, M, d):
     ops._call("mts_add_ln_fwd", a_d.data_ptr(), r_d.data_ptr(), g_d.data_ptr(), b_d.data_ptr(), M, d, 1e-12,
               y.data_ptr(), hl[0].data_ptr(), hl[1].data_ptr(), kp, pre_d.data_ptr(), stats.data_ptr(), ops._stream())
     close(y, ref.detach().float(), rtol=1e-4, atol=1e-5)
-    assert float(((hl[0] + hl[1])[:, :d] - y).abs().max()) <= 2.0 ** -21 * float(y.abs().max())
-    assert float(hl[:, :, d:].abs().max() if kp > d else 0.0) == 0.0
+    check_operand_pair(hl[0], hl[1], y, side=0)
     dx, dhl = torch.empty(M, d, device=dev), torch.empty(2, M, kp, device=dev)
     dgb = torch.empty(2, d, device=dev)
     ws = torch.empty(_lib.load().mts_ln_bwd_ws_bytes(M, d) // 4, device=dev)
@@ -623,7 +633,7 @@ def test_layer_norm_forward_backward(dev, M, d):
     close(dx, pre.grad.float(), rtol=1e-4, atol=1e-5 * float(pre.grad.abs().max()))
     close(dgb[0], gamma.grad.float(), rtol=1e-4, atol=1e-5 * float(gamma.grad.abs().max()))
     close(dgb[1], beta.grad.float(), rtol=1e-4, atol=1e-5 * float(beta.grad.abs().max()))
-    assert float(((dhl[0] + dhl[1])[:, :d] - dx).abs().max()) <= 2.0 ** -21 * float(dx.abs().max())
+    check_operand_pair(dhl[0], dhl[1], dx, side=0)
 
 
 def test_transformer_golden_backward(dev, golden):
