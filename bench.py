@@ -307,9 +307,10 @@ def transformer_bench(m, dev, rank, world, steps, barrier):
     if gemm:
         tf = tokens * XF_GEMM_FLOPS_PER_TOKEN * c["L"] / (sum(gemm) / 1e3) / 1e12
         out["roofline_dense"] = {"kernel": "gemm_tf32x3_kernel (24 launches)", "bound": "tensor",
-                                 "achieved_tflops_fp32_equiv": tf, "achieved_tflops_tf32_issued": 3 * tf,
-                                 "note": "3xTF32: three tensor-core products per fp32-grade product; TF32 dense peak is "
-                                         "half the bf16 figure in MEASURED_PEAKS.json"}
+                                 "achieved_tflops_fp32_equiv": tf, "achieved_tflops_issued": 2 * tf,
+                                 "note": "error-compensated TF32: one TF32 product + one bf16 correction product per "
+                                         "fp32-grade product (issued = 2x); measured bound is L2 -> SM operand traffic "
+                                         "(8 B per operand element), see DESIGN.md section 4"}
     return out
 
 
@@ -485,7 +486,7 @@ def run_ours(args, rank, world, local_rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": c["B"], "global_batch": c["B"] * world,
-                   "l2": "4 rotating input sets (275 MB) exceed the 126 MB L2", "gemm": "tcgen05 3xTF32",
+                   "l2": "4 rotating input sets (275 MB) exceed the 126 MB L2", "gemm": "tcgen05 TF32 + bf16 correction",
                    "launch": "one CUDA graph per input set (7 kernels)" if graphs is not None else "eager launches",
                    "recurrence": "tcgen05 3xTF32, W_hh resident in TMEM" if rec_name.endswith("_tc") else "packed-fp32 FMA",
                    "parallelism": f"dp{world} (episodes sharded, final all_gather of tags)" if world > 1 else "single GPU"},

@@ -17,6 +17,7 @@
 //   warps 2-5: epilogue -- tcgen05.ld 32x32b from the 2-deep TMEM accumulator ring, bias / GELU, global store
 // Pipelines: smem full/empty mbarrier ring (TMA <-> MMA), TMEM full/empty ring (MMA <-> epilogue).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -71,6 +72,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 (SW128) [61,64)
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -112,6 +129,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {  // arrives on `bar` in every CTA of the mask
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -129,7 +152,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int BN>
+// CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster compute vertically adjacent output tiles
+// (same N tile): each loads its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory.
+// The kernel is bound by L2 -> SM operand traffic: 8 bytes per operand element, 96 KB per CTA per k-block against
+// ~43 B/clk/SM of L2 bandwidth (6300 B/clk chip-wide) = ~2250 cycles, twice the 1024 cycles of the 8 MMAs.  Measured:
+// multicast across 2 CTAs gains 2-3 % (the L2 already merges the two unicast reads), across 4 / 8 CTAs it LOSES 40 %
+// (32-row TMA boxes, 4-8 CTAs in lockstep).  The remedy that really halves the B bytes per SM is the 2-SM MMA
+// (cta_group::2): next round.
+template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -147,7 +177,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+  // tiles_m counts GROUPS of CL vertically adjacent 128-row tiles; this CTA takes row tile (group * CL + crank)
+  const int tiles_m = ((M + TC_BM - 1) / TC_BM + CL - 1) / CL, tiles_n = (N + BN - 1) / BN;
   // work item = (output tile, K split).  splits > 1 (long-K, few-tile products such as weight gradients, which would
   // otherwise leave most SMs idle): every item reduces its K range and adds its partial tile into C with fp32 atomics
   // (C holds zeros or the running sum; the bias rides on split 0).
@@ -156,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int kb_per = (total_kb + splits - 1) / splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { bar_init(s_u32(&full_bar[s]), 1); bar_init(s_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < kStages; ++s) { bar_init(s_u32(&full_bar[s]), 1); bar_init(s_u32(&empty_bar[s]), CL); }
     for (int a = 0; a < 2; ++a) { bar_init(s_u32(&tfull_bar[a]), 1); bar_init(s_u32(&tempty_bar[a]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -168,6 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers exist before any multicast load / commit can reach them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -180,19 +215,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      for (int item = cluster_id; item < num_tiles; item += n_clusters) {
         const int tile = item / splits, sp = item % splits;
-        const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+        const int m0 = ((tile / tiles_n) * CL + (int)crank) * TC_BM, n0 = (tile % tiles_n) * BN;
         const int kb0 = sp * kb_per, kb1 = min(total_kb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
-          bar_wait(s_u32(&empty_bar[stage]), phase ^ 1);
+          bar_wait(s_u32(&empty_bar[stage]), phase ^ 1);  // CL == 2: BOTH CTAs have consumed this stage
           const uint32_t fb = s_u32(&full_bar[stage]);
           bar_expect_tx(fb, Cfg::kStageBytes);
           const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
           tma_load_2d(base, &map_a_hi, kb * TC_BK, m0, fb);
           tma_load_2d(base + Cfg::kABytes, &map_a_lo, kb * 2 * TC_BK, m0, fb);  // bf16 elements: 64 per k-block
-          tma_load_2d(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
-          tma_load_2d(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * 2 * TC_BK, n0, fb);
+          if (CL == 1) {
+            tma_load_2d(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
+            tma_load_2d(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * 2 * TC_BK, n0, fb);
+          } else {  // my 1/CL slice of the B tile (rows n0 + crank * BN/CL ...), delivered to every CTA at the same offsets
+            const uint32_t part = crank * (uint32_t)(Cfg::kBBytes / CL);
+            tma_load_2d_mc(base + 2 * Cfg::kABytes + part, &map_b_hi, kb * TC_BK, n0 + (int)crank * (BN / CL), fb, kMask);
+            tma_load_2d_mc(base + 2 * Cfg::kABytes + Cfg::kBBytes + part, &map_b_lo, kb * 2 * TC_BK,
+                           n0 + (int)crank * (BN / CL), fb, kMask);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -205,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      for (int item = cluster_id; item < num_tiles; item += n_clusters) {
         const int sp = item % splits;
         const int kb0 = sp * kb_per, kb1 = min(total_kb, kb0 + kb_per);
         if (kb0 >= kb1) continue;  // empty trailing split: nothing to add (the epilogue skips it too)
@@ -225,7 +267,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));  // K = 8 fp32 = 32 B
             umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_c, 1);                     // K = 16 bf16 = 32 B
           }
-          umma_commit(s_u32(&empty_bar[stage]));  // smem slot free once these MMAs have read it
+          if (CL == 1) umma_commit(s_u32(&empty_bar[stage]));  // smem slot free once these MMAs have read it
+          else umma_commit_mc(s_u32(&empty_bar[stage]), kMask);  // ... tells both producers (the peer writes B here too)
           if (kb == kb1 - 1) umma_commit(s_u32(&tfull_bar[acc_stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -237,10 +280,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+    for (int item = cluster_id; item < num_tiles; item += n_clusters) {
       const int tile = item / splits, sp = item % splits;
       if (sp * kb_per >= total_kb) continue;
-      const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+      const int m0 = ((tile / tiles_n) * CL + (int)crank) * TC_BM, n0 = (tile % tiles_n) * BN;
       bar_wait(s_u32(&tfull_bar[acc_stage]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int m = m0 + q * 32 + lane;
@@ -292,6 +335,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still deliver into its shared memory / barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
@@ -343,18 +387,28 @@ template <int BN>
 static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
                      float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
+  const int tiles_m1 = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
+  // clusters of 2 (B tile multicast) whenever there are at least two row tiles; MTS_GEMM_CLUSTER=1 keeps single CTAs
+  static const char *force = getenv("MTS_GEMM_CLUSTER");
+  int CL = tiles_m1 >= 2 ? 2 : 1;
+  if (force) {
+    const int want = atoi(force);
+    if ((want == 1 || want == 2) && tiles_m1 >= want) CL = want;  // 4 / 8 were measured ~1.7x SLOWER (32-row boxes, lockstep)
+  }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if ((rc = make_map(&ma_hi, A_hi, M, Kp, TC_BM))) return rc;
   if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM, true))) return rc;
-  if ((rc = make_map(&mb_hi, B_hi, N, Kp, BN))) return rc;
-  if ((rc = make_map(&mb_lo, B_lo, N, Kp, BN, true))) return rc;
+  if ((rc = make_map(&mb_hi, B_hi, N, Kp, BN / CL))) return rc;
+  if ((rc = make_map(&mb_lo, B_lo, N, Kp, BN / CL, true))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+  const int tiles = ((tiles_m1 + CL - 1) / CL) * tiles_n;  // cluster work items before the K split
+  const int slots = kNumSMs / CL;                           // clusters resident at once
   // Split K (a) when the output has too few tiles to fill the device and K is long (weight gradients: K = all tokens)
   // and (b) ALWAYS beyond 3072 elements of K: the tensor core truncates when it aligns addends to its fp32
   // accumulator, a drift that grows linearly with K (measured 9e-6 of the output scale at K = 896); chunks of <= 2048
@@ -362,8 +416,8 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
   int splits = 1;
   const int num_kb = Kp / TC_BK;
   if (epilogue != 2) {
-    if (tiles * 2 <= kNumSMs && num_kb >= 32) {
-      splits = kNumSMs / tiles;
+    if (tiles * 2 <= slots && num_kb >= 32) {
+      splits = slots / tiles;
       if (splits > num_kb / 8) splits = num_kb / 8;
     }
     if (num_kb > 96 && splits < (num_kb + 63) / 64) splits = (num_kb + 63) / 64;
@@ -375,9 +429,26 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
     zero_matrix_kernel<<<zg, 256, 0, st>>>(C, M, N, ldc);
   }
   const int items = tiles * splits;
-  const int grid = items < kNumSMs ? items : kNumSMs;
-  gemm_tf32x3_kernel<BN><<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc,
-                                                                   epilogue, accumulate, splits);
+  const int grid = (items < slots ? items : slots) * CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = (unsigned)CL;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  if (CL == 2) {
+    MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
+                                accumulate, splits));
+  } else {
+    MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 1>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
+                                accumulate, splits));
+  }
   MTS_LAUNCH_CHECK();
   return 0;
 }
