@@ -34,8 +34,8 @@ int mts_device_ok(void);               /* 0 when the current device is compute c
 /* ------------------------------------------------------------------------------------------------
  * Operand preparation.  The tensor-core GEMM (mts_gemm_tf32x3) takes every fp32 operand X [rows, K] as a pair
  *   hi : fp32 [rows, Kp]  the values themselves, zero beyond K (kind::tf32 reads the top 19 bits of each word)
- *   lo : the SAME byte size, holding bf16 [rows, 2 Kp]: per 32-wide K block 64 values, for an A operand
- *        [ bf16(x_k), k = 0..31 | bf16(x_k - trunc_tf32(x_k)), k = 0..31 ], for a B operand the halves swapped
+ *   lo : the SAME byte size, holding bf16 [rows, 2 Kp]: per 16-wide K block 32 values, for an A operand
+ *        [ bf16(x_k), k = 0..15 | bf16(x_k - trunc_tf32(x_k)), k = 0..15 ], for a B operand the halves swapped
  * with Kp = K rounded up to a multiple of 32.  Every kernel below that has (hi, lo) outputs writes this format
  * (A side unless it takes a `side` argument).
  * ---------------------------------------------------------------------------------------------- */

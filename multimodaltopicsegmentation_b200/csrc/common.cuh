@@ -69,9 +69,9 @@ __device__ __forceinline__ float tf32_rn(float x) {
 //            magnitude, so 8-bit mantissas leave a relative error of ~2^-19; bf16 runs K = 16 per MMA: 2 instead of 3
 //            instruction streams per product]
 //   "hi" array : fp32 [rows, Kp], the values themselves, zero beyond the logical width
-//   "lo" array : same byte size, holding bf16 [rows, 2 Kp]: per 32-wide K block 64 values --
-//                A operand (side 0): [ bf16(x_k), k = 0..31 | bf16(rest x_k), k = 0..31 ],  B operand (side 1): halves swapped,
-//                so that one K = 64 bf16 block of A times the same block of B sums both correction terms.
+//   "lo" array : same byte size, holding bf16 [rows, 2 Kp]: per 16-wide K block 32 values (64 bytes) --
+//                A operand (side 0): [ bf16(x_k), k = 0..15 | bf16(rest x_k), k = 0..15 ],  B operand (side 1): halves swapped,
+//                so that one K = 32 bf16 block of A times the same block of B (two K = 16 MMAs) sums both correction terms.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_rest_exact(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ uint32_t bf16x2_bits(float first, float second) {  // `first` at the lower address
@@ -82,19 +82,19 @@ __device__ __forceinline__ uint32_t bf16x2_bits(float first, float second) {  //
 __device__ __forceinline__ uint16_t bf16_bits(float x) { return (uint16_t)(bf16x2_bits(x, 0.0f) & 0xFFFFu); }
 // row = start of one operand row of the "lo" array (Kp floats = 2 Kp bf16); k = logical K index
 __device__ __forceinline__ void corr_store1(float *row, int k, float x, int side) {
-  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 5) * 64 + (k & 31);
-  b[side ? 32 : 0] = bf16_bits(x);
-  b[side ? 0 : 32] = bf16_bits(tf32_rest_exact(x));
+  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 4) * 32 + (k & 15);
+  b[side ? 16 : 0] = bf16_bits(x);
+  b[side ? 0 : 16] = bf16_bits(tf32_rest_exact(x));
 }
 __device__ __forceinline__ void corr_store2(float *row, int k, float2 v, int side) {  // k even
-  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 5) * 64 + (k & 31);
-  *reinterpret_cast<uint32_t *>(b + (side ? 32 : 0)) = bf16x2_bits(v.x, v.y);
-  *reinterpret_cast<uint32_t *>(b + (side ? 0 : 32)) = bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y));
+  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 4) * 32 + (k & 15);
+  *reinterpret_cast<uint32_t *>(b + (side ? 16 : 0)) = bf16x2_bits(v.x, v.y);
+  *reinterpret_cast<uint32_t *>(b + (side ? 0 : 16)) = bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y));
 }
 __device__ __forceinline__ void corr_store4(float *row, int k, float4 v, int side) {  // k a multiple of 4
-  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 5) * 64 + (k & 31);
-  *reinterpret_cast<uint2 *>(b + (side ? 32 : 0)) = make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
-  *reinterpret_cast<uint2 *>(b + (side ? 0 : 32)) =
+  uint16_t *b = reinterpret_cast<uint16_t *>(row) + (k >> 4) * 32 + (k & 15);
+  *reinterpret_cast<uint2 *>(b + (side ? 16 : 0)) = make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
+  *reinterpret_cast<uint2 *>(b + (side ? 0 : 16)) =
       make_uint2(bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y)), bf16x2_bits(tf32_rest_exact(v.z), tf32_rest_exact(v.w)));
 }
 

@@ -5,7 +5,7 @@
 //   truncates, measured) and rest = x - hi (exact, <= 13 bits, ~2^-11 of the magnitude).
 //       D += hi(A) hi(B)^T                                  4 MMAs kind::tf32 (K = 8) on the RAW fp32 operands
 //          + bf16(A) bf16(rest B)^T + bf16(rest A) bf16(B)^T   4 MMAs kind::f16 (bf16, K = 16) on the packed correction
-//                                                              operand: 64 bf16 per 32-wide K block, halves ordered
+//                                                              operand: 32 bf16 per 16-wide K block, halves ordered
 //                                                              (x | rest) for A and (rest | x) for B  (common.cuh)
 //   The correction terms are 2^-11 of the product, so bf16's 8-bit mantissa leaves ~2^-19 relative error -- and the
 //   correction costs ONE instruction stream instead of the two of a 3xTF32 scheme (8 instead of 12 MMAs per k-block).
@@ -157,8 +157,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // The kernel is bound by L2 -> SM operand traffic: 8 bytes per operand element, 96 KB per CTA per k-block against
 // ~43 B/clk/SM of L2 bandwidth (6300 B/clk chip-wide) = ~2250 cycles, twice the 1024 cycles of the 8 MMAs.  Measured:
 // multicast across 2 CTAs gains 2-3 % (the L2 already merges the two unicast reads), across 4 / 8 CTAs it LOSES 40 %
-// (32-row TMA boxes, 4-8 CTAs in lockstep).  The remedy that really halves the B bytes per SM is the 2-SM MMA
-// (cta_group::2): next round.
+// (32-row TMA boxes, 4-8 CTAs in lockstep).  A 256 x 256-tile single-CTA variant (k-blocks of 16 = 64-byte TMA rows,
+// SWIZZLE_64B, 3 stages, un-buffered accumulators: 1.5x fewer operand bytes per MAC on paper) was also built and
+// measured 20-30 % SLOWER (245760 x 2688 x 896: 5.46 vs 4.57 ms): half-cache-line TMA rows cost more than they save.
+// The remedy that really halves the B bytes per SM with full 128-byte rows is the 2-SM MMA (cta_group::2): next round.
 template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,

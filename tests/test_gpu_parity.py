@@ -44,7 +44,7 @@ def tags_equal(tags, arr):
 
 def check_operand_pair(hi, lo, x, side):
     """(hi, lo) as the tensor-core GEMM wants them (include/mts_b200.h "Operand preparation"): hi = x zero-padded to Kp;
-    lo = bf16 [rows, 2 Kp], per 32-wide K block [bf16(x) | bf16(x - trunc_tf32(x))] for an A operand, swapped for B."""
+    lo = bf16 [rows, 2 Kp], per 16-wide K block [bf16(x) | bf16(x - trunc_tf32(x))] for an A operand, swapped for B."""
     rows, K = x.shape
     kp = hi.shape[1]
     assert kp % 32 == 0 and kp >= K and tuple(lo.shape) == (rows, kp)
@@ -52,10 +52,10 @@ def check_operand_pair(hi, lo, x, side):
     xp = torch.zeros(rows, kp, device=x.device)
     xp[:, :K] = x
     rest = xp - (xp.view(torch.int32) & ~0x1FFF).view(torch.float32)
-    blocks = lo.contiguous().view(torch.bfloat16).view(rows, kp // 32, 2, 32)
+    blocks = lo.contiguous().view(torch.bfloat16).view(rows, kp // 16, 2, 16)
     first, second = (rest, xp) if side else (xp, rest)
-    assert torch.equal(blocks[:, :, 0], first.to(torch.bfloat16).view(rows, kp // 32, 32))
-    assert torch.equal(blocks[:, :, 1], second.to(torch.bfloat16).view(rows, kp // 32, 32))
+    assert torch.equal(blocks[:, :, 0], first.to(torch.bfloat16).view(rows, kp // 16, 16))
+    assert torch.equal(blocks[:, :, 1], second.to(torch.bfloat16).view(rows, kp // 16, 16))
 
 
 def close(a, b, rtol=RTOL, atol=ATOL, msg=""):
