@@ -6,9 +6,10 @@
 // hidden units [32r, 32r+32) and the matching 128 gate rows of W_hh.  Per step:
 //   cell phase  (4 epilogue warps, thread = 1 unit x 4 episodes): dh = dy + sum of the 8 partial products received
 //               from the cluster, gate derivatives, dp -> dgx in HBM and -> the B operand (hi/lo) in shared memory;
-//   matvec      partial dh_prev[256 x 16] = W_hh[my 128 rows, :]^T dp[my 128 rows, 16]: 96 tcgen05.mma 128x16x8
-//               (two M blocks x 16 k-steps x 3xTF32), the transposed weight slice resident in TENSOR MEMORY
-//               (hi 2 x 128 columns, lo 2 x 96 columns + a 32 KB shared-memory tail), accumulators in TMEM;
+//   matvec      partial dh_prev[256 x 16] = W_hh[my 128 rows, :]^T dp[my 128 rows, 16]: 64 tcgen05.mma 128x16
+//               (two M blocks x 4 gate blocks x (4 kind::tf32 K = 8 + 4 bf16 K = 16): TF32 product + packed bf16
+//               correction product, common.cuh), the transposed weight slice resident in TENSOR MEMORY (raw fp32
+//               2 x 128 columns, packed correction 2 x 96 columns + a 32 KB shared-memory tail), accumulators in TMEM;
 //   reduce-scatter: each CTA reads its accumulators (tcgen05.ld) and pushes the 32 x 16 block of every owner CTA
 //               into that CTA's receive buffer with st.async (DSMEM) completing on its mbarrier -- 16 KB per CTA per
 //               step, the same volume as the forward all-gather.
@@ -92,23 +93,27 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
           for (int kb = 0; kb < 4; ++kb) {
-            float hi[32], lo[32];
+            float hi[32], cr[32];  // cr: two 16-k blocks of [bf16(W) x16 | bf16(rest W) x16], packed 2 per word
             const float *col = W + (size_t)(kb * kH + rank * kUnits) * kH + m;  // W_hh[gate kb, unit 32 r + j][m]
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = __ldg(col + (size_t)j * kH);
-              hi[j] = x;
-              lo[j] = tc::tf32_rest(x);
-            }
+            for (int j = 0; j < 32; ++j) hi[j] = __ldg(col + (size_t)j * kH);
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float x0 = hi[blk * 16 + 2 * j], x1 = hi[blk * 16 + 2 * j + 1];
+                cr[blk * 16 + j] = __uint_as_float(bf16x2_bits(x0, x1));
+                cr[blk * 16 + 8 + j] = __uint_as_float(bf16x2_bits(tf32_rest_exact(x0), tf32_rest_exact(x1)));
+              }
             tc::tmem_st32(trow + (uint32_t)((mb ? TB_HI1 : TB_HI0) + kb * 32), hi);
             if (kb < 3) {
-              tc::tmem_st32(trow + (uint32_t)((mb ? TB_LO1 : TB_LO0) + kb * 32), lo);
+              tc::tmem_st32(trow + (uint32_t)((mb ? TB_LO1 : TB_LO0) + kb * 32), cr);
             } else {
               const int r = q * 32 + lane;
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4 *>(wtail + mb * 16384 + r * 128 + ((i ^ (r & 7)) << 4)) =
-                    make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                    make_float4(cr[4 * i], cr[4 * i + 1], cr[4 * i + 2], cr[4 * i + 3]);
             }
           }
         }
@@ -134,7 +139,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
 
     if (warp == 0) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = tc::idesc_tf32(128, TB_NB);
+      constexpr uint32_t idesc = tc::idesc_tf32(128, TB_NB), idesc_c = tc::idesc_bf16(128, TB_NB);
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t tail_a = tc::s_u32(wtail), bhi_a = tc::s_u32(bhi), blo_a = tc::s_u32(blo);
       const bool leader = tc::elect_one();
@@ -155,9 +160,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
               const uint64_t bl = tc::desc_sw128(blo_a + kb * (TB_NB * 128) + k * 32);
               if (leader) {
                 tc::umma_tf32_ts(d_tmem, a_hi + (uint32_t)(kb * 32 + k * 8), bh, idesc, (kb | k) != 0);
-                if (kb < 3) tc::umma_tf32_ts(d_tmem, a_lo + (uint32_t)(kb * 32 + k * 8), bh, idesc, 1);
-                else tc::umma_tf32_ss(d_tmem, tc::desc_sw128(tail_a + mb * 16384 + k * 32), bh, idesc, 1);
-                tc::umma_tf32_ts(d_tmem, a_hi + (uint32_t)(kb * 32 + k * 8), bl, idesc, 1);
+                if (kb < 3) tc::umma_bf16_ts(d_tmem, a_lo + (uint32_t)(kb * 32 + k * 8), bl, idesc_c, 1);
+                else tc::umma_bf16_ss(d_tmem, tc::desc_sw128(tail_a + mb * 16384 + k * 32), bl, idesc_c, 1);
               }
             }
           }
@@ -232,16 +236,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
             float *o = dgx + dgx_enc + ((size_t)bq[i] * T + t) * 8 * kH + gcol;
             o[0] = dpi; o[kH] = dpf; o[2 * kH] = dpg; o[3 * kH] = dpo;
           }
-          // B operand: row e (episode), K index = gate * 32 + unit -> K-block = gate
+          // B operand: row e (episode), K index = gate * 32 + unit -> K-block = gate.  Raw fp32 for the TF32 product,
+          // and the packed correction operand (B side: per 16-k block [bf16(rest) x16 | bf16(dp) x16])
           const uint32_t off = tc::sw128_offset(e, cu);
-          *reinterpret_cast<float *>(bhi + 0 * (TB_NB * 128) + off) = dpi;
-          *reinterpret_cast<float *>(bhi + 1 * (TB_NB * 128) + off) = dpf;
-          *reinterpret_cast<float *>(bhi + 2 * (TB_NB * 128) + off) = dpg;
-          *reinterpret_cast<float *>(bhi + 3 * (TB_NB * 128) + off) = dpo;
-          *reinterpret_cast<float *>(blo + 0 * (TB_NB * 128) + off) = tc::tf32_rest_raw(dpi);
-          *reinterpret_cast<float *>(blo + 1 * (TB_NB * 128) + off) = tc::tf32_rest_raw(dpf);
-          *reinterpret_cast<float *>(blo + 2 * (TB_NB * 128) + off) = tc::tf32_rest_raw(dpg);
-          *reinterpret_cast<float *>(blo + 3 * (TB_NB * 128) + off) = tc::tf32_rest_raw(dpo);
+          const int cb = (cu >> 4) * 64 + (cu & 15) * 2;  // byte offset of bf16(rest dp[cu]) inside the 128-byte row
+          const uint32_t off_lo = (uint32_t)(e * 128 + ((((cb >> 4) ^ (e & 7)) << 4) | (cb & 15)));
+          const uint32_t off_hb = (uint32_t)(e * 128 + (((((cb + 32) >> 4) ^ (e & 7)) << 4) | (cb & 15)));
+          const float dpv[4] = {dpi, dpf, dpg, dpo};
+#pragma unroll
+          for (int gsel = 0; gsel < 4; ++gsel) {
+            *reinterpret_cast<float *>(bhi + gsel * (TB_NB * 128) + off) = dpv[gsel];
+            *reinterpret_cast<uint16_t *>(blo + gsel * (TB_NB * 128) + off_lo) = bf16_bits(tf32_rest_exact(dpv[gsel]));
+            *reinterpret_cast<uint16_t *>(blo + gsel * (TB_NB * 128) + off_hb) = bf16_bits(dpv[gsel]);
+          }
         }
         if (s + 1 < nsteps) {
           tc::fence_proxy_async();   // generic-proxy writes of the operand -> visible to tcgen05.mma

@@ -4,14 +4,17 @@
 //
 // One cluster of 8 CTAs advances a tile of 16 episodes of one (direction, encoder).  CTA r owns hidden units
 // [32r, 32r+32) = 128 gate rows of W_hh and keeps them ON CHIP for the whole sequence, split for 3xTF32:
-//     W = W_hi + W_lo,  W_hi = what kind::tf32 reads of the fp32 word (top 19 bits), W_lo = tf32(W - W_hi)
-//     W_hi : TENSOR MEMORY, 128 lanes x 256 columns   } the A operand of the .ts form of tcgen05.mma: measured
-//     W_lo : TENSOR MEMORY, 128 lanes x 224 columns   } ~14 cycles per 128x16x8 MMA against ~38 when A is read from
-//     W_lo tail (k >= 224): shared memory, 16 KB      } shared memory (4 KB of A per instruction at 128 B/clk)
-// (2 MB of split weights per direction do not fit the shared memory of 8 SMs; TMEM holds all but 16 KB per CTA,
-//  the last 32 TMEM columns hold the accumulator.)
+//     W = W_hi + rest,  W_hi = what kind::tf32 reads of the raw fp32 word (top 19 bits), rest = W - W_hi (exact)
+//     W h ~= W_hi h_hi [kind::tf32] + bf16(W) bf16(rest h) + bf16(rest W) bf16(h) [kind::f16/bf16, one packed product:
+//            the same error-compensation scheme as the GEMM, common.cuh] -- 64 instead of 96 MMAs per step
+//     W raw fp32      : TENSOR MEMORY, 128 lanes x 256 columns                } the A operand of the .ts form of
+//     W correction    : TENSOR MEMORY, 128 lanes x 224 columns (bf16 pairs:   } tcgen05.mma: measured ~14 cycles per
+//                       per 16 k [bf16(W) | bf16(rest W)], k < 224)           } 128x16 MMA against ~38 when A is read
+//     correction tail (k >= 224): shared memory, 16 KB                        } from shared memory
+// (2 MB of operands per direction do not fit the shared memory of 8 SMs; TMEM holds all but 16 KB per CTA, the last
+//  32 TMEM columns hold the accumulator.)
 // Per step, per CTA:
-//     pre[128 x 16] = W_hi h + W_lo h + W_hi h_lo          96 tcgen05.mma 128x16x8, accumulator in TMEM
+//     pre[128 x 16] = W_hi h_hi + correction               32 + 32 tcgen05.mma 128x16, accumulator in TMEM
 //     epilogue warps: tcgen05.ld -> + gx -> sigmoid/tanh -> shared-memory transpose -> cell update (c in
 //     registers) -> h_t to HBM and, as raw fp32, straight into the B-operand buffers (K-block r) of all 8 CTAs
 //     with st.async (DSMEM) completing on the receivers' mbarriers; the receivers only derive h_lo.
@@ -133,22 +136,25 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
 #pragma unroll 1
         for (int kk = 0; kk < 8; ++kk) {
           const int src_blk = ((int)rank - kk) & 7;
-          float hi[32], lo[32];
+          float hi[32], cr[32];   // cr: 32 packed words = 64 bf16 = two 16-k blocks of [bf16(W) x16 | bf16(rest W) x16]
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 x = __ldg(reinterpret_cast<const float4 *>(wrow + src_blk * 32) + i);
             hi[4 * i + 0] = x.x; hi[4 * i + 1] = x.y; hi[4 * i + 2] = x.z; hi[4 * i + 3] = x.w;
-            lo[4 * i + 0] = tc::tf32_rest(x.x); lo[4 * i + 1] = tc::tf32_rest(x.y);
-            lo[4 * i + 2] = tc::tf32_rest(x.z); lo[4 * i + 3] = tc::tf32_rest(x.w);
+            const int blk = i >> 2, j = (i & 3) * 2;  // 16-k block, word pair inside its halves
+            cr[blk * 16 + j] = __uint_as_float(bf16x2_bits(x.x, x.y));
+            cr[blk * 16 + j + 1] = __uint_as_float(bf16x2_bits(x.z, x.w));
+            cr[blk * 16 + 8 + j] = __uint_as_float(bf16x2_bits(tf32_rest_exact(x.x), tf32_rest_exact(x.y)));
+            cr[blk * 16 + 8 + j + 1] = __uint_as_float(bf16x2_bits(tf32_rest_exact(x.z), tf32_rest_exact(x.w)));
           }
           tc::tmem_st32(trow + (uint32_t)(kk * 32), hi);  // raw fp32 words: the tensor core reads their top 19 bits
           if (kk < 7) {
-            tc::tmem_st32(trow + (uint32_t)(TR_WLO_COL + kk * 32), lo);
+            tc::tmem_st32(trow + (uint32_t)(TR_WLO_COL + kk * 32), cr);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               *reinterpret_cast<float4 *>(wtail + r * 128 + ((i ^ (r & 7)) << 4)) =
-                  make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                  make_float4(cr[4 * i], cr[4 * i + 1], cr[4 * i + 2], cr[4 * i + 3]);
           }
         }
         tc::tmem_wait_st();
@@ -181,7 +187,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
 
     if (wr == 0) {
       // ===================== MMA issuer: warp-uniform control flow, one elected lane issues =====================
-      constexpr uint32_t idesc = tc::idesc_tf32(128, TR_NB);
+      constexpr uint32_t idesc = tc::idesc_tf32(128, TR_NB), idesc_c = tc::idesc_bf16(128, TR_NB);
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t d_tmem = tb + acc_col;
       const uint32_t tail_a = tc::s_u32(wtail), blo_a = tc::s_u32(blo);
@@ -209,11 +215,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t bd = tc::desc_sw128(bhi_a + kb * (TR_NB * 128) + k * 32);
-              if (leader) {
-                tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, (kb | k) != 0);
-                if (kb < 7) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(TR_WLO_COL + kb * 32 + k * 8), bd, idesc, 1);
-                else tc::umma_tf32_ss(d_tmem, tc::desc_sw128(tail_a + k * 32), bd, idesc, 1);
-              }
+              if (leader) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, (kb | k) != 0);
             }
           }
         }
@@ -228,8 +230,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
             for (int kb = 4 * g; kb < 4 * g + 4; ++kb) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
+                // correction product: 64 bf16 per slot = 4 MMAs of K = 16; A = packed (W | rest W), B = packed (rest h | h)
                 const uint64_t bd = tc::desc_sw128(blo_a + kb * (TR_NB * 128) + k * 32);
-                if (leader) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, 1);
+                if (leader) {
+                  if (kb < 7) tc::umma_bf16_ts(d_tmem, tb + (uint32_t)(TR_WLO_COL + kb * 32 + k * 8), bd, idesc_c, 1);
+                  else tc::umma_bf16_ss(d_tmem, tc::desc_sw128(tail_a + k * 32), bd, idesc_c, 1);
+                }
               }
             }
           }
@@ -281,9 +287,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
             if (g == 0) TR_STAMP(6);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int f4 = g * 512 + et + TR_EPI * i;
+              const int f4 = g * 512 + et + TR_EPI * i;   // physical 16-byte granule of the raw-h buffer
               const float4 v = src[f4];
-              dst[f4] = make_float4(tc::tf32_rest_raw(v.x), tc::tf32_rest_raw(v.y), tc::tf32_rest_raw(v.z), tc::tf32_rest_raw(v.w));
+              // granule -> (slot, episode row e, logical 4-k chunk c): the fp32 buffer is SWIZZLE_128B, chunk = phys ^ (e & 7)
+              const int e = (f4 >> 3) & 15, c = (f4 & 7) ^ (e & 7);
+              // the correction operand of this slot: 64 bf16 per row = two 16-k blocks of [bf16(rest) x16 | bf16(h) x16] (B side)
+              const int blk = c >> 2, kk = (c & 3) * 4;              // 16-k block, first k inside it
+              uint8_t *rowp = reinterpret_cast<uint8_t *>(dst) + (f4 >> 7) * (TR_NB * 128) + e * 128;
+              const int off_lo = blk * 64 + kk * 2, off_hb = off_lo + 32;   // byte offsets inside the 128-byte row
+              *reinterpret_cast<uint2 *>(rowp + ((((off_lo >> 4) ^ (e & 7)) << 4) | (off_lo & 15))) =
+                  make_uint2(bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y)), bf16x2_bits(tf32_rest_exact(v.z), tf32_rest_exact(v.w)));
+              *reinterpret_cast<uint2 *>(rowp + ((((off_hb >> 4) ^ (e & 7)) << 4) | (off_hb & 15))) =
+                  make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
             }
             tc::fence_proxy_async();   // generic-proxy writes of h_lo -> visible to tcgen05.mma
             tc::bar_arrive(tc::s_u32(&lo_ready[g]));
