@@ -79,18 +79,25 @@ class ClockSampler:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        """Median SM clock over the samples taken UNDER LOAD (power draw >= 60 % of the highest seen: the legs contain
+        host-side set-up during which the GPU idles), throttle reasons over all samples."""
+        rows, reasons = [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                rows.append((float(r[0]), float(r[1]), float(r[2])))
                 for name, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except (ValueError, IndexError):
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(reasons), "samples": 0}
+        pmax = max(p for _, _, p in rows)
+        loaded = [r for r in rows if r[2] >= 0.6 * pmax]
+        return {"sm_mhz": statistics.median(r[0] for r in loaded), "sm_max_mhz": max(r[1] for r in rows),
+                "reasons": sorted(reasons), "samples": len(rows), "samples_under_load": len(loaded),
+                "power_w_max": pmax}
 
 
 def peaks():
@@ -422,12 +429,13 @@ def run_ours(args, rank, world, local_rank):
             device_step = eager if "eager" in dir() else device_step
     ops.reset_launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        start.record()
-        for i in range(args.steps):
-            device_step(i)
-        end.record()
-        barrier()
+    clk = ClockSampler(local_rank)   # re-entered around every GPU-busy timed leg; the samples accumulate
+    clk.__enter__()
+    start.record()
+    for i in range(args.steps):
+        device_step(i)
+    end.record()
+    barrier()
     launches = ops.launch_count() if graphs is None else 7 * args.steps  # graph replays launch the captured 7 kernels
     ms = start.elapsed_time(end)
     t = torch.tensor([ms], device=dev)
@@ -457,13 +465,16 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    clk.__exit__(None, None, None)
 
-    train = train_bench(m, dev, rank, world, max(3, args.steps // 2), barrier)
+    with clk:
+        train = train_bench(m, dev, rank, world, max(3, args.steps // 2), barrier)
     xf = None
     if not args.skip_transformer:
         del dev_sets, pinned
         torch.cuda.empty_cache()
-        xf = transformer_bench(m, dev, rank, world, max(3, args.steps // 4), barrier)
+        with clk:
+            xf = transformer_bench(m, dev, rank, world, max(3, args.steps // 4), barrier)
 
     if rank != 0:
         return
