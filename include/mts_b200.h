@@ -207,7 +207,8 @@ int mts_crf_nll_bwd(const float *emis, const float *tags, int64_t ldt, const int
  * ---------------------------------------------------------------------------------------------- */
 /* LongformerEmbeddings (HF modeling_longformer.py:401-442): y[b,t,:] = LN(x[b,t,:] + pos[t+2,:] + typ[:]).
  *   x [B,S,d] with batch stride x_bstride (elements); pos = the full position table [>= S+2, d]; d % 4 == 0.
- *   y [B*S,d]; optional y_hi/y_lo [B*S,Kp] = TF32 halves of y for the next GEMM (both or neither);
+ *   y [B*S,d]; optional y_hi/y_lo [B*S,Kp] = the operand pair of y for the next GEMM; y_hi may be NULL when Kp == d
+ *   (y itself is then the `hi` operand: no duplicate write);
  *   optional sum_out [B*S,d] (pre-LN values) and stats [B*S,2] = (mean, rstd), saved for the backward pass. */
 int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *pos, const float *typ, const float *gamma,
                      const float *beta, int B, int S, int d, float eps, float *y, float *y_hi, float *y_lo, int Kp,
@@ -236,7 +237,8 @@ int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t *lengths, 
 
 /* Backward of the encoder pieces (the reference: autograd through HF LongformerModel).
  * mts_ln_bwd: dy, pre (pre-LN values), stats (mean, rstd) as saved by the forward calls -> dx [M,d] (+ its TF32
- *   halves dx_hi/dx_lo [M,Kp], both or neither), dgamma [d], dbeta [d] (overwritten); ws >= mts_ln_bwd_ws_bytes. */
+ *   operand pair dx_hi/dx_lo [M,Kp]; dx_hi may be NULL when Kp == d), dgamma [d], dbeta [d] (overwritten);
+ *   ws >= mts_ln_bwd_ws_bytes. */
 int64_t mts_ln_bwd_ws_bytes(int M, int d);
 int mts_ln_bwd(const float *dy, const float *pre, const float *stats, const float *gamma, int M, int d, float *dx,
                float *dx_hi, float *dx_lo, int Kp, float *dgamma, float *dbeta, void *ws, void *stream);

@@ -88,14 +88,17 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
         o.z = (v[i].z - mean) * rstd * g.z + be.z;
         o.w = (v[i].w - mean) * rstd * g.w + be.w;
         reinterpret_cast<float4 *>(y + (int64_t)row * d)[c] = o;
-        if (y_hi) {
-          reinterpret_cast<float4 *>(y_hi + (int64_t)row * Kp)[c] = o;
+        if (y_lo) {  // operand pair for the next GEMM; y itself serves as `hi` when no K padding is needed (y_hi == NULL)
+          if (y_hi) reinterpret_cast<float4 *>(y_hi + (int64_t)row * Kp)[c] = o;
           corr_store4(y_lo + (int64_t)row * Kp, 4 * c, o, 0);
         }
       }
     }
-    if (y_hi)
-      for (int c = d + lane; c < Kp; c += 32) { y_hi[(int64_t)row * Kp + c] = 0.0f; corr_store1(y_lo + (int64_t)row * Kp, c, 0.0f, 0); }
+    if (y_lo)
+      for (int c = d + lane; c < Kp; c += 32) {
+        if (y_hi) y_hi[(int64_t)row * Kp + c] = 0.0f;
+        corr_store1(y_lo + (int64_t)row * Kp, c, 0.0f, 0);
+      }
   }
 }
 
@@ -550,8 +553,9 @@ static int ln_args_ok(const char *who, int M, int d, const float *y_hi, const fl
   (void)who;
   if (M <= 0 || d <= 0) { set_error("layer norm: empty shape"); return MTS_E_BADARG; }
   if (d % 4 != 0 || d > 128 * LN_MAXV) { set_error("layer norm: width must be a multiple of 4 and <= 2048"); return MTS_E_UNSUPPORTED; }
-  if ((y_hi == nullptr) != (y_lo == nullptr)) { set_error("layer norm: hi and lo go together"); return MTS_E_BADARG; }
-  if (y_hi && (Kp % 32 != 0 || Kp < d)) { set_error("layer norm: Kp must be a multiple of 32 and >= d"); return MTS_E_BADARG; }
+  if (y_hi && !y_lo) { set_error("layer norm: hi without lo"); return MTS_E_BADARG; }
+  if (y_lo && !y_hi && Kp != d) { set_error("layer norm: y can only stand in for hi when Kp == d"); return MTS_E_BADARG; }
+  if (y_lo && (Kp % 32 != 0 || Kp < d)) { set_error("layer norm: Kp must be a multiple of 32 and >= d"); return MTS_E_BADARG; }
   return 0;
 }
 

@@ -51,14 +51,17 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const float *__restrict_
         o.z = rstd * (g[i].z - m1 - xh[i].z * m2);
         o.w = rstd * (g[i].w - m1 - xh[i].w * m2);
         reinterpret_cast<float4 *>(dx + (int64_t)row * d)[c] = o;
-        if (dx_hi) {
-          reinterpret_cast<float4 *>(dx_hi + (int64_t)row * Kp)[c] = o;
+        if (dx_lo) {  // dx itself serves as `hi` when Kp == d (dx_hi == NULL)
+          if (dx_hi) reinterpret_cast<float4 *>(dx_hi + (int64_t)row * Kp)[c] = o;
           corr_store4(dx_lo + (int64_t)row * Kp, 4 * c, o, 0);
         }
       }
     }
-    if (dx_hi)
-      for (int c = d + lane; c < Kp; c += 32) { dx_hi[(int64_t)row * Kp + c] = 0.0f; corr_store1(dx_lo + (int64_t)row * Kp, c, 0.0f, 0); }
+    if (dx_lo)
+      for (int c = d + lane; c < Kp; c += 32) {
+        if (dx_hi) dx_hi[(int64_t)row * Kp + c] = 0.0f;
+        corr_store1(dx_lo + (int64_t)row * Kp, c, 0.0f, 0);
+      }
   }
 }
 
@@ -466,8 +469,9 @@ extern "C" int mts_ln_bwd(const float *dy, const float *pre, const float *stats,
   MTS_REQUIRE(dy && pre && stats && gamma && dx && dgamma && dbeta && ws, MTS_E_BADARG, "ln_bwd: null pointer");
   MTS_REQUIRE(M > 0 && d > 0, MTS_E_BADARG, "ln_bwd: empty shape");
   MTS_REQUIRE(d % 4 == 0 && d <= 128 * LNB_MAXV, MTS_E_UNSUPPORTED, "ln_bwd: width must be a multiple of 4 and <= 2048");
-  MTS_REQUIRE((dx_hi == nullptr) == (dx_lo == nullptr), MTS_E_BADARG, "ln_bwd: hi and lo go together");
-  MTS_REQUIRE(!dx_hi || (Kp % 32 == 0 && Kp >= d), MTS_E_BADARG, "ln_bwd: Kp");
+  MTS_REQUIRE(!(dx_hi && !dx_lo), MTS_E_BADARG, "ln_bwd: hi without lo");
+  MTS_REQUIRE(!(dx_lo && !dx_hi) || Kp == d, MTS_E_BADARG, "ln_bwd: dx can only stand in for hi when Kp == d");
+  MTS_REQUIRE(!dx_lo || (Kp % 32 == 0 && Kp >= d), MTS_E_BADARG, "ln_bwd: Kp");
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = ln_chunks(M);
   const int rows_per = (M + chunks - 1) / chunks;

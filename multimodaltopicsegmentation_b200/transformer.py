@@ -180,17 +180,19 @@ def _ln(mode, a, b, typ, gamma, beta, B, S, d, want_split, save):
     dev = a.device
     y = torch.empty((M, d), device=dev, dtype=torch.float32)
     kp = _pad32(d)
-    hl = torch.empty((2, M, kp), device=dev, dtype=torch.float32) if want_split else None
+    hi = lo = None
+    if want_split:  # the GEMM's `hi` operand is the fp32 tensor itself: y stands in for it when no K padding is needed
+        lo = torch.empty((M, kp), device=dev, dtype=torch.float32)
+        hi = None if kp == d else torch.empty((M, kp), device=dev, dtype=torch.float32)
     pre = torch.empty((M, d), device=dev, dtype=torch.float32) if save else None
     stats = torch.empty((M, 2), device=dev, dtype=torch.float32) if save else None
-    hi, lo = (hl[0], hl[1]) if want_split else (None, None)
     if mode == 0:
         _call("mts_embed_ln_fwd", _ptr(a), a.stride(0), _ptr(b), _ptr(typ), _ptr(gamma), _ptr(beta), B, S, d, LN_EPS,
               _ptr(y), _ptr(hi), _ptr(lo), kp, _ptr(pre), _ptr(stats), _stream())
     else:
         _call("mts_add_ln_fwd", _ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), M, d, LN_EPS, _ptr(y), _ptr(hi), _ptr(lo), kp,
               _ptr(pre), _ptr(stats), _stream())
-    return y, hi, lo, pre, stats
+    return y, (y if (want_split and hi is None) else hi), lo, pre, stats
 
 
 def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):

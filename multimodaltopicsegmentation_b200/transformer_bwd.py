@@ -22,12 +22,13 @@ def _ln_bwd(dy, pre, stats, gamma, M, d):
     dev = dy.device
     kp = _pad32(d)
     dx = torch.empty((M, d), device=dev, dtype=torch.float32)
-    hl = torch.empty((2, M, kp), device=dev, dtype=torch.float32)
+    lo = torch.empty((M, kp), device=dev, dtype=torch.float32)
+    hi = None if kp == d else torch.empty((M, kp), device=dev, dtype=torch.float32)  # dx itself is the `hi` operand
     dgb = torch.empty((2, d), device=dev, dtype=torch.float32)
     ws = torch.empty(_lib.load().mts_ln_bwd_ws_bytes(M, d) // 4, device=dev, dtype=torch.float32)
-    _call("mts_ln_bwd", _ptr(dy), _ptr(pre), _ptr(stats), _ptr(gamma), M, d, _ptr(dx), _ptr(hl[0]), _ptr(hl[1]), kp,
+    _call("mts_ln_bwd", _ptr(dy), _ptr(pre), _ptr(stats), _ptr(gamma), M, d, _ptr(dx), _ptr(hi), _ptr(lo), kp,
           _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), _stream())
-    return dx, hl, dgb[0], dgb[1]
+    return dx, (dx if hi is None else hi, lo), dgb[0], dgb[1]
 
 
 def _dense_param_grads(dy, x, M, n_out, n_in):
