@@ -34,9 +34,8 @@ def _lens(lengths, x):
 def _tags_to_lists(tags_dev, lens, as_bool):
     """One device->host copy of the uint8 tag matrix, then the reference's per-episode crop (CRF.py:369)."""
     host = tags_dev.cpu().numpy()
-    if as_bool:
-        return [host[b, :n].astype(bool).tolist() for b, n in enumerate(lens.host)]
-    return [host[b, :n].astype(int).tolist() for b, n in enumerate(lens.host)]
+    full = (host.astype(bool) if as_bool else host.astype(int)).tolist()  # one conversion for the whole matrix
+    return [row if n == len(row) else row[:n] for row, n in zip(full, lens.host)]
 
 
 class RNN(nn.Module):
