@@ -112,9 +112,10 @@ int mts_lstm_rec_fwd(const float *gx, const float *w_hh, const int32_t *lengths,
 /* The same recurrence on the tensor cores (H == 256 only): W_hh split for 3xTF32 and kept on chip for the whole
  * sequence (hi half in shared memory, lo half in tensor memory), tiles of 16 episodes per 8-CTA cluster,
  * tcgen05.mma per step, h exchanged through distributed shared memory.  Same arguments and results (to fp32
- * rounding) as mts_lstm_rec_fwd. */
+ * rounding) as mts_lstm_rec_fwd, plus y_corr [B*T, 2H] or NULL (n_enc == 1 only): the packed bf16 correction operand
+ * of y (A side), so that the next layer's input projection reads (y, y_corr) directly -- no split pass. */
 int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
-                        int B, int T, int H, float *y, float *gates, void *stream);
+                        int B, int T, int H, float *y, float *gates, float *y_corr, void *stream);
 
 /* Profiling hook of the tensor-core recurrence: installs (or, with NULL, removes) a device buffer of 4 x 12 int64
  * into which CTA 0 writes clock64() stamps of the phases of steps 8..11 (see csrc/lstm_rec_tc.cu). */

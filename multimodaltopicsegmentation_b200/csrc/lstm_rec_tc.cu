@@ -64,7 +64,7 @@ template <bool SAVE, int NT>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREADS * NT, 1)
     lstm_fwd_tc_kernel(const float *__restrict__ gx, const float *__restrict__ w_hh,
                        const int32_t *__restrict__ lengths, const int32_t *__restrict__ order, int B, int T, int n_enc,
-                       int n_tiles, float *__restrict__ y, float *__restrict__ gates) {
+                       int n_tiles, float *__restrict__ y, float *__restrict__ gates, float *__restrict__ y_corr) {
   constexpr int THREADS = TR_SUB_THREADS * NT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -358,6 +358,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
         if (s < my_len) {
           const int t = dir ? my_len - 1 - s : s;
           *reinterpret_cast<float4 *>(y + ((size_t)my_b * T + t) * ycols + ycol) = hn;
+          // the next layer's GEMM takes y itself as its fp32 operand; its packed bf16 correction operand is written here
+          if (y_corr) corr_store4(y_corr + ((size_t)my_b * T + t) * ycols, (int)ycol, hn, 0);
           if (SAVE) {
             float *gs = gates + ((gate_base + my_b) * T + t) * 5 * kH + rank * kUnits + 4 * cj;
             *reinterpret_cast<float4 *>(gs) = ig;
@@ -370,8 +372,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
       }
       // zero the padded tail of my (episode, 4 units) columns
       if (my_b >= 0)
-        for (int t = my_len; t < T; ++t)
-          *reinterpret_cast<float4 *>(y + ((size_t)my_b * T + t) * ycols + ycol) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = my_len; t < T; ++t) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4 *>(y + ((size_t)my_b * T + t) * ycols + ycol) = z;
+          if (y_corr) corr_store4(y_corr + ((size_t)my_b * T + t) * ycols, (int)ycol, z, 0);
+        }
     }
     // the MMA thread's phase counters must follow the epilogue's view of h_full (it skips nothing), and vice versa
     tc::tc_fence_before();
@@ -420,10 +425,11 @@ extern "C" int mts_debug_rec_profile(long long *buf) {
 
 // tensor-core forward recurrence; same arguments as mts_lstm_rec_fwd, H must be 256
 extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order,
-                                   int n_enc, int B, int T, int H, float *y, float *gates, void *stream) {
+                                   int n_enc, int B, int T, int H, float *y, float *gates, float *y_corr, void *stream) {
   MTS_REQUIRE(gx && w_hh && lengths && y, MTS_E_BADARG, "lstm_rec_fwd_tc: null pointer");
   MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0, MTS_E_BADARG, "lstm_rec_fwd_tc: bad shape");
   MTS_REQUIRE(H == kH, MTS_E_UNSUPPORTED, "lstm_rec_fwd_tc: the tensor-core recurrence serves H == 256");
+  MTS_REQUIRE(!y_corr || n_enc == 1, MTS_E_UNSUPPORTED, "lstm_rec_fwd_tc: the fused correction operand needs n_enc == 1");
   MTS_REQUIRE((n_enc * 2 * kH) % 4 == 0 && (((uintptr_t)y | (uintptr_t)gx | (uintptr_t)w_hh) & 15) == 0, MTS_E_BADARG,
               "lstm_rec_fwd_tc: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -442,13 +448,13 @@ extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int
   const bool two = force ? (force[0] == '2') : (items1 > cap);
   if (!two) {
     const unsigned grid = (unsigned)((items1 < cap ? items1 : cap) * kCluster);
-    if (gates) lstm_fwd_tc_kernel<true, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
-    else lstm_fwd_tc_kernel<false, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+    if (gates) lstm_fwd_tc_kernel<true, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates, y_corr);
+    else lstm_fwd_tc_kernel<false, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates, y_corr);
   } else {
     const int items2 = ((n_tiles + 1) / 2) * 2 * n_enc;
     const unsigned grid = (unsigned)((items2 < cap ? items2 : cap) * kCluster);
-    if (gates) lstm_fwd_tc_kernel<true, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
-    else lstm_fwd_tc_kernel<false, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates);
+    if (gates) lstm_fwd_tc_kernel<true, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates, y_corr);
+    else lstm_fwd_tc_kernel<false, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates, y_corr);
   }
   MTS_LAUNCH_CHECK();
   return 0;

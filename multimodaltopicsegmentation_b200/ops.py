@@ -255,7 +255,7 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
     dev = x1.device
     layers = packed.get()
     saved = []
-    y_prev = None
+    y_prev = y_corr = None
     for layer in range(L):
         gx = torch.empty((n_enc, B * T, 8 * H), device=dev, dtype=torch.float32)
         for e in range(n_enc):
@@ -264,6 +264,8 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
                     a_hi, a_lo = pack_rows_split(x1, x2, B, T)
                 else:
                     a_hi, a_lo = pack_rows_split(x1 if e == 0 else xs2, None, B, T)
+            elif y_corr is not None:  # the recurrence wrote the correction operand of y; y itself is the fp32 operand
+                a_hi, a_lo = y_prev.view(B * T, 2 * H), y_corr
             else:
                 src = y_prev.view(B * T, n_enc * 2 * H)[:, e * 2 * H:(e + 1) * 2 * H]
                 a_hi, a_lo = split_tf32(src, cols=2 * H, ld=n_enc * 2 * H, rows=B * T)
@@ -277,8 +279,16 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
                             ldc=8 * H)
         y = torch.empty((B, T, n_enc * 2 * H), device=dev, dtype=torch.float32)
         gates = torch.empty((n_enc, 2, B, T, 5, H), device=dev, dtype=torch.float32) if save else None
-        _call("mts_lstm_rec_fwd_tc" if (H == 256 and REC_IMPL == "tc") else "mts_lstm_rec_fwd", _ptr(gx),
-              _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order), n_enc, B, T, H, _ptr(y), _ptr(gates), _stream())
+        if H == 256 and REC_IMPL == "tc":
+            # early fusion, more layers above: the kernel also writes the GEMM operand of the next layer's input
+            y_corr = (torch.empty((B * T, 2 * H), device=dev, dtype=torch.float32)
+                      if (n_enc == 1 and layer + 1 < L and GEMM_IMPL != "simt") else None)
+            _call("mts_lstm_rec_fwd_tc", _ptr(gx), _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order), n_enc, B, T,
+                  H, _ptr(y), _ptr(gates), _ptr(y_corr), _stream())
+        else:
+            y_corr = None
+            _call("mts_lstm_rec_fwd", _ptr(gx), _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order), n_enc, B, T,
+                  H, _ptr(y), _ptr(gates), _stream())
         saved.append((y_prev, y, gates))
         y_prev = y
     return y_prev, saved

@@ -42,7 +42,7 @@ REC_NAME = "mts_lstm_rec_fwd" if os.environ.get("MTS_REC_IMPL", "tc") == "fma" e
 
 def rec_call(gx, whh, lens, y, gates, B, T, H=256, n_enc=1):
     ops._call(REC_NAME, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T,
-              H, y.data_ptr(), 0 if gates is None else gates.data_ptr(), ops._stream())
+              H, y.data_ptr(), 0 if gates is None else gates.data_ptr(), *((0,) if REC_NAME.endswith("_tc") else ()), ops._stream())
 
 
 def bench_rec():

@@ -58,7 +58,7 @@ def run(name, gx, whh, lens, B, T, H, n_enc, save):
     y = torch.full((B, T, n_enc * 2 * H), float("nan"), device=dev)
     gates = torch.full((n_enc, 2, B, T, 5, H), float("nan"), device=dev) if save else None
     ops._call(name, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T, H,
-              y.data_ptr(), 0 if gates is None else gates.data_ptr(), ops._stream())
+              y.data_ptr(), 0 if gates is None else gates.data_ptr(), *((0,) if name.endswith("_tc") else ()), ops._stream())
     torch.cuda.synchronize()
     return y, gates
 
@@ -156,7 +156,7 @@ def sweep():
         lens = ops.Lengths([T] * B, dev, T)
         y = torch.empty((B, T, 2 * H), device=dev)
         call = lambda name: ops._call(name, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), 1,
-                                      B, T, H, y.data_ptr(), 0, ops._stream())
+                                      B, T, H, y.data_ptr(), 0, *((0,) if name.endswith("_tc") else ()), ops._stream())
         a = timeit(lambda: call("mts_lstm_rec_fwd"))
         b = timeit(lambda: call("mts_lstm_rec_fwd_tc"))
         print(f"{B:5d} {a:9.3f} ({a * 1e3 / T:6.2f}) {b:9.3f} ({b * 1e3 / T:6.2f}) {B * T * 10240 / b / 1e6:10.1f}", flush=True)
@@ -172,7 +172,7 @@ def timeline(B=16, T=40):
     y = torch.empty((B, T, 2 * H), device=dev)
     buf = torch.zeros(4 * 12, dtype=torch.int64, device=dev)
     call = lambda: ops._call("mts_lstm_rec_fwd_tc", gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
-                             lens.order.data_ptr(), 1, B, T, H, y.data_ptr(), 0, ops._stream())
+                             lens.order.data_ptr(), 1, B, T, H, y.data_ptr(), 0, 0, ops._stream())
     call(); call()
     ops._call("mts_debug_rec_profile", buf.data_ptr())
     call()

@@ -716,11 +716,18 @@ def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save):
         y = torch.full((B, T, n_enc * 2 * H), float("nan"), device=dev)
         gates = torch.full((n_enc, 2, B, T, 5, H), float("nan"), device=dev) if save else None
         ops._call(name, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T, H,
-                  y.data_ptr(), 0 if gates is None else gates.data_ptr(), ops._stream())
+                  y.data_ptr(), 0 if gates is None else gates.data_ptr(), *((0,) if name.endswith("_tc") else ()), ops._stream())
         return y, gates
 
     y_f, g_f = run("mts_lstm_rec_fwd")
     y_t, g_t = run("mts_lstm_rec_fwd_tc")
+    if n_enc == 1:  # fused operand of the next layer's input projection: (y, y_corr) is a valid A-side operand pair
+        y2 = torch.full((B, T, 2 * H), float("nan"), device=dev)
+        corr = torch.full((B * T, 2 * H), float("nan"), device=dev)
+        ops._call("mts_lstm_rec_fwd_tc", gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H,
+                  y2.data_ptr(), 0, corr.data_ptr(), ops._stream())
+        assert torch.equal(y2, y_t)
+        check_operand_pair(y2.view(B * T, 2 * H), corr, y2.view(B * T, 2 * H), side=0)
     assert not bool(torch.isnan(y_t).any())          # every position written (zeros beyond len_b)
     for b, n in enumerate(lengths):
         assert float(y_t[b, n:].abs().max() if n < T else 0.0) == 0.0
@@ -835,7 +842,7 @@ def test_recurrence_backward_tensor_core_vs_fma(dev, B, T, n_enc):
     y = torch.empty((B, T, n_enc * 2 * H), device=dev)
     gates = torch.zeros((n_enc, 2, B, T, 5, H), device=dev)
     ops._call("mts_lstm_rec_fwd_tc", gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T,
-              H, y.data_ptr(), gates.data_ptr(), ops._stream())
+              H, y.data_ptr(), gates.data_ptr(), 0, ops._stream())
     dy = torch.randn((B, T, n_enc * 2 * H), device=dev, generator=g)
     whh_t = whh.transpose(2, 3).contiguous()
     d_f = torch.full((n_enc, B * T, 8 * H), float("nan"), device=dev)
