@@ -91,6 +91,13 @@ if __name__ == "__main__":
         bench_rec()
     elif what == "gemm":
         bench_gemm()
+    elif what == "gemm_big":
+        M, N, K = 65536, 2048, 896
+        a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)
+        c = torch.empty(M, N, device=dev)
+        a_hi, a_lo = ops.split_tf32(a); b_hi, b_lo = ops.split_tf32(b, side=ops.B_SIDE)
+        ms = timeit(lambda: ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, c, M, N, epilogue=1))
+        print(f"{M} x {N} x {K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s fp32-equivalent")
     elif what == "gemm_one":
         M, N, K = 19200, 2048, 896
         a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)
