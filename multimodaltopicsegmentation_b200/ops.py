@@ -294,6 +294,16 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
     return y_prev, saved
 
 
+def bilstm_stack(x1, x2, xs2, lens, packed, n_enc):
+    """The bi-LSTM stack as the modules call it.  Inference (grad mode off, or nothing to differentiate) skips autograd
+    and, with it, the per-step gate record the backward pass needs (5 H floats per sentence and direction)."""
+    flat = packed.flat_params()
+    if not (torch.is_grad_enabled() and any(p.requires_grad for p in flat)):
+        rnn0 = packed.rnns[0]
+        return _lstm_stack_forward(x1, x2, xs2, lens, packed, rnn0.hidden_size, rnn0.num_layers, n_enc, save=False)[0]
+    return BiLstmStackFn.apply(x1, x2, xs2, lens, packed, n_enc, *flat)
+
+
 class BiLstmStackFn(torch.autograd.Function):
     """Differentiable (w.r.t. the LSTM parameters) bi-LSTM stack.  Inputs are data, so layer-0 dX is skipped
     (SURVEY.md section 8a')."""
@@ -302,7 +312,7 @@ class BiLstmStackFn(torch.autograd.Function):
     def forward(ctx, x1, x2, xs2, lens, packed, n_enc, *flat):
         rnn0 = packed.rnns[0]
         H, L = rnn0.hidden_size, rnn0.num_layers
-        need = any(ctx.needs_input_grad)  # grad mode is off inside forward(); this reflects the caller's mode
+        need = any(ctx.needs_input_grad)  # true even under no_grad: callers go through bilstm_stack()
         y, saved = _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save=need)
         if need:
             ctx.x1, ctx.x2, ctx.xs2, ctx.lens, ctx.packed, ctx.n_enc = x1, x2, xs2, lens, packed, n_enc

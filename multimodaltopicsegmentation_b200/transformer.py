@@ -305,7 +305,10 @@ class Longformer_Local_Attention(nn.Module):
             x = x.contiguous()
         lens = lengths if isinstance(lengths, ops.Lengths) else ops.Lengths(lengths, x.device, x.shape[1])
         packed = self.packed()
-        return EncoderFn.apply(x, lens, packed, self.nhead, self.reaches, *packed.used_parameters())
+        params = packed.used_parameters()
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in params)):  # inference: nothing saved
+            return encoder_forward(x, lens, packed, self.nhead, self.reaches, save=False)[0]
+        return EncoderFn.apply(x, lens, packed, self.nhead, self.reaches, *params)
 
 
 class Transformer_segmenter(nn.Module):
