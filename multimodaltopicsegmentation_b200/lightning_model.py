@@ -207,6 +207,49 @@ class TextSegmenter(_Base):
         self.log_dict(results, on_epoch=True, prog_bar=True)
         return results
 
+    # ---- threshold search (lightning_model.py:436-553; dead code in the reference, whose hook is renamed) ------------
+    def threshold_search(self, scores, target, lengths, thresholds=None):
+        """The reference's sweep over np.arange(0.05, 1, 0.05) as ONE batched device evaluation (SURVEY.md section 8f
+        row 2): all 19 thresholded tag matrices are scored by a single mts_seg_metrics launch.  `scores` [B, T, 1|2]
+        device tensor as returned by the model (two columns: column 1 is compared, as the reference does at :462; one
+        column: its sigmoid), `target` [B, T].  Selection follows the reference: strict improvement, first best wins;
+        Pk / WD are minimised from 1, F1 maximised from -1.  Sets and returns (self.best_th, results dict)."""
+        from decimal import Decimal
+
+        if self.metric.lower() in ("b", "scaiano"):
+            raise NotImplementedError("B / WinPR evaluation is outside the hot path (SURVEY.md section 2 row 9)")
+        ths = np.arange(0.05, 1, 0.05) if thresholds is None else np.asarray(thresholds, dtype=np.float64)
+        lens = lengths if isinstance(lengths, ops.Lengths) else ops.Lengths(lengths, scores.device, scores.shape[1])
+        B, n_th = lens.B, len(ths)
+        with torch.no_grad():
+            p = scores[:, : lens.T, 1] if scores.shape[2] > 1 else torch.sigmoid(scores[:, : lens.T, 0])
+            th_dev = torch.tensor(ths, dtype=torch.float64, device=p.device).view(n_th, 1, 1)
+            tags = (p.unsqueeze(0).double() > th_dev).to(torch.uint8).view(n_th * B, lens.T)  # np compares in float64 too
+            tgt = target[:, : lens.T].float().unsqueeze(0).expand(n_th, B, lens.T).reshape(n_th * B, lens.T)
+            many = ops.Lengths(lens.host * n_th, p.device, lens.T)
+            counts = ops.seg_metrics(tags, tgt, many, zero_last=self.eb).view(n_th, B, 8).cpu().tolist()
+        minimise = self.metric.lower() in ("pk", "wd")
+        best, best_idx, results = (1 if minimise else -1), 0, []
+        for index, th in enumerate(ths):
+            loss_pk = loss_f1 = loss_wd = 0.0
+            for pk, wd, windows, _k, tp, fp, fn, _segs in counts[index]:
+                pk_val = float(Decimal(pk) / Decimal(windows)) if windows > 0 else 0.0
+                loss_pk += pk_val
+                loss_wd += float(Decimal(wd) / Decimal(windows)) if windows > 0 else pk_val
+                denom = 2 * tp + fp + fn
+                loss_f1 += 2.0 * tp / denom if denom else 0.0
+            res = {"Pk_loss": loss_pk / B, "F1_loss": loss_f1 / B, "WD_loss": loss_wd / B}
+            key = {"F1": "F1_loss", "WD": "WD_loss"}.get(self.metric, "Pk_loss")
+            val = res.pop(key)
+            res["valid_loss"] = val
+            results.append(res)
+            if (val < best) if (key != "F1_loss") else (val > best):
+                best, best_idx, self.best_th = val, index, th
+        chosen = results[best_idx]
+        chosen["threshold"] = self.best_th if not isinstance(self.best_th, list) and self.best_th is not None else 0.4
+        self.log_dict(chosen, on_epoch=True, prog_bar=True)
+        return chosen["threshold"], chosen
+
     def predict_step(self, batch, batch_idx):
         xs, lengths = self._inputs(batch)
         _, tags = self.model(*xs, lengths)

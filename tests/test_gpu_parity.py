@@ -919,3 +919,44 @@ def test_test_step_device_metrics_equal_host_walk(dev, arch, eb):
     assert set(on_device) == set(on_host)
     for k in on_host:
         assert on_device[k] == on_host[k], (k, on_device[k], on_host[k])
+
+
+@pytest.mark.parametrize("metric", ["Pk", "WD", "F1"])
+def test_threshold_search_equals_host_sweep(dev, metric):
+    """The batched device sweep picks the same threshold and reports the same numbers as the reference's loop over
+    np.arange(0.05, 1, 0.05) (lightning_model.py:436-553) evaluated with the host metrics."""
+    from multimodaltopicsegmentation_b200 import TextSegmenter
+    from multimodaltopicsegmentation_b200.metrics import compute_Pk, compute_window_diff, f1_boundary
+
+    g = torch.Generator().manual_seed(5)
+    lengths = [40, 17, 29, 64, 8]
+    B, T = len(lengths), max(lengths)
+    scores = torch.randn(B, T, 1, generator=g) * 2.0
+    target = (torch.rand(B, T, generator=g) < 0.15).float()
+    for b, n in enumerate(lengths):
+        target[b, n - 1] = 0
+        target[b, n:] = -1
+    seg = TextSegmenter(2, 20, 256, num_layers=1, architecture="BiLSTM", loss_fn="FocalLoss", metric=metric).to(dev)
+    th, res = seg.threshold_search(scores.to(dev), target.to(dev), lengths)
+    # host restatement of the reference loop
+    p = torch.sigmoid(scores.to(dev)[:, :, 0]).cpu().numpy()  # the same probabilities the device sweep thresholds
+    minimise = metric != "F1"
+    best, best_th, best_res = (1 if minimise else -1), None, None
+    for t in np.arange(0.05, 1, 0.05):
+        pk = wd = f1 = 0.0
+        for b, n in enumerate(lengths):
+            tag, tgt = p[b, :n] > t, target[b, :n].numpy()
+            pk += float(compute_Pk(np.array(tag), tgt))
+            f1 += f1_boundary(tgt.astype(int), np.array(tag).astype(int))
+            try:
+                wd += float(compute_window_diff(np.array(tag), tgt))
+            except AssertionError:
+                wd += float(compute_Pk(np.array(tag), tgt))
+        r = {"Pk_loss": pk / B, "F1_loss": f1 / B, "WD_loss": wd / B}
+        val = r.pop({"F1": "F1_loss", "WD": "WD_loss"}.get(metric, "Pk_loss"))
+        r["valid_loss"] = val
+        if (val < best) if minimise else (val > best):
+            best, best_th, best_res = val, t, r
+    assert th == best_th
+    for k in best_res:
+        assert res[k] == best_res[k], (k, res[k], best_res[k])
