@@ -282,14 +282,15 @@ def transformer_bench(m, dev, rank, world, steps, barrier):
     ops.PROFILE = None
     # e2e: host (pinned) embeddings in, host tag lists out
     host = xs[0].cpu().pin_memory()
+    prefetcher = m.DevicePrefetcher(None, dev)   # one set of staging buffers for all passes, as over epochs
     def e2e(n):
         batches = ({"src_tokens": host, "src_lengths": lengths} for _ in range(n))
-        for i, batch in enumerate(m.DevicePrefetcher(batches, dev)):
+        for i, batch in enumerate(prefetcher.iterate(batches)):
             seg.predict_step(batch, i)
-    e2e(1)
+    e2e(2)
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(2, steps // 2)
+    n_e2e = max(4, 2 * steps)   # the first copy of a pass cannot overlap anything: enough steps to amortise it
     e2e(n_e2e)
     barrier()
     e2e_s = (time.perf_counter() - t0) / n_e2e

@@ -66,6 +66,12 @@ int mts_transpose_split(const float *src, int64_t bstride, int64_t ld, int rows,
 int mts_gather_pad(const float *src, const int64_t *offsets, const int32_t *lengths, const int32_t *ids, int B, int T,
                    int D, float pad, float *out, void *stream);
 
+/* Token rows between the padded layout [B*S, d] (to_padded = 0: src) and the ragged layout [sum(len), d]
+ * (to_padded = 1: src), offsets int32 [B] = exclusive prefix sums of lengths.  to_padded = 1 fills the padded rows
+ * with `pad`; to_padded = 0 copies the valid rows only.  d % 4 == 0.  See "Row layouts" below. */
+int mts_ragged_copy(const float *src, float *dst, const int32_t *lengths, const int32_t *offsets, int B, int S, int d,
+                    int to_padded, float pad, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ GELU), fp32 in / fp32 out.
  *   replaces: nn.LSTM's input projection (models/NeuralArchitectures.py:113), nn.Linear heads
@@ -205,15 +211,23 @@ int mts_crf_nll_bwd(const float *emis, const float *tags, int64_t ldt, const int
  * attention, LayerNorm eps 1e-12, GELU(erf)).  The dense layers are mts_gemm_tf32x3; these are the fused
  * kernels around them.  Every kernel takes `lengths` -- the reference's host-built mask tensors
  * (create_masks_huggingface, RestrictedTransformerLayer.py:101-116) are never materialised.
+ *
+ * Row layouts.  offsets == NULL: the reference's padded layout, token (b, t) is row b*S + t of every [B*S, .]
+ * tensor.  offsets != NULL (int32 [B], offsets[b] = sum of the lengths before b): the RAGGED layout -- only the
+ * N = sum(len_b) valid sentences have rows, token (b, t < len_b) is row offsets[b] + t and every token tensor is
+ * [N, .].  Padded sentences never influence valid ones (their keys are masked, HF :578-585), so all results at valid
+ * positions are identical; the dense layers, LayerNorms and GELU simply run on N instead of B*S rows.  lse / delta
+ * keep their [B, nheads, S] shape in both layouts.
  * ---------------------------------------------------------------------------------------------- */
 /* LongformerEmbeddings (HF modeling_longformer.py:401-442): y[b,t,:] = LN(x[b,t,:] + pos[t+2,:] + typ[:]).
  *   x [B,S,d] with batch stride x_bstride (elements); pos = the full position table [>= S+2, d]; d % 4 == 0.
  *   y [B*S,d]; optional y_hi/y_lo [B*S,Kp] = the operand pair of y for the next GEMM; y_hi may be NULL when Kp == d
  *   (y itself is then the `hi` operand: no duplicate write);
- *   optional sum_out [B*S,d] (pre-LN values) and stats [B*S,2] = (mean, rstd), saved for the backward pass. */
+ *   optional sum_out [B*S,d] (pre-LN values) and stats [B*S,2] = (mean, rstd), saved for the backward pass.
+ *   lengths/offsets (both or neither): write the outputs in the ragged layout (x stays [B,S,d]). */
 int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *pos, const float *typ, const float *gamma,
                      const float *beta, int B, int S, int d, float eps, float *y, float *y_hi, float *y_lo, int Kp,
-                     float *sum_out, float *stats, void *stream);
+                     float *sum_out, float *stats, const int32_t *lengths, const int32_t *offsets, void *stream);
 /* LongformerSelfOutput / LongformerOutput (:1060-1071, :1119-1130): y = LN(a + res); a is the dense output
  *   (bias already added by the GEMM epilogue).  sum_out may alias a. */
 int mts_add_ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, int M, int d, float eps,
@@ -228,13 +242,15 @@ int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, flo
  *   rows i >= len_b give exact zeros (:578).  hd % 4 == 0, hd <= 128.
  *   out [B*S, nheads*hd] and/or its TF32 halves out_hi/out_lo [B*S,Kp] (Kp == nheads*hd);
  *   lse [B,nheads,S] or NULL: log-sum-exp of every query row, saved for the backward pass. */
-int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads, int hd, int w,
-                      float *out, float *out_hi, float *out_lo, int Kp, float *lse, void *stream);
+int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
+                      int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
+                      void *stream);
 /* The same on the tensor cores: warp-level mma.sync m16n8k8 TF32 with 3xTF32 compensation for Q K^T and P V, S kept in
  * registers (hd in {8,16,32,64,112,128}).  Same contract and results; on B200 it runs at the speed of the CUDA-core
  * kernel (measured), so mts_band_attn_fwd stays the default; MTS_ATTN_IMPL=mma switches the default entry over. */
-int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads, int hd, int w,
-                          float *out, float *out_hi, float *out_lo, int Kp, float *lse, void *stream);
+int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
+                          int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
+                          void *stream);
 
 /* Backward of the encoder pieces (the reference: autograd through HF LongformerModel).
  * mts_ln_bwd: dy, pre (pre-LN values), stats (mean, rstd) as saved by the forward calls -> dx [M,d] (+ its TF32
@@ -248,13 +264,14 @@ int mts_gelu_bwd(const float *dz, const float *zp, int rows, int cols, int Kp, f
                  void *stream);
 /* dpos[t,:] = sum_b dpre[b,t,:]  (gradient rows 2..S+1 of the position table; the token-type gradient is the
  * column sum of dpos, mts_colsum). */
-int mts_embed_bwd(const float *dpre, int B, int S, int d, float *dpos, void *stream);
+int mts_embed_bwd(const float *dpre, int B, int S, int d, float *dpos, const int32_t *lengths, const int32_t *offsets,
+                  void *stream);
 /* Banded attention backward: qkv, lse as in the forward call, o = forward output [B*S, nheads*hd], d_o its
  * gradient -> dqkv [B*S, ld] = [dq | dk | dv] (dq already includes the 1/sqrt(hd) factor), zero at padded rows.
  * delta_ws: B*nheads*S floats of scratch. */
 int mts_band_attn_bwd(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
-                      const int32_t *lengths, int B, int S, int nheads, int hd, int w, float *dqkv, float *delta_ws,
-                      void *stream);
+                      const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int hd, int w, float *dqkv,
+                      float *delta_ws, void *stream);
 
 #ifdef __cplusplus
 }

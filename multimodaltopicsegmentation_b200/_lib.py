@@ -44,16 +44,18 @@ SIGNATURES = {
     "mts_crf_viterbi": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mts_crf_nll_fwd": (c_int, [_P, _P, c_int64, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mts_crf_nll_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
-    "mts_embed_ln_fwd": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_int, _P, _P, _P]),
+    "mts_embed_ln_fwd": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_int, _P, _P, _P, _P,
+                                 _P]),
     "mts_add_ln_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, _P, _P, _P, c_int, _P, _P, _P]),
     "mts_gelu_split": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
-    "mts_band_attn_fwd": (c_int, [_P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
-    "mts_band_attn_fwd_mma": (c_int, [_P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
+    "mts_band_attn_fwd": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
+    "mts_band_attn_fwd_mma": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
     "mts_ln_bwd_ws_bytes": (c_int64, [c_int, c_int]),
     "mts_ln_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, _P]),
     "mts_gelu_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
-    "mts_embed_bwd": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
-    "mts_band_attn_bwd": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "mts_ragged_copy": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
+    "mts_embed_bwd": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "mts_band_attn_bwd": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
 }
 
 _lib = None

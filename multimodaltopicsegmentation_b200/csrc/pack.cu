@@ -90,6 +90,24 @@ __global__ void __launch_bounds__(256) gather_pad_kernel(const float *__restrict
   }
 }
 
+// token rows between the padded [B*S, d] layout and the ragged [sum(len), d] layout (offsets int32 [B])
+__global__ void __launch_bounds__(256) ragged_copy_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst,
+                                                          const int32_t *__restrict__ lengths,
+                                                          const int32_t *__restrict__ offsets, int B, int S, int nv,
+                                                          int to_padded, float pad) {
+  const int64_t total = (int64_t)B * S * nv;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % nv);
+    const int64_t row = idx / nv;
+    const int b = (int)(row / S), t = (int)(row % S);
+    const bool valid = t < lengths[b];
+    const int64_t rrow = (int64_t)offsets[b] + t;
+    if (to_padded) dst[idx] = valid ? __ldg(src + rrow * nv + c) : make_float4(pad, pad, pad, pad);
+    else if (valid) dst[rrow * nv + c] = __ldg(src + idx);
+  }
+}
+
 }  // namespace mts
 
 using namespace mts;
@@ -139,6 +157,17 @@ extern "C" int mts_gather_pad(const float *src, const int64_t *offsets, const in
   MTS_REQUIRE(src && offsets && lengths && ids && out, MTS_E_BADARG, "gather_pad: null pointer");
   MTS_REQUIRE(B > 0 && T > 0 && D > 0, MTS_E_BADARG, "gather_pad: bad shape");
   gather_pad_kernel<<<grid_for((int64_t)B * T * D), 256, 0, (cudaStream_t)stream>>>(src, offsets, lengths, ids, B, T, D, pad, out);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mts_ragged_copy(const float *src, float *dst, const int32_t *lengths, const int32_t *offsets, int B, int S,
+                               int d, int to_padded, float pad, void *stream) {
+  MTS_REQUIRE(src && dst && lengths && offsets, MTS_E_BADARG, "ragged_copy: null pointer");
+  MTS_REQUIRE(B > 0 && S > 0 && d > 0 && d % 4 == 0, MTS_E_BADARG, "ragged_copy: bad shape (d must be a multiple of 4)");
+  MTS_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, MTS_E_BADARG, "ragged_copy: tensors must be 16-byte aligned");
+  ragged_copy_kernel<<<grid_for((int64_t)B * S * (d / 4)), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), lengths, offsets, B, S, d / 4, to_padded, pad);
   MTS_LAUNCH_CHECK();
   return 0;
 }

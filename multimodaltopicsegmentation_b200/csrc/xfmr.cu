@@ -33,14 +33,21 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
                                                      const float *__restrict__ gamma, const float *__restrict__ beta,
                                                      int M, int S, int d, float eps, float *__restrict__ y,
                                                      float *__restrict__ y_hi, float *__restrict__ y_lo, int Kp,
-                                                     float *__restrict__ sum_out, float *__restrict__ stats) {
+                                                     float *__restrict__ sum_out, float *__restrict__ stats,
+                                                     const int32_t *__restrict__ lengths,
+                                                     const int32_t *__restrict__ offsets) {
   const int lane = threadIdx.x & 31;
   const int nv = d >> 2;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+  for (int in_row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; in_row < M; in_row += warps) {
     const float4 *pa, *pb;
+    int row = in_row;
     if (MODE == 0) {
-      const int bi = row / S, t = row % S;
+      const int bi = in_row / S, t = in_row % S;
+      if (offsets) {  // ragged output: valid sentences only, episode bi starts at row offsets[bi]
+        if (t >= lengths[bi]) continue;
+        row = offsets[bi] + t;
+      }
       pa = reinterpret_cast<const float4 *>(a + (int64_t)bi * a_bstride + (int64_t)t * d);
       pb = reinterpret_cast<const float4 *>(b + (int64_t)(t + 2) * d);
     } else {
@@ -137,9 +144,10 @@ static size_t ba_smem_bytes(int hd) {
 }
 
 __global__ void __launch_bounds__(BA_THREADS, 2)
-    band_attn_fwd_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths, int S,
-                         int nheads, int hd, int w, float *__restrict__ out, float *__restrict__ out_hi,
-                         float *__restrict__ out_lo, int Kp, float *__restrict__ lse) {
+    band_attn_fwd_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths,
+                         const int32_t *__restrict__ offsets, int S, int nheads, int hd, int w,
+                         float *__restrict__ out, float *__restrict__ out_hi, float *__restrict__ out_lo, int Kp,
+                         float *__restrict__ lse) {
   extern __shared__ __align__(16) float sm[];
   const int RS = ba_row_stride(hd);
   float *Qs = sm;
@@ -154,7 +162,9 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = nheads * hd, nv = hd >> 2;
   const int len = min(max(lengths[b], 0), S);
-  const int64_t row0 = (int64_t)b * S;
+  // ragged layout (offsets != NULL): episode b owns rows offsets[b] .. offsets[b] + len - 1 and nothing beyond
+  const int64_t row0 = offsets ? (int64_t)offsets[b] : (int64_t)b * S;
+  const int Sq = offsets ? len : S;  // rows of this episode that exist in memory
   const int cg = tid % nv, rg = tid / nv;  // phase-3 mapping: 4 head columns x 4 queries
   const bool pv_thread = rg < BA_BQ / 4;
 
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int i = q0 + rg * 4 + r;
-        if (i < S) {
+        if (i < Sq) {
           const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
           if (out) reinterpret_cast<float4 *>(out + (row0 + i) * d + head * hd)[cg] = z;
           if (out_hi) {
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
   for (int idx = tid; idx < BA_BQ * nv; idx += BA_THREADS) {
     const int r = idx / nv, c = idx % nv;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < S) {
+    if (q0 + r < Sq) {
       v = __ldg(reinterpret_cast<const float4 *>(qkv + (row0 + q0 + r) * ld + head * hd) + c);
       v.x /= scale; v.y /= scale; v.z /= scale; v.w /= scale;  // query_vectors /= sqrt(head_dim) (HF :513)
     }
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int i = q0 + rg * 4 + r;
-      if (i >= S) continue;
+      if (i >= Sq) continue;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < len) {
         const float inv = 1.0f / l_s[rg * 4 + r];
@@ -339,9 +349,9 @@ __device__ __forceinline__ uint32_t tf32_lo_bits(float x, uint32_t hi) { return 
 
 template <int NHD>  // head dim / 8
 __global__ void __launch_bounds__(BM_THREADS, 2)
-    band_attn_fwd_mma_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths, int S,
-                             int nheads, int w, float *__restrict__ out, float *__restrict__ out_hi,
-                             float *__restrict__ out_lo, int Kp, float *__restrict__ lse) {
+    band_attn_fwd_mma_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths,
+                             const int32_t *__restrict__ offsets, int S, int nheads, int w, float *__restrict__ out,
+                             float *__restrict__ out_hi, float *__restrict__ out_lo, int Kp, float *__restrict__ lse) {
   constexpr int HD = NHD * 8, RS = HD + 4, NV = HD / 4;
   extern __shared__ __align__(16) float sm[];
   float *Ks = sm;                 // [64][RS]  (first holds the scaled Q tile)
@@ -352,14 +362,16 @@ __global__ void __launch_bounds__(BM_THREADS, 2)
   const int g = lane >> 2, t = lane & 3;
   const int d = nheads * HD;
   const int len = min(max(lengths[b], 0), S);
-  const int64_t row0 = (int64_t)b * S;
+  // ragged layout (offsets != NULL): episode b owns rows offsets[b] .. offsets[b] + len - 1 and nothing beyond
+  const int64_t row0 = offsets ? (int64_t)offsets[b] : (int64_t)b * S;
+  const int Sq = offsets ? len : S;  // rows of this episode that exist in memory
   const int r0 = q0 + 16 * warp;             // first query row of this warp
   const int ia = r0 + g, ib = r0 + g + 8;    // the two rows this thread holds
 
   if (q0 >= len) {  // whole block is padding: exact zeros
     for (int idx = tid; idx < BM_BQ * NV; idx += BM_THREADS) {
       const int r = idx / NV, c = idx % NV;
-      if (q0 + r < S) {
+      if (q0 + r < Sq) {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (out) reinterpret_cast<float4 *>(out + (row0 + q0 + r) * d + head * HD)[c] = z;
         if (out_hi) {
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(BM_THREADS, 2)
   for (int idx = tid; idx < BM_BQ * NV; idx += BM_THREADS) {
     const int r = idx / NV, c = idx % NV;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < S) {
+    if (q0 + r < Sq) {
       v = __ldg(reinterpret_cast<const float4 *>(qkv + (row0 + q0 + r) * ld + head * HD) + c);
       v.x /= scale; v.y /= scale; v.z /= scale; v.w /= scale;
     }
@@ -506,7 +518,7 @@ __global__ void __launch_bounds__(BM_THREADS, 2)
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int i = half ? ib : ia;
-    if (i >= S) continue;
+    if (i >= Sq) continue;
     const float inv = half ? inv_b : inv_a;
 #pragma unroll
     for (int n = 0; n < NHD; ++n) {
@@ -524,8 +536,8 @@ __global__ void __launch_bounds__(BM_THREADS, 2)
 }
 
 template <int NHD>
-static int launch_band_mma(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads, int w, float *out,
-                           float *out_hi, float *out_lo, int Kp, float *lse, cudaStream_t st) {
+static int launch_band_mma(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
+                           int nheads, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse, cudaStream_t st) {
   constexpr int HD = NHD * 8;
   const size_t smem = sizeof(float) * 2 * BM_TK * (HD + 4);
   static bool attr_set = false;
@@ -534,7 +546,8 @@ static int launch_band_mma(const float *qkv, int64_t ld, const int32_t *lengths,
     attr_set = true;
   }
   const dim3 grid((S + BM_BQ - 1) / BM_BQ, nheads, B);
-  band_attn_fwd_mma_kernel<NHD><<<grid, BM_THREADS, smem, st>>>(qkv, ld, lengths, S, nheads, w, out, out_hi, out_lo, Kp, lse);
+  band_attn_fwd_mma_kernel<NHD><<<grid, BM_THREADS, smem, st>>>(qkv, ld, lengths, offsets, S, nheads, w, out, out_hi, out_lo,
+                                                                Kp, lse);
   MTS_LAUNCH_CHECK();
   return 0;
 }
@@ -561,15 +574,17 @@ static int ln_args_ok(const char *who, int M, int d, const float *y_hi, const fl
 
 extern "C" int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *pos, const float *typ,
                                 const float *gamma, const float *beta, int B, int S, int d, float eps, float *y,
-                                float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats, void *stream) {
+                                float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats,
+                                const int32_t *lengths, const int32_t *offsets, void *stream) {
   MTS_REQUIRE(x && pos && typ && gamma && beta && y, MTS_E_BADARG, "embed_ln_fwd: null pointer");
+  MTS_REQUIRE(!offsets || lengths, MTS_E_BADARG, "embed_ln_fwd: ragged output needs the lengths");
   MTS_REQUIRE(B > 0 && S > 0, MTS_E_BADARG, "embed_ln_fwd: empty shape");
   int rc = ln_args_ok("embed_ln_fwd", B * S, d, y_hi, y_lo, Kp);
   if (rc) return rc;
   const int M = B * S;
   const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);
   ln_fwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bstride, pos, typ, gamma, beta, M, S, d, eps, y, y_hi,
-                                                            y_lo, Kp, sum_out, stats);
+                                                            y_lo, Kp, sum_out, stats, lengths, offsets);
   MTS_LAUNCH_CHECK();
   return 0;
 }
@@ -582,7 +597,7 @@ extern "C" int mts_add_ln_fwd(const float *a, const float *res, const float *gam
   if (rc) return rc;
   const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);
   ln_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, 0, res, nullptr, gamma, beta, M, 0, d, eps, y, y_hi, y_lo,
-                                                            Kp, sum_out, stats);
+                                                            Kp, sum_out, stats, nullptr, nullptr);
   MTS_LAUNCH_CHECK();
   return 0;
 }
@@ -596,9 +611,9 @@ extern "C" int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, 
   return 0;
 }
 
-extern "C" int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads,
-                                     int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
-                                     void *stream) {
+extern "C" int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B,
+                                     int S, int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp,
+                                     float *lse, void *stream) {
   MTS_REQUIRE(qkv && lengths && (out || out_hi), MTS_E_BADARG, "band_attn_fwd_mma: null pointer");
   MTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), MTS_E_BADARG, "band_attn_fwd_mma: hi and lo go together");
   MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_fwd_mma: bad shape");
@@ -606,21 +621,21 @@ extern "C" int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t
   MTS_REQUIRE(!out_hi || Kp == nheads * hd, MTS_E_UNSUPPORTED, "band_attn_fwd_mma: the split output needs Kp == model width");
   cudaStream_t st = (cudaStream_t)stream;
   switch (hd) {
-    case 8: return launch_band_mma<1>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
-    case 16: return launch_band_mma<2>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
-    case 32: return launch_band_mma<4>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
-    case 64: return launch_band_mma<8>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
-    case 112: return launch_band_mma<14>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
-    case 128: return launch_band_mma<16>(qkv, ld, lengths, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 8: return launch_band_mma<1>(qkv, ld, lengths, offsets, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 16: return launch_band_mma<2>(qkv, ld, lengths, offsets, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 32: return launch_band_mma<4>(qkv, ld, lengths, offsets, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 64: return launch_band_mma<8>(qkv, ld, lengths, offsets, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 112: return launch_band_mma<14>(qkv, ld, lengths, offsets, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
+    case 128: return launch_band_mma<16>(qkv, ld, lengths, offsets, B, S, nheads, w, out, out_hi, out_lo, Kp, lse, st);
     default: break;
   }
   set_error("band_attn_fwd_mma: head dim must be one of 8, 16, 32, 64, 112, 128");
   return MTS_E_UNSUPPORTED;
 }
 
-extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, int B, int S, int nheads,
-                                 int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
-                                 void *stream) {
+extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B,
+                                 int S, int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp,
+                                 float *lse, void *stream) {
   MTS_REQUIRE(qkv && lengths && (out || out_hi), MTS_E_BADARG, "band_attn_fwd: null pointer");
   MTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), MTS_E_BADARG, "band_attn_fwd: hi and lo go together");
   MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_fwd: bad shape");
@@ -632,7 +647,7 @@ extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *le
   // MTS_ATTN_IMPL=mma routes to the tensor-core kernel (same results; measured the same speed on B200)
   static const char *impl = getenv("MTS_ATTN_IMPL");
   if (impl && impl[0] == 'm' && (hd == 8 || hd == 16 || hd == 32 || hd == 64 || hd == 112 || hd == 128))
-    return mts_band_attn_fwd_mma(qkv, ld, lengths, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, stream);
+    return mts_band_attn_fwd_mma(qkv, ld, lengths, offsets, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, stream);
   const size_t smem = ba_smem_bytes(hd);
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -640,8 +655,8 @@ extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *le
     smem_set = smem;
   }
   const dim3 grid((S + BA_BQ - 1) / BA_BQ, nheads, B);
-  band_attn_fwd_kernel<<<grid, BA_THREADS, smem, (cudaStream_t)stream>>>(qkv, ld, lengths, S, nheads, hd, w, out, out_hi,
-                                                                        out_lo, Kp, lse);
+  band_attn_fwd_kernel<<<grid, BA_THREADS, smem, (cudaStream_t)stream>>>(qkv, ld, lengths, offsets, S, nheads, hd, w, out,
+                                                                        out_hi, out_lo, Kp, lse);
   MTS_LAUNCH_CHECK();
   return 0;
 }

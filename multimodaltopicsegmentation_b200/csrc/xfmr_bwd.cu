@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float *__restrict__
 
 // dpos[t, :] = sum_b dpre[b, t, :]
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const float *__restrict__ dpre, int B, int S, int d,
-                                                        float *__restrict__ dpos) {
+                                                        float *__restrict__ dpos, const int32_t *__restrict__ lengths,
+                                                        const int32_t *__restrict__ offsets) {
   const int nv = d >> 2;
   const int64_t total = (int64_t)S * nv;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -130,7 +131,9 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float *__restrict_
     const int64_t t = idx / nv;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int b = 0; b < B; ++b) {
-      const float4 v = __ldg(reinterpret_cast<const float4 *>(dpre + ((int64_t)b * S + t) * d) + c);
+      if (offsets && t >= lengths[b]) continue;  // ragged rows: position t of episode b exists only below its length
+      const int64_t row = offsets ? (int64_t)offsets[b] + t : (int64_t)b * S + t;
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(dpre + row * d) + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     reinterpret_cast<float4 *>(dpos + t * d)[c] = acc;
@@ -154,8 +157,8 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc)
 __global__ void __launch_bounds__(BB_THREADS, 2)
     band_attn_bwd_dq_kernel(const float *__restrict__ qkv, int64_t ld, const float *__restrict__ o,
                             const float *__restrict__ dO, const float *__restrict__ lse,
-                            const int32_t *__restrict__ lengths, int S, int nheads, int hd, int w,
-                            float *__restrict__ dqkv, float *__restrict__ delta) {
+                            const int32_t *__restrict__ lengths, const int32_t *__restrict__ offsets, int S,
+                            int nheads, int hd, int w, float *__restrict__ dqkv, float *__restrict__ delta) {
   extern __shared__ __align__(16) float sm[];
   const int RS = bb_row_stride(hd);
   float *Qs = sm;                       // [32][RS] scaled queries
@@ -170,7 +173,9 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = nheads * hd, nv = hd >> 2;
   const int len = min(max(lengths[b], 0), S);
-  const int64_t row0 = (int64_t)b * S;
+  // ragged layout (offsets != NULL): episode b owns rows offsets[b] .. offsets[b] + len - 1 and nothing beyond
+  const int64_t row0 = offsets ? (int64_t)offsets[b] : (int64_t)b * S;
+  const int Sq = offsets ? len : S;  // rows of this episode that exist in memory
   const int cg = tid % nv, rg = tid / nv;
   const bool out_thread = rg < BB_OWN / 4;
   const int64_t stat0 = ((int64_t)b * nheads + head) * S;
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int i = q0 + rg * 4 + r;
-        if (i < S) reinterpret_cast<float4 *>(dqkv + (row0 + i) * ld + head * hd)[cg] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < Sq) reinterpret_cast<float4 *>(dqkv + (row0 + i) * ld + head * hd)[cg] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (tid < BB_OWN && q0 + tid < S) delta[stat0 + q0 + tid] = 0.0f;
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int i = q0 + rg * 4 + r;
-      if (i >= S) continue;
+      if (i >= Sq) continue;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < len) v = make_float4(acc_o[r][0] / scale, acc_o[r][1] / scale, acc_o[r][2] / scale, acc_o[r][3] / scale);
       reinterpret_cast<float4 *>(dqkv + (row0 + i) * ld + head * hd)[cg] = v;
@@ -307,8 +312,8 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
 __global__ void __launch_bounds__(BB_THREADS, 2)
     band_attn_bwd_dkv_kernel(const float *__restrict__ qkv, int64_t ld, const float *__restrict__ dO,
                              const float *__restrict__ lse, const float *__restrict__ delta,
-                             const int32_t *__restrict__ lengths, int S, int nheads, int hd, int w,
-                             float *__restrict__ dqkv) {
+                             const int32_t *__restrict__ lengths, const int32_t *__restrict__ offsets, int S,
+                             int nheads, int hd, int w, float *__restrict__ dqkv) {
   extern __shared__ __align__(16) float sm[];
   const int RS = bb_row_stride(hd);
   float *Ks = sm;                        // [32][RS] own keys
@@ -324,7 +329,9 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
   const int tid = threadIdx.x;
   const int d = nheads * hd, nv = hd >> 2;
   const int len = min(max(lengths[b], 0), S);
-  const int64_t row0 = (int64_t)b * S;
+  // ragged layout (offsets != NULL): episode b owns rows offsets[b] .. offsets[b] + len - 1 and nothing beyond
+  const int64_t row0 = offsets ? (int64_t)offsets[b] : (int64_t)b * S;
+  const int Sq = offsets ? len : S;  // rows of this episode that exist in memory
   const int cg = tid % nv, rg = tid / nv;
   const bool out_thread = rg < BB_OWN / 4;
   const int64_t stat0 = ((int64_t)b * nheads + head) * S;
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int kj = k0 + rg * 4 + r;
-      if (kj >= S) continue;
+      if (kj >= Sq) continue;
       float *base = dqkv + (row0 + kj) * ld + head * hd;
       reinterpret_cast<float4 *>(base + d)[cg] = make_float4(dk[r][0], dk[r][1], dk[r][2], dk[r][3]);
       reinterpret_cast<float4 *>(base + 2 * d)[cg] = make_float4(dv[r][0], dv[r][1], dv[r][2], dv[r][3]);
@@ -493,17 +500,19 @@ extern "C" int mts_gelu_bwd(const float *dz, const float *zp, int rows, int cols
   return 0;
 }
 
-extern "C" int mts_embed_bwd(const float *dpre, int B, int S, int d, float *dpos, void *stream) {
+extern "C" int mts_embed_bwd(const float *dpre, int B, int S, int d, float *dpos, const int32_t *lengths,
+                             const int32_t *offsets, void *stream) {
   MTS_REQUIRE(dpre && dpos, MTS_E_BADARG, "embed_bwd: null pointer");
+  MTS_REQUIRE(!offsets || lengths, MTS_E_BADARG, "embed_bwd: ragged rows need the lengths");
   MTS_REQUIRE(B > 0 && S > 0 && d > 0 && d % 4 == 0, MTS_E_BADARG, "embed_bwd: bad shape");
-  embed_bwd_kernel<<<ew_grid2((int64_t)S * (d / 4)), 256, 0, (cudaStream_t)stream>>>(dpre, B, S, d, dpos);
+  embed_bwd_kernel<<<ew_grid2((int64_t)S * (d / 4)), 256, 0, (cudaStream_t)stream>>>(dpre, B, S, d, dpos, lengths, offsets);
   MTS_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int mts_band_attn_bwd(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
-                                 const int32_t *lengths, int B, int S, int nheads, int hd, int w, float *dqkv,
-                                 float *delta_ws, void *stream) {
+                                 const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int hd, int w,
+                                 float *dqkv, float *delta_ws, void *stream) {
   MTS_REQUIRE(qkv && o && d_o && lse && lengths && dqkv && delta_ws, MTS_E_BADARG, "band_attn_bwd: null pointer");
   MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_bwd: bad shape");
   MTS_REQUIRE(hd % 4 == 0 && hd <= 128, MTS_E_UNSUPPORTED, "band_attn_bwd: head dim must be a multiple of 4 and <= 128");
@@ -522,10 +531,10 @@ extern "C" int mts_band_attn_bwd(const float *qkv, int64_t ld, const float *o, c
   }
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid((S + BB_OWN - 1) / BB_OWN, nheads, B);
-  band_attn_bwd_dq_kernel<<<grid, BB_THREADS, smem_dq, st>>>(qkv, ld, o, d_o, lse, lengths, S, nheads, hd, w, dqkv,
-                                                             delta_ws);
-  band_attn_bwd_dkv_kernel<<<grid, BB_THREADS, smem_dkv, st>>>(qkv, ld, d_o, lse, delta_ws, lengths, S, nheads, hd, w,
-                                                               dqkv);
+  band_attn_bwd_dq_kernel<<<grid, BB_THREADS, smem_dq, st>>>(qkv, ld, o, d_o, lse, lengths, offsets, S, nheads, hd, w,
+                                                             dqkv, delta_ws);
+  band_attn_bwd_dkv_kernel<<<grid, BB_THREADS, smem_dkv, st>>>(qkv, ld, d_o, lse, delta_ws, lengths, offsets, S, nheads,
+                                                               hd, w, dqkv);
   MTS_LAUNCH_CHECK();
   return 0;
 }

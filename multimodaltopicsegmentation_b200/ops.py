@@ -89,11 +89,16 @@ class Lengths:
         self.T = max(host)  # pad_packed_sequence crops the time axis to max(lengths)
         self.N = sum(host)
         order = sorted(range(self.B), key=lambda i: -host[i])
-        both = torch.tensor([host, order], dtype=torch.int32)
+        offs, run = [], 0
+        for n in host:  # exclusive prefix sums: first row of every episode in the ragged token layout
+            offs.append(run)
+            run += n
+        both = torch.tensor([host, order, offs], dtype=torch.int32)
         both = both.pin_memory() if torch.cuda.is_available() else both
         dev = both.to(device, non_blocking=True)
         self.dev = dev[0]
         self.order = dev[1]
+        self.offs = dev[2]
 
 
 # --------------------------------------------------------------------------------------------------------

@@ -174,9 +174,10 @@ class PackedEncoder:
         return ent
 
 
-def _ln(mode, a, b, typ, gamma, beta, B, S, d, want_split, save):
-    """mode 0: embeddings LN over x=a [B,S,d] with position table b; mode 1: LN(a + b) over [M,d] rows."""
-    M = B * S
+def _ln(mode, a, b, typ, gamma, beta, B, S, d, want_split, save, lens=None):
+    """mode 0: embeddings LN over x=a [B,S,d] with position table b (lens given: ragged output rows);
+    mode 1: LN(a + b) over [M,d] rows (M = B, S = 1)."""
+    M = lens.N if lens is not None else B * S
     dev = a.device
     y = torch.empty((M, d), device=dev, dtype=torch.float32)
     kp = _pad32(d)
@@ -188,44 +189,59 @@ def _ln(mode, a, b, typ, gamma, beta, B, S, d, want_split, save):
     stats = torch.empty((M, 2), device=dev, dtype=torch.float32) if save else None
     if mode == 0:
         _call("mts_embed_ln_fwd", _ptr(a), a.stride(0), _ptr(b), _ptr(typ), _ptr(gamma), _ptr(beta), B, S, d, LN_EPS,
-              _ptr(y), _ptr(hi), _ptr(lo), kp, _ptr(pre), _ptr(stats), _stream())
+              _ptr(y), _ptr(hi), _ptr(lo), kp, _ptr(pre), _ptr(stats), _ptr(lens.dev) if lens is not None else 0,
+              _ptr(lens.offs) if lens is not None else 0, _stream())
     else:
         _call("mts_add_ln_fwd", _ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), M, d, LN_EPS, _ptr(y), _ptr(hi), _ptr(lo), kp,
               _ptr(pre), _ptr(stats), _stream())
     return y, (y if (want_split and hi is None) else hi), lo, pre, stats
 
 
+# Token layout inside the encoder: "ragged" (default) keeps rows only for the sum(len) valid sentences, so the dense
+# layers, LayerNorms and GELU do no work on padding (45 % of the rows at configs[2]); "padded" is the reference's
+# [B*S] layout.  Valid positions come out identical either way (padded keys are masked); with the ragged layout the
+# padded positions of the returned hidden state are exact zeros instead of the reference's don't-care values.
+LAYOUT = __import__("os").environ.get("MTS_XF_LAYOUT", "ragged")
+
+
 def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
     """x [B,S,d] -> last hidden state [B,S,d].  `reaches[l]` = one-sided window of layer l.
     With save=True also returns what the backward pass needs."""
     B, S, d = x.shape
-    M = B * S
+    ragged = LAYOUT == "ragged"
+    M = lens.N if ragged else B * S
+    offs = _ptr(lens.offs) if ragged else 0
     dev = x.device
     hd = d // nheads
     m = packed.params
     layers = packed.get()
     emb = m.embeddings
     h, h_hi, h_lo, pre0, st0 = _ln(0, x, emb.position_embeddings.weight.detach(), emb.token_type_embeddings.weight.detach()[0],
-                                   emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), B, S, d, True, save)
-    saved = {"emb": (pre0, st0), "layers": []}
+                                   emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), B, S, d, True, save,
+                                   lens if ragged else None)
+    saved = {"emb": (pre0, st0), "layers": [], "ragged": ragged}
     for l, ent in enumerate(layers):
         lyr = m.encoder.layer[l]
         F = lyr.intermediate.dense.out_features
         qkv = torch.empty((M, 3 * d), device=dev, dtype=torch.float32)
         ops.gemm_tf32x3(h_hi, h_lo, ent["wqkv"][0], ent["wqkv"][1], ent["bqkv"], qkv, M, 3 * d, epilogue=1)
         kp = _pad32(d)
-        a_hl = torch.empty((2, M, kp), device=dev, dtype=torch.float32)
         lse = torch.empty((B, nheads, S), device=dev, dtype=torch.float32) if save else None
-        a = torch.empty((M, d), device=dev, dtype=torch.float32) if (save or kp != d) else None
-        if kp == d:
-            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), B, S, nheads, hd, reaches[l], _ptr(a),
-                  _ptr(a_hl[0]), _ptr(a_hl[1]), kp, _ptr(lse), _stream())
+        if kp == d:  # the attention output is its own `hi` operand; the kernel adds the correction operand
+            a = torch.empty((M, d), device=dev, dtype=torch.float32)
+            a_lo = torch.empty((M, kp), device=dev, dtype=torch.float32)
+            a_hi = a
+            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), offs, B, S, nheads, hd, reaches[l], 0,
+                  _ptr(a_hi), _ptr(a_lo), kp, _ptr(lse), _stream())
         else:  # widths that are not a multiple of 32: plain output, then the generic (zero-padding) split
-            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), B, S, nheads, hd, reaches[l], _ptr(a), 0, 0, 0,
-                  _ptr(lse), _stream())
-            _call("mts_split_tf32", _ptr(a), d, M, d, kp, ops.A_SIDE, _ptr(a_hl[0]), _ptr(a_hl[1]), _stream())
+            a = torch.empty((M, d), device=dev, dtype=torch.float32)
+            a_hl = torch.empty((2, M, kp), device=dev, dtype=torch.float32)
+            a_hi, a_lo = a_hl[0], a_hl[1]
+            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), offs, B, S, nheads, hd, reaches[l], _ptr(a), 0, 0,
+                  0, _ptr(lse), _stream())
+            _call("mts_split_tf32", _ptr(a), d, M, d, kp, ops.A_SIDE, _ptr(a_hi), _ptr(a_lo), _stream())
         t = torch.empty((M, d), device=dev, dtype=torch.float32)
-        ops.gemm_tf32x3(a_hl[0], a_hl[1], ent["wo"][0], ent["wo"][1], ent["bo"], t, M, d, epilogue=1)
+        ops.gemm_tf32x3(a_hi, a_lo, ent["wo"][0], ent["wo"][1], ent["bo"], t, M, d, epilogue=1)
         ln1 = lyr.attention.output.LayerNorm
         y, y_hi, y_lo, pre1, st1 = _ln(1, t, h, None, ln1.weight.detach(), ln1.bias.detach(), M, 1, d, True, save)
         zp = torch.empty((M, F), device=dev, dtype=torch.float32)
@@ -243,6 +259,10 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
         if save:
             saved["layers"].append({"h_in": h_in, "qkv": qkv, "lse": lse, "a": a, "pre1": pre1, "st1": st1,
                                     "y": y, "zp": zp, "z": z, "pre2": pre2, "st2": st2})
+    if ragged:  # back to the caller's [B,S,d] layout, padded sentences zero
+        out = torch.empty((B, S, d), device=dev, dtype=torch.float32)
+        _call("mts_ragged_copy", _ptr(h), _ptr(out), _ptr(lens.dev), _ptr(lens.offs), B, S, d, 1, 0.0, _stream())
+        return out, saved
     return h.view(B, S, d), saved
 
 

@@ -50,14 +50,20 @@ def _dense_param_grads(dy, x, M, n_out, n_in):
 def encoder_backward(ctx, dout):
     saved, lens, packed, nheads, reaches = ctx.saved, ctx.lens, ctx.packed, ctx.nheads, ctx.reaches
     B, S, d = ctx.shape
-    M = B * S
+    ragged = saved["ragged"]
+    M = lens.N if ragged else B * S
+    offs = _ptr(lens.offs) if ragged else 0
     hd = d // nheads
     dev = dout.device
     m = packed.params
     n_layers = len(m.encoder.layer)
     per = packed.PER_LAYER
     grads = [None] * (4 + per * n_layers)
-    dh = dout.reshape(M, d)
+    if ragged:  # gradient rows of the valid sentences only, in the forward pass's ragged order
+        dh = torch.empty((M, d), device=dev, dtype=torch.float32)
+        _call("mts_ragged_copy", _ptr(dout), _ptr(dh), _ptr(lens.dev), _ptr(lens.offs), B, S, d, 0, 0.0, _stream())
+    else:
+        dh = dout.reshape(M, d)
     for l in range(n_layers - 1, -1, -1):
         lyr = m.encoder.layer[l]
         sv = saved["layers"][l]
@@ -90,7 +96,7 @@ def encoder_backward(ctx, dout):
         # ---- banded attention ----------------------------------------------------------------------------------
         dqkv = torch.empty((M, 3 * d), device=dev, dtype=torch.float32)
         delta = torch.empty((B, nheads, S), device=dev, dtype=torch.float32)
-        _call("mts_band_attn_bwd", _ptr(sv["qkv"]), 3 * d, _ptr(sv["a"]), _ptr(da), _ptr(sv["lse"]), _ptr(lens.dev), B, S,
+        _call("mts_band_attn_bwd", _ptr(sv["qkv"]), 3 * d, _ptr(sv["a"]), _ptr(da), _ptr(sv["lse"]), _ptr(lens.dev), offs, B, S,
               nheads, hd, reaches[l], _ptr(dqkv), _ptr(delta), _stream())
         # ---- qkv = h_in Wqkv^T + b;  dh_in = dqkv Wqkv + dpre1 (skip path) ---------------------------------------
         dwqkv, dbqkv = _dense_param_grads(dqkv, sv["h_in"], M, 3 * d, d)
@@ -104,7 +110,8 @@ def encoder_backward(ctx, dout):
     pre0, st0 = saved["emb"]
     dpre0, _, dg0, db0 = _ln_bwd(dh, pre0, st0, emb.LayerNorm.weight.detach(), M, d)
     dpos = torch.zeros_like(emb.position_embeddings.weight)
-    _call("mts_embed_bwd", _ptr(dpre0), B, S, d, dpos.data_ptr() + 4 * 2 * d, _stream())
+    _call("mts_embed_bwd", _ptr(dpre0), B, S, d, dpos.data_ptr() + 4 * 2 * d, _ptr(lens.dev) if ragged else 0, offs,
+          _stream())
     dtyp = torch.zeros_like(emb.token_type_embeddings.weight)
     ops.colsum(dpos.data_ptr() + 4 * 2 * d, d, S, d, dtyp[0])
     grads[0], grads[1], grads[2], grads[3] = dtyp, dpos, dg0, db0

@@ -117,10 +117,10 @@ if __name__ == "__main__":
         lens = ops.Lengths(lengths, dev, S)
         hl = torch.empty(2, B * S, d, device=dev)
         for _ in range(3):
-            ops._call("mts_band_attn_fwd", qkv.data_ptr(), 3 * d, lens.dev.data_ptr(), B, S, h, hd, w, 0, hl[0].data_ptr(),
+            ops._call("mts_band_attn_fwd", qkv.data_ptr(), 3 * d, lens.dev.data_ptr(), 0, B, S, h, hd, w, 0, hl[0].data_ptr(),
                       hl[1].data_ptr(), d, 0, ops._stream())
         torch.cuda.synchronize()
-        ms = timeit(lambda: ops._call("mts_band_attn_fwd", qkv.data_ptr(), 3 * d, lens.dev.data_ptr(), B, S, h, hd, w, 0,
+        ms = timeit(lambda: ops._call("mts_band_attn_fwd", qkv.data_ptr(), 3 * d, lens.dev.data_ptr(), 0, B, S, h, hd, w, 0,
                                       hl[0].data_ptr(), hl[1].data_ptr(), d, 0, ops._stream()), iters=3, warmup=0)
         n = int(lengths.sum())
         print(f"band_attn_fwd w={w}: {ms:.3f} ms, {n * 16 * d / ms / 1e6:.1f} GB/s algorithmic ({n} valid tokens)")

@@ -466,6 +466,21 @@ def load_params_allow_unused(module, fx, dev):
     return module.to(dev)
 
 
+def _to_ragged(t, lens, B, S):
+    """[B*S, c] padded rows -> [sum(len), c] valid rows."""
+    return torch.cat([t.view(B, S, -1)[b, :n] for b, n in enumerate(lens)], dim=0).contiguous()
+
+
+def _to_padded(t, lens, B, S):
+    out = torch.zeros(B, S, t.shape[1], dtype=t.dtype, device=t.device)
+    o = 0
+    for b, n in enumerate(lens):
+        out[b, :n] = t[o:o + n]
+        o += n
+    return out.view(B * S, -1)
+
+
+@pytest.mark.parametrize("layout", ["padded", "ragged"])
 @pytest.mark.parametrize("entry", ["mts_band_attn_fwd", "mts_band_attn_fwd_mma"])
 @pytest.mark.parametrize("B,S,h,hd,w,lens", [
     (2, 24, 4, 8, 4, [24, 13]),
@@ -474,8 +489,9 @@ def load_params_allow_unused(module, fx, dev):
     (2, 96, 2, 32, 100, [96, 50]),      # window wider than the episode: dense attention
     (1, 700, 1, 16, 360, [650]),        # default-config reach (window 120 x 6 layers)
 ])
-def test_band_attention_forward(dev, B, S, h, hd, w, lens, entry):
-    """CUDA-core kernel and mma.sync tensor-core kernel against the numpy restatement of HF's banded attention."""
+def test_band_attention_forward(dev, B, S, h, hd, w, lens, entry, layout):
+    """CUDA-core kernel and mma.sync tensor-core kernel against the numpy restatement of HF's banded attention, in the
+    reference's padded row layout and in the ragged layout (valid sentences only; include/mts_b200.h "Row layouts")."""
     from multimodaltopicsegmentation_b200 import ops
     from oracle import ref_numpy as rn
 
@@ -483,26 +499,43 @@ def test_band_attention_forward(dev, B, S, h, hd, w, lens, entry):
     d = h * hd
     qkv = torch.randn(B * S, 3 * d, generator=g)
     L = ops.Lengths(lens, dev, S)
-    qkv_d = qkv.to(dev)
-    out = torch.empty(B * S, d, device=dev)
+    ragged = layout == "ragged"
+    offs = L.offs.data_ptr() if ragged else 0
+    qkv_d = (_to_ragged(qkv, lens, B, S) if ragged else qkv).to(dev)
+    rows = qkv_d.shape[0]
+    out = torch.full((rows + 1, d), 7.0, device=dev)  # one guard row behind the last valid one
     lse = torch.empty(B, h, S, device=dev)
-    ops._call(entry, qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
+    ops._call(entry, qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), offs, B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
               lse.data_ptr(), ops._stream())
+    assert float((out[rows] - 7.0).abs().max()) == 0.0
+    out = out[:rows]
     split = lambda t: t.view(B, S, h, hd).permute(0, 2, 1, 3).numpy()
     q = split(qkv[:, :d]) / np.float32(np.sqrt(hd))
     ref = rn.banded_attention(q.astype(np.float32), split(qkv[:, d:2 * d]), split(qkv[:, 2 * d:]), lens, w)
-    got = out.view(B, S, h, hd).permute(0, 2, 1, 3)
+    full = _to_padded(out, lens, B, S) if ragged else out
+    got = full.view(B, S, h, hd).permute(0, 2, 1, 3)
     close(got, ref, rtol=1e-4, atol=1e-5)
-    for b, n in enumerate(lens):  # padded queries: exact zeros (HF modeling_longformer.py:578)
-        assert float(out.view(B, S, d)[b, n:].abs().max() if n < S else 0.0) == 0.0
+    if not ragged:
+        for b, n in enumerate(lens):  # padded queries: exact zeros (HF modeling_longformer.py:578)
+            assert float(out.view(B, S, d)[b, n:].abs().max() if n < S else 0.0) == 0.0
     if d % 32 == 0:  # fused operand split
-        hl = torch.empty(2, B * S, d, device=dev)
-        ops._call(entry, qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, 0, hl[0].data_ptr(),
+        hl = torch.empty(2, rows, d, device=dev)
+        ops._call(entry, qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), offs, B, S, h, hd, w, 0, hl[0].data_ptr(),
                   hl[1].data_ptr(), d, 0, ops._stream())
         check_operand_pair(hl[0], hl[1], out, side=0)
 
 
-def test_transformer_golden_forward(dev, golden):
+@pytest.fixture(params=["ragged", "padded"])
+def xf_layout(request, monkeypatch):
+    """Both token layouts of the encoder (transformer.LAYOUT): ragged = valid sentences only (default), padded = the
+    reference's [B*S] rows."""
+    from multimodaltopicsegmentation_b200 import transformer
+
+    monkeypatch.setattr(transformer, "LAYOUT", request.param)
+    return request.param
+
+
+def test_transformer_golden_forward(dev, golden, xf_layout):
     from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
 
     fx = golden("transformer_focal")
@@ -513,17 +546,23 @@ def test_transformer_golden_forward(dev, golden):
     lengths = torch.from_numpy(fx["i:lengths"])
     m.th = float(fx["i:th"])
     hidden = m.model(x, lengths)
-    close(hidden, fx["o:hidden"])
     scores, tags = m(x, lengths)
     assert tuple(scores.shape) == fx["o:scores"].shape  # time axis = S for the transformer
-    close(scores, fx["o:scores"], atol=1e-4)  # classification weights were scaled x20 in the fixture
+    if xf_layout == "padded":  # the reference's layout: padded positions carry the reference's values too
+        close(hidden, fx["o:hidden"])
+        close(scores, fx["o:scores"], atol=1e-4)  # classification weights were scaled x20 in the fixture
+    else:  # valid sentences identical; padded sentences are exact zeros (they have no rows inside the encoder)
+        for b, n in enumerate(lengths.tolist()):
+            close(hidden[b, :n], fx["o:hidden"][b, :n])
+            close(scores[b, :n], fx["o:scores"][b, :n], atol=1e-4)
+            assert float(hidden[b, n:].abs().max() if n < hidden.shape[1] else 0.0) == 0.0
     tags_equal(tags, fx["o:tags"])
     with torch.no_grad():
         loss = m.loss(x, lengths, torch.from_numpy(fx["i:y"]).to(dev))
     close(loss, fx["o:loss"])
 
 
-def test_transformer_vs_hf_twin(dev):
+def test_transformer_vs_hf_twin(dev, xf_layout):
     """Medium shapes against the HF LongformerModel twin (oracle/ref_torch.py), ragged lengths."""
     from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
     from oracle import ref_torch as rt
@@ -577,29 +616,38 @@ def _dense_band_attention_torch(qkv, lens, B, S, h, hd, w):
     (2, 130, 3, 64, 8, [130, 31]),
     (1, 300, 1, 16, 120, [280]),
 ])
-def test_band_attention_backward(dev, B, S, h, hd, w, lens):
+@pytest.mark.parametrize("layout", ["padded", "ragged"])
+def test_band_attention_backward(dev, B, S, h, hd, w, lens, layout):
     from multimodaltopicsegmentation_b200 import ops
 
     g = torch.Generator().manual_seed(S + hd + w + 1)
     d = h * hd
     qkv = torch.randn(B * S, 3 * d, generator=g, dtype=torch.float64).requires_grad_(True)
     do = torch.randn(B * S, d, generator=g, dtype=torch.float64)
+    ragged = layout == "ragged"
+    if ragged:  # the ragged layout has no rows for padded sentences: their upstream gradient does not exist
+        for b, n in enumerate(lens):
+            do.view(B, S, d)[b, n:] = 0
     ref = _dense_band_attention_torch(qkv, lens, B, S, h, hd, w)
     ref.backward(do)
     L = ops.Lengths(lens, dev, S)
-    qkv_d = qkv.detach().float().to(dev)
-    out = torch.empty(B * S, d, device=dev)
+    offs = L.offs.data_ptr() if ragged else 0
+    pack = (lambda t: _to_ragged(t, lens, B, S)) if ragged else (lambda t: t)
+    qkv_d = pack(qkv.detach().float()).to(dev)
+    rows = qkv_d.shape[0]
+    out = torch.empty(rows, d, device=dev)
     lse = torch.empty(B, h, S, device=dev)
-    ops._call("mts_band_attn_fwd", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
+    ops._call("mts_band_attn_fwd", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), offs, B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
               lse.data_ptr(), ops._stream())
-    close(out, ref.detach().float(), rtol=1e-4, atol=1e-5)
-    dqkv = torch.full((B * S, 3 * d), float("nan"), device=dev)
+    close(out, pack(ref.detach().float()), rtol=1e-4, atol=1e-5)
+    dqkv = torch.full((rows + 1, 3 * d), float("nan"), device=dev)
     delta = torch.empty(B, h, S, device=dev)
-    do_d = do.float().to(dev)
+    do_d = pack(do.float()).to(dev)
     ops._call("mts_band_attn_bwd", qkv_d.data_ptr(), 3 * d, out.data_ptr(), do_d.data_ptr(), lse.data_ptr(),
-              L.dev.data_ptr(), B, S, h, hd, w, dqkv.data_ptr(), delta.data_ptr(), ops._stream())
+              L.dev.data_ptr(), offs, B, S, h, hd, w, dqkv.data_ptr(), delta.data_ptr(), ops._stream())
+    assert bool(torch.isnan(dqkv[rows]).all())  # nothing written behind the last row
     scale = float(qkv.grad.abs().max())
-    close(dqkv, qkv.grad.float(), rtol=1e-4, atol=2e-5 * scale)
+    close(dqkv[:rows], pack(qkv.grad.float()), rtol=1e-4, atol=2e-5 * scale)
 
 
 @pytest.mark.parametrize("M,d", [(37, 32), (1000, 896), (300, 1024), (64, 100)])
@@ -636,7 +684,7 @@ def test_layer_norm_forward_backward(dev, M, d):
     check_operand_pair(dhl[0], dhl[1], dx, side=0)
 
 
-def test_transformer_golden_backward(dev, golden):
+def test_transformer_golden_backward(dev, golden, xf_layout):
     from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
 
     fx = golden("transformer_focal")
@@ -660,7 +708,7 @@ def test_transformer_golden_backward(dev, golden):
             assert p.grad is None, k
 
 
-def test_transformer_training_vs_hf_twin(dev):
+def test_transformer_training_vs_hf_twin(dev, xf_layout):
     from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
     from oracle import ref_torch as rt
 
