@@ -8,7 +8,8 @@
 Workload (BASELINE.json configs[0] shape, the configuration the sentences/sec metric is quoted on):
 early-fusion BiLSTM segmenter, 64 episodes x 300 sentences, 384-d text + 512-d audio embeddings, hidden 256,
 2 layers, sigmoid head thresholded at 0.5.  A step = one inference pass over one batch: operand packing
-(fused concat), two input-projection GEMMs (tcgen05 3xTF32), two bidirectional recurrence launches, head+decode.
+(fused concat), two input-projection GEMMs (tcgen05, TF32 + bf16 error compensation), two bidirectional recurrence
+launches, head+decode.
 
   value  : sentences/s with the inputs resident in HBM (CUDA events over exactly K steps, max over ranks).
   e2e    : the same through TextSegmenter.predict_step with HOST (pinned) inputs, H2D copies and the D2H of the
@@ -313,12 +314,15 @@ def transformer_bench(m, dev, rank, world, steps, barrier):
                                      "algorithmic_bytes_per_launch": n_sent * XF_ATTN_BYTES_PER_TOKEN,
                                      "ms_per_layer": attn}
     if gemm:
-        tf = tokens * XF_GEMM_FLOPS_PER_TOKEN * c["L"] / (sum(gemm) / 1e3) / 1e12
-        out["roofline_dense"] = {"kernel": "gemm_tf32x3_kernel (24 launches)", "bound": "tensor",
+        from multimodaltopicsegmentation_b200 import transformer as xf
+        rows = n_sent if xf.LAYOUT == "ragged" else tokens   # the dense layers only see the valid sentences
+        tf = rows * XF_GEMM_FLOPS_PER_TOKEN * c["L"] / (sum(gemm) / 1e3) / 1e12
+        out["roofline_dense"] = {"kernel": "gemm_tf32x3_2sm_kernel / gemm_tf32x3_kernel (24 launches)", "bound": "tensor",
+                                 "rows_per_launch": rows, "token_layout": xf.LAYOUT,
                                  "achieved_tflops_fp32_equiv": tf, "achieved_tflops_issued": 2 * tf,
                                  "note": "error-compensated TF32: one TF32 product + one bf16 correction product per "
-                                         "fp32-grade product (issued = 2x); measured bound is L2 -> SM operand traffic "
-                                         "(8 B per operand element), see DESIGN.md section 4"}
+                                         "fp32-grade product (issued = 2x); measured bound is the chip-wide L2 read "
+                                         "throughput (8 B per operand element), see DESIGN.md section 4"}
     return out
 
 
@@ -503,7 +507,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "per_gpu_batch": c["B"], "global_batch": c["B"] * world,
                    "l2": "4 rotating input sets (275 MB) exceed the 126 MB L2", "gemm": "tcgen05 TF32 + bf16 correction",
                    "launch": f"one CUDA graph per input set ({launches_per_step} kernels)" if graphs is not None else "eager launches",
-                   "recurrence": "tcgen05 3xTF32, W_hh resident in TMEM" if rec_name.endswith("_tc") else "packed-fp32 FMA",
+                   "recurrence": "tcgen05 TF32 + bf16 correction, W_hh resident in TMEM" if rec_name.endswith("_tc") else "packed-fp32 FMA",
                    "parallelism": f"dp{world} (episodes sharded, final all_gather of tags)" if world > 1 else "single GPU"},
         "e2e": {"value": total_sent / e2e_s, "unit": "sentences/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "DevicePrefetcher (side-stream H2D of the next batch) -> TextSegmenter.predict_step, pinned host tensors in, "

@@ -11,3 +11,6 @@ echo "rec full rc=$?"
 python tests/bench_kernels.py gemm_one > gpurun_out/gemm_one_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 1 -c 1 -o gpurun_out/gemm_full python tests/bench_kernels.py gemm_one > gpurun_out/ncu_gemm_full.log 2>&1
 echo "gemm full rc=$?"
+python tests/bench_kernels.py attn_one 48 > gpurun_out/attn_one_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:band_attn_fwd -s 3 -c 1 -o gpurun_out/attn_full python tests/bench_kernels.py attn_one 48 > gpurun_out/ncu_attn_full.log 2>&1
+echo "attn full rc=$?"
