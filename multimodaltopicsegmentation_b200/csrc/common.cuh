@@ -98,6 +98,15 @@ __device__ __forceinline__ void corr_store4(float *row, int k, float4 v, int sid
       make_uint2(bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y)), bf16x2_bits(tf32_rest_exact(v.z), tf32_rest_exact(v.w)));
 }
 
+__device__ __forceinline__ void corr_store8(float *row, int k, float4 a, float4 b, int side) {  // k a multiple of 8
+  uint16_t *p = reinterpret_cast<uint16_t *>(row) + (k >> 4) * 32 + (k & 15);
+  *reinterpret_cast<uint4 *>(p + (side ? 16 : 0)) =
+      make_uint4(bf16x2_bits(a.x, a.y), bf16x2_bits(a.z, a.w), bf16x2_bits(b.x, b.y), bf16x2_bits(b.z, b.w));
+  *reinterpret_cast<uint4 *>(p + (side ? 0 : 16)) =
+      make_uint4(bf16x2_bits(tf32_rest_exact(a.x), tf32_rest_exact(a.y)), bf16x2_bits(tf32_rest_exact(a.z), tf32_rest_exact(a.w)),
+                 bf16x2_bits(tf32_rest_exact(b.x), tf32_rest_exact(b.y)), bf16x2_bits(tf32_rest_exact(b.z), tf32_rest_exact(b.w)));
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 }  // namespace mts

@@ -24,6 +24,55 @@ __global__ void __launch_bounds__(256) pack_rows_split_kernel(const float *__res
   }
 }
 
+// The same, 8 consecutive K elements per thread (two 16-byte loads, two 16-byte `hi` stores, two 16-byte halves of the
+// correction operand): needs D1, D2 multiples of 8 and 16-byte aligned rows.  src2 may be NULL (D2 = 0).
+__global__ void __launch_bounds__(256) pack_rows_split_v8_kernel(const float *__restrict__ src1, int64_t bstride1, int D1,
+                                                                 const float *__restrict__ src2, int64_t bstride2, int D2,
+                                                                 int B, int T, int Kp, float *__restrict__ hi,
+                                                                 float *__restrict__ lo) {
+  const int k8n = Kp >> 3;
+  const int64_t total = (int64_t)B * T * k8n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % k8n) << 3;
+    const int64_t row = idx / k8n;
+    const int b = (int)(row / T), t = (int)(row % T);
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    const float *p = nullptr;
+    if (k < D1) p = src1 + (int64_t)b * bstride1 + (int64_t)t * D1 + k;
+    else if (k < D1 + D2) p = src2 + (int64_t)b * bstride2 + (int64_t)t * D2 + (k - D1);
+    if (p) {
+      v0 = __ldcs(reinterpret_cast<const float4 *>(p));      // streamed once: do not keep in L2 ahead of the GEMM operands
+      v1 = __ldcs(reinterpret_cast<const float4 *>(p) + 1);
+    }
+    float4 *h = reinterpret_cast<float4 *>(hi + row * Kp + k);
+    h[0] = v0;
+    h[1] = v1;
+    corr_store8(lo + row * Kp, k, v0, v1, 0);
+  }
+}
+
+__global__ void __launch_bounds__(256) split_tf32_v8_kernel(const float *__restrict__ src, int64_t ld, int rows, int cols,
+                                                            int Kp, int side, float *__restrict__ hi,
+                                                            float *__restrict__ lo) {
+  const int k8n = Kp >> 3;
+  const int64_t total = (int64_t)rows * k8n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % k8n) << 3;
+    const int64_t r = idx / k8n;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (k < cols) {  // cols % 8 == 0: a group is entirely inside or entirely padding
+      v0 = __ldg(reinterpret_cast<const float4 *>(src + r * ld + k));
+      v1 = __ldg(reinterpret_cast<const float4 *>(src + r * ld + k) + 1);
+    }
+    float4 *h = reinterpret_cast<float4 *>(hi + r * Kp + k);
+    h[0] = v0;
+    h[1] = v1;
+    corr_store8(lo + r * Kp, k, v0, v1, side);
+  }
+}
+
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ src, int64_t ld, int rows, int cols,
                                                          int Kp, int side, float *__restrict__ hi, float *__restrict__ lo) {
   const int64_t total = (int64_t)rows * Kp;
@@ -124,8 +173,15 @@ extern "C" int mts_pack_rows_split(const float *src1, int64_t bstride1, int D1, 
   MTS_REQUIRE(D2 == 0 || src2, MTS_E_BADARG, "pack_rows_split: D2 > 0 without src2");
   MTS_REQUIRE(B > 0 && T > 0 && D1 > 0 && D2 >= 0, MTS_E_BADARG, "pack_rows_split: bad shape");
   MTS_REQUIRE(Kp % 32 == 0 && Kp >= D1 + D2, MTS_E_BADARG, "pack_rows_split: Kp must be a multiple of 32 and >= D1 + D2");
-  pack_rows_split_kernel<<<grid_for((int64_t)B * T * Kp), 256, 0, (cudaStream_t)stream>>>(src1, bstride1, D1, src2,
-                                                                                         bstride2, D2, B, T, Kp, hi, lo);
+  const bool al16 = ((((uintptr_t)src1 | (uintptr_t)src2 | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0) &&
+                    bstride1 % 4 == 0 && bstride2 % 4 == 0;
+  if (al16 && D1 % 8 == 0 && D2 % 8 == 0) {
+    pack_rows_split_v8_kernel<<<grid_for((int64_t)B * T * (Kp / 8)), 256, 0, (cudaStream_t)stream>>>(
+        src1, bstride1, D1, src2, bstride2, D2, B, T, Kp, hi, lo);
+  } else {
+    pack_rows_split_kernel<<<grid_for((int64_t)B * T * Kp), 256, 0, (cudaStream_t)stream>>>(src1, bstride1, D1, src2,
+                                                                                           bstride2, D2, B, T, Kp, hi, lo);
+  }
   MTS_LAUNCH_CHECK();
   return 0;
 }
@@ -135,7 +191,12 @@ extern "C" int mts_split_tf32(const float *src, int64_t ld, int rows, int cols, 
   MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "split_tf32: null pointer");
   MTS_REQUIRE(rows > 0 && cols > 0 && Kp % 32 == 0 && Kp >= cols, MTS_E_BADARG, "split_tf32: bad shape");
   MTS_REQUIRE(side == 0 || side == 1, MTS_E_BADARG, "split_tf32: side must be 0 (A operand) or 1 (B operand)");
-  split_tf32_kernel<<<grid_for((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, side, hi, lo);
+  if (((((uintptr_t)src | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0) && ld % 4 == 0 && cols % 8 == 0) {
+    split_tf32_v8_kernel<<<grid_for((int64_t)rows * (Kp / 8)), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, side,
+                                                                                               hi, lo);
+  } else {
+    split_tf32_kernel<<<grid_for((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, side, hi, lo);
+  }
   MTS_LAUNCH_CHECK();
   return 0;
 }

@@ -30,3 +30,40 @@ for i in range(20):
     a, b, l = pinned[i % 4]; a.to(dev, non_blocking=True); b.to(dev, non_blocking=True)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
 print(f"H2D alone: {dt/20*1e3:.3f} ms/step ({68.8e6*20/dt/1e9:.1f} GB/s)")
+
+# host-side cost of one predict_step with device-resident inputs (no H2D): where the CPU time goes
+from multimodaltopicsegmentation_b200 import ops
+a, b, l = host[0]
+ad, bd = a.to(dev), b.to(dev)
+batch = {"src_tokens": (ad, bd), "src_lengths": l}
+for _ in range(5):
+    seg.predict_step(batch, 0)
+torch.cuda.synchronize()
+N = 30
+t0 = time.perf_counter()
+for _ in range(N):
+    ops.Lengths(l, dev, 300)
+t_len = (time.perf_counter() - t0) / N
+torch.cuda.synchronize()
+lens = ops.Lengths(l, dev, 300)
+model = seg.model
+t0 = time.perf_counter()
+for _ in range(N):
+    with torch.no_grad():
+        feats = model.model((ad, bd), lens)
+        scores, tags = ops.head_decode(feats, model.classification.weight, model.classification.bias, lens, 0.5)
+t_issue = (time.perf_counter() - t0) / N
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(N):
+    out = seg.predict_step(batch, 0)
+t_full = (time.perf_counter() - t0) / N
+torch.cuda.synchronize()
+from multimodaltopicsegmentation_b200 import modules
+t0 = time.perf_counter()
+for _ in range(N):
+    modules._tags_to_lists(tags, lens, True)
+t_lists = (time.perf_counter() - t0) / N
+t_d2h = 0.0
+print(f"Lengths() {t_len*1e3:.3f} ms | issue of the 6 launches (no sync) {t_issue*1e3:.3f} ms | tags D2H {t_d2h*1e3:.3f} ms | "
+      f"lists {t_lists*1e3:.3f} ms | predict_step (sync) {t_full*1e3:.3f} ms")
