@@ -109,10 +109,22 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs run on rank 0 alone and may use the whole host."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def cpu_reference(steps, warmup, sample_batches=1):
     """The reference's CPU implementation of the path = the oracle's torch twin (nn.LSTM etc. on host cores)."""
     from oracle import ref_torch as rt
 
+    use_all_host_threads()
     torch.manual_seed(0)
     c = CFG
     model = rt.Segmenter(2, c["D1"] + c["D2"], c["H"], num_layers=c["L"], loss_fn="FocalLoss", threshold=0.5)
@@ -203,6 +215,8 @@ def train_bench(m, dev, rank, world, steps, barrier):
 
 def cpu_train_reference():
     from oracle import ref_torch as rt
+
+    use_all_host_threads()
 
     c = TRAIN_CFG
     torch.manual_seed(0)
@@ -328,6 +342,8 @@ def transformer_bench(m, dev, rank, world, steps, barrier):
 
 def cpu_transformer_reference():
     from oracle import ref_torch as rt
+
+    use_all_host_threads()
 
     c = XF_CFG
     torch.manual_seed(0)
