@@ -103,6 +103,14 @@ class TextSegmenter(_Base):
     def forward(self, x):
         return self.model(x)
 
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Checkpoints written under transformers 4.24 (the reference's pin) carry HF's non-parameter
+        `embeddings.position_ids` buffer, which newer HF versions (and this package) do not register: tolerated
+        (SURVEY.md section 10).  Everything else stays strict."""
+        if any(k.endswith("embeddings.position_ids") for k in state_dict):
+            state_dict = {k: v for k, v in state_dict.items() if not k.endswith("embeddings.position_ids")}
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
     # ---- steps --------------------------------------------------------------------------------------------
     def _inputs(self, batch):
         sentence, lengths = batch["src_tokens"], batch["src_lengths"]

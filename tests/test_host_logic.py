@@ -116,3 +116,44 @@ def test_error_conventions():
         seg.test_step({"src_tokens": torch.zeros(1, 2, 4), "src_lengths": torch.tensor([2]), "tgt_tokens": torch.zeros(1, 2)}, 0)
     opt = TextSegmenter(2, 4, 4, architecture="BiLSTM", loss_fn="FocalLoss", optimizer="Adam", lr=1e-3).configure_optimizers()
     assert opt["optimizer"].defaults["eps"] == 1e-7 and opt["lr_scheduler"]["monitor"] == "val_loss"
+
+
+def test_checkpoint_round_trip_like_predict_py(golden, tmp_path):
+    """SURVEY.md section 8f row 4 (wire format): a PL-style .ckpt ({'state_dict': ...} with the reference's key names,
+    here the golden parameters of the unmodified reference) loads through TextSegmenter.load_from_checkpoint with the
+    keyword arguments predict.py:228-241 passes, key for key; a checkpoint saved from our module loads back; the HF
+    4.24 `position_ids` buffer of old transformer checkpoints is tolerated."""
+    from multimodaltopicsegmentation_b200 import TextSegmenter
+
+    fx = golden("bilstm_binarycrossentropy")
+    ref_params = {"model." + k[2:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("p:")}
+    path = tmp_path / "best.ckpt"
+    torch.save({"state_dict": ref_params, "epoch": 3, "global_step": 120, "optimizer_states": [], "lr_schedulers": []}, path)
+    seg = TextSegmenter.load_from_checkpoint(str(path), architecture="BiLSTM", tagset_size=2, embedding_dim=12, hidden_dim=8,
+                                             bidirectional=True, lr=1e-3, num_layers=2, loss_fn="BinaryCrossEntropy",
+                                             dropout_in=0.0, dropout_out=0.0, threshold=0.5)
+    got = seg.state_dict()
+    assert set(got) == set(ref_params)
+    for k, v in ref_params.items():
+        assert torch.equal(got[k], v), k
+    # our own save -> load
+    path2 = tmp_path / "ours.ckpt"
+    torch.save({"state_dict": seg.state_dict()}, path2)
+    again = TextSegmenter.load_from_checkpoint(str(path2), architecture="BiLSTM", tagset_size=2, embedding_dim=12,
+                                               hidden_dim=8, num_layers=2, loss_fn="BinaryCrossEntropy")
+    for k, v in seg.state_dict().items():
+        assert torch.equal(again.state_dict()[k], v), k
+    # a mismatching head (CrossEntropy checkpoints have a 2-row classifier) must fail loudly, as predict.py expects
+    with pytest.raises((RuntimeError, KeyError)):
+        TextSegmenter.load_from_checkpoint(str(path), architecture="BiLSTM", tagset_size=2, embedding_dim=12, hidden_dim=8,
+                                           num_layers=2, loss_fn="CrossEntropy")
+    # transformer checkpoint written under transformers 4.24: extra position_ids buffer
+    tr = TextSegmenter(2, 32, 16, num_layers=2, architecture="Transformer", loss_fn="FocalLoss", nheads=4, attention_window=4)
+    sd = dict(tr.state_dict())
+    sd["model.model.model.embeddings.position_ids"] = torch.arange(4096).unsqueeze(0)
+    path3 = tmp_path / "xf.ckpt"
+    torch.save({"state_dict": sd}, path3)
+    back = TextSegmenter.load_from_checkpoint(str(path3), architecture="Transformer", tagset_size=2, embedding_dim=32,
+                                              hidden_dim=16, num_layers=2, loss_fn="FocalLoss", nheads=4, attention_window=4)
+    for k, v in tr.state_dict().items():
+        assert torch.equal(back.state_dict()[k], v), k
