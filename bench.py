@@ -12,7 +12,7 @@ early-fusion BiLSTM segmenter, 64 episodes x 300 sentences, 384-d text + 512-d a
 launches, head+decode.
 
   value  : sentences/s with the inputs resident in HBM (CUDA events over exactly K steps, max over ranks).
-  e2e    : the same through TextSegmenter.predict_step with HOST (pinned) inputs, H2D copies and the D2H of the
+  e2e    : the same through TextSegmenter.predict_batches with HOST (pinned) inputs, H2D copies and the D2H of the
            tags inside the timed region.
   roofline: the LSTM recurrence kernel (dominant), algorithmic HBM bytes per launch / its CUDA-event time.
   cpu_baseline: the oracle's torch-CPU restatement of the reference (same library calls as the reference) on the
@@ -300,8 +300,8 @@ def transformer_bench(m, dev, rank, world, steps, barrier):
     prefetcher = m.DevicePrefetcher(None, dev)   # one set of staging buffers for all passes, as over epochs
     def e2e(n):
         batches = ({"src_tokens": host, "src_lengths": lengths} for _ in range(n))
-        for i, batch in enumerate(prefetcher.iterate(batches)):
-            seg.predict_step(batch, i)
+        for _ in seg.predict_batches(prefetcher.iterate(batches)):
+            pass
     e2e(2)
     barrier()
     t0 = time.perf_counter()
@@ -318,7 +318,7 @@ def transformer_bench(m, dev, rank, world, steps, barrier):
            "tokens_per_step_per_gpu": tokens, "gpu_launches_per_step": launches / steps,
            "e2e": {"value": n_sent * world / e2e_s, "unit": "sentences/s", "h2d_bytes_per_step": host.numel() * 4,
                    "d2h_bytes_per_step": tokens,
-                   "api": "DevicePrefetcher -> TextSegmenter.predict_step, pinned host tensors in, host tag lists out"},
+                   "api": "DevicePrefetcher -> TextSegmenter.predict_batches, pinned host tensors in, host tag lists out"},
            "kernel_ms_per_step": {k: sum(v) for k, v in prof.items()}}
     if attn:
         per_layer = [n_sent * XF_ATTN_BYTES_PER_TOKEN / (x / 1e3) / 1e9 for x in attn]
@@ -410,11 +410,11 @@ def run_ours(args, rank, world, local_rank):
     prefetcher = m.DevicePrefetcher(None, dev)
 
     def e2e_run(n):
-        # public API: DevicePrefetcher (H2D of batch i+1 on a side stream) + TextSegmenter.predict_step, which returns
-        # host lists -- so every step includes its H2D copies and the D2H of its tags
+        # public API: DevicePrefetcher (H2D of batch i+1 on a side stream) + TextSegmenter.predict_batches, which yields
+        # predict_step's host lists for every batch -- so every step includes its H2D copies and the D2H of its tags
         out = None
-        for i, batch in enumerate(prefetcher.iterate(host_batches(n))):
-            out = seg.predict_step(batch, i)
+        for out in seg.predict_batches(prefetcher.iterate(host_batches(n))):
+            pass
         return out
 
     # ---- device-resident timing ------------------------------------------------------------------------
@@ -526,8 +526,9 @@ def run_ours(args, rank, world, local_rank):
                    "recurrence": "tcgen05 TF32 + bf16 correction, W_hh resident in TMEM" if rec_name.endswith("_tc") else "packed-fp32 FMA",
                    "parallelism": f"dp{world} (episodes sharded, final all_gather of tags)" if world > 1 else "single GPU"},
         "e2e": {"value": total_sent / e2e_s, "unit": "sentences/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "api": "DevicePrefetcher (side-stream H2D of the next batch) -> TextSegmenter.predict_step, pinned host tensors in, "
-                       "host tag lists out"},
+                "d2h_bytes_per_step": d2h, "api": "DevicePrefetcher (side-stream H2D of the next batch) -> TextSegmenter.predict_batches (the "
+                       "trainer.predict loop over predict_step, device work of batch i+1 enqueued before the tags of batch i "
+                       "are awaited), pinned host tensors in, host tag lists out"},
         "gpu_launches": launches,
         "roofline": {"kernel": ("lstm_fwd_tc_kernel" if rec_name.endswith("_tc") else "lstm_fwd_cluster_kernel") +
                                " (one launch per layer, both directions)", "bound": "hbm",

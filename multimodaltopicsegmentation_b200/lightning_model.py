@@ -263,6 +263,38 @@ class TextSegmenter(_Base):
         _, tags = self.model(*xs, lengths)
         return tags
 
+    def predict_batches(self, batches):
+        """The loop `pl.Trainer.predict` runs over `predict_step` (the reference's predict.py), pipelined: the kernels
+        of batch i+1 are enqueued before the tags of batch i are awaited, so the device does not idle while the host
+        turns a tag matrix into Python lists.  Yields, in order, exactly what `predict_step` returns for each batch.
+        Combine with `DevicePrefetcher` for host-resident batches."""
+        from .modules import _host_tags_to_lists
+
+        as_bool = not isinstance(self.model, BiRnnCrf)   # Viterbi paths are int lists, thresholded tags bool lists
+        ring, slot, pending = [None, None, None], 0, None   # pinned landing buffers for the tag matrices, reused
+
+        def finish(item):
+            host, ev, lens = item
+            ev.synchronize()
+            return _host_tags_to_lists(host.numpy(), lens, as_bool)
+
+        for batch in batches:
+            xs, lengths = self._inputs(batch)
+            _, tags_dev, lens = self.model.decode_device(*xs, lengths)
+            buf = ring[slot]
+            if buf is None or buf.numel() < tags_dev.numel():
+                buf = ring[slot] = torch.empty(tags_dev.numel(), dtype=torch.uint8, pin_memory=True)
+            host = buf[: tags_dev.numel()].view(tags_dev.shape)
+            host.copy_(tags_dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            slot = (slot + 1) % len(ring)
+            if pending is not None:
+                yield finish(pending)
+            pending = (host, ev, lens)
+        if pending is not None:
+            yield finish(pending)
+
     # ---- optimisers (lightning_model.py:759-781) ---------------------------------------------------------------
     def configure_optimizers(self):
         if self.optimizer == "SGD":

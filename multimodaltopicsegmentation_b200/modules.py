@@ -31,11 +31,15 @@ def _lens(lengths, x):
     return ops.Lengths(lengths, x.device, x.shape[1])
 
 
-def _tags_to_lists(tags_dev, lens, as_bool):
-    """One device->host copy of the uint8 tag matrix, then the reference's per-episode crop (CRF.py:369)."""
-    host = tags_dev.cpu().numpy()
+def _host_tags_to_lists(host, lens, as_bool):
+    """uint8 tag matrix on the host (numpy) -> the reference's per-episode cropped lists (CRF.py:369)."""
     full = (host.astype(bool) if as_bool else host.astype(int)).tolist()  # one conversion for the whole matrix
     return [row if n == len(row) else row[:n] for row, n in zip(full, lens.host)]
+
+
+def _tags_to_lists(tags_dev, lens, as_bool):
+    """One device->host copy of the uint8 tag matrix, then the per-episode crop."""
+    return _host_tags_to_lists(tags_dev.cpu().numpy(), lens, as_bool)
 
 
 class RNN(nn.Module):

@@ -1008,3 +1008,31 @@ def test_threshold_search_equals_host_sweep(dev, metric):
     assert th == best_th
     for k in best_res:
         assert res[k] == best_res[k], (k, res[k], best_res[k])
+
+
+@pytest.mark.parametrize("arch", ["BiLSTM", "biLSTMCRF", "Transformer", "BiLSTMLateFusion"])
+def test_predict_batches_equals_predict_step(dev, arch):
+    """The pipelined prediction loop yields, batch by batch, what predict_step returns."""
+    from multimodaltopicsegmentation_b200 import DevicePrefetcher, TextSegmenter
+
+    torch.manual_seed(4)
+    g = torch.Generator().manual_seed(44)
+    late = arch == "BiLSTMLateFusion"
+    kw = dict(nheads=4, attention_window=4) if arch == "Transformer" else {}
+    seg = TextSegmenter(2, [12, 20] if late else 32, 256 if "LSTM" in arch or "CRF" in arch else 16, num_layers=2,
+                        architecture=arch, loss_fn="FocalLoss", threshold=0.5, **kw).to(dev).eval()
+    batches = []
+    for i in range(5):
+        B, T = 3 + i, 24
+        lengths = torch.randint(1, T + 1, (B,), generator=g)
+        lengths[0] = T
+        b = {"src_tokens": torch.randn(B, T, 12 if late else 32, generator=g).pin_memory(), "src_lengths": lengths}
+        if late:
+            b["src_tokens2"] = torch.randn(B, T, 20, generator=g).pin_memory()
+        batches.append(b)
+    one_by_one = [seg.predict_step(b, i) for i, b in enumerate(DevicePrefetcher(batches, dev))]
+    piped = list(seg.predict_batches(DevicePrefetcher(batches, dev)))
+    assert len(piped) == len(one_by_one) == 5
+    for a, b in zip(piped, one_by_one):
+        assert a == b
+        assert all(type(x) is type(y) for ra, rb in zip(a, b) for x, y in zip(ra, rb))
