@@ -158,6 +158,11 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# DRAM traffic of ONE lstm_fwd_tc_kernel launch at the cfg1 shape (64 x 300, inference) from the ncu --set full capture in
+# profiles/r01_ncu_summary.md: 159.46 MB read + 25.64 MB written (algorithmic: 157.3 MB gx in + 39.3 MB h out; part of
+# the output is still in L2 when the kernel ends)
+NCU_REC_DRAM_BYTES = 159459840 + 25640448
+
 TRAIN_CFG = dict(B=10, D1=384, D2=512, H=256, L=2, Tmin=84, Tmax=2437)
 TRAIN_WORKLOAD = ("configs[1]: early-fusion BiLSTM focal-loss training step (fwd + BPTT + Adam), NonNews-shaped batch of 10 "
                   "episodes, 84..2437 sentences, 896-d inputs, H256 x 2 layers")
@@ -533,7 +538,10 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"kernel": ("lstm_fwd_tc_kernel" if rec_name.endswith("_tc") else "lstm_fwd_cluster_kernel") +
                                " (one launch per layer, both directions)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": rec_bytes,
+                     "traffic": NCU_REC_DRAM_BYTES if rec_name.endswith("_tc") else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one lstm_fwd_tc_kernel launch at this "
+                                       "shape, ncu --set full (profiles/r01_ncu_summary.md, state r01k)",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": rec_bytes,
                      "avg_launch_ms": rec_ms,
                      "note": "latency-bound at 64 episodes per GPU (T serial steps; per step: tcgen05 MMAs, DSMEM all-gather of "
                              "h, gate epilogue): see DESIGN.md section 4 and profiles/ for the B sweep"},

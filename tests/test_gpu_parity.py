@@ -342,7 +342,8 @@ def _oracle_pair(dev, D, H, L, loss_fn="FocalLoss", seed=0):
     return ref, ours.to(dev)
 
 
-@pytest.mark.parametrize("B,T,D,lens", [(11, 37, 40, None), (8, 64, 896, "full"), (17, 300, 64, None)])
+@pytest.mark.parametrize("B,T,D,lens", [(11, 37, 40, None), (8, 64, 896, "full"), (17, 300, 64, None),
+                                        (1, 1, 40, "full"), (1, 2, 33, "full"), (2, 3, 896, None), (65, 9, 16, None)])
 def test_bilstm_h256_forward_backward(dev, B, T, D, lens):
     g = torch.Generator().manual_seed(B * T)
     ref, ours = _oracle_pair(dev, D, 256, 2)
@@ -1036,3 +1037,23 @@ def test_predict_batches_equals_predict_step(dev, arch):
     for a, b in zip(piped, one_by_one):
         assert a == b
         assert all(type(x) is type(y) for ra, rb in zip(a, b) for x, y in zip(ra, rb))
+
+
+@pytest.mark.parametrize("S,lens", [(1, [1, 1]), (7, [7, 1]), (33, [33, 20, 2])])
+def test_transformer_odd_sequence_lengths_vs_numpy(dev, S, lens, xf_layout):
+    """Sequence lengths HF itself cannot run (S must be a multiple of every layer's window there):
+    the banded encoder against the numpy restatement of the same arithmetic, valid positions."""
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+    from oracle import ref_numpy as rn
+
+    torch.manual_seed(S)
+    g = torch.Generator().manual_seed(100 + S)
+    tr = Transformer_segmenter(2, 32, 16, num_layers=2, nheads=4, loss_fn="FocalLoss", window_size=4).to(dev).eval()
+    x = torch.randn(len(lens), S, 32, generator=g)
+    tl = torch.tensor(lens)
+    with torch.no_grad():
+        hid = tr.model(x.to(dev), tl)
+    params = {k: v.detach().cpu().numpy() for k, v in tr.state_dict().items()}
+    ref = rn.longformer_encoder(x.numpy(), tl.numpy(), params, 4, rn.pyramid_windows(2, 4))
+    for b, n in enumerate(lens):
+        close(hid[b, :n], ref[b, :n], rtol=1e-4, atol=2e-5)
