@@ -208,18 +208,25 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
   const int kbeg = max(0, q0 - w), kend = min(len, q0 + BA_BQ + w);
   const int qg = tid >> 4, kg = tid & 15;  // phase-1 mapping
 
-  for (int k0 = kbeg; k0 < kend; k0 += BA_TK) {
+  // K / V tiles arrive by cp.async (16-byte LDGSTS, zero-filled beyond kend) and overlap the arithmetic without extra
+  // buffers: V_t is requested at the top of tile t and only awaited before phase 3; K_{t+1} is requested as soon as
+  // phase 1 of tile t has released the K buffer.
+  auto request_tile = [&](float *dst, int k0, int which) {
     for (int idx = tid; idx < BA_TK * nv; idx += BA_THREADS) {
       const int r = idx / nv, c = idx % nv;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (k0 + r < kend) {
-        const float *base = qkv + (row0 + k0 + r) * ld + head * hd;
-        kv = __ldg(reinterpret_cast<const float4 *>(base + d) + c);
-        vv = __ldg(reinterpret_cast<const float4 *>(base + 2 * d) + c);
-      }
-      reinterpret_cast<float4 *>(Ks + r * RS)[c] = kv;
-      reinterpret_cast<float4 *>(Vs + r * RS)[c] = vv;
+      const bool valid = k0 + r < kend;
+      const float *src = valid ? qkv + (row0 + k0 + r) * ld + head * hd + which * d + 4 * c : qkv;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + r * RS + 4 * c)),
+                   "l"(src), "r"(valid ? 16 : 0)
+                   : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  request_tile(Ks, kbeg, 1);
+
+  for (int k0 = kbeg; k0 < kend; k0 += BA_TK) {
+    request_tile(Vs, k0, 2);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // K_t has landed (V_t may still be in flight)
     __syncthreads();
     // ---- phase 1: scores --------------------------------------------------------------------------------
     {
@@ -251,6 +258,8 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
       }
     }
     __syncthreads();
+    const bool more = k0 + BA_TK < kend;
+    if (more) request_tile(Ks, k0 + BA_TK, 1);
     // ---- phase 2: running softmax -----------------------------------------------------------------------
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
@@ -272,6 +281,8 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
         al_s[r] = alpha;
       }
     }
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");  // V_t has landed (K_{t+1} may still be in flight)
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- phase 3: O = alpha O + P V ----------------------------------------------------------------------
     if (pv_thread) {
@@ -641,6 +652,7 @@ extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *le
   MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_fwd: bad shape");
   MTS_REQUIRE(hd % 4 == 0 && hd <= 128, MTS_E_UNSUPPORTED, "band_attn_fwd: head dim must be a multiple of 4 and <= 128");
   MTS_REQUIRE(ld % 4 == 0 && ld >= 3 * nheads * hd, MTS_E_BADARG, "band_attn_fwd: qkv row stride");
+  MTS_REQUIRE(((uintptr_t)qkv & 15) == 0, MTS_E_BADARG, "band_attn_fwd: qkv must be 16-byte aligned");
   MTS_REQUIRE(!out_hi || (Kp % 32 == 0 && Kp >= nheads * hd), MTS_E_BADARG, "band_attn_fwd: Kp");
   MTS_REQUIRE(!out_hi || Kp == nheads * hd, MTS_E_UNSUPPORTED,
               "band_attn_fwd: the split output needs a model width that is a multiple of 32");
