@@ -130,9 +130,11 @@ __global__ void __launch_bounds__(256) gelu_split_kernel(const float *__restrict
 // staged in shared memory and ONLY the tiles intersecting [q0 - w, q0 + 32 + w) x [0, len_b) are read
 // (HF's sliding chunks compute 2w x 2w blocks and mask half of them away).  Running-max softmax in fp32
 // (HF: softmax in fp32, modeling_longformer.py:573), exact zeros for padded queries (:578).
-//   phase 1  S = Q K^T   thread = 2 queries x 4 keys, float4 along the head dimension
+//   phase 1  S = Q K^T   warp = 8 keys of the tile, thread = 4 queries x 2 keys, float4 along the head dimension
 //   phase 2  row max / exp / sum by warp shuffles (4 rows per warp), rescale factors to shared memory
-//   phase 3  O = alpha O + P V   thread = 4 queries x 4 head columns
+//   phase 3  O = alpha O + P V   warp = 4 float4 head columns, thread = 4 queries x 1 float4 column
+// In both product phases a warp-wide 16-byte load covers 8 consecutive rows x 16 bytes or 4 x 16 contiguous bytes:
+// one shared-memory wavefront (the first version's mapping needed 2-4), which is what bounded the kernel.
 // Shared rows are padded to a stride = 4 (mod 8) words so that 8 consecutive rows read as float4 hit
 // 8 distinct bank groups.
 // ---------------------------------------------------------------------------------------------------------
@@ -165,14 +167,19 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
   // ragged layout (offsets != NULL): episode b owns rows offsets[b] .. offsets[b] + len - 1 and nothing beyond
   const int64_t row0 = offsets ? (int64_t)offsets[b] : (int64_t)b * S;
   const int Sq = offsets ? len : S;  // rows of this episode that exist in memory
-  const int cg = tid % nv, rg = tid / nv;  // phase-3 mapping: 4 head columns x 4 queries
-  const bool pv_thread = rg < BA_BQ / 4;
+  // Lane mappings chosen so that a warp-wide 16-byte shared-memory load touches at most 128 contiguous-bank bytes
+  // (one wavefront): the 8 lane groups (lane >> 2) take 8 consecutive rows, the 4 lanes of a group 4 consecutive
+  // 16-byte columns.  Phase 1: warp = 8 keys of the tile, thread = 4 queries (qgrp + 8a) x 2 keys.  Phase 3: warp = 4
+  // float4 head columns, thread = 4 queries (qgrp + 8r) x 1 float4 column.
+  const int qgrp = lane >> 2;
+  const int cg = 4 * warp + (lane & 3);   // phase 3 / output: my float4 column of the head
+  const bool pv_thread = cg < nv;
 
   if (q0 >= len) {  // whole block is padding: exact zeros
     if (pv_thread) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int i = q0 + rg * 4 + r;
+        const int i = q0 + qgrp + 8 * r;
         if (i < Sq) {
           const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
           if (out) reinterpret_cast<float4 *>(out + (row0 + i) * d + head * hd)[cg] = z;
@@ -199,14 +206,12 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
   }
   if (tid < BA_BQ) { m_s[tid] = -INFINITY; l_s[tid] = 0.0f; al_s[tid] = 0.0f; }
 
-  float o[4][4];
+  float2 o2[4][2];   // 4 queries x (columns 0-1, columns 2-3) of my float4 head column
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) o[r][c] = 0.0f;
+  for (int r = 0; r < 4; ++r) o2[r][0] = o2[r][1] = make_float2(0.0f, 0.0f);
 
   const int kbeg = max(0, q0 - w), kend = min(len, q0 + BA_BQ + w);
-  const int qg = tid >> 4, kg = tid & 15;  // phase-1 mapping
+  const int kq = 8 * warp + (lane & 3);   // phase 1: my keys of the tile are kq and kq + 4
 
   // K / V tiles arrive by cp.async (16-byte LDGSTS, zero-filled beyond kend) and overlap the arithmetic without extra
   // buffers: V_t is requested at the top of tile t and only awaited before phase 3; K_{t+1} is requested as soon as
@@ -230,30 +235,33 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
     __syncthreads();
     // ---- phase 1: scores --------------------------------------------------------------------------------
     {
-      float acc[2][4];
+      // packed fp32 FMAs (FFMA2): Blackwell issues scalar FFMA at half rate.  Pairs run over consecutive head
+      // dimensions: (even-index sum, odd-index sum), added at the end.
+      float2 acc2[4][2];
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[a][j] = 0.0f;
-      const float4 *qa = reinterpret_cast<const float4 *>(Qs + qg * RS);
-      const float4 *qb = reinterpret_cast<const float4 *>(Qs + (qg + 16) * RS);
+      for (int a = 0; a < 4; ++a) acc2[a][0] = acc2[a][1] = make_float2(0.0f, 0.0f);
+      const float4 *qp = reinterpret_cast<const float4 *>(Qs + qgrp * RS);
+      const float4 *kp0 = reinterpret_cast<const float4 *>(Ks + kq * RS);
+      const float4 *kp1 = reinterpret_cast<const float4 *>(Ks + (kq + 4) * RS);
+      const int qstep = 8 * RS / 4;   // 8 query rows further, in float4
       for (int c = 0; c < nv; ++c) {
-        const float4 x0 = qa[c], x1 = qb[c];
+        const float4 ka = kp0[c], kb = kp1[c];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 kk = reinterpret_cast<const float4 *>(Ks + (kg + 16 * j) * RS)[c];
-          acc[0][j] = fmaf(x0.x, kk.x, fmaf(x0.y, kk.y, fmaf(x0.z, kk.z, fmaf(x0.w, kk.w, acc[0][j]))));
-          acc[1][j] = fmaf(x1.x, kk.x, fmaf(x1.y, kk.y, fmaf(x1.z, kk.z, fmaf(x1.w, kk.w, acc[1][j]))));
+        for (int a = 0; a < 4; ++a) {
+          const float4 x = qp[a * qstep + c];
+          const float2 xl = make_float2(x.x, x.y), xh = make_float2(x.z, x.w);
+          acc2[a][0] = __ffma2_rn(xh, make_float2(ka.z, ka.w), __ffma2_rn(xl, make_float2(ka.x, ka.y), acc2[a][0]));
+          acc2[a][1] = __ffma2_rn(xh, make_float2(kb.z, kb.w), __ffma2_rn(xl, make_float2(kb.x, kb.y), acc2[a][1]));
         }
       }
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        const int i = q0 + qg + 16 * a;
+      for (int a = 0; a < 4; ++a) {
+        const int i = q0 + qgrp + 8 * a;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kj = k0 + kg + 16 * j;
+        for (int j = 0; j < 2; ++j) {
+          const int kj = k0 + kq + 4 * j;
           const bool ok = (i < len) && (kj < kend) && (kj >= i - w) && (kj <= i + w);
-          Ps[(qg + 16 * a) * BA_PS + kg + 16 * j] = ok ? acc[a][j] : -INFINITY;
+          Ps[(qgrp + 8 * a) * BA_PS + kq + 4 * j] = ok ? acc2[a][j].x + acc2[a][j].y : -INFINITY;
         }
       }
     }
@@ -288,25 +296,24 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
     if (pv_thread) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const float al = al_s[rg * 4 + r];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) o[r][c] *= al;
+        const float al = al_s[qgrp + 8 * r];
+        o2[r][0] = __fmul2_rn(o2[r][0], make_float2(al, al));
+        o2[r][1] = __fmul2_rn(o2[r][1], make_float2(al, al));
       }
 #pragma unroll 4
       for (int k4 = 0; k4 < BA_TK / 4; ++k4) {
         float4 p[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) p[r] = reinterpret_cast<const float4 *>(Ps + (rg * 4 + r) * BA_PS)[k4];
+        for (int r = 0; r < 4; ++r) p[r] = reinterpret_cast<const float4 *>(Ps + (qgrp + 8 * r) * BA_PS)[k4];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const float4 vv = reinterpret_cast<const float4 *>(Vs + (4 * k4 + kk) * RS)[cg];
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const float pk = kk == 0 ? p[r].x : kk == 1 ? p[r].y : kk == 2 ? p[r].z : p[r].w;
-            o[r][0] = fmaf(pk, vv.x, o[r][0]);
-            o[r][1] = fmaf(pk, vv.y, o[r][1]);
-            o[r][2] = fmaf(pk, vv.z, o[r][2]);
-            o[r][3] = fmaf(pk, vv.w, o[r][3]);
+            const float2 pk2 = make_float2(pk, pk);
+            o2[r][0] = __ffma2_rn(pk2, make_float2(vv.x, vv.y), o2[r][0]);
+            o2[r][1] = __ffma2_rn(pk2, make_float2(vv.z, vv.w), o2[r][1]);
           }
         }
       }
@@ -317,12 +324,12 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
   if (pv_thread) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int i = q0 + rg * 4 + r;
+      const int i = q0 + qgrp + 8 * r;
       if (i >= Sq) continue;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < len) {
-        const float inv = 1.0f / l_s[rg * 4 + r];
-        v = make_float4(o[r][0] * inv, o[r][1] * inv, o[r][2] * inv, o[r][3] * inv);
+        const float inv = 1.0f / l_s[qgrp + 8 * r];
+        v = make_float4(o2[r][0].x * inv, o2[r][0].y * inv, o2[r][1].x * inv, o2[r][1].y * inv);
       }
       if (out) reinterpret_cast<float4 *>(out + (row0 + i) * d + head * hd)[cg] = v;
       if (out_hi) {

@@ -112,7 +112,7 @@ if __name__ == "__main__":
         d = h * hd
         g = torch.Generator(device=dev).manual_seed(0)
         qkv = torch.randn(B * S, 3 * d, device=dev, generator=g)
-        lengths = torch.randint(100, S + 1, (B,))
+        lengths = torch.randint(100, S + 1, (B,), generator=torch.Generator().manual_seed(7))
         lengths[0] = S
         lens = ops.Lengths(lengths, dev, S)
         hl = torch.empty(2, B * S, d, device=dev)
