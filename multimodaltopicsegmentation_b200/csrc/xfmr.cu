@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(256) gelu_split_kernel(const float *__restrict
 // staged in shared memory and ONLY the tiles intersecting [q0 - w, q0 + 32 + w) x [0, len_b) are read
 // (HF's sliding chunks compute 2w x 2w blocks and mask half of them away).  Running-max softmax in fp32
 // (HF: softmax in fp32, modeling_longformer.py:573), exact zeros for padded queries (:578).
-//   phase 1  S = Q K^T   warp = 8 keys of the tile, thread = 4 queries x 2 keys, float4 along the head dimension
-//   phase 2  row max / exp / sum by warp shuffles (4 rows per warp), rescale factors to shared memory
-//   phase 3  O = alpha O + P V   warp = 4 float4 head columns, thread = 4 queries x 1 float4 column
-// In both product phases a warp-wide 16-byte load covers 8 consecutive rows x 16 bytes or 4 x 16 contiguous bytes:
-// one shared-memory wavefront (the first version's mapping needed 2-4), which is what bounded the kernel.
+//   phases 1 + 2  S = Q K^T and the running softmax, warp-local: warp = 4 queries x the 64 keys of the tile (thread =
+//             4 queries x 2 keys, float4 along the head dimension, FFMA2); row max / exp / sum by shuffles, the four rows
+//             interleaved; running statistics in registers; P and the rescale factors go to shared memory
+//   phase 3   O = alpha O + P V   warp = 4 float4 head columns, thread = 4 queries x 1 float4 column (FFMA2)
+// Three block-wide barriers per tile; K / V tiles by cp.async.
 // Shared rows are padded to a stride = 4 (mod 8) words so that 8 consecutive rows read as float4 hit
 // 8 distinct bank groups.
 // ---------------------------------------------------------------------------------------------------------
@@ -167,10 +167,9 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
   // ragged layout (offsets != NULL): episode b owns rows offsets[b] .. offsets[b] + len - 1 and nothing beyond
   const int64_t row0 = offsets ? (int64_t)offsets[b] : (int64_t)b * S;
   const int Sq = offsets ? len : S;  // rows of this episode that exist in memory
-  // Lane mappings chosen so that a warp-wide 16-byte shared-memory load touches at most 128 contiguous-bank bytes
-  // (one wavefront): the 8 lane groups (lane >> 2) take 8 consecutive rows, the 4 lanes of a group 4 consecutive
-  // 16-byte columns.  Phase 1: warp = 8 keys of the tile, thread = 4 queries (qgrp + 8a) x 2 keys.  Phase 3: warp = 4
-  // float4 head columns, thread = 4 queries (qgrp + 8r) x 1 float4 column.
+  // Phase-3 lane mapping: a warp-wide 16-byte shared-memory load touches 128 contiguous-bank bytes (one wavefront):
+  // the 8 lane groups (lane >> 2) take 8 consecutive P rows, the 4 lanes of a group 4 consecutive 16-byte V columns;
+  // warp = 4 float4 head columns, thread = 4 queries (qgrp + 8r) x 1 float4 column.
   const int qgrp = lane >> 2;
   const int cg = 4 * warp + (lane & 3);   // phase 3 / output: my float4 column of the head
   const bool pv_thread = cg < nv;
@@ -204,26 +203,33 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
     }
     reinterpret_cast<float4 *>(Qs + r * RS)[c] = v;
   }
-  if (tid < BA_BQ) { m_s[tid] = -INFINITY; l_s[tid] = 0.0f; al_s[tid] = 0.0f; }
+  float m_run[4], l_run[4];   // running max / sum of my warp's 4 query rows (same value in every lane)
+#pragma unroll
+  for (int a = 0; a < 4; ++a) { m_run[a] = -INFINITY; l_run[a] = 0.0f; }
 
   float2 o2[4][2];   // 4 queries x (columns 0-1, columns 2-3) of my float4 head column
 #pragma unroll
   for (int r = 0; r < 4; ++r) o2[r][0] = o2[r][1] = make_float2(0.0f, 0.0f);
 
   const int kbeg = max(0, q0 - w), kend = min(len, q0 + BA_BQ + w);
-  const int kq = 8 * warp + (lane & 3);   // phase 1: my keys of the tile are kq and kq + 4
 
   // K / V tiles arrive by cp.async (16-byte LDGSTS, zero-filled beyond kend) and overlap the arithmetic without extra
   // buffers: V_t is requested at the top of tile t and only awaited before phase 3; K_{t+1} is requested as soon as
   // phase 1 of tile t has released the K buffer.
+  // (row, 16-byte column) of my first piece of a tile and the step to my next one: no division in the loops
+  const int r_first = tid / nv, c_first = tid % nv, r_step = BA_THREADS / nv, c_step = BA_THREADS % nv;
   auto request_tile = [&](float *dst, int k0, int which) {
-    for (int idx = tid; idx < BA_TK * nv; idx += BA_THREADS) {
-      const int r = idx / nv, c = idx % nv;
+    const float *gbase = qkv + (row0 + k0) * ld + head * hd + which * d;
+    int r = r_first, c = c_first;
+    while (r < BA_TK) {
       const bool valid = k0 + r < kend;
-      const float *src = valid ? qkv + (row0 + k0 + r) * ld + head * hd + which * d + 4 * c : qkv;
+      const float *src = valid ? gbase + (int64_t)r * ld + 4 * c : qkv;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + r * RS + 4 * c)),
                    "l"(src), "r"(valid ? 16 : 0)
                    : "memory");
+      r += r_step;
+      c += c_step;
+      if (c >= nv) { c -= nv; ++r; }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -233,65 +239,68 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
     request_tile(Vs, k0, 2);
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // K_t has landed (V_t may still be in flight)
     __syncthreads();
-    // ---- phase 1: scores --------------------------------------------------------------------------------
+    // ---- phases 1 + 2: scores and running softmax, warp-local (warp = 4 queries x the 64 keys of the tile) -------
     {
       // packed fp32 FMAs (FFMA2): Blackwell issues scalar FFMA at half rate.  Pairs run over consecutive head
       // dimensions: (even-index sum, odd-index sum), added at the end.
       float2 acc2[4][2];
 #pragma unroll
       for (int a = 0; a < 4; ++a) acc2[a][0] = acc2[a][1] = make_float2(0.0f, 0.0f);
-      const float4 *qp = reinterpret_cast<const float4 *>(Qs + qgrp * RS);
-      const float4 *kp0 = reinterpret_cast<const float4 *>(Ks + kq * RS);
-      const float4 *kp1 = reinterpret_cast<const float4 *>(Ks + (kq + 4) * RS);
-      const int qstep = 8 * RS / 4;   // 8 query rows further, in float4
+      const float4 *qp = reinterpret_cast<const float4 *>(Qs + 4 * warp * RS);
+      const float4 *kp0 = reinterpret_cast<const float4 *>(Ks + lane * RS);
+      const float4 *kp1 = reinterpret_cast<const float4 *>(Ks + (lane + 32) * RS);
+      const int qstep = RS / 4;   // next query row, in float4
       for (int c = 0; c < nv; ++c) {
         const float4 ka = kp0[c], kb = kp1[c];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          const float4 x = qp[a * qstep + c];
+          const float4 x = qp[a * qstep + c];   // same address in every lane: broadcast
           const float2 xl = make_float2(x.x, x.y), xh = make_float2(x.z, x.w);
           acc2[a][0] = __ffma2_rn(xh, make_float2(ka.z, ka.w), __ffma2_rn(xl, make_float2(ka.x, ka.y), acc2[a][0]));
           acc2[a][1] = __ffma2_rn(xh, make_float2(kb.z, kb.w), __ffma2_rn(xl, make_float2(kb.x, kb.y), acc2[a][1]));
         }
       }
+      float sc[4][2], mx[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        const int i = q0 + qgrp + 8 * a;
+        const int i = q0 + 4 * warp + a;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int kj = k0 + kq + 4 * j;
+          const int kj = k0 + lane + 32 * j;
           const bool ok = (i < len) && (kj < kend) && (kj >= i - w) && (kj <= i + w);
-          Ps[(qgrp + 8 * a) * BA_PS + kq + 4 * j] = ok ? acc2[a][j].x + acc2[a][j].y : -INFINITY;
+          sc[a][j] = ok ? acc2[a][j].x + acc2[a][j].y : -INFINITY;
         }
+        mx[a] = fmaxf(sc[a][0], sc[a][1]);
       }
-    }
-    __syncthreads();
-    const bool more = k0 + BA_TK < kend;
-    if (more) request_tile(Ks, k0 + BA_TK, 1);
-    // ---- phase 2: running softmax -----------------------------------------------------------------------
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int r = warp * 4 + rr;
-      const float s0 = Ps[r * BA_PS + lane], s1 = Ps[r * BA_PS + lane + 32];
-      const float mx = warp_max(fmaxf(s0, s1));
-      const float m_old = m_s[r];
-      const float m_new = fmaxf(m_old, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-      const float p0 = expf(s0 - m_use), p1 = expf(s1 - m_use);
-      const float sum = warp_sum(p0 + p1);
-      Ps[r * BA_PS + lane] = p0;
-      Ps[r * BA_PS + lane + 32] = p1;
-      __syncwarp();
-      if (lane == 0) {
-        const float alpha = expf(m_old - m_use);
-        m_s[r] = m_new;
-        l_s[r] = l_s[r] * alpha + sum;
-        al_s[r] = alpha;
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+      float ps[4], alpha[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float m_new = fmaxf(m_run[a], mx[a]);
+        const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+        const float p0 = expf(sc[a][0] - m_use), p1 = expf(sc[a][1] - m_use);
+        Ps[(4 * warp + a) * BA_PS + lane] = p0;
+        Ps[(4 * warp + a) * BA_PS + lane + 32] = p1;
+        ps[a] = p0 + p1;
+        alpha[a] = expf(m_run[a] - m_use);
+        m_run[a] = m_new;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ps[a] += __shfl_xor_sync(0xffffffffu, ps[a], off);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        l_run[a] = l_run[a] * alpha[a] + ps[a];
+        if (lane == 0) al_s[4 * warp + a] = alpha[a];
       }
     }
-    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");  // V_t has landed (K_{t+1} may still be in flight)
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // my pieces of V_t have landed
+    __syncthreads();                                       // P, alpha and V_t visible to all; the K buffer is free
+    if (k0 + BA_TK < kend) request_tile(Ks, k0 + BA_TK, 1);
     // ---- phase 3: O = alpha O + P V ----------------------------------------------------------------------
     if (pv_thread) {
 #pragma unroll
@@ -320,6 +329,11 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
     }
     __syncthreads();
   }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { m_s[4 * warp + a] = m_run[a]; l_s[4 * warp + a] = l_run[a]; }
+  }
+  __syncthreads();
 
   if (pv_thread) {
 #pragma unroll
