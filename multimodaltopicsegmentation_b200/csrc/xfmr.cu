@@ -25,9 +25,9 @@ namespace mts {
 // outputs: y fp32, optional (hi, lo) TF32 halves [M, Kp] for the next GEMM, optional pre-LN sum and
 // (mean, rstd) for the backward pass.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LN_MAXV = 16;  // float4 per lane -> d <= 2048
+constexpr int LN_MAXV = 16;  // float4 per lane -> d <= 2048 (MAXV = 8 serves d <= 1024 with half the registers)
 
-template <int MODE>
+template <int MODE, int MAXV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a, int64_t a_bstride,
                                                      const float *__restrict__ b, const float *__restrict__ typ,
                                                      const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -54,11 +54,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
       pa = reinterpret_cast<const float4 *>(a + (int64_t)row * d);
       pb = reinterpret_cast<const float4 *>(b + (int64_t)row * d);
     }
-    float4 v[LN_MAXV];
+    // float4 column of register i: lanes own PAIRS of adjacent float4 (8 consecutive elements), so that the packed
+    // correction operand goes out in 16-byte pieces (corr_store8)
+#define LN_COL(i) (2 * (lane + 32 * ((i) >> 1)) + ((i) & 1))
+    float4 v[MAXV];
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-      const int c = lane + 32 * i;
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = LN_COL(i);
       if (c < nv) {
         float4 x = __ldg(pa + c);
         const float4 r = __ldg(pb + c);
@@ -74,8 +77,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
     const float mean = warp_sum(s) / (float)d;
     float q = 0.0f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-      if (lane + 32 * i < nv) {
+    for (int i = 0; i < MAXV; ++i) {
+      if (LN_COL(i) < nv) {
         const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
         q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
       }
@@ -83,24 +86,29 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
     const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + eps);
     if (stats && lane == 0) { stats[2 * (int64_t)row] = mean; stats[2 * (int64_t)row + 1] = rstd; }
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nv) {
-        if (sum_out) reinterpret_cast<float4 *>(sum_out + (int64_t)row * d)[c] = v[i];
-        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + c);
-        const float4 be = __ldg(reinterpret_cast<const float4 *>(beta) + c);
-        float4 o;
-        o.x = (v[i].x - mean) * rstd * g.x + be.x;
-        o.y = (v[i].y - mean) * rstd * g.y + be.y;
-        o.z = (v[i].z - mean) * rstd * g.z + be.z;
-        o.w = (v[i].w - mean) * rstd * g.w + be.w;
-        reinterpret_cast<float4 *>(y + (int64_t)row * d)[c] = o;
-        if (y_lo) {  // operand pair for the next GEMM; y itself serves as `hi` when no K padding is needed (y_hi == NULL)
-          if (y_hi) reinterpret_cast<float4 *>(y_hi + (int64_t)row * Kp)[c] = o;
-          corr_store4(y_lo + (int64_t)row * Kp, 4 * c, o, 0);
+    for (int i = 0; i < MAXV; i += 2) {
+      const int c = LN_COL(i);   // even float4 column; c + 1 is register i + 1
+      float4 o[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (c + h < nv) {
+          if (sum_out) reinterpret_cast<float4 *>(sum_out + (int64_t)row * d)[c + h] = v[i + h];
+          const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + c + h);
+          const float4 be = __ldg(reinterpret_cast<const float4 *>(beta) + c + h);
+          o[h].x = (v[i + h].x - mean) * rstd * g.x + be.x;
+          o[h].y = (v[i + h].y - mean) * rstd * g.y + be.y;
+          o[h].z = (v[i + h].z - mean) * rstd * g.z + be.z;
+          o[h].w = (v[i + h].w - mean) * rstd * g.w + be.w;
+          reinterpret_cast<float4 *>(y + (int64_t)row * d)[c + h] = o[h];
+          if (y_hi) reinterpret_cast<float4 *>(y_hi + (int64_t)row * Kp)[c + h] = o[h];
         }
       }
+      if (y_lo) {  // operand pair for the next GEMM; y itself serves as `hi` when no K padding is needed (y_hi == NULL)
+        if (c + 1 < nv) corr_store8(y_lo + (int64_t)row * Kp, 4 * c, o[0], o[1], 0);
+        else if (c < nv) corr_store4(y_lo + (int64_t)row * Kp, 4 * c, o[0], 0);
+      }
     }
+#undef LN_COL
     if (y_lo)
       for (int c = d + lane; c < Kp; c += 32) {
         if (y_hi) y_hi[(int64_t)row * Kp + c] = 0.0f;
@@ -122,6 +130,33 @@ __global__ void __launch_bounds__(256) gelu_split_kernel(const float *__restrict
     if (act && k < cols) act[r * cols + k] = v;
     hi[idx] = v;
     corr_store1(lo + r * Kp, k, v, 0);
+  }
+}
+
+// the same, 8 consecutive columns per thread (16-byte loads and stores); needs cols % 8 == 0 and 16-byte aligned rows
+__global__ void __launch_bounds__(256) gelu_split_v8_kernel(const float *__restrict__ src, int64_t ld, int rows, int cols,
+                                                            int Kp, float *__restrict__ act, float *__restrict__ hi,
+                                                            float *__restrict__ lo) {
+  const int k8n = Kp >> 3;
+  const int64_t total = (int64_t)rows * k8n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % k8n) << 3;
+    const int64_t r = idx / k8n;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (k < cols) {
+      v0 = __ldg(reinterpret_cast<const float4 *>(src + r * ld + k));
+      v1 = __ldg(reinterpret_cast<const float4 *>(src + r * ld + k) + 1);
+      v0 = make_float4(gelu_erf(v0.x), gelu_erf(v0.y), gelu_erf(v0.z), gelu_erf(v0.w));
+      v1 = make_float4(gelu_erf(v1.x), gelu_erf(v1.y), gelu_erf(v1.z), gelu_erf(v1.w));
+      if (act) {
+        reinterpret_cast<float4 *>(act + r * cols + k)[0] = v0;
+        reinterpret_cast<float4 *>(act + r * cols + k)[1] = v1;
+      }
+    }
+    reinterpret_cast<float4 *>(hi + r * Kp + k)[0] = v0;
+    reinterpret_cast<float4 *>(hi + r * Kp + k)[1] = v1;
+    corr_store8(lo + r * Kp, k, v0, v1, 0);
   }
 }
 
@@ -615,8 +650,12 @@ extern "C" int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *
   if (rc) return rc;
   const int M = B * S;
   const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);
-  ln_fwd_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bstride, pos, typ, gamma, beta, M, S, d, eps, y, y_hi,
-                                                            y_lo, Kp, sum_out, stats, lengths, offsets);
+  if (d <= 1024)
+    ln_fwd_kernel<0, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bstride, pos, typ, gamma, beta, M, S, d, eps, y, y_hi,
+                                                                 y_lo, Kp, sum_out, stats, lengths, offsets);
+  else
+    ln_fwd_kernel<0, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bstride, pos, typ, gamma, beta, M, S, d, eps, y, y_hi,
+                                                                  y_lo, Kp, sum_out, stats, lengths, offsets);
   MTS_LAUNCH_CHECK();
   return 0;
 }
@@ -628,8 +667,12 @@ extern "C" int mts_add_ln_fwd(const float *a, const float *res, const float *gam
   int rc = ln_args_ok("add_ln_fwd", M, d, y_hi, y_lo, Kp);
   if (rc) return rc;
   const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);
-  ln_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, 0, res, nullptr, gamma, beta, M, 0, d, eps, y, y_hi, y_lo,
-                                                            Kp, sum_out, stats, nullptr, nullptr);
+  if (d <= 1024)
+    ln_fwd_kernel<1, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(a, 0, res, nullptr, gamma, beta, M, 0, d, eps, y, y_hi, y_lo,
+                                                                 Kp, sum_out, stats, nullptr, nullptr);
+  else
+    ln_fwd_kernel<1, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(a, 0, res, nullptr, gamma, beta, M, 0, d, eps, y, y_hi, y_lo,
+                                                                  Kp, sum_out, stats, nullptr, nullptr);
   MTS_LAUNCH_CHECK();
   return 0;
 }
@@ -638,7 +681,10 @@ extern "C" int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, 
                               float *lo, void *stream) {
   MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "gelu_split: null pointer");
   MTS_REQUIRE(rows > 0 && cols > 0 && Kp % 32 == 0 && Kp >= cols, MTS_E_BADARG, "gelu_split: bad shape");
-  gelu_split_kernel<<<ew_grid((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, act, hi, lo);
+  if (cols % 8 == 0 && ld % 4 == 0 && ((((uintptr_t)src | (uintptr_t)act | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0))
+    gelu_split_v8_kernel<<<ew_grid((int64_t)rows * (Kp / 8)), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, act, hi, lo);
+  else
+    gelu_split_kernel<<<ew_grid((int64_t)rows * Kp), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, Kp, act, hi, lo);
   MTS_LAUNCH_CHECK();
   return 0;
 }
