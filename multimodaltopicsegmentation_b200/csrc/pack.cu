@@ -90,17 +90,20 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
 // operands must be K-major along the token axis for the tensor-core kernel):
 //   out[c, r] = src[(r / T) * bstride + (r % T + shift) * ld + c]   for 0 <= r % T + shift < lengths[r / T],  else 0
 // written as (hi, lo) TF32 halves [cols, Kp], columns r >= rows zero-filled.  shift = -1 / +1 yields the h_{t-1} /
-// h_{t+1} operand of dW_hh without a shifted copy of the hidden states.  32 x 32 tiles through shared memory:
+// h_{t+1} operand of dW_hh without a shifted copy of the hidden states.  64 x 32 tiles through shared memory:
 // coalesced reads along the source columns, coalesced writes along the token axis.
 __global__ void __launch_bounds__(256) transpose_split_kernel(const float *__restrict__ src, int64_t bstride, int64_t ld,
                                                              int rows, int cols, int T, int shift,
                                                              const int32_t *__restrict__ lengths, int Kp, int side,
                                                              float *__restrict__ hi, float *__restrict__ lo) {
-  __shared__ float tile[32][33];
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  // tile = 64 tokens (r) x 32 source columns (c).  Read: a warp takes 32 consecutive columns of one token (128
+  // contiguous bytes).  Write: a thread takes 8 consecutive tokens of one column: two 16-byte stores of the fp32 operand
+  // and two 16-byte halves of the packed correction operand.
+  __shared__ float tile[64][33];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const int r = r0 + ty + 8 * i, c = c0 + tx;
     float v = 0.0f;
     if (r < rows && c < cols) {
@@ -111,14 +114,15 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float *__res
     tile[ty + 8 * i][tx] = v;
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = c0 + ty + 8 * i, r = r0 + tx;
-    if (c < cols && r < Kp) {
-      const float v = tile[tx][ty + 8 * i];
-      hi[(int64_t)c * Kp + r] = v;
-      corr_store1(lo + (int64_t)c * Kp, r, v, side);
-    }
+  const int c = c0 + (threadIdx.x >> 3), rr = (threadIdx.x & 7) * 8, r = r0 + rr;
+  if (c < cols && r < Kp) {  // Kp % 32 == 0 and r % 8 == 0: a group of 8 tokens is entirely inside [0, Kp) or outside
+    const int cl = threadIdx.x >> 3;
+    const float4 v0 = make_float4(tile[rr][cl], tile[rr + 1][cl], tile[rr + 2][cl], tile[rr + 3][cl]);
+    const float4 v1 = make_float4(tile[rr + 4][cl], tile[rr + 5][cl], tile[rr + 6][cl], tile[rr + 7][cl]);
+    float4 *h = reinterpret_cast<float4 *>(hi + (int64_t)c * Kp + r);
+    h[0] = v0;
+    h[1] = v1;
+    corr_store8(lo + (int64_t)c * Kp, r, v0, v1, side);
   }
 }
 
@@ -206,7 +210,8 @@ extern "C" int mts_transpose_split(const float *src, int64_t bstride, int64_t ld
   MTS_REQUIRE(src && hi && lo, MTS_E_BADARG, "transpose_split: null pointer");
   MTS_REQUIRE(rows > 0 && cols > 0 && T > 0 && Kp % 32 == 0 && Kp >= rows, MTS_E_BADARG, "transpose_split: bad shape");
   MTS_REQUIRE(shift >= -1 && shift <= 1, MTS_E_BADARG, "transpose_split: shift must be -1, 0 or +1");
-  const dim3 grid((unsigned)(Kp / 32), (unsigned)((cols + 31) / 32));
+  MTS_REQUIRE((((uintptr_t)hi | (uintptr_t)lo) & 15) == 0, MTS_E_BADARG, "transpose_split: outputs must be 16-byte aligned");
+  const dim3 grid((unsigned)((Kp + 63) / 64), (unsigned)((cols + 31) / 32));
   MTS_REQUIRE(grid.y <= 65535, MTS_E_UNSUPPORTED, "transpose_split: too many columns");
   transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, bstride, ld, rows, cols, T, shift, lengths, Kp, side, hi, lo);
   MTS_LAUNCH_CHECK();
