@@ -33,6 +33,16 @@ def length_mask(T, lengths):
     return torch.arange(T)[None, :] < torch.as_tensor(lengths)[:, None]
 
 
+def reference_mask_loop(max_len, lengths):
+    """What create_masks_huggingface costs (RestrictedTransformerLayer.py:101-116): a Python loop over every (episode,
+    position) comparing an int with a 0-d tensor.  Same values as length_mask; used only to TIME the reference's host
+    step (bench.py reports the CPU baseline with and without it)."""
+    mask = []
+    for index in range(len(lengths)):
+        mask.append([1 if pos < lengths[index] else 0 for pos in range(max_len)])
+    return torch.tensor(mask)
+
+
 class Encoder(nn.Module):
     def __init__(self, embed_size, hidden_size, num_layers=1, bidirectional=True):
         super().__init__()
