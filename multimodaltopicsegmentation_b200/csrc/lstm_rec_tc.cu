@@ -285,10 +285,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
           for (int g = 0; g < 2; ++g) {
             tc::bar_wait_wd(tc::s_u32(&h_full[p * 2 + g]), ph_h[p]);
             if (g == 0) TR_STAMP(6);
+            float4 hv[4];   // all four loads first: the stores below may alias them as far as the compiler can tell
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hv[i] = src[g * 512 + et + TR_EPI * i];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int f4 = g * 512 + et + TR_EPI * i;   // physical 16-byte granule of the raw-h buffer
-              const float4 v = src[f4];
+              const float4 v = hv[i];
               // granule -> (slot, episode row e, logical 4-k chunk c): the fp32 buffer is SWIZZLE_128B, chunk = phys ^ (e & 7)
               const int e = (f4 >> 3) & 15, c = (f4 & 7) ^ (e & 7);
               // the correction operand of this slot: 64 bf16 per row = two 16-k blocks of [bf16(rest) x16 | bf16(h) x16] (B side)
