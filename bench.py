@@ -215,7 +215,7 @@ def train_bench(m, dev, rank, world, steps, barrier):
     return {"metric": "training episodes/sec", "value": c["B"] * world / (ms / 1e3), "unit": "episodes/s",
             "ms_per_step": ms, "steps": steps, "workload": TRAIN_WORKLOAD, "sentences_per_step_per_gpu": n_sent,
             "gpu_launches_per_step": ops.launch_count() / steps, "grad_bucket_bytes": bucket.nbytes,
-            "last_loss": float(loss)}
+            "last_loss": float(loss.detach())}
 
 
 def cpu_train_reference():
