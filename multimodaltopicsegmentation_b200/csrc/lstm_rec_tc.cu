@@ -64,7 +64,11 @@ template <bool SAVE, int NT>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREADS * NT, 1)
     lstm_fwd_tc_kernel(const float *__restrict__ gx, const float *__restrict__ w_hh,
                        const int32_t *__restrict__ lengths, const int32_t *__restrict__ order, int B, int T, int n_enc,
-                       int n_tiles, float *__restrict__ y, float *__restrict__ gates, float *__restrict__ y_corr) {
+                       int n_tiles, int ept, float *__restrict__ y, float *__restrict__ gates,
+                       float *__restrict__ y_corr) {
+  // ept = episodes per tile (<= TR_NB).  With fewer sequences than 16 x the resident clusters the host spreads them over
+  // ALL clusters: the MMAs cost the same at any N <= 16, while the gate phase, the h exchange and the correction-operand
+  // derivation shrink with the number of episodes a cluster carries.  Rows >= ept of the operand buffers stay zero.
   constexpr int THREADS = TR_SUB_THREADS * NT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -165,13 +169,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
     // ---- tile bookkeeping, zero initial state ---------------------------------------------------------------
     const int st = tid - sub * TR_SUB_THREADS;  // thread index inside the pipeline
     if (st < TR_NB) {
-      const int slot = tile * TR_NB + st;
-      const int bq = (tile < n_tiles && slot < B) ? (order ? order[slot] : slot) : -1;
+      const int slot = tile * ept + st;
+      const int bq = (tile < n_tiles && st < ept && slot < B) ? (order ? order[slot] : slot) : -1;
       bq_s[st] = bq;
       len_s[st] = (bq >= 0) ? min(max(lengths[bq], 0), T) : 0;
     }
     for (int idx = st; idx < TR_B_BYTES / 16; idx += TR_SUB_THREADS) {
       reinterpret_cast<float4 *>(bhi)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // h_{-1} = 0 (buffer 0)
+      reinterpret_cast<float4 *>(bhi + TR_B_BYTES)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // rows >= ept are never sent
       reinterpret_cast<float4 *>(blo)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tc::fence_proxy_async();
@@ -201,8 +206,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
         const int p = s & 1;
         TR_STAMP(0);
         if (leader && s + 1 < nsteps) {
-          tc::bar_expect_tx(tc::s_u32(&h_full[(p ^ 1) * 2 + 0]), TR_B_BYTES / 2);
-          tc::bar_expect_tx(tc::s_u32(&h_full[(p ^ 1) * 2 + 1]), TR_B_BYTES / 2);
+          tc::bar_expect_tx(tc::s_u32(&h_full[(p ^ 1) * 2 + 0]), 4 * ept * 128);   // 4 K-block slots x ept rows x 128 B
+          tc::bar_expect_tx(tc::s_u32(&h_full[(p ^ 1) * 2 + 1]), 4 * ept * 128);
         }
         const uint32_t bhi_a = tc::s_u32(bhi + p * TR_B_BYTES);
 #pragma unroll
@@ -286,10 +291,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
             tc::bar_wait_wd(tc::s_u32(&h_full[p * 2 + g]), ph_h[p]);
             if (g == 0) TR_STAMP(6);
             float4 hv[4];   // all four loads first: the stores below may alias them as far as the compiler can tell
+            const bool my_row = ((et >> 3) & 15) < ept;   // my granules all belong to episode row (et >> 3) & 15
+            if (my_row) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hv[i] = src[g * 512 + et + TR_EPI * i];
+              for (int i = 0; i < 4; ++i) hv[i] = src[g * 512 + et + TR_EPI * i];
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+              if (!my_row) break;
               const int f4 = g * 512 + et + TR_EPI * i;   // physical 16-byte granule of the raw-h buffer
               const float4 v = hv[i];
               // granule -> (slot, episode row e, logical 4-k chunk c): the fp32 buffer is SWIZZLE_128B, chunk = phys ^ (e & 7)
@@ -333,11 +342,16 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
         const float zs = (q == 2) ? -2.0f * 1.4426950408889634f : -1.4426950408889634f;
         const float oa = (q == 2) ? 2.0f : 1.0f, ob = (q == 2) ? -1.0f : 0.0f;
 #pragma unroll
-        for (int e = 0; e < TR_NB; ++e) {
-          const float z = pre[e] + gxc[e];
-          const float sg = __fdividef(1.0f, 1.0f + exp2f(z * zs));
-          act[(q * TR_NB + e) * 32 + lane] = fmaf(sg, oa, ob);
-        }
+        // fully unrolled over 4, 8 or 16 columns (uniform choice): the MUFU latency needs the independent chains, a
+        // branch per column group was measured 60 % slower
+#define TR_ACT(NCOL)                                                          \
+  _Pragma("unroll") for (int e = 0; e < (NCOL); ++e) {                        \
+    const float z = pre[e] + gxc[e];                                          \
+    const float sg = __fdividef(1.0f, 1.0f + exp2f(z * zs));                  \
+    act[(q * TR_NB + e) * 32 + lane] = fmaf(sg, oa, ob);                      \
+  }
+        if (ept > 8) { TR_ACT(16) } else if (ept > 4) { TR_ACT(8) } else { TR_ACT(4) }
+#undef TR_ACT
         if (sub == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         TR_STAMP(10);
@@ -352,7 +366,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
           c[2] = fmaf(fg.z, c[2], ig.z * gg.z); c[3] = fmaf(fg.w, c[3], ig.w * gg.w);
           hn = make_float4(og.x * tanh_fast(c[0]), og.y * tanh_fast(c[1]), og.z * tanh_fast(c[2]), og.w * tanh_fast(c[3]));
         }
-        if (s + 1 < nsteps) {  // h_s, raw fp32, into K-block `rank` of every CTA's next B buffer
+        if (s + 1 < nsteps && ce < ept) {  // h_s, raw fp32, into K-block `rank` of every CTA's next B buffer
           const uint32_t boff = (uint32_t)((p ^ 1) * TR_B_BYTES), moff = (uint32_t)((p ^ 1) * 16);
 #pragma unroll
           for (int r = 0; r < kCluster; ++r) st_async_v4(raddr[r] + boff, hn, rbar[r] + moff);
@@ -444,20 +458,32 @@ extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int
     MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<2>()));
     cap = tc_max_active_clusters(lstm_fwd_tc_kernel<false, 2>, 2 * TR_SUB_THREADS, tr_smem<2>());
   }
-  const int n_tiles = (B + TR_NB - 1) / TR_NB;
+  // episodes per tile: 16 when the tiles outnumber the resident clusters; otherwise as few as spreading the batch over
+  // all clusters allows (a cluster's step gets shorter with fewer episodes, the MMAs cost the same)
+  int ept = TR_NB;
+  {
+    const int per_dir = cap / (2 * n_enc);   // clusters one (direction, encoder) can have
+    if (per_dir >= 1 && (B + TR_NB - 1) / TR_NB <= per_dir) {
+      const int want = (B + per_dir - 1) / per_dir;
+      ept = want < 1 ? 1 : (want > TR_NB ? TR_NB : want);
+    }
+  }
+  static const char *force_ept = getenv("MTS_REC_EPT");
+  if (force_ept && atoi(force_ept) >= 1 && atoi(force_ept) <= TR_NB) ept = atoi(force_ept);
+  const int n_tiles = (B + ept - 1) / ept;
   const int items1 = n_tiles * 2 * n_enc;
   // one tile per cluster while everything fits in a single wave; otherwise two tile pipelines per cluster
   static const char *force = getenv("MTS_REC_NT");
   const bool two = force ? (force[0] == '2') : (items1 > cap);
   if (!two) {
     const unsigned grid = (unsigned)((items1 < cap ? items1 : cap) * kCluster);
-    if (gates) lstm_fwd_tc_kernel<true, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates, y_corr);
-    else lstm_fwd_tc_kernel<false, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates, y_corr);
+    if (gates) lstm_fwd_tc_kernel<true, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr);
+    else lstm_fwd_tc_kernel<false, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr);
   } else {
     const int items2 = ((n_tiles + 1) / 2) * 2 * n_enc;
     const unsigned grid = (unsigned)((items2 < cap ? items2 : cap) * kCluster);
-    if (gates) lstm_fwd_tc_kernel<true, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates, y_corr);
-    else lstm_fwd_tc_kernel<false, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, y, gates, y_corr);
+    if (gates) lstm_fwd_tc_kernel<true, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr);
+    else lstm_fwd_tc_kernel<false, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr);
   }
   MTS_LAUNCH_CHECK();
   return 0;
