@@ -36,7 +36,10 @@ constexpr int TB_SMEM = TB_SMEM_USED > 120 * 1024 ? TB_SMEM_USED : 120 * 1024;  
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1)
     lstm_bwd_tc_kernel(const float *__restrict__ dy, const float *__restrict__ gates, const float *__restrict__ w_hh,
                        const int32_t *__restrict__ lengths, const int32_t *__restrict__ order, int B, int T, int n_enc,
-                       int n_tiles, float *__restrict__ dgx) {
+                       int n_tiles, int ept, float *__restrict__ dgx) {
+  // ept = episodes per tile (<= TB_NB), as in the forward kernel: a small batch is spread over all resident clusters.
+  // Episode slot sl of a tile sits in operand row 4 * (sl % 4) + sl / 4, so that the four cell warps (warp w owns rows
+  // 4w .. 4w + 3) share the present episodes evenly; rows of absent slots stay zero and are skipped.
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *wtail = smem;                                    // [2][128 rows x 128 B]
@@ -73,6 +76,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
   const uint32_t tmem_base = *tmem_slot;
 
   uint32_t ph_part[2] = {0, 0}, ph_b = 0, ph_acc = 0;
+  const int nf4 = ept < 4 ? ept : 4;   // groups of 4 operand rows (= cell warps) that hold at least one episode
   const int et = tid - 32;             // 0..127 over the epilogue warps
   const int q = warp & 3;              // TMEM lane quarter this warp may read
   const int cu = et & 31, cg4 = et >> 5;  // cell role: unit cu, episodes 4 cg4 .. 4 cg4 + 3
@@ -123,11 +127,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
       cur_enc = enc;
     }
     if (tid < TB_NB) {
-      const int slot = tile * TB_NB + tid;
-      const int bq = (slot < B) ? (order ? order[slot] : slot) : -1;
+      const int sl = (tid >> 2) + 4 * (tid & 3);   // episode slot held by operand row `tid`
+      const int slot = tile * ept + sl;
+      const int bq = (sl < ept && slot < B) ? (order ? order[slot] : slot) : -1;
       bq_s[tid] = bq;
       len_s[tid] = (bq >= 0) ? min(max(lengths[bq], 0), T) : 0;
     }
+    for (int idx = tid; idx < 2 * TB_B_BYTES / 16; idx += TB_THREADS)   // bhi and blo: rows of absent slots stay zero
+      reinterpret_cast<float4 *>(bhi)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
@@ -145,7 +152,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
       const bool leader = tc::elect_one();
       for (int s = 0; s + 1 < nsteps; ++s) {   // the last step's product would feed nothing
         const int p = s & 1;
-        if (leader) tc::bar_expect_tx(tc::s_u32(&part_full[p ^ 1]), 8 * 32 * TB_NB * 4);
+        if (leader) tc::bar_expect_tx(tc::s_u32(&part_full[p ^ 1]), 8 * 32 * nf4 * 16);   // nf4 float4 per (source, unit)
         tc::bar_wait_wd(tc::s_u32(b_ready), ph_b); ph_b ^= 1;
         tc::tc_fence_after();
 #pragma unroll
@@ -179,6 +186,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
       int len[4], bq[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { len[i] = len_s[4 * cg4 + i]; bq[i] = bq_s[4 * cg4 + i]; }
+      const int n_i = min(4, max(0, (ept - cg4 + 3) >> 2));   // episodes this warp's threads carry (rows 4 cg4 + i, i < n_i)
       // saved activations of the step being visited (cur) and prefetched for the next one (nx)
       float ig[4], fg[4], gg[4], og[4], dyv[4], c_cur[4], c_prev[4], dc[4];
       float n_ig[4], n_fg[4], n_gg[4], n_og[4], n_dy[4], n_cp[4];
@@ -213,7 +221,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
           tc::bar_wait_wd(tc::s_u32(&part_full[p]), ph_part[p]); ph_part[p] ^= 1;
           const float *rb = recv + p * TB_RECV_FLOATS + cu * TB_ROW + 4 * cg4;
 #pragma unroll
-          for (int src = 0; src < 8; ++src) {
+          for (int src = 0; src < 8 && n_i > 0; ++src) {
             const float4 v = *reinterpret_cast<const float4 *>(rb + src * 32 * TB_ROW);
             dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
           }
@@ -221,6 +229,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
         // ---- cell backward: 1 unit x 4 episodes --------------------------------------------------------------------
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          if (i >= n_i) break;   // warp-uniform
           const int e = 4 * cg4 + i;
           float dpi = 0.f, dpf = 0.f, dpg = 0.f, dpo = 0.f;
           if (s < len[i]) {
@@ -280,6 +289,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TB_THREADS, 1
           const uint32_t boff = (uint32_t)((p ^ 1) * TB_RECV_FLOATS * 4), moff = (uint32_t)((p ^ 1) * 8);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            if (j >= nf4) break;
             st_async_v4(r_addr0 + boff + 16 * j, make_float4(d0[4 * j], d0[4 * j + 1], d0[4 * j + 2], d0[4 * j + 3]), r_bar0 + moff);
             st_async_v4(r_addr1 + boff + 16 * j, make_float4(d1[4 * j], d1[4 * j + 1], d1[4 * j + 2], d1[4 * j + 3]), r_bar1 + moff);
           }
@@ -344,10 +354,20 @@ extern "C" int mts_lstm_rec_bwd_tc(const float *dy, const float *gates, const fl
     }
     cap = n;
   }
-  const int n_tiles = (B + TB_NB - 1) / TB_NB;
+  int ept = TB_NB;   // see mts_lstm_rec_fwd_tc: few episodes per tile when the batch is smaller than 16 x the clusters
+  {
+    const int per_dir = cap / (2 * n_enc);
+    if (per_dir >= 1 && (B + TB_NB - 1) / TB_NB <= per_dir) {
+      const int want = (B + per_dir - 1) / per_dir;
+      ept = want < 1 ? 1 : (want > TB_NB ? TB_NB : want);
+    }
+  }
+  static const char *force_ept = getenv("MTS_REC_EPT");
+  if (force_ept && atoi(force_ept) >= 1 && atoi(force_ept) <= TB_NB) ept = atoi(force_ept);
+  const int n_tiles = (B + ept - 1) / ept;
   const int items = n_tiles * 2 * n_enc;
   const unsigned grid = (unsigned)((items < cap ? items : cap) * kCluster);
-  lstm_bwd_tc_kernel<<<grid, TB_THREADS, TB_SMEM, st>>>(dy, gates, w_hh, lengths, order, B, T, n_enc, n_tiles, dgx);
+  lstm_bwd_tc_kernel<<<grid, TB_THREADS, TB_SMEM, st>>>(dy, gates, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, dgx);
   MTS_LAUNCH_CHECK();
   return 0;
 }
