@@ -157,3 +157,12 @@ def test_checkpoint_round_trip_like_predict_py(golden, tmp_path):
                                               hidden_dim=16, num_layers=2, loss_fn="FocalLoss", nheads=4, attention_window=4)
     for k, v in tr.state_dict().items():
         assert torch.equal(back.state_dict()[k], v), k
+
+
+def test_reference_mask_loop_equals_vectorised_mask():
+    """oracle/ref_torch.reference_mask_loop restates create_masks_huggingface's Python loop (timed by bench.py); it must
+    produce the mask the oracle's vectorised length_mask produces."""
+    lengths = torch.tensor([7, 1, 12, 5])
+    m = rt.reference_mask_loop(12, lengths)
+    assert m.shape == (4, 12) and m.dtype == torch.int64
+    assert torch.equal(m.bool(), rt.length_mask(12, lengths))
