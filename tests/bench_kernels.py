@@ -64,7 +64,15 @@ def bench_rec():
     whh_t = whh.transpose(2, 3).contiguous()
     ms = timeit(lambda: ops._call("mts_lstm_rec_bwd", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), whh_t.data_ptr(),
                                   lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H, dgx.data_ptr(), ops._stream()))
-    print(f"backward B=64 T=300: {ms:.3f} ms  ({ms * 1e3 / T:.2f} us/step)")
+    print(f"backward, packed-FMA kernel (mts_lstm_rec_bwd) B=64 T=300: {ms:.3f} ms  ({ms * 1e3 / T:.2f} us/step)")
+    for Bb in (8, 10, 16, 64, 128):
+        gx, whh, lens, y, gates = rec_setup(Bb, T, save=True)
+        rec_call(gx, whh, lens, y, gates, Bb, T)
+        dy = torch.randn_like(y)
+        dgx = torch.empty_like(gx)
+        ms = timeit(lambda: ops._call("mts_lstm_rec_bwd_tc", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
+                                      lens.order.data_ptr(), 1, Bb, T, H, dgx.data_ptr(), ops._stream()))
+        print(f"backward, tensor-core kernel (mts_lstm_rec_bwd_tc) B={Bb} T=300: {ms:.3f} ms  ({ms * 1e3 / T:.2f} us/step)")
 
 
 def bench_gemm():
