@@ -10,6 +10,6 @@ from .lightning_model import TextSegmenter  # noqa: F401
 from .load_datasets_precomputed import (ResidentDataset, cross_validation_split, load_dataset_for_inference,  # noqa: F401
                                         load_dataset_from_precomputed)
 from .metrics import compute_Pk, compute_window_diff, get_boundaries  # noqa: F401
-from .modules import CRF, RNN, BiLSTM, BiLSTMLateFusion, BiRnnCrf  # noqa: F401
+from .modules import CRF, RNN, BiLSTM, BiLSTMLateFusion, BiLSTMLateFusionCrf, BiRnnCrf  # noqa: F401
 
 __version__ = "0.1.0"

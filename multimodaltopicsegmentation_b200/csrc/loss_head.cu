@@ -416,11 +416,8 @@ extern "C" int mts_seg_metrics(const uint8_t *tags, int64_t ld_tags, const float
   MTS_REQUIRE(B > 0 && T > 0, MTS_E_BADARG, "seg_metrics: bad shape");
   const size_t smem = (size_t)2 * (T + 1) * sizeof(int32_t);
   MTS_REQUIRE(smem <= 200 * 1024, MTS_E_UNSUPPORTED, "seg_metrics: episodes longer than 25 000 sentences are not supported");
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  if (smem > 48 * 1024)  // per call: the attribute is per device, and a process may drive several
     MTS_CUDA(cudaFuncSetAttribute(mts::seg_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   mts::seg_metrics_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(tags, ld_tags, target, ldt, lengths, T, zero_last, out);
   MTS_LAUNCH_CHECK();
   return 0;

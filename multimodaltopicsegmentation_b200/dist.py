@@ -30,6 +30,35 @@ def rank():
     return dist.get_rank() if is_dist() else 0
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it allocates
+    afterwards (first touch) and its copy-issuing thread sit next to the GPU's PCIe root.  One process per GPU: without
+    this, all ranks' staging memory may land on one node and the host->device streams of 8 GPUs share that node's
+    memory controllers.  Returns the node, or None when the topology cannot be read (then nothing is changed)."""
+    import os
+
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_indices(lengths, rank_, world_):
     """Episodes of one global batch owned by `rank_`: sort by length (descending), deal round-robin.
     Balances the number of sentences -- and the recurrence step count -- across ranks."""
@@ -70,13 +99,18 @@ def all_reduce_sum_scalar(value, device):
 
 
 class GradBucket:
-    """One flat fp32 buffer aliased by every parameter's .grad; all_reduce() sums it across ranks in one call."""
+    """One flat fp32 buffer aliased by every parameter's .grad; all_reduce() sums it across ranks in one call.
+    One extra slot behind the gradients carries this rank's normalisation count (valid sentences, or episodes for the
+    CRF): reduced in the SAME collective, it gives every rank the global count on the device -- no scalar all-reduce and
+    no device->host sync before the step."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.buf = torch.zeros(total + 1, dtype=torch.float32, device=dev)
+        self.flat = self.buf[:total]          # the gradients
+        self.count = self.buf[total:]         # [1]: local count before, global count after all_reduce(with_count=True)
         off = 0
         for p in self.params:
             n = p.numel()
@@ -84,12 +118,12 @@ class GradBucket:
             off += n
 
     def zero(self):
-        self.flat.zero_()
+        self.buf.zero_()
 
-    def all_reduce(self, async_op=False):
+    def all_reduce(self, async_op=False, with_count=False):
         if not is_dist():
             return None
-        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        return dist.all_reduce(self.buf if with_count else self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
 
     @property
     def nbytes(self):
@@ -105,18 +139,36 @@ def gather_tags(tags_dev):
     return out
 
 
-def train_step(segmenter, batch, optimizer, bucket):
+def local_count(segmenter, lengths):
+    """What this rank's loss is normalised by: valid sentences (focal / BCE / CE heads), episodes (CRF NLL mean)."""
+    if hasattr(segmenter.model, "crf"):
+        return len(lengths)
+    return int(torch.as_tensor(lengths).sum()) if torch.is_tensor(lengths) else int(sum(int(v) for v in lengths))
+
+
+def train_step(segmenter, batch, optimizer, bucket, global_count=None):
     """One data-parallel optimisation step on this rank's shard of the global batch.
-    `batch` is already this rank's shard (see shard_batch) and already on the device."""
+    `batch` is already this rank's shard (see shard_batch) and already on the device; `src_lengths` stays on the host.
+
+    global_count given (the sampler knows the whole global batch's lengths): the loss is normalised by it directly and
+    the gradients are summed by one all-reduce.  Otherwise the rank back-propagates its UN-normalised loss sum, puts its
+    local count into the bucket's last slot, and ONE all-reduce sums gradients and counts together; the division by the
+    global count happens on the device.  Either way there is no host synchronisation inside the step.
+    Returns this rank's share of the global mean loss (the sum over ranks is the un-sharded loss)."""
     xs, lengths = segmenter._inputs(batch)
-    dev = xs[0][0].device if isinstance(xs[0], (tuple, list)) else xs[0].device
     model = segmenter.model
-    crf = hasattr(model, "crf")
-    local = len(lengths) if crf else int(torch.as_tensor(lengths).sum())
-    global_count = all_reduce_sum_scalar(local, dev)
     bucket.zero()
-    loss = model.loss(*xs, lengths, batch["tgt_tokens"], global_count=global_count)
-    loss.backward()
-    bucket.all_reduce()
+    if global_count is not None or not is_dist():
+        count = global_count if global_count is not None else local_count(segmenter, lengths)
+        loss = model.loss(*xs, lengths, batch["tgt_tokens"], global_count=count)
+        loss.backward()
+        bucket.all_reduce()
+    else:
+        loss_sum = model.loss(*xs, lengths, batch["tgt_tokens"], global_count=1.0)
+        loss_sum.backward()
+        bucket.count.fill_(float(local_count(segmenter, lengths)))
+        bucket.all_reduce(with_count=True)
+        bucket.flat.div_(bucket.count)
+        loss = loss_sum.detach() / bucket.count[0]
     optimizer.step()
-    return loss  # this rank's share of the global mean; the sum over ranks is the un-sharded loss
+    return loss

@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import ops
 from .metrics import compute_Pk, compute_window_diff, f1_boundary
-from .modules import BiLSTM, BiLSTMLateFusion, BiRnnCrf
+from .modules import BiLSTM, BiLSTMLateFusion, BiLSTMLateFusionCrf, BiRnnCrf
 
 try:  # pragma: no cover - depends on the environment
     import pytorch_lightning as pl
@@ -72,6 +72,12 @@ class TextSegmenter(_Base):
                                           bidirectional=bidirectional, dropout_in=dropout_in, dropout_out=dropout_out,
                                           batch_first=batch_first, LSTM=LSTM, loss_fn=loss_fn, threshold=threshold,
                                           alpha=alpha, gamma=gamma)
+            self.double_input = True
+        elif architecture == "BiLSTMLateFusionCRF":  # additive: BASELINE configs[3]'s dual encoder with the CRF output layer
+            self.cos = False
+            self.model = BiLSTMLateFusionCrf(tagset_size, embedding_dim, hidden_dim, num_layers=num_layers,
+                                             bidirectional=bidirectional, dropout_in=dropout_in, dropout_out=dropout_out,
+                                             batch_first=batch_first, LSTM=LSTM)
             self.double_input = True
         elif architecture == "Transformer":
             from .transformer import Transformer_segmenter
@@ -270,7 +276,7 @@ class TextSegmenter(_Base):
         Combine with `DevicePrefetcher` for host-resident batches."""
         from .modules import _host_tags_to_lists
 
-        as_bool = not isinstance(self.model, BiRnnCrf)   # Viterbi paths are int lists, thresholded tags bool lists
+        as_bool = not hasattr(self.model, "crf")   # Viterbi paths are int lists, thresholded tags bool lists
         ring, slot, pending = [None, None, None], 0, None   # pinned landing buffers for the tag matrices, reused
 
         def finish(item):

@@ -107,6 +107,10 @@ def load_dataset_from_precomputed(embedding_directory, lab_file, delete_last_sen
             print("Warning: {} has no data".format(name))
             continue
         labs[name][-1] = 0
+        if keep_modalities and len(mods) > 2:
+            # the device path takes a (first, rest) pair: modalities beyond the second (a third '+' directory, the timing
+            # features) are concatenated onto the second one, which keeps the column order of the reference's torch.cat
+            mods = [mods[0], torch.cat([m.float() for m in mods[1:]], axis=-1)]
         embs = tuple(mods) if keep_modalities else torch.cat(mods, axis=-1)
         if mask_inner_sentences:
             original.append((embs, labs[name].copy(), file))

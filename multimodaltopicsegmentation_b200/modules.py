@@ -116,10 +116,14 @@ def _head_loss(mod, feats, lens, tags, global_count=None):
     scores = ops.HeadFn.apply(feats, mod.classification.weight, mod.classification.bias)
     kind = ops.LOSS_KINDS[mod.loss_name]
     tags = ops._check(tags.to(feats.device), "tags")
-    if kind == 2:
+    if global_count is not None:
+        # data parallel: normalise by the count over ALL ranks (for CrossEntropy that is the number of non-ignored
+        # targets = the number of valid sentences, since the collater pads the tags with -1 exactly beyond len_b)
+        inv = 1.0 / float(global_count)
+    elif kind == 2:
         inv = -1.0  # CrossEntropyLoss(ignore_index=-1): the kernel counts the non-ignored targets itself
     else:
-        inv = 1.0 / float(global_count if global_count is not None else lens.N)
+        inv = 1.0 / float(lens.N)
     return ops.SegLossFn.apply(scores, tags, lens, kind, mod.alpha, mod.gamma, inv)
 
 
@@ -209,6 +213,43 @@ class BiLSTMLateFusion(nn.Module):
         lens = _lens(lenghts, x1)
         with torch.no_grad():
             return (*_head_decode_device(self, self._features(x1, x2, lens), lens, threshold), lens)
+
+
+class BiLSTMLateFusionCrf(nn.Module):
+    """Late-fusion dual encoder with a CRF output layer: text and audio bi-LSTM stacks -> cat [B,T,4H] -> CRF(4H, tags).
+    BASELINE configs[3] names this combination; the reference has both halves (BiLSTMLateFusion, models/CRF.py:371-479,
+    and CRF, :98-240) but no class wiring them, so this is the composition SURVEY.md fact 6 describes for BiRnnCrf,
+    applied to the late-fusion encoder.  Parameter names: model1.rnn.*, model2.rnn.*, crf.fc.*, crf.transitions."""
+
+    def __init__(self, tagset_size, embedding_dim, hidden_dim, num_layers=1, bidirectional=True, dropout_in=0.0,
+                 dropout_out=0.0, batch_first=True, LSTM=True):
+        super().__init__()
+        self.embedding_dim, self.hidden_dim, self.tagset_size = embedding_dim, hidden_dim, tagset_size
+        self.device = "cuda"
+        self.model1 = RNN(embedding_dim[0], hidden_dim, num_layers, tagset_size, bidirectional, dropout_in, dropout_out,
+                          batch_first=batch_first, LSTM=LSTM)
+        self.model2 = RNN(embedding_dim[1], hidden_dim, num_layers, tagset_size, bidirectional, dropout_in, dropout_out,
+                          batch_first=batch_first, LSTM=LSTM)
+        self.crf = CRF(hidden_dim * 4, tagset_size)
+        self.th = None
+        self._packed = None
+
+    _features = BiLSTMLateFusion._features
+
+    def loss(self, x1, x2, lengths, tags, segments=None, global_count=None):
+        lens = _lens(lengths, x1)
+        return self.crf.loss(self._features(x1, x2, lens), tags[:, : lens.T], lens, global_count=global_count)
+
+    def forward(self, x1, x2, lenghts, threshold=None):
+        lens = _lens(lenghts, x1)
+        with torch.no_grad():
+            return self.crf(self._features(x1, x2, lens), lens)
+
+    def decode_device(self, x1, x2, lenghts, threshold=None):
+        lens = _lens(lenghts, x1)
+        with torch.no_grad():
+            best, paths = ops.crf_viterbi(self.crf.emissions(self._features(x1, x2, lens)), lens, self.crf.transitions)
+        return best, paths.to(torch.uint8), lens
 
 
 class CRF(nn.Module):

@@ -59,6 +59,10 @@ def _check(t, name, dtype=torch.float32):
         raise _lib.MtsError(f"{name} must live on a CUDA device: this package has no CPU path")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # the C ABI launches on the CUDA runtime's current device and on torch's current stream of that device
+        raise _lib.MtsError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                            "wrap the call in torch.cuda.device(tensor.device)")
     return t
 
 
@@ -119,8 +123,22 @@ def split_tf32(src2d, cols=None, ld=None, rows=None, side=A_SIDE):
     return out[0], out[1]
 
 
+def _rows_ok(x, name, B, T):
+    """The packing kernel reads src + b * bstride + t * D + k: rows of one episode must be dense (stride(1) == D,
+    stride(2) == 1).  A view that is not (e.g. x[:, :, :D1] of a fused tensor) is made contiguous here."""
+    if x is None:
+        return None
+    _check(x, name)
+    if x.dim() != 3 or x.shape[0] < B or x.shape[1] < T:
+        raise ValueError(f"{name}: expected [B >= {B}, T >= {T}, D], got {tuple(x.shape)}")
+    if x.stride(2) != 1 or x.stride(1) != x.shape[2]:
+        x = x.contiguous()
+    return x
+
+
 def pack_rows_split(x1, x2, B, T):
     """[x1[b,:T] | x2[b,:T]] -> (hi, lo) [B*T, pad32(D1+D2)] (early fusion concat + crop + split, one kernel)"""
+    x1, x2 = _rows_ok(x1, "input", B, T), _rows_ok(x2, "second input", B, T)
     D1 = x1.shape[2]
     D2 = 0 if x2 is None else x2.shape[2]
     kp = _pad32(D1 + D2)
@@ -302,6 +320,9 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
 def bilstm_stack(x1, x2, xs2, lens, packed, n_enc):
     """The bi-LSTM stack as the modules call it.  Inference (grad mode off, or nothing to differentiate) skips autograd
     and, with it, the per-step gate record the backward pass needs (5 H floats per sentence and direction)."""
+    # dense rows for the forward packing kernel AND the backward weight-gradient transposes (both index by strides)
+    x1, x2, xs2 = (_rows_ok(x1, "input", lens.B, lens.T), _rows_ok(x2, "second input", lens.B, lens.T),
+                   _rows_ok(xs2, "second encoder input", lens.B, lens.T))
     flat = packed.flat_params()
     if not (torch.is_grad_enabled() and any(p.requires_grad for p in flat)):
         rnn0 = packed.rnns[0]
@@ -410,9 +431,11 @@ class BiLstmStackFn(torch.autograd.Function):
                 base = 8 * layer
                 g = grads[e]
                 g[base + 0], g[base + 1] = dwih[:4 * H], dwhh[0]
-                g[base + 2], g[base + 3] = db[:4 * H], db[:4 * H]
+                # b_ih and b_hh receive the same gradient but must not share storage: AccumulateGrad may adopt the
+                # tensors as .grad, and an in-place op on one (clip_grad_norm_, a second backward) would hit both
+                g[base + 2], g[base + 3] = db[:4 * H], db[:4 * H].clone()
                 g[base + 4], g[base + 5] = dwih[4 * H:], dwhh[1]
-                g[base + 6], g[base + 7] = db[4 * H:], db[4 * H:]
+                g[base + 6], g[base + 7] = db[4 * H:], db[4 * H:].clone()
             dy = dy_next
         flat = [g for e in range(n_enc) for g in grads[e]]
         ctx.saved = None

@@ -55,12 +55,24 @@ def _worker(rank, world, port, out_dir):
     loss = model.loss(shard["src_tokens"], shard["src_lengths"], shard["tgt_tokens"]) * (n_local / n_global)
     loss.backward()
     bucket.all_reduce()
+    flat1 = bucket.flat.clone()
+    # second protocol (dist.train_step without a known global count): un-normalised local loss SUM, the local count rides
+    # in the bucket's extra slot, ONE all-reduce for both, division on the device -- no host synchronisation
+    bucket.zero()
+    loss_sum = model.loss(shard["src_tokens"], shard["src_lengths"], shard["tgt_tokens"]) * n_local
+    loss_sum.backward()
+    bucket.count.fill_(float(n_local))
+    bucket.all_reduce(with_count=True)
+    count_after = float(bucket.count[0])
+    bucket.flat.div_(bucket.count)
+    flat2 = bucket.flat.clone()
+    bucket.flat.copy_(flat1)
     tags = torch.full((4, 14), 255, dtype=torch.uint8)
     tags[: len(idx), 0] = torch.tensor(idx, dtype=torch.uint8)
     gathered = mdist.gather_tags(tags)
     total = torch.tensor([float(loss)], dtype=torch.float64)
     dist.all_reduce(total)
-    torch.save({"idx": idx, "n_global": n_global, "flat": bucket.flat.clone(), "loss_sum": total.item(),
+    torch.save({"idx": idx, "n_global": n_global, "flat": bucket.flat.clone(), "flat2": flat2, "count_after": count_after, "loss_sum": total.item(),
                 "grad_is_view": all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in bucket.params),
                 "gathered": [g[:, 0].tolist() for g in gathered], "T": shard["src_tokens"].shape[1]},
                os.path.join(out_dir, f"rank{rank}.pt"))
@@ -90,6 +102,10 @@ def test_sharded_backward_plus_one_allreduce_equals_unsharded(tmp_path):
     assert torch.equal(r0["flat"], r1["flat"])  # every rank holds the same reduced bucket
     np.testing.assert_allclose(r0["flat"].numpy(), flat.numpy(), rtol=1e-4, atol=1e-7)
     np.testing.assert_allclose(r0["loss_sum"], float(loss), rtol=1e-5)
+    # the fused-count protocol gives the same gradients and every rank learns the global count from the collective
+    assert r0["count_after"] == r1["count_after"] == float(batch["src_lengths"].sum())
+    assert torch.equal(r0["flat2"], r1["flat2"])
+    np.testing.assert_allclose(r0["flat2"].numpy(), flat.numpy(), rtol=1e-4, atol=1e-7)
     assert r0["grad_is_view"] and r1["grad_is_view"]
     # final gather: rank order, fixed-size buffers
     assert r0["gathered"] == r1["gathered"]

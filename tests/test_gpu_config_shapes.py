@@ -1,0 +1,334 @@
+"""GPU parity at the shapes bench.py times (`pytest -m gpu`): the default tcgen05 path of every benchmarked
+configuration against the CPU oracle (oracle/ref_torch.py = the reference's own torch calls, pinned by the goldens).
+
+  cfg4  BiLSTMLateFusion, H 256, D (384, 512), ragged batch       (reference models/CRF.py:371-479)
+  cfg2  early-fusion BiLSTM focal training step at NonNews lengths (84..2437), and the RNN -> CRF composition
+        (models/CRF.py:130-216, 274-356) at H 256
+  cfg5  8192-sentence episodes, 1024-d                              (models/NeuralArchitectures.py:83-145)
+  DP    CrossEntropy head under sharding (global-count normalisation)
+
+Every test prints the measured element-wise worst case next to the tolerance it asserts, and the number of
+thresholded decisions it had to skip because the oracle's probability sits within 1e-6 of the threshold.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import multimodaltopicsegmentation_b200 as m
+
+    m.ops.device_ok()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _report(name, got, ref):
+    """max abs error, the tensor's scale, and the worst element-wise relative error over elements above 1e-3 of scale"""
+    got = got.detach().cpu().double()
+    ref = ref.detach().cpu().double()
+    err = (got - ref).abs()
+    scale = float(ref.abs().max())
+    big = ref.abs() > 1e-3 * scale
+    rel = float((err[big] / ref.abs()[big]).max()) if bool(big.any()) else 0.0
+    print(f"  {name}: max|err| {float(err.max()):.3e}  scale {scale:.3e}  norm-wise {float(err.max()) / max(scale, 1e-30):.2e}  "
+          f"worst element-wise rel (|ref| > 1e-3 scale) {rel:.2e}")
+    return float(err.max()), scale, rel
+
+
+def _tags_agree(tags, tags_ref, s_ref, lengths, th, col=0):
+    """Thresholded tags must agree wherever the oracle's probability is not within 1e-6 of the threshold; returns the
+    number of skipped near-ties (reported)."""
+    p = torch.sigmoid(s_ref)[:, :, col]
+    skipped = 0
+    for b, n in enumerate(lengths.tolist()):
+        for t in range(n):
+            if abs(float(p[b, t]) - th) <= 1e-6:
+                skipped += 1
+            else:
+                assert tags[b][t] == tags_ref[b][t], (b, t, float(p[b, t]))
+    print(f"  thresholded tags: {int(lengths.sum())} decisions compared, {skipped} skipped as |sigmoid(z) - th| <= 1e-6")
+    return skipped
+
+
+def _grads_close(ours, ref, rtol=1e-4):
+    ref_grads = dict(ref.named_parameters())
+    worst = 0.0
+    for k, prm in ours.named_parameters():
+        gr = ref_grads[k].grad
+        err, scale, _ = _report("grad " + k, prm.grad, gr)
+        assert err <= rtol * scale + 1e-7, (k, err, scale)
+        worst = max(worst, err / max(scale, 1e-30))
+    print(f"  worst norm-wise gradient error {worst:.2e} (contract {rtol:.0e})")
+
+
+def test_cfg4_late_fusion_h256_vs_oracle(dev):
+    """Both encoders in one n_enc = 2 launch per layer on the tcgen05 recurrence, against the oracle's LateFusion."""
+    from multimodaltopicsegmentation_b200 import BiLSTMLateFusion
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(4)
+    g = torch.Generator().manual_seed(44)
+    B, T, D1, D2, H = 24, 150, 384, 512, 256
+    ref = rt.LateFusion(2, [D1, D2], H, num_layers=2, loss_fn="FocalLoss")
+    with torch.no_grad():
+        ref.classification.weight.mul_(4.0)
+    ours = BiLSTMLateFusion(2, [D1, D2], H, num_layers=2, loss_fn="FocalLoss")
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev)
+    x1, x2 = torch.randn(B, T, D1, generator=g), torch.randn(B, T, D2, generator=g)
+    lengths = torch.randint(20, T + 1, (B,), generator=g)
+    lengths[3] = T
+    y = (torch.rand(B, T, generator=g) < 0.07).float()
+    for b, n in enumerate(lengths.tolist()):
+        y[b, n:] = -1
+    ref.th = ours.th = 0.5
+    s_ref, tags_ref = ref(x1, x2, lengths)
+    s, tags = ours(x1.to(dev), x2.to(dev), lengths)
+    err, scale, _ = _report("scores", s, s_ref)
+    assert err <= 1e-4 * scale + 2e-5
+    _tags_agree(tags, tags_ref, s_ref.detach(), lengths, 0.5)
+    loss_ref = ref.loss(x1, x2, lengths, y)
+    loss_ref.backward()
+    loss = ours.loss(x1.to(dev), x2.to(dev), lengths, y.to(dev))
+    loss.backward()
+    print(f"  loss {float(loss):.7f} vs oracle {float(loss_ref):.7f}")
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    _grads_close(ours, ref)
+
+
+def test_cfg4_late_fusion_crf_h256_vs_oracle(dev):
+    """The CRF output layer over the late-fusion encoder (BASELINE configs[3]): NLL, gradients and Viterbi against the
+    oracle's LateFusion encoders + ChainCRF composed the same way."""
+    from multimodaltopicsegmentation_b200 import BiLSTMLateFusionCrf
+    from oracle import c_oracle
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(14)
+    g = torch.Generator().manual_seed(144)
+    B, T, D1, D2, H = 12, 90, 384, 512, 256
+    enc = rt.LateFusion(2, [D1, D2], H, num_layers=2, loss_fn="FocalLoss")
+    crf = rt.ChainCRF(4 * H, 2)
+    ours = BiLSTMLateFusionCrf(2, [D1, D2], H, num_layers=2)
+    sd = {k: v for k, v in enc.state_dict().items() if not k.startswith("classification")}
+    sd.update({"crf." + k: v for k, v in crf.state_dict().items()})
+    ours.load_state_dict(sd)
+    ours = ours.to(dev)
+    x1, x2 = torch.randn(B, T, D1, generator=g), torch.randn(B, T, D2, generator=g)
+    lengths = torch.randint(10, T + 1, (B,), generator=g)
+    lengths[1] = T
+    y = (torch.rand(B, T, generator=g) < 0.1).float()
+    mask = rt.length_mask(T, lengths)
+    loss_ref = crf.loss(enc._features(x1, x2, lengths), y, mask)
+    loss_ref.backward()
+    loss = ours.loss(x1.to(dev), x2.to(dev), lengths, y.to(dev))
+    loss.backward()
+    print(f"  NLL {float(loss):.6f} vs oracle {float(loss_ref):.6f}")
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    ref_grads = {k: p.grad for k, p in enc.named_parameters() if not k.startswith("classification")}
+    ref_grads.update({"crf." + k: p.grad for k, p in crf.named_parameters()})
+    for k, prm in ours.named_parameters():
+        err, scale, _ = _report("grad " + k, prm.grad, ref_grads[k])
+        assert err <= 1e-4 * scale + 1e-7, k
+    with torch.no_grad():
+        best, paths = ours(x1.to(dev), x2.to(dev), lengths)
+        emis = ours.crf.emissions(ours._features(x1.to(dev), x2.to(dev), ours_lens(lengths, dev, T))).cpu().numpy()
+    b_c, p_c = c_oracle.crf_viterbi(np.ascontiguousarray(emis), lengths.numpy(),
+                                    np.ascontiguousarray(ours.crf.transitions.detach().cpu().numpy()))
+    assert np.array_equal(best.cpu().numpy(), b_c)
+    for b, n in enumerate(lengths.tolist()):
+        assert [int(v) for v in paths[b]] == p_c[b, :n].tolist()
+
+
+def ours_lens(lengths, dev, T):
+    from multimodaltopicsegmentation_b200 import ops
+
+    return ops.Lengths(lengths, dev, T)
+
+
+def _nonnews_batch(seed, B=10, D=896, tmin=84, tmax=2437):
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(tmin, tmax + 1, (B,), generator=g)
+    lengths[B // 2] = tmax
+    T = int(lengths.max())
+    x = torch.randn(B, T, D, generator=g)
+    y = (torch.rand(B, T, generator=g) < 0.07).float()
+    for b, n in enumerate(lengths.tolist()):
+        x[b, n:] = 0
+        y[b, n - 1] = 0
+    return x, y, lengths, T
+
+
+def test_cfg2_training_step_at_nonnews_lengths_vs_oracle(dev):
+    """One focal-loss training step at the benchmarked length (10 episodes, up to 2437 sentences, 896-d): loss and every
+    gradient against autograd through the oracle.  This is the K = 24 370-token contraction of the weight gradients
+    and a 2437-step BPTT on the tensor cores."""
+    from multimodaltopicsegmentation_b200 import BiLSTM
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(2)
+    x, y, lengths, T = _nonnews_batch(22)
+    ypad = y.clone()
+    for b, n in enumerate(lengths.tolist()):
+        ypad[b, n:] = -1
+    ref = rt.Segmenter(2, 896, 256, num_layers=2, loss_fn="FocalLoss")
+    ours = BiLSTM(2, 896, 256, num_layers=2, loss_fn="FocalLoss")
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev)
+    loss_ref = ref.loss(x, lengths, ypad)
+    loss_ref.backward()
+    loss = ours.loss(x.to(dev), lengths, ypad.to(dev))
+    loss.backward()
+    print(f"  T = {T}, {int(lengths.sum())} sentences; loss {float(loss):.7f} vs oracle {float(loss_ref):.7f}")
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    _grads_close(ours, ref)
+
+
+def test_cfg2_birnncrf_h256_vs_oracle(dev):
+    """RNN -> CRF at H 256: NLL and its gradients against the oracle's EncoderCRF; Viterbi paths and scores BIT-EXACT
+    against the C oracle run on the very emissions the device produced (north_star: "bit-exact given identical
+    emissions"), and equal to the torch oracle's paths wherever the two emission sets decode identically."""
+    from multimodaltopicsegmentation_b200 import BiRnnCrf
+    from oracle import c_oracle
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(6)
+    x, y, lengths, T = _nonnews_batch(66, B=10, D=896, tmin=84, tmax=1200)
+    ref = rt.EncoderCRF(2, 896, 256, num_layers=2)
+    ours = BiRnnCrf(2, 896, 256, num_layers=2)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev)
+    loss_ref = ref.loss(x, lengths, y)
+    loss_ref.backward()
+    loss = ours.loss(x.to(dev), lengths, y.to(dev))
+    loss.backward()
+    print(f"  T = {T}; NLL {float(loss):.6f} vs oracle {float(loss_ref):.6f}")
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    _grads_close(ours, ref)
+    # decode
+    with torch.no_grad():
+        best, paths = ours(x.to(dev), lengths)
+        emis = ours.crf.emissions(ours.model(x.to(dev), lengths)).cpu().numpy()
+        best_ref, paths_ref = ref(x, lengths)
+    trans = ours.crf.transitions.detach().cpu().numpy()
+    b_c, p_c = c_oracle.crf_viterbi(np.ascontiguousarray(emis), lengths.numpy(), np.ascontiguousarray(trans))
+    assert np.array_equal(best.cpu().numpy(), b_c), "Viterbi scores must be bit-exact given identical emissions"
+    for b, n in enumerate(lengths.tolist()):
+        assert [int(v) for v in paths[b]] == p_c[b, :n].tolist(), f"episode {b}: path differs from the C oracle"
+    differ = sum(int(a != r) for pa, pr in zip(paths, paths_ref) for a, r in zip(pa, pr))
+    _report("Viterbi best score vs torch oracle (its own emissions)", best, best_ref)
+    print(f"  Viterbi vs the torch oracle decoding ITS emissions: {differ} of {int(lengths.sum())} tags differ "
+          "(emissions agree to ~1e-5; a differing tag needs a tie inside that band)")
+    assert differ <= 2
+
+
+def test_cfg5_8192_sentence_logits_vs_oracle(dev):
+    """Two 8192-sentence, 1024-d episodes through the 2-layer BiLSTM: logits against the oracle (nn.LSTM on the host),
+    measured worst case reported.  The recurrence error does not grow with T here because the gates contract."""
+    from multimodaltopicsegmentation_b200 import BiLSTM
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(58)
+    B, T, D, H = 2, 8192, 1024, 256
+    ref = rt.Segmenter(2, D, H, num_layers=2, loss_fn="FocalLoss")
+    with torch.no_grad():
+        ref.classification.weight.mul_(4.0)
+    ours = BiLSTM(2, D, H, num_layers=2, loss_fn="FocalLoss")
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev)
+    x = torch.randn(B, T, D, generator=g)
+    lengths = torch.tensor([T, 6001])
+    ref.th = ours.th = 0.5
+    with torch.no_grad():
+        s_ref, tags_ref = ref(x, lengths)
+    s, tags = ours(x.to(dev), lengths)
+    worst = 0.0
+    for b, n in enumerate(lengths.tolist()):
+        err, scale, _ = _report(f"logits episode {b} ({n} sentences)", s[b, :n], s_ref[b, :n])
+        worst = max(worst, err / scale)
+        # first and last 256 positions separately: both directions have run their full length at one of the two ends
+        _report("  first 256", s[b, :256], s_ref[b, :256])
+        _report("  last 256", s[b, n - 256:n], s_ref[b, n - 256:n])
+        assert err <= 1e-4 * scale + 2e-5
+    _tags_agree(tags, tags_ref, s_ref, lengths, 0.5)
+    print(f"  worst norm-wise logit error at T = 8192: {worst:.2e} (contract 1e-4)")
+
+
+@pytest.mark.parametrize("loss_fn", ["CrossEntropy", "FocalLoss"])
+def test_sharded_loss_heads_sum_to_the_unsharded_gradient(dev, loss_fn):
+    """Data parallelism without processes: the batch split in two shards, each back-propagated with the loss normalised
+    by the GLOBAL count (what dist.train_step passes), gradients summed -- must equal the un-sharded gradient of the
+    oracle.  CrossEntropy used to normalise by the local count."""
+    from multimodaltopicsegmentation_b200 import BiLSTM
+    from multimodaltopicsegmentation_b200 import dist as mdist
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(8)
+    g = torch.Generator().manual_seed(88)
+    B, T, D, H = 9, 40, 48, 256
+    ref = rt.Segmenter(2, D, H, num_layers=1, loss_fn=loss_fn)
+    ours = BiLSTM(2, D, H, num_layers=1, loss_fn=loss_fn)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev)
+    x = torch.randn(B, T, D, generator=g)
+    lengths = torch.randint(3, T + 1, (B,), generator=g)
+    lengths[0] = T
+    y = (torch.rand(B, T, generator=g) < 0.2).float()
+    for b, n in enumerate(lengths.tolist()):
+        x[b, n:] = 0
+        y[b, n:] = -1
+    batch = {"src_tokens": x, "src_tokens2": None, "src_lengths": lengths, "tgt_tokens": y, "id": torch.arange(B), "domain": None}
+    loss_ref = ref.loss(x, lengths, y)
+    loss_ref.backward()
+    n_global = int(lengths.sum())
+    total = 0.0
+    for r in range(2):
+        shard, _ = mdist.shard_batch(batch, r, 2)
+        loss = ours.loss(shard["src_tokens"].to(dev), shard["src_lengths"], shard["tgt_tokens"].to(dev), global_count=n_global)
+        loss.backward()   # .grad accumulates over the two shards = the all-reduce(SUM)
+        total += float(loss)
+    print(f"  {loss_fn}: summed shard losses {total:.7f} vs un-sharded oracle {float(loss_ref):.7f}")
+    assert abs(total - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    _grads_close(ours, ref)
+
+
+def test_non_contiguous_modalities_and_bias_gradients(dev):
+    """(text, audio) given as column slices of one fused tensor (stride(1) != D) must give the same result as dense
+    copies (the packing kernel assumed dense rows); b_ih / b_hh gradients must not share storage, so
+    that clip_grad_norm_ and a second accumulated backward behave as with nn.LSTM."""
+    from multimodaltopicsegmentation_b200 import BiLSTM
+
+    torch.manual_seed(9)
+    g = torch.Generator().manual_seed(99)
+    B, T, D1, D2 = 5, 30, 24, 40
+    m = BiLSTM(2, D1 + D2, 256, num_layers=2, loss_fn="FocalLoss").to(dev)
+    x = torch.randn(B, T, D1 + D2, generator=g).to(dev)
+    lengths = torch.tensor([30, 7, 19, 30, 2])
+    y = (torch.rand(B, T, generator=g) < 0.2).float().to(dev)
+    m.th = 0.5
+    s_dense, _ = m((x[:, :, :D1].contiguous(), x[:, :, D1:].contiguous()), lengths)
+    s_view, _ = m((x[:, :, :D1], x[:, :, D1:]), lengths)
+    s_fused, _ = m(x, lengths)
+    assert torch.equal(s_dense, s_view) and torch.equal(s_dense, s_fused)
+    loss = m.loss((x[:, :, :D1], x[:, :, D1:]), lengths, y)
+    loss.backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    rnn = m.model.rnn
+    assert rnn.bias_ih_l0.grad.data_ptr() != rnn.bias_hh_l0.grad.data_ptr()
+    assert torch.equal(rnn.bias_ih_l0.grad, rnn.bias_hh_l0.grad)
+    # a second backward accumulates exactly once into each bias
+    m.loss(x, lengths, y).backward()
+    for k, p in m.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), 2 * g1[k].cpu().numpy(), rtol=1e-5, atol=1e-9, err_msg=k)
+    # clipping scales every gradient by the same factor (aliased bias grads would be scaled twice)
+    total = torch.nn.utils.clip_grad_norm_(m.parameters(), 1e-3)
+    coef = 1e-3 / (float(total) + 1e-6)
+    for k, p in m.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), 2 * coef * g1[k].cpu().numpy(), rtol=1e-4, atol=1e-12, err_msg=k)
