@@ -247,10 +247,23 @@ int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, cons
                       void *stream);
 /* The same on the tensor cores: warp-level mma.sync m16n8k8 TF32 with 3xTF32 compensation for Q K^T and P V, S kept in
  * registers (hd in {8,16,32,64,112,128}).  Same contract and results; on B200 it runs at the speed of the CUDA-core
- * kernel (measured), so mts_band_attn_fwd stays the default; MTS_ATTN_IMPL=mma switches the default entry over. */
+ * kernel (measured).  Kept as a second implementation; MTS_ATTN_IMPL=mma switches the default entry over to it. */
 int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
                           int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
                           void *stream);
+/* The CUDA-core (packed FFMA2) kernel: any head dim that is a multiple of 4 and <= 128.  mts_band_attn_fwd falls back
+ * to it for head dims the tcgen05 kernel is not instantiated for. */
+int mts_band_attn_fwd_simt(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
+                           int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
+                           void *stream);
+/* The tcgen05 kernel (csrc/attn_tc.cu), the default behind mts_band_attn_fwd: Q K^T and P V as tcgen05.mma (TF32 +
+ * packed bf16 correction, both operands' corrections derived on chip), S / P / O in tensor memory, fp32 softmax from
+ * tcgen05.ld.  Replaces HF's sliding-chunk einsums (modeling_longformer.py:758-867; call site
+ * models/RestrictedTransformerLayer.py:131).  Head dims 16, 32, 64, 112, 128 (mts_band_attn_tc_supported). */
+int mts_band_attn_tc_supported(int hd);
+int mts_band_attn_fwd_tc(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
+                         int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
+                         void *stream);
 
 /* Backward of the encoder pieces (the reference: autograd through HF LongformerModel).
  * mts_ln_bwd: dy, pre (pre-LN values), stats (mean, rstd) as saved by the forward calls -> dx [M,d] (+ its TF32

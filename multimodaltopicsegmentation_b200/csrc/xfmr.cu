@@ -714,6 +714,19 @@ extern "C" int mts_band_attn_fwd_mma(const float *qkv, int64_t ld, const int32_t
 extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B,
                                  int S, int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp,
                                  float *lse, void *stream) {
+  // Default: the tcgen05 kernel (attn_tc.cu) for the head dims it is instantiated for; MTS_ATTN_IMPL=simt / mma select
+  // the CUDA-core kernel below / the mma.sync kernel instead (second implementations for the tests).
+  static const char *impl = getenv("MTS_ATTN_IMPL");
+  if (impl && impl[0] == 'm' && (hd == 8 || hd == 16 || hd == 32 || hd == 64 || hd == 112 || hd == 128))
+    return mts_band_attn_fwd_mma(qkv, ld, lengths, offsets, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, stream);
+  if (!(impl && impl[0] == 's') && mts_band_attn_tc_supported(hd) && (!out_hi || Kp == nheads * hd))
+    return mts_band_attn_fwd_tc(qkv, ld, lengths, offsets, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, stream);
+  return mts_band_attn_fwd_simt(qkv, ld, lengths, offsets, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, stream);
+}
+
+extern "C" int mts_band_attn_fwd_simt(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B,
+                                      int S, int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp,
+                                      float *lse, void *stream) {
   MTS_REQUIRE(qkv && lengths && (out || out_hi), MTS_E_BADARG, "band_attn_fwd: null pointer");
   MTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), MTS_E_BADARG, "band_attn_fwd: hi and lo go together");
   MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_fwd: bad shape");
@@ -723,10 +736,6 @@ extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *le
   MTS_REQUIRE(!out_hi || (Kp % 32 == 0 && Kp >= nheads * hd), MTS_E_BADARG, "band_attn_fwd: Kp");
   MTS_REQUIRE(!out_hi || Kp == nheads * hd, MTS_E_UNSUPPORTED,
               "band_attn_fwd: the split output needs a model width that is a multiple of 32");
-  // MTS_ATTN_IMPL=mma routes to the tensor-core kernel (same results; measured the same speed on B200)
-  static const char *impl = getenv("MTS_ATTN_IMPL");
-  if (impl && impl[0] == 'm' && (hd == 8 || hd == 16 || hd == 32 || hd == 64 || hd == 112 || hd == 128))
-    return mts_band_attn_fwd_mma(qkv, ld, lengths, offsets, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, stream);
   const size_t smem = ba_smem_bytes(hd);
   static size_t smem_set = 0;
   if (smem > smem_set) {

@@ -325,10 +325,12 @@ def test_non_contiguous_modalities_and_bias_gradients(dev):
     assert torch.equal(rnn.bias_ih_l0.grad, rnn.bias_hh_l0.grad)
     # a second backward accumulates exactly once into each bias
     m.loss(x, lengths, y).backward()
-    for k, p in m.named_parameters():
-        np.testing.assert_allclose(p.grad.cpu().numpy(), 2 * g1[k].cpu().numpy(), rtol=1e-5, atol=1e-9, err_msg=k)
+    for k, p in m.named_parameters():  # (split-K atomics: the two passes agree to rounding, not bit for bit)
+        ref2 = 2 * g1[k].cpu().numpy()
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref2, rtol=1e-4, atol=1e-5 * float(np.abs(ref2).max()), err_msg=k)
     # clipping scales every gradient by the same factor (aliased bias grads would be scaled twice)
     total = torch.nn.utils.clip_grad_norm_(m.parameters(), 1e-3)
     coef = 1e-3 / (float(total) + 1e-6)
     for k, p in m.named_parameters():
-        np.testing.assert_allclose(p.grad.cpu().numpy(), 2 * coef * g1[k].cpu().numpy(), rtol=1e-4, atol=1e-12, err_msg=k)
+        ref2 = 2 * coef * g1[k].cpu().numpy()
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref2, rtol=1e-4, atol=1e-5 * float(np.abs(ref2).max()), err_msg=k)

@@ -482,19 +482,28 @@ def _to_padded(t, lens, B, S):
 
 
 @pytest.mark.parametrize("layout", ["padded", "ragged"])
-@pytest.mark.parametrize("entry", ["mts_band_attn_fwd", "mts_band_attn_fwd_mma"])
+@pytest.mark.parametrize("entry", ["mts_band_attn_fwd", "mts_band_attn_fwd_tc", "mts_band_attn_fwd_simt", "mts_band_attn_fwd_mma"])
 @pytest.mark.parametrize("B,S,h,hd,w,lens", [
     (2, 24, 4, 8, 4, [24, 13]),
     (3, 200, 2, 112, 48, [200, 77, 1]),
     (2, 130, 3, 64, 8, [130, 31]),
     (2, 96, 2, 32, 100, [96, 50]),      # window wider than the episode: dense attention
     (1, 700, 1, 16, 360, [650]),        # default-config reach (window 120 x 6 layers)
+    (5, 960, 8, 112, 48, [960, 100, 513, 128, 129]),   # configs[2] geometry: many work items per CTA, block-edge lengths
+    (3, 300, 2, 128, 0, [300, 1, 64]),  # reach 0: every token attends to itself only
+    (2, 260, 1, 112, 40, [260, 257]),
 ])
 def test_band_attention_forward(dev, B, S, h, hd, w, lens, entry, layout):
-    """CUDA-core kernel and mma.sync tensor-core kernel against the numpy restatement of HF's banded attention, in the
-    reference's padded row layout and in the ragged layout (valid sentences only; include/mts_b200.h "Row layouts")."""
-    from multimodaltopicsegmentation_b200 import ops
+    """The tcgen05 kernel (the default), the CUDA-core kernel and the mma.sync kernel against the numpy restatement of
+    HF's banded attention, in the reference's padded row layout and in the ragged layout (valid sentences only;
+    include/mts_b200.h "Row layouts")."""
+    from multimodaltopicsegmentation_b200 import _lib, ops
     from oracle import ref_numpy as rn
+
+    if entry == "mts_band_attn_fwd_tc" and not _lib.load().mts_band_attn_tc_supported(hd):
+        pytest.skip("the tcgen05 kernel is instantiated for head dims 16, 32, 64, 112, 128")
+    if entry == "mts_band_attn_fwd_mma" and hd not in (8, 16, 32, 64, 112, 128):
+        pytest.skip("mma.sync kernel: head dims 8, 16, 32, 64, 112, 128")
 
     g = torch.Generator().manual_seed(S + hd + w)
     d = h * hd
