@@ -261,6 +261,8 @@ int mts_band_attn_fwd_simt(const float *qkv, int64_t ld, const int32_t *lengths,
  * tcgen05.ld.  Replaces HF's sliding-chunk einsums (modeling_longformer.py:758-867; call site
  * models/RestrictedTransformerLayer.py:131).  Head dims 16, 32, 64, 112, 128 (mts_band_attn_tc_supported). */
 int mts_band_attn_tc_supported(int hd);
+/* development hook: a device buffer of 6 x 5 x 40 int64 receives clock64() stamps of CTA 0's first work items (NULL: off) */
+int mts_debug_attn_profile(long long *buf);
 int mts_band_attn_fwd_tc(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
                          int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
                          void *stream);

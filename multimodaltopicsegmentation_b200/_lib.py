@@ -53,6 +53,7 @@ SIGNATURES = {
     "mts_band_attn_fwd_simt": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
     "mts_band_attn_fwd_tc": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
     "mts_band_attn_tc_supported": (c_int, [c_int]),
+    "mts_debug_attn_profile": (c_int, [_P]),
     "mts_ln_bwd_ws_bytes": (c_int64, [c_int, c_int]),
     "mts_ln_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, _P]),
     "mts_gelu_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
