@@ -8,7 +8,7 @@
 // with the error-compensated operand scheme of the GEMM (common.cuh): x = hi + rest, hi = what kind::tf32 reads of
 // the raw fp32 word,
 //     S   = Q K^T  ~= hi(Q) hi(K)^T [kind::tf32]  +  bf16(Q) bf16(rest K)^T + bf16(rest Q) bf16(K)^T [kind::f16, packed]
-//     O_t = P V    ~= hi(P) hi(V)   [kind::tf32]  +  bf16(P) bf16(rest V)   + bf16(rest P) bf16(V)   [kind::f16, packed]
+//     O  += P V    ~= hi(P) hi(V)   [kind::tf32]  +  bf16(P) bf16(rest V)   + bf16(rest P) bf16(V)   [kind::f16, packed]
 // i.e. fp32-grade scores and outputs (relative error ~2^-19 per product).  The packed correction operands are
 // derived ON CHIP from the raw fp32 rows (nothing but q, k, v is read from HBM, nothing but o written).
 //
@@ -16,28 +16,27 @@
 //                               S / P tiles [128,192) [192,256): the accumulator of Q K^T, overwritten IN PLACE by
 //                                  the raw fp32 probabilities = the A operand of P V
 //                               packed bf16 correction operand of P [256,320) [320,384)
-//                               O_t accumulator [384, 384+HD)
+//                               O accumulator [384, 384+HD), accumulated over the key tiles of an item
 // Shared memory: packed correction operand of Q (K-major SWIZZLE_128B planes of 32 head columns), the K tile (raw +
 //   packed correction, K-major: N = keys, K = head dim) and the V tile (raw + packed correction, MN-major: N = head
-//   dim, K = keys).  A K-major [rows][32 fp32] plane and an MN-major [K rows][32 fp32 of N] plane hold the same rows;
-//   only the swizzle differs (tf32 MN-major operands exist in the SWIZZLE_128B_BASE32B layout only).
+//   dim, K = keys; tf32 MN-major operands exist in the SWIZZLE_128B_BASE32B layout only).
 //
-// Warp roles (13 working warps):
-//   warps 0-3   softmax: thread = query row.  Per key tile: tcgen05.ld S, band / length mask, running max (fp32),
-//               p = 2^((s - m) log2 e), row sums, tcgen05.st P (raw + packed correction), rescale factor to shared memory.
-//   warps 4-7   correction, Q loader and epilogue: thread = query row.  Loads the NEXT item's Q during the current item's
-//               last tile (coalesced, transposed through shared memory): raw rows into tensor memory, the packed
-//               correction operand into shared memory.  O accumulates in tensor memory over the key tiles; the
-//               running maximum is only moved when a tile exceeds it by more than RESCALE_TH (p stays <= e^TH, harmless
-//               in fp32), so the rescale O *= alpha (tcgen05.ld / st) is rare.  At the end o / l, transposed through
-//               shared memory, row-contiguous stores of o (+ the packed correction operand the next GEMM wants) and
-//               the log-sum-exp.
-//   warps 8-9   K producer, warps 10-11 V producer: global -> registers (prefetched one tile ahead of the buffer
-//               hand-over) -> raw plane + correction plane, fence.proxy.async, mbarrier.
-//   warp 12     TMEM allocation + the single MMA-issuing thread (warps 13-15 exist only because registers are allocated
-//               per group of 4 warps: they release theirs to the producers and wait at the final barrier).
-// All hand-overs are mbarriers; the tensor pipe, the MUFU pipe, the load path and the epilogue of consecutive tiles
-// (and consecutive items) overlap.
+// Warps: 8 UNIFORM worker warps + 1 MMA-issuing warp.  (A first version gave every job its own warps -- softmax, rescale,
+// loaders -- with one warp per scheduler and job: correct, but bound by instruction fetch at 0.2 IPC, ncu: 2.5 stalled
+// "no instruction" warp-cycles per issued instruction, instruction-cache hit rate 65-72 %.  Now all CUDA-core work is
+// done by the same eight warps running the same code, phase after phase, two warps per scheduler.)
+//   worker warp w: TMEM lane quarter q = w & 3 (rows 32 q .. 32 q + 31), column half ch = w >> 2.  Per key tile, in order:
+//     1. operands of the NEXT tile's S: (new item: Q rows -> tensor memory + packed correction -> shared memory,
+//        coalesced loads transposed through shared memory;) K tile: global -> registers (prefetched one tile ahead)
+//        -> raw plane + packed correction plane; fence.proxy.async; mbarrier.  The MMA warp then issues S_{t+1}.
+//     2. softmax of tile t on my 32 rows x 32 columns: tcgen05.ld S, band / length mask, partial row maxima exchanged
+//        with the partner warp through shared memory, p = 2^((s - m) log2 e), tcgen05.st P (raw + packed correction).
+//        The reference maximum of a row only moves when a tile exceeds it by RESCALE_TH (p <= e^TH, harmless in fp32),
+//        so the rescale O *= alpha (tcgen05.ld / st) is rare.  16-key blocks outside the band of the warp's rows are skipped.
+//     3. V tile of tile t: registers -> raw plane + packed correction plane.  The MMA warp then issues O += P V.
+//   After the last tile: o / l transposed through shared memory, row-contiguous stores of o (+ the packed correction
+//   operand the next GEMM wants) and the log-sum-exp.
+//   The tensor pipe works on S_{t+1} during the softmax of tile t and on P V of tile t during the next tile's phase 1.
 #include <stdlib.h>
 
 #include "tcgen05_utils.cuh"
@@ -46,9 +45,11 @@ namespace mts {
 namespace atc {
 
 constexpr int BQ = 128, KT = 64;
-constexpr int THREADS = 16 * 32;   // 13 working warps; registers are allocated in units of 4 warps anyway
+constexpr int WORKERS = 256;               // 8 uniform worker warps
+constexpr int THREADS = 12 * 32;           // + warp 8 (MMA issuer); warps 9-11 idle (registers are allocated per 4 warps)
 constexpr uint32_t COL_Q = 0, COL_S = 128, COL_PC = 256, COL_O = 384;
-constexpr int TRS = 36;  // floats per row of a per-warp 32 x 32 transposition buffer (144 B: 16-byte aligned rows, conflict-free)
+constexpr int META_B = 512;                // episodes whose (length, offset) are cached in shared memory
+constexpr int TRS = 20;  // floats per row of a per-warp 32 x 16 transposition buffer (80 B: 16-byte aligned rows)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_TH = 5.5f;  // the reference maximum of a row moves only when a tile's maximum exceeds it by this much
 
@@ -58,6 +59,7 @@ struct Cfg {
   static constexpr int NP = (HD + 31) / 32;   // 32-column planes of a raw fp32 / packed-correction operand
   static constexpr int NPV = (HD + 63) / 64;  // 64-column planes of the MN-major bf16 correction operand of V
   static constexpr int C8 = HD / 8;           // 8-float units per row
+  static constexpr int NC = HD / 16;          // 16-column chunks per row
   static constexpr int QC_BYTES = NP * BQ * 128;
   static constexpr int KH_BYTES = NP * KT * 128;
   static constexpr int VC_BYTES = NPV * 2 * KT * 128;
@@ -67,17 +69,17 @@ struct Cfg {
   static constexpr int OFF_VH = OFF_KC + KH_BYTES;
   static constexpr int OFF_VC = OFF_VH + KH_BYTES;
   static constexpr int OFF_TR = OFF_VC + VC_BYTES;
-  static constexpr int TR_BYTES = 4 * 32 * TRS * 4;   // the four correction / Q-loader / epilogue warps
-  static constexpr int OFF_ALPHA = OFF_TR + TR_BYTES;        // [2][128]
-  static constexpr int OFF_FIN = OFF_ALPHA + 2 * BQ * 4;     // [2][128] x {1 / l, lse}
-  static constexpr int OFF_BAR = OFF_FIN + 2 * BQ * 2 * 4;
-  static constexpr int USED = OFF_BAR + 16 * 8 + 16;
+  static constexpr int TR_BYTES = 8 * 32 * TRS * 4;
+  static constexpr int OFF_MX = OFF_TR + TR_BYTES;           // [2 tile parity][2 column halves][128] partial row maxima
+  static constexpr int OFF_LS = OFF_MX + 2 * 2 * BQ * 4;     // [2 column halves][128] partial row sums
+  static constexpr int OFF_BAR = OFF_LS + 2 * BQ * 4;
+  static constexpr int OFF_META = OFF_BAR + 16 * 8 + 16;     // [2][META_B] int32: lengths, offsets of the first META_B episodes
+  static constexpr int USED = OFF_META + 2 * META_B * 4;
   // every CTA allocates all 512 TMEM columns, so two CTAs must never share an SM: ask for more than half its shared memory
   static constexpr int SMEM = (USED + 1024) > 120 * 1024 ? (USED + 1024) : 120 * 1024;
 };
 
-enum { B_QREADY = 0, B_QFREE, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL0, B_SFULL1, B_PREADY0, B_PREADY1, B_OFULL, B_OREADY,
-       B_AREADY0, B_AREADY1, B_FREADY0, B_FREADY1, B_COUNT };
+enum { B_QREADY = 0, B_QFREE, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL0, B_SFULL1, B_PREADY0, B_PREADY1, B_ODONE, B_OFREE, B_COUNT };
 static_assert(B_COUNT <= 16, "barrier block holds 16 mbarriers");
 
 // MN-major SWIZZLE_128B descriptor (16-bit operands): LBO = byte stride between 128-byte chunks along N, SBO = between
@@ -146,6 +148,25 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -159,40 +180,96 @@ __device__ __forceinline__ float4 rest4(float4 v) {
   return make_float4(tf32_rest_exact(v.x), tf32_rest_exact(v.y), tf32_rest_exact(v.z), tf32_rest_exact(v.w));
 }
 
-// Optional in-kernel timeline (off unless mts_debug_attn_profile() installs a buffer): CTA 0 stamps clock64() at the
-// hand-over points of its first AP_ITEMS active items -- role 0 softmax, 1 correction, 2 K producer, 3 V producer, 4 MMA.
+// Optional in-kernel timeline (off unless mts_debug_attn_profile() installs a buffer): CTA 0 stamps clock64() at the phase
+// boundaries of its first AP_ITEMS active items -- role 0 = worker thread 0, role 4 = the MMA thread.
 constexpr int AP_ITEMS = 6, AP_ROLES = 5, AP_SLOTS = 40;
 __device__ long long *g_atc_prof = nullptr;
+#ifdef MTS_ATTN_TIMELINE
 #define AP_STAMP(role, slot)                                                                                     \
   do {                                                                                                           \
     if (prof && item_g < (uint32_t)AP_ITEMS && (slot) < AP_SLOTS)                                                \
       prof[((int)item_g * AP_ROLES + (role)) * AP_SLOTS + (slot)] = clock64();                                    \
   } while (0)
+#else
+#define AP_STAMP(role, slot) \
+  do {                       \
+    (void)prof;              \
+  } while (0)
+#endif
 
+// mbarrier wait with the watchdog of tc::bar_wait_wd (a protocol error traps instead of hanging the GPU).  Inline: an
+// out-of-line spin makes every wait a call site, and the ~150 live registers of a worker get saved around each.
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) { tc::bar_wait_wd(bar, parity); }
+
+// The sequence of work items of a CTA: item = (episode b, query block qb, head), head fastest; CTA c takes items c, c + step, ...
+struct Seq {
+  int nheads, n_qb, S, w, n_items, step;
+  int s_head, s_qb, s_b;   // step decomposed: step = (s_b * n_qb + s_qb) * nheads + s_head
+  const int32_t *lengths, *offsets;
+  uint32_t meta;           // shared-memory copy of (lengths, offsets) of the first META_B episodes: a global load per look-up
+                           // would put an L2 round trip on every step of the tile cursors
+};
 // one work item, as every role derives it (same arithmetic everywhere keeps the roles' barrier phases in step)
 struct Item {
-  int b, head, q0, len, Sq, kbeg, kend, nt;
+  int idx, b, qb, head;    // position in the sequence
+  int q0, len, Sq, kbeg, kend, nt;
   int64_t row0;
   bool active;
 };
-__device__ __forceinline__ Item make_item(int item, int nheads, int n_qb, int S, int w, const int32_t *__restrict__ lengths,
-                                          const int32_t *__restrict__ offsets) {
-  Item it;
-  it.head = item % nheads;
-  const int rest = item / nheads;
-  it.q0 = (rest % n_qb) * BQ;
-  it.b = rest / n_qb;
-  it.len = min(max(__ldg(lengths + it.b), 0), S);
+__device__ __forceinline__ void item_fill(Item &it, const Seq &sq) {
+  it.q0 = it.qb * BQ;
+  it.active = false;
+  it.nt = 0;
+  if (it.idx >= sq.n_items) return;
+  const bool cached = it.b < META_B;
+  it.len = min(max(cached ? lds_i32(sq.meta + 4 * it.b) : __ldg(sq.lengths + it.b), 0), sq.S);
   // ragged layout (offsets != NULL): episode b owns rows offsets[b] .. offsets[b] + len - 1 and nothing beyond
-  it.row0 = offsets ? (int64_t)__ldg(offsets + it.b) : (int64_t)it.b * S;
-  it.Sq = offsets ? it.len : S;
+  it.row0 = sq.offsets ? (int64_t)(cached ? lds_i32(sq.meta + 4 * (META_B + it.b)) : __ldg(sq.offsets + it.b)) : (int64_t)it.b * sq.S;
+  it.Sq = sq.offsets ? it.len : sq.S;
   it.active = it.q0 < it.len;
-  it.kbeg = max(0, it.q0 - w);
-  it.kend = min(it.len, it.q0 + BQ + w);
+  it.kbeg = max(0, it.q0 - sq.w);
+  it.kend = min(it.len, it.q0 + BQ + sq.w);
   it.nt = it.active ? (it.kend - it.kbeg + KT - 1) / KT : 0;
-  return it;
 }
-
+__device__ __forceinline__ void item_first(Item &it, const Seq &sq, int start) {
+  it.idx = start;
+  it.head = start % sq.nheads;
+  const int rest = start / sq.nheads;
+  it.qb = rest % sq.n_qb;
+  it.b = rest / sq.n_qb;
+  item_fill(it, sq);
+}
+__device__ __forceinline__ void item_step(Item &it, const Seq &sq) {   // the CTA's next item (active or not)
+  it.idx += sq.step;
+  it.head += sq.s_head;
+  int c = it.head >= sq.nheads;
+  it.head -= c ? sq.nheads : 0;
+  it.qb += sq.s_qb + c;
+  c = it.qb >= sq.n_qb;
+  it.qb -= c ? sq.n_qb : 0;
+  it.b += sq.s_b + c;
+  item_fill(it, sq);
+}
+// position in a CTA's sequence of key tiles (item-major): active item + tile inside it; valid = not past the end
+struct Cursor {
+  Item it;
+  int t;
+  bool valid;
+};
+__device__ __forceinline__ void cursor_settle(Cursor &c, const Seq &sq) {   // skip inactive items
+  while (c.it.idx < sq.n_items && !c.it.active) item_step(c.it, sq);
+  c.t = 0;
+  c.valid = c.it.idx < sq.n_items;
+}
+__device__ __forceinline__ void cursor_first(Cursor &c, const Seq &sq, int start) {
+  item_first(c.it, sq, start);
+  cursor_settle(c, sq);
+}
+__device__ __forceinline__ void cursor_advance(Cursor &c, const Seq &sq) {   // next key tile (possibly the next active item's first)
+  if (++c.t < c.it.nt) return;
+  item_step(c.it, sq);
+  cursor_settle(c, sq);
+}
 
 // descriptor = (constant upper word, lower word = (address >> 4) | LBO << 16): stepping through an operand only adds to the
 // lower word
@@ -217,460 +294,458 @@ __device__ __noinline__ void issue_qk(bool leader, uint32_t d_s, uint32_t q_tmem
   }
 }
 
-// 32-column group g of a row: its width (the last group of HD = 112 is 16 wide)
-template <int HD>
-__device__ __forceinline__ constexpr int group_width(int g) { return (HD - 32 * g) >= 32 ? 32 : (HD - 32 * g); }
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
 
-// Registers: launched with 128 per thread (512 threads); the four warpgroups then re-split the CTA's pool with setmaxnreg
-// to 144 (softmax) + 112 (correction) + 176 (producers: a whole tile share in flight) + 80 (MMA issuer and its 3 idle warps).
+// A key / value tile share of one worker warp: rows 8 w .. 8 w + 7 of the tile.  One warp instruction covers whole rows:
+// lane = 16-byte piece p of a row (HD / 4 pieces; 32 / (HD / 4) rows per instruction), because the L1 pipe serves one
+// 128-byte line per cycle: a load or store that touches 16 lines for 512 bytes costs 4x one that touches 4.
+template <int HD>
+struct TileRegs {
+  static constexpr int LPR = HD / 4;                    // 16-byte pieces per row
+  static constexpr int RPI = 32 / LPR > 0 ? 32 / LPR : 1;   // rows per warp instruction
+  static constexpr int NI = 8 / RPI;                    // instructions per warp and tile
+  float4 v[NI];
+};
+
+// global -> registers.  gthread = qkv + (first row of the episode) * ld + (k or v block) + head * HD + 4 p; keys beyond kend
+// load as zeros (P is 0 there; 0 * garbage could be NaN)
+template <int HD>
+__device__ __forceinline__ void tile_fetch(TileRegs<HD> &tr, const float *__restrict__ gthread, int64_t ld, int row0, int kend,
+                                           int lane) {
+  using T = TileRegs<HD>;
+  const int rsub = lane / T::LPR;
+#pragma unroll
+  for (int i = 0; i < T::NI; ++i) {
+    const int row = row0 + i * T::RPI + rsub;
+    tr.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rsub < T::RPI && row < kend) tr.v[i] = __ldg(reinterpret_cast<const float4 *>(gthread + (int64_t)row * ld));
+  }
+}
+
+// registers -> raw plane + packed correction plane (tile-local row = 8 wk + i * RPI + rsub, piece p = columns 4 p .. 4 p + 3)
+//   raw plane     K (K-major, SWIZZLE_128B): 16-byte chunk (p & 7) XOR (row & 7) of plane p >> 3
+//                 V (MN-major tf32, SWIZZLE_128B_BASE32B): 32-byte unit ((p >> 1) & 3) XOR (row & 3), half p & 1
+//   correction    K (K-major packed, B side: per 16 columns [bf16(rest) x16 | bf16(x) x16]): 8 bytes at 8 (p & 3) of the
+//                   rest half / the x half of 64-byte block (p >> 2) & 1 of plane p >> 3
+//                 V (MN-major packed: K' rows per 16 keys [rest v x16 | v x16], 64 head columns per 128-byte row): 8 bytes at
+//                   column byte 8 (p & 15) of K' row (key >> 4) * 32 + (key & 15) (+ 16 for the v half), plane p >> 4
+template <int HD, bool IS_V>
+__device__ __forceinline__ void tile_store(const TileRegs<HD> &tr, uint32_t hi_base, uint32_t co_base, int wk, int lane) {
+  using T = TileRegs<HD>;
+  const int rsub = lane / T::LPR, p = lane % T::LPR;
+  if (rsub >= T::RPI) return;
+#pragma unroll
+  for (int i = 0; i < T::NI; ++i) {
+    const int row = 8 * wk + i * T::RPI + rsub;
+    const float4 x = tr.v[i];
+    const uint2 xb = make_uint2(bf16x2_bits(x.x, x.y), bf16x2_bits(x.z, x.w));
+    const uint2 rb = make_uint2(bf16x2_bits(tf32_rest_exact(x.x), tf32_rest_exact(x.y)),
+                                bf16x2_bits(tf32_rest_exact(x.z), tf32_rest_exact(x.w)));
+    const uint32_t prow = (uint32_t)((p >> 3) * (KT * 128) + row * 128);
+    if (!IS_V) {
+      sts128(hi_base + prow + (uint32_t)(((p & 7) ^ (row & 7)) << 4), f4_bits(x));
+      const int chunk = ((p >> 2) & 1) * 4 + ((p & 3) >> 1);
+      const uint32_t ca = co_base + prow + (uint32_t)(((chunk ^ (row & 7)) << 4) + 8 * (p & 1));
+      const uint32_t cx = co_base + prow + (uint32_t)((((chunk + 2) ^ (row & 7)) << 4) + 8 * (p & 1));
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ca), "r"(rb.x), "r"(rb.y) : "memory");
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(cx), "r"(xb.x), "r"(xb.y) : "memory");
+    } else {
+      sts128(hi_base + prow + (uint32_t)(((((p >> 1) & 3) ^ (row & 3)) << 5) + 16 * (p & 1)), f4_bits(x));
+      const int rr = (row >> 4) * 32 + (row & 15);
+      const uint32_t ca = co_base + (uint32_t)((p >> 4) * (2 * KT * 128) + rr * 128 + (((((p & 15) >> 1)) ^ (rr & 7)) << 4) + 8 * (p & 1));
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ca), "r"(rb.x), "r"(rb.y) : "memory");
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ca + 16 * 128), "r"(xb.x), "r"(xb.y) : "memory");
+    }
+  }
+}
+
 template <int HD>
 __global__ void __launch_bounds__(THREADS, 1)
     band_attn_fwd_tc_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths,
                             const int32_t *__restrict__ offsets, int B, int S, int nheads, int w, float *__restrict__ out,
                             float *__restrict__ out_hi, float *__restrict__ out_lo, int Kp, float *__restrict__ lse) {
   using C = Cfg<HD>;
-  constexpr int NG = (HD + 31) / 32;   // 32-column groups of a row
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = tc::s_u32(smem);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
-  float *alpha_s = reinterpret_cast<float *>(smem + C::OFF_ALPHA);
-  float *fin_s = reinterpret_cast<float *>(smem + C::OFF_FIN);
+  int32_t *meta_p = reinterpret_cast<int32_t *>(smem + C::OFF_META);
+  const uint32_t mx_s = sbase + C::OFF_MX, ls_s = sbase + C::OFF_LS;
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int d = nheads * HD;
-  const int n_qb = (S + BQ - 1) / BQ;
-  const int n_items = B * n_qb * nheads;
+  Seq sq;
+  sq.nheads = nheads;
+  sq.n_qb = (S + BQ - 1) / BQ;
+  sq.S = S;
+  sq.w = w;
+  sq.n_items = B * sq.n_qb * nheads;
+  sq.step = gridDim.x;
+  sq.s_head = sq.step % nheads;
+  sq.s_qb = (sq.step / nheads) % sq.n_qb;
+  sq.s_b = (sq.step / nheads) / sq.n_qb;
+  sq.lengths = lengths;
+  sq.offsets = offsets;
+  sq.meta = sbase + C::OFF_META;
 #define BAR(i) (sbase + (uint32_t)(C::OFF_BAR + 8 * (i)))
-  // first active work item of this CTA at or after index `from` (stride gridDim.x); n_items if there is none
-  auto next_active = [&](int from, Item &it) {
-    for (; from < n_items; from += gridDim.x) {
-      it = make_item(from, nheads, n_qb, S, w, lengths, offsets);
-      if (it.active) return from;
-    }
-    return n_items;
-  };
 
   if (threadIdx.x == 0) {
-    tc::bar_init(BAR(B_QREADY), 128);
+    tc::bar_init(BAR(B_QREADY), WORKERS);
     tc::bar_init(BAR(B_QFREE), 1);
-    tc::bar_init(BAR(B_KFULL), 64);
+    tc::bar_init(BAR(B_KFULL), WORKERS);
     tc::bar_init(BAR(B_KEMPTY), 1);
-    tc::bar_init(BAR(B_VFULL), 64);
+    tc::bar_init(BAR(B_VFULL), WORKERS);
     tc::bar_init(BAR(B_VEMPTY), 1);
     tc::bar_init(BAR(B_SFULL0), 1);
     tc::bar_init(BAR(B_SFULL1), 1);
-    tc::bar_init(BAR(B_PREADY0), 128);
-    tc::bar_init(BAR(B_PREADY1), 128);
-    tc::bar_init(BAR(B_OFULL), 1);
-    tc::bar_init(BAR(B_OREADY), 128);
-    tc::bar_init(BAR(B_AREADY0), 128);
-    tc::bar_init(BAR(B_AREADY1), 128);
-    tc::bar_init(BAR(B_FREADY0), 128);
-    tc::bar_init(BAR(B_FREADY1), 128);
+    tc::bar_init(BAR(B_PREADY0), WORKERS);
+    tc::bar_init(BAR(B_PREADY1), WORKERS);
+    tc::bar_init(BAR(B_ODONE), 1);
+    tc::bar_init(BAR(B_OFREE), WORKERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) tc::tmem_alloc<512>(tc::s_u32(tmem_slot));
+  if (warp == 8) tc::tmem_alloc<512>(tc::s_u32(tmem_slot));
+  for (int e = threadIdx.x; e < min(B, META_B); e += THREADS) {
+    meta_p[e] = lengths[e];
+    meta_p[META_B + e] = offsets ? offsets[e] : 0;
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // =============================== softmax warps: thread = query row ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
-    const int r = warp * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    long long *prof = (blockIdx.x == 0 && threadIdx.x == 0) ? g_atc_prof : nullptr;
-    uint32_t item_g = 0, tile_g = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const Item it = make_item(item, nheads, n_qb, S, w, lengths, offsets);
-      if (!it.active) continue;
-      AP_STAMP(0, 0);
-      const int i = it.q0 + r;
-      float m_run = -INFINITY, l_run = 0.0f;
-#pragma unroll 1
-      for (int t = 0; t < it.nt; ++t, ++tile_g) {
-        const int buf = tile_g & 1;
-        const int k0 = it.kbeg + t * KT;
-        // valid tile-local key range [clo, clo + nvalid) of my row: band |i - j| <= w, j < kend (<= len); empty for padded queries
-        const int clo = max(0, i - w - k0);
-        const int chi = (i < it.len) ? min(it.kend - k0, i + w + 1 - k0) : 0;
-        const unsigned nvalid = (unsigned)max(chi - clo, 0);
-        tc::bar_wait_wd(BAR(B_SFULL0 + buf), (tile_g >> 1) & 1);
-        tc::tc_fence_after();
-        AP_STAMP(0, 3 + 4 * t);
-        float s[KT];
-        tmem_ld32_nowait(trow + COL_S + 64 * buf, s);
-        tmem_ld32_nowait(trow + COL_S + 64 * buf + 32, s + 32);
-        tmem_wait_ld();
-        AP_STAMP(0, 4 + 4 * t);
-        // 16-key blocks that no row of this warp can see (outside the band of its 32 rows, or beyond the episode) are not
-        // evaluated at all: their probabilities are stored as zeros.  Warp-uniform, so no divergence.
-        unsigned live = 0;
-#pragma unroll
-        for (int blk = 0; blk < KT / 16; ++blk)
-          if (__any_sync(0xffffffffu, clo < 16 * blk + 16 && chi > 16 * blk)) live |= 1u << blk;
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains (one warp per scheduler: ILP matters)
-#pragma unroll
-        for (int blk = 0; blk < KT / 16; ++blk) {
-          if (!(live & (1u << blk))) continue;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int c = 16 * blk + e;
-            s[c] = ((unsigned)(c - clo) < nvalid) ? s[c] : -INFINITY;
-            mx4[e & 3] = fmaxf(mx4[e & 3], s[c]);
-          }
-        }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        // reference maximum: moved only when this tile exceeds it by more than RESCALE_TH (first valid tile: always)
-        float alpha = 1.0f;
-        if (mx > m_run + RESCALE_TH) {   // false while mx == -inf; true for the first finite mx (m_run == -inf)
-          if (m_run != -INFINITY) { alpha = ex2f((m_run - mx) * LOG2E); l_run *= alpha; }
-          m_run = mx;
-        }
-        alpha_s[buf * BQ + r] = alpha;
-        tc::bar_arrive(BAR(B_AREADY0 + buf));   // the correction warps may rescale O while the exponentials run
-        AP_STAMP(0, 5 + 4 * t);
-        const float mb = (m_run == -INFINITY) ? 0.0f : -m_run * LOG2E;
-        float ps4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-        for (int blk = 0; blk < KT / 16; ++blk) {
-          uint32_t ph[16], pc[16];
-          if (live & (1u << blk)) {
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const float p0 = ex2f(fmaf(s[16 * blk + e], LOG2E, mb)), p1 = ex2f(fmaf(s[16 * blk + e + 1], LOG2E, mb));
-              ps4[(e >> 1) & 3] += p0 + p1;
-              ph[e] = __float_as_uint(p0);
-              ph[e + 1] = __float_as_uint(p1);
-              pc[e >> 1] = bf16x2_bits(p0, p1);
-              pc[8 + (e >> 1)] = bf16x2_bits(tf32_rest_exact(p0), tf32_rest_exact(p1));
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) ph[e] = pc[e] = 0u;
-          }
-          tmem_st16(trow + COL_S + 64 * buf + 16 * blk, ph);    // raw fp32 probabilities, in place of the scores
-          tmem_st16(trow + COL_PC + 64 * buf + 16 * blk, pc);   // [bf16(p) x16 | bf16(rest p) x16]
-        }
-        l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-        if (t == it.nt - 1) {
-          const bool live = (i < it.len) && (l_run > 0.0f);
-          fin_s[((item_g & 1) * BQ + r) * 2] = live ? 1.0f / l_run : 0.0f;
-          fin_s[((item_g & 1) * BQ + r) * 2 + 1] = live ? m_run + logf(l_run) : 0.0f;
-          tc::bar_arrive(BAR(B_FREADY0 + (item_g & 1)));
-        }
-        tc::tmem_wait_st();
-        tc::tc_fence_before();
-        tc::bar_arrive(BAR(B_PREADY0 + buf));
-        AP_STAMP(0, 6 + 4 * t);
-      }
-      ++item_g;
-    }
-  } else if (warp < 8) {
-    // =============================== correction, Q loader and epilogue warps: thread = query row ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-    const int q = warp - 4, r = q * 32 + lane;
+  if (warp < 8) {
+    // ======================================= worker warps =======================================
+    const int q = warp & 3, ch = warp >> 2;          // TMEM lane quarter, column half
+    const int r = q * 32 + lane;                     // my query row inside the item
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float *tr = reinterpret_cast<float *>(smem + C::OFF_TR) + q * 32 * TRS;
+    const uint32_t tr = sbase + (uint32_t)(C::OFF_TR + warp * 32 * TRS * 4);   // my warp's transposition buffer (shared-space address:
+                                                                             // a generic pointer makes every access a generic LD / ST)
     const float inv_scale = 1.0f / sqrtf((float)HD);   // HF divides q by sqrt(head_dim) (:513); the product differs by <= 1 ulp
-    long long *prof = (blockIdx.x == 0 && threadIdx.x == 128) ? g_atc_prof : nullptr;
-    uint32_t item_g = 0, tile_g = 0;
+    const int pce = lane % TileRegs<HD>::LPR;         // tile share: my 16-byte piece of the rows 8 warp .. 8 warp + 7
+    long long *prof = (blockIdx.x == 0 && threadIdx.x == 0) ? g_atc_prof : nullptr;
+    uint32_t item_g = 0, tile_g = 0;                 // items / tiles completed (softmax view)
+    uint32_t k_cnt = 0, v_cnt = 0, q_cnt = 0;        // K tiles, V tiles, Q blocks handed over so far
 
-    // Q of one item: coalesced loads (a warp instruction = 4 rows x 128 contiguous bytes), transposed through the warp's
-    // buffer so that every lane holds ITS row, raw fp32 -> tensor memory, packed correction operand -> shared memory.
-    // `idx` = position of the item in this CTA's sequence of active items.
-    auto load_q = [&](const Item &qi, uint32_t idx) {
-      tc::bar_wait_wd(BAR(B_QFREE), (idx & 1) ^ 1);   // every S = Q K^T of the previous item has completed
-      tc::tc_fence_after();
-      const float *qbase = qkv + qi.row0 * ld + qi.head * HD;
-      const int rr0 = lane >> 3, c4 = lane & 7;
-      float4 nx[8];
-      auto fetch = [&](int g) {
-#pragma unroll
-        for (int i2 = 0; i2 < 8; ++i2) {
-          const int gi = qi.q0 + q * 32 + rr0 + 4 * i2;
-          nx[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gi < qi.Sq && 32 * g + 4 * c4 < HD)
-            nx[i2] = __ldg(reinterpret_cast<const float4 *>(qbase + (int64_t)gi * ld + 32 * g) + c4);
-        }
-      };
-      fetch(0);
-#pragma unroll 1   // (rolled: the instruction cache holds five roles' loops at once)
-      for (int g = 0; g < NG; ++g) {
-        const int wd = min(32, HD - 32 * g);
-#pragma unroll
-        for (int i2 = 0; i2 < 8; ++i2)
-          *reinterpret_cast<float4 *>(tr + (rr0 + 4 * i2) * TRS + 4 * c4) =
-              make_float4(nx[i2].x * inv_scale, nx[i2].y * inv_scale, nx[i2].z * inv_scale, nx[i2].w * inv_scale);
-        __syncwarp();
-        if (g + 1 < NG) fetch(g + 1);   // the next group's loads fly while this one is converted
-        float4 x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4 *>(tr + lane * TRS + 4 * j);
-        __syncwarp();
-#pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {   // the two 16-column chunks of the group
-          if (16 * hc < wd) {
-            const int c = 2 * g + hc;
-            uint32_t raw[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              raw[4 * j] = __float_as_uint(x[4 * hc + j].x); raw[4 * j + 1] = __float_as_uint(x[4 * hc + j].y);
-              raw[4 * j + 2] = __float_as_uint(x[4 * hc + j].z); raw[4 * j + 3] = __float_as_uint(x[4 * hc + j].w);
-            }
-            tmem_st16(trow + COL_Q + 16 * c, raw);
-            // packed correction operand, A side: per 16 columns [bf16(x) x16 | bf16(rest) x16] = 4 chunks of 16 bytes
-            const uint32_t rowa = sbase + C::OFF_QC + (uint32_t)(g * (BQ * 128) + r * 128);
-            const int cb = hc * 4, sw = r & 7;
-            sts128(rowa + (((cb + 0) ^ sw) << 4), bf16x8(x[4 * hc], x[4 * hc + 1]));
-            sts128(rowa + (((cb + 1) ^ sw) << 4), bf16x8(x[4 * hc + 2], x[4 * hc + 3]));
-            sts128(rowa + (((cb + 2) ^ sw) << 4), bf16x8(rest4(x[4 * hc]), rest4(x[4 * hc + 1])));
-            sts128(rowa + (((cb + 3) ^ sw) << 4), bf16x8(rest4(x[4 * hc + 2]), rest4(x[4 * hc + 3])));
-          }
-        }
-      }
-      tc::tmem_wait_st();
-      tc::fence_proxy_async();
-      tc::tc_fence_before();
-      tc::bar_arrive(BAR(B_QREADY));
-    };
-
-    Item cur, nxt;
-    int cur_i = next_active(blockIdx.x, cur);
-    if (cur_i < n_items) load_q(cur, 0);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const Item it = make_item(item, nheads, n_qb, S, w, lengths, offsets);
+    // ck: the tile whose K share sits in kreg (the next one to hand over); cv: the tile whose V share is fetched next
+    Cursor ck, cv;
+    TileRegs<HD> kreg, vreg;
+    cursor_first(ck, sq, blockIdx.x);
+    cv = ck;
+    if (ck.valid) {
+      tile_fetch<HD>(kreg, qkv + ck.it.row0 * ld + d + ck.it.head * HD + 4 * pce, ld, ck.it.kbeg + 8 * warp, ck.it.kend, lane);
+      tile_fetch<HD>(vreg, qkv + cv.it.row0 * ld + 2 * d + cv.it.head * HD + 4 * pce, ld, cv.it.kbeg + 8 * warp, cv.it.kend, lane);
+      cursor_advance(cv, sq);
+    }
+    bool started = false;   // the sequence's first tile still needs its S operands (done by a virtual pass t = -1)
+    Item it;
+    for (item_first(it, sq, blockIdx.x); it.idx < sq.n_items; item_step(it, sq)) {
       float inv = 0.0f, lse_v = 0.0f;
       if (it.active) {
-        const int nxt_i = next_active(item + gridDim.x, nxt);
+        AP_STAMP(0, 0);
+        const int i = it.q0 + r;
+        float m_run = -INFINITY, l_run = 0.0f;
 #pragma unroll 1
-        for (int t = 0; t < it.nt; ++t, ++tile_g) {
-          // tile t's rescale factor is known as soon as its row maxima are (tile 0: 1 by construction, but its barrier
-          // phase must still be consumed)
-          tc::bar_wait_wd(BAR(B_AREADY0 + (tile_g & 1)), (tile_g >> 1) & 1);
-          if (t > 0) {
-            const float alpha = alpha_s[(tile_g & 1) * BQ + r];
-            tc::bar_wait_wd(BAR(B_OFULL), (tile_g - 1) & 1);   // O holds tiles 0..t-1 completely
-            tc::tc_fence_after();
-            if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-              for (int c0 = 0; c0 < HD; c0 += 16) {
-                float v[16];
-                uint32_t u[16];
-                tmem_ld16_nowait(trow + COL_O + c0, v);
-                tmem_wait_ld();
+        for (int t = started ? 0 : -1; t < it.nt; ++t) {
+          // ---- phase 1: operands of the NEXT S tile of the sequence (its K share is in kreg already) -------------------
+          if (ck.valid) {
+            if (ck.t == 0) {
+              // The tile opens a new item: its Q (16-column chunks c = ch, ch + 2, ...).  Coalesced loads (a warp instruction =
+              // 8 rows x 64 contiguous bytes), all chunks in flight at once, transposed through the warp's buffer so that
+              // every lane holds ITS row; raw fp32 -> tensor memory, packed correction operand (A side: per 16 columns
+              // [bf16(x) x16 | bf16(rest) x16]) -> shared memory.
+              const Item &qi = ck.it;
+              AP_STAMP(0, 20);
+              const float *qbase = qkv + qi.row0 * ld + qi.head * HD + 4 * (lane & 3);
+              const int rr0 = lane >> 2;
+              constexpr int MYC = (C::NC + 1) / 2;
+              float4 nx[MYC][4];
+              // straight-line, unconditional loads (rows beyond the episode: clamped address, value zeroed by the scale
+              // factor below) -- a branch around each load made the compiler put the first use next to it, i.e. one exposed
+              // memory latency per load (measured: 12 000 cycles for these 16 loads)
+              float sc[4];
+              const float *qrow[4];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) u[e] = __float_as_uint(v[e] * alpha);
-                tmem_st16(trow + COL_O + c0, u);
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const int gi = qi.q0 + q * 32 + rr0 + 8 * i2;
+                sc[i2] = gi < qi.Sq ? inv_scale : 0.0f;
+                qrow[i2] = qbase + (int64_t)min(gi, qi.Sq - 1) * ld;
               }
+#pragma unroll
+              for (int k = 0; k < MYC; ++k) {
+                const int c = min(ch + 2 * k, C::NC - 1);   // (an odd chunk count: the last slot of column half 1 re-reads, unused)
+#pragma unroll
+                for (int i2 = 0; i2 < 4; ++i2) nx[k][i2] = __ldg(reinterpret_cast<const float4 *>(qrow[i2] + 16 * c));
+              }
+              AP_STAMP(0, 21);
+              bar_wait(BAR(B_QFREE), (q_cnt & 1) ^ 1);   // every S = Q K^T of the previous item has completed
+              tc::tc_fence_after();
+              AP_STAMP(0, 22);
+#pragma unroll
+              for (int k = 0; k < MYC; ++k) {
+                const int c = ch + 2 * k;
+                if (c >= C::NC) break;
+#pragma unroll
+                for (int i2 = 0; i2 < 4; ++i2)
+                  sts128f(tr + 4 * ((rr0 + 8 * i2) * TRS + 4 * (lane & 3)),
+                          make_float4(nx[k][i2].x * sc[i2], nx[k][i2].y * sc[i2], nx[k][i2].z * sc[i2], nx[k][i2].w * sc[i2]));
+                __syncwarp();
+                float4 x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = lds128f(tr + 4 * (lane * TRS + 4 * j));
+                __syncwarp();
+                uint32_t raw[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  raw[4 * j] = __float_as_uint(x[j].x); raw[4 * j + 1] = __float_as_uint(x[j].y);
+                  raw[4 * j + 2] = __float_as_uint(x[j].z); raw[4 * j + 3] = __float_as_uint(x[j].w);
+                }
+                tmem_st16(trow + COL_Q + 16 * c, raw);
+                const uint32_t rowa = sbase + C::OFF_QC + (uint32_t)((c >> 1) * (BQ * 128) + r * 128);
+                const int cb = (c & 1) * 4, sw = r & 7;
+                sts128(rowa + (((cb + 0) ^ sw) << 4), bf16x8(x[0], x[1]));
+                sts128(rowa + (((cb + 1) ^ sw) << 4), bf16x8(x[2], x[3]));
+                sts128(rowa + (((cb + 2) ^ sw) << 4), bf16x8(rest4(x[0]), rest4(x[1])));
+                sts128(rowa + (((cb + 3) ^ sw) << 4), bf16x8(rest4(x[2]), rest4(x[3])));
+              }
+              AP_STAMP(0, 23);
               tc::tmem_wait_st();
+              tc::fence_proxy_async();
+              tc::tc_fence_before();
+              tc::bar_arrive(BAR(B_QREADY));
+              AP_STAMP(0, 24);
+              ++q_cnt;
             }
-            tc::tc_fence_before();
+            bar_wait(BAR(B_KEMPTY), (k_cnt & 1) ^ 1);   // the S product that read the previous K tile has completed
+            AP_STAMP(0, 25);
+            tile_store<HD, false>(kreg, sbase + C::OFF_KH, sbase + C::OFF_KC, warp, lane);
+            tc::fence_proxy_async();
+            tc::bar_arrive(BAR(B_KFULL));
+            AP_STAMP(0, 26);
+            ++k_cnt;
+            cursor_advance(ck, sq);
+            AP_STAMP(0, 27);
+            if (ck.valid)   // prefetch the K share of the S tile after that
+              tile_fetch<HD>(kreg, qkv + ck.it.row0 * ld + d + ck.it.head * HD + 4 * pce, ld, ck.it.kbeg + ck.t * KT + 8 * warp,
+                             ck.it.kend, lane);
           }
-          // t == 0: this tile's P V overwrites O; my own reads of the previous item's O are behind me
-          tc::bar_arrive(BAR(B_OREADY));
-          AP_STAMP(1, t);
+          if (t < 0) {   // virtual pass: only the operands of the sequence's first S tile
+            started = true;
+            continue;
+          }
+          AP_STAMP(0, 1 + 4 * t);
+          // ---- phase 2: softmax of tile t, my 32 rows x 32 columns -------------------------------------------------------
+          const int buf = tile_g & 1;
+          const int k0 = it.kbeg + t * KT + 32 * ch;   // first key of my column half
+          // valid column range [clo, clo + nvalid) of my row inside my half: band |i - j| <= w, j < kend (<= len)
+          const int clo = max(0, i - w - k0);
+          const int chi = (i < it.len) ? min(it.kend - k0, i + w + 1 - k0) : 0;
+          const unsigned nvalid = (unsigned)max(min(chi, 32) - clo, 0);
+          bar_wait(BAR(B_SFULL0 + buf), (tile_g >> 1) & 1);
+          tc::tc_fence_after();
+          AP_STAMP(0, 2 + 4 * t);
+          float s[32];
+          tmem_ld32_nowait(trow + COL_S + 64 * buf + 32 * ch, s);
+          tmem_wait_ld();
+          // 16-key blocks that no row of this warp can see are not evaluated: their probabilities are stored as zeros
+          unsigned live = 0;
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk)
+            if (__any_sync(0xffffffffu, clo < 16 * blk + 16 && chi > 16 * blk)) live |= 1u << blk;
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            if (!(live & (1u << blk))) continue;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int c = 16 * blk + e;
+              s[c] = ((unsigned)(c - clo) < nvalid) ? s[c] : -INFINITY;
+              mx4[e & 3] = fmaxf(mx4[e & 3], s[c]);
+            }
+          }
+          // row maximum over both column halves: exchange with the partner warp
+          float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          sts_f32(mx_s + 4 * ((buf * 2 + ch) * BQ + r), mx);
+          pair_sync(q);
+          mx = fmaxf(mx, lds_f32(mx_s + 4 * ((buf * 2 + (ch ^ 1)) * BQ + r)));
+          // reference maximum: moved only when this tile exceeds it by more than RESCALE_TH (first valid tile: always)
+          float alpha = 1.0f;
+          if (mx > m_run + RESCALE_TH) {   // false while mx == -inf; true for the first finite mx (m_run == -inf)
+            if (m_run != -INFINITY) { alpha = ex2f((m_run - mx) * LOG2E); l_run *= alpha; }
+            m_run = mx;
+          }
+          if (t > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+            // rare: rescale my column half of O (16-column chunks c = ch, ch + 2, ...); the previous P V must be complete
+            bar_wait(BAR(B_VEMPTY), (v_cnt & 1) ^ 1);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int c = ch; c < C::NC; c += 2) {
+              float v[16];
+              uint32_t u[16];
+              tmem_ld16_nowait(trow + COL_O + 16 * c, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) u[e] = __float_as_uint(v[e] * alpha);
+              tmem_st16(trow + COL_O + 16 * c, u);
+            }
+          }
+          const float mb = (m_run == -INFINITY) ? 0.0f : -m_run * LOG2E;
+          float ps4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            uint32_t ph[16], pc[16];
+            if (live & (1u << blk)) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) {
+                const float p0 = ex2f(fmaf(s[16 * blk + e], LOG2E, mb)), p1 = ex2f(fmaf(s[16 * blk + e + 1], LOG2E, mb));
+                ps4[(e >> 1) & 3] += p0 + p1;
+                ph[e] = __float_as_uint(p0);
+                ph[e + 1] = __float_as_uint(p1);
+                pc[e >> 1] = bf16x2_bits(p0, p1);
+                pc[8 + (e >> 1)] = bf16x2_bits(tf32_rest_exact(p0), tf32_rest_exact(p1));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) ph[e] = pc[e] = 0u;
+            }
+            tmem_st16(trow + COL_S + 64 * buf + 32 * ch + 16 * blk, ph);    // raw fp32 probabilities, in place of the scores
+            tmem_st16(trow + COL_PC + 64 * buf + 32 * ch + 16 * blk, pc);   // [bf16(p) x16 | bf16(rest p) x16]
+          }
+          l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+          tc::tmem_wait_st();
+          tc::tc_fence_before();
+          tc::bar_arrive(BAR(B_PREADY0 + buf));
+          AP_STAMP(0, 3 + 4 * t);
+          // ---- phase 3: V tile of tile t (prefetched), then prefetch the next V tile of the sequence --------------------
+          bar_wait(BAR(B_VEMPTY), (v_cnt & 1) ^ 1);   // the P V product that read the previous V tile has completed
+          tile_store<HD, true>(vreg, sbase + C::OFF_VH, sbase + C::OFF_VC, warp, lane);
+          tc::fence_proxy_async();
+          tc::bar_arrive(BAR(B_VFULL));
+          ++v_cnt;
+          if (cv.valid) {
+            tile_fetch<HD>(vreg, qkv + cv.it.row0 * ld + 2 * d + cv.it.head * HD + 4 * pce, ld, cv.it.kbeg + cv.t * KT + 8 * warp,
+                           cv.it.kend, lane);
+            cursor_advance(cv, sq);
+          }
+          ++tile_g;
+          AP_STAMP(0, 4 + 4 * t);
         }
-        // while the last tile's softmax and P V run: bring in the NEXT item's Q (its S products can then start before this
-        // item's epilogue is over)
-        if (nxt_i < n_items) load_q(nxt, item_g + 1);
-        AP_STAMP(1, 19);
-        tc::bar_wait_wd(BAR(B_FREADY0 + (item_g & 1)), (item_g >> 1) & 1);
-        inv = fin_s[((item_g & 1) * BQ + r) * 2];
-        lse_v = fin_s[((item_g & 1) * BQ + r) * 2 + 1];
-        tc::bar_wait_wd(BAR(B_OFULL), (tile_g - 1) & 1);   // the last P V of the item has completed
+        // row sums of the two column halves
+        sts_f32(ls_s + 4 * (ch * BQ + r), l_run);
+        pair_sync(q);
+        const float l_tot = l_run + lds_f32(ls_s + 4 * ((ch ^ 1) * BQ + r));
+        const bool alive = (i < it.len) && (l_tot > 0.0f);
+        inv = alive ? 1.0f / l_tot : 0.0f;
+        lse_v = alive ? m_run + logf(l_tot) : 0.0f;
+        pair_sync(q);   // ls_s may be rewritten by the next item only after both have read
+        bar_wait(BAR(B_ODONE), item_g & 1);   // the last P V of the item has completed
         tc::tc_fence_after();
-        AP_STAMP(1, 20);
+        AP_STAMP(0, 38);
       }
       // ---- o / l, transposed through the warp's buffer, row-contiguous stores (+ the next GEMM's correction operand) ----
       // (inactive item = a block of padded queries: exact zeros, HF :578; nothing exists there in the ragged layout)
       if (it.q0 < it.Sq) {
 #pragma unroll 1
-        for (int g = 0; g < NG; ++g) {
-          const int wd = min(32, HD - 32 * g);
-          float v[32];
+        for (int c = ch; c < C::NC; c += 2) {
+          float v[16];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = 0.0f;
+          for (int e = 0; e < 16; ++e) v[e] = 0.0f;
           if (it.active) {
-            if (wd == 32) tmem_ld32_nowait(trow + COL_O + 32 * g, v);
-            else tmem_ld16_nowait(trow + COL_O + 32 * g, v);
+            tmem_ld16_nowait(trow + COL_O + 16 * c, v);
             tmem_wait_ld();
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4 *>(tr + lane * TRS + 4 * j) =
-                make_float4(v[4 * j] * inv, v[4 * j + 1] * inv, v[4 * j + 2] * inv, v[4 * j + 3] * inv);
+          for (int j = 0; j < 4; ++j)
+            sts128f(tr + 4 * (lane * TRS + 4 * j), make_float4(v[4 * j] * inv, v[4 * j + 1] * inv, v[4 * j + 2] * inv, v[4 * j + 3] * inv));
           __syncwarp();
+          // a warp instruction = 8 rows x 64 contiguous bytes (4 lanes per row): raw values, then the packed correction
+          // operand of the 16-column block: [bf16(x) 0-7 | bf16(x) 8-15 | bf16(rest) 0-7 | bf16(rest) 8-15], 16 bytes per lane
 #pragma unroll
           for (int i2 = 0; i2 < 4; ++i2) {
-            const int rr = (lane >> 2) + 8 * i2, c8 = lane & 3, gi = it.q0 + q * 32 + rr;
-            if (8 * c8 < wd && gi < it.Sq) {
-              const float4 a = *reinterpret_cast<const float4 *>(tr + rr * TRS + 8 * c8);
-              const float4 b2 = *reinterpret_cast<const float4 *>(tr + rr * TRS + 8 * c8 + 4);
-              const int col = it.head * HD + 32 * g + 8 * c8;
-              if (out) {
-                float4 *dst = reinterpret_cast<float4 *>(out + (it.row0 + gi) * d + col);
-                dst[0] = a;
-                dst[1] = b2;
-              }
+            const int rr = (lane >> 2) + 8 * i2, pc4 = lane & 3, gi = it.q0 + q * 32 + rr;
+            if (gi < it.Sq) {
+              const int col = it.head * HD + 16 * c;
+              const float4 a = lds128f(tr + 4 * (rr * TRS + 4 * pc4));
+              if (out) *reinterpret_cast<float4 *>(out + (it.row0 + gi) * d + col + 4 * pc4) = a;
               if (out_hi) {
-                float4 *dst = reinterpret_cast<float4 *>(out_hi + (it.row0 + gi) * Kp + col);
-                dst[0] = a;
-                dst[1] = b2;
-                corr_store8(out_lo + (it.row0 + gi) * Kp, col, a, b2, 0);
+                *reinterpret_cast<float4 *>(out_hi + (it.row0 + gi) * Kp + col + 4 * pc4) = a;
+                float4 e0 = lds128f(tr + 4 * (rr * TRS + 8 * (pc4 & 1)));
+                float4 e1 = lds128f(tr + 4 * (rr * TRS + 8 * (pc4 & 1) + 4));
+                if (pc4 >= 2) { e0 = rest4(e0); e1 = rest4(e1); }
+                // the operand row holds 2 Kp bf16 in Kp floats: block (col / 16) starts at float col (= 64 bytes per 16 columns)
+                *reinterpret_cast<uint4 *>(out_lo + (it.row0 + gi) * Kp + col + 4 * pc4) = bf16x8(e0, e1);
               }
             }
           }
           __syncwarp();
         }
-        tc::tc_fence_before();
       }
       if (it.active) {
-        AP_STAMP(1, 21);
+        tc::tc_fence_before();
+        tc::bar_arrive(BAR(B_OFREE));   // my reads of O are done: the next item's first P V may overwrite it
+        AP_STAMP(0, 39);
         ++item_g;
       }
-      if (lse && it.q0 + r < S) lse[((int64_t)it.b * nheads + it.head) * S + it.q0 + r] = lse_v;
+      if (ch == 0 && lse && it.q0 + r < S) lse[((int64_t)it.b * nheads + it.head) * S + it.q0 + r] = lse_v;
     }
-  } else if (warp < 12) {
-    // =============================== K (warps 8-9) and V (warps 10-11) producers ===============================
-    // a producer thread keeps a whole tile's share (up to 16 units of 8 floats) in registers between the prefetch and the
-    // hand-over of the buffer: it takes the registers the correction and MMA warpgroups release
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
-    const int which = (warp < 10) ? 1 : 2;                 // column block of the qkv row: 1 = k, 2 = v
-    const int wp = warp & 1;                               // my warp inside the producer pair
-    // lane -> (row inside a group of 8 keys, unit inside a 32-column plane): a warp instruction touches 8 rows x 128
-    // contiguous bytes in global memory, and its four 8-lane phases hit 8 distinct 16-byte bank groups in shared memory
-    const int rl = lane & 7, cq = lane >> 3;
-    constexpr int NJ = 4 * C::NP;                          // (8-key group, plane) pairs per warp
-    const uint32_t hi_base = sbase + (uint32_t)(which == 1 ? C::OFF_KH : C::OFF_VH);
-    const uint32_t co_base = sbase + (uint32_t)(which == 1 ? C::OFF_KC : C::OFF_VC);
-    const uint32_t full = BAR(which == 1 ? B_KFULL : B_VFULL), empty = BAR(which == 1 ? B_KEMPTY : B_VEMPTY);
-    // Every row this lane touches is (a multiple of 8) + rl, so all swizzle terms depend on (rl, cq) only: the addresses
-    // inside a tile are per-thread constants plus compile-time offsets.
-    //   raw plane     K (K-major, SWIZZLE_128B): 16-byte chunks 2 cq, 2 cq + 1 XOR rl
-    //                 V (MN-major tf32, SWIZZLE_128B_BASE32B): 32-byte unit cq XOR (rl & 3)
-    //   correction    K (K-major packed, B side: per 16 columns [bf16(rest) x16 | bf16(x) x16]): chunks cb, cb + 2 XOR rl
-    //                 V (MN-major packed: K' rows per 16 keys [rest v x16 | v x16], 64 head columns per 128-byte row):
-    //                   chunk (4 (plane & 1) + cq) XOR rl of K' row (key >> 4) * 32 + (key & 15) (+ 16 for the v half)
-    const uint32_t h_off0 = hi_base + (uint32_t)(rl * 128 + (which == 1 ? (((2 * cq) ^ rl) << 4) : ((cq ^ (rl & 3)) << 5)));
-    const uint32_t h_off1 = hi_base + (uint32_t)(rl * 128 + (which == 1 ? (((2 * cq + 1) ^ rl) << 4) : (((cq ^ (rl & 3)) << 5) + 16)));
-    const int cbk = (cq >> 1) * 4 + (cq & 1);
-    const uint32_t c_offA = co_base + (uint32_t)(rl * 128 + (which == 1 ? ((cbk ^ rl) << 4) : ((cq ^ rl) << 4)));
-    const uint32_t c_offB = co_base + (uint32_t)(rl * 128 + (which == 1 ? (((cbk + 2) ^ rl) << 4) : (((4 + cq) ^ rl) << 4)));
-    long long *prof = (blockIdx.x == 0 && (threadIdx.x == 256 || threadIdx.x == 320)) ? g_atc_prof : nullptr;
-    uint32_t tile_g = 0, item_g = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const Item it = make_item(item, nheads, n_qb, S, w, lengths, offsets);
-      if (!it.active) continue;
-      const float *gbase = qkv + it.row0 * ld + which * d + it.head * HD + 8 * cq;
-#pragma unroll 1
-      for (int t = 0; t < it.nt; ++t, ++tile_g) {
-        const int k0 = it.kbeg + t * KT;
-        const int nrows = it.kend - k0 - rl;   // my row 8 g + rl exists iff 8 g < nrows
-        const float *tbase = gbase + (int64_t)(k0 + rl) * ld;
-        float4 va[NJ], vb[NJ];
-        AP_STAMP(1 + which, 3 * t);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int cmb = 2 * j + wp, g8 = cmb & 7, pl = cmb >> 3;
-          va[j] = vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);   // keys beyond kend: zeros (P is 0 there; 0 * garbage could be NaN)
-          if (4 * pl + cq < C::C8 && 8 * g8 < nrows) {
-            const float4 *src = reinterpret_cast<const float4 *>(tbase + (int64_t)(8 * g8) * ld + 32 * pl);
-            va[j] = __ldg(src);
-            vb[j] = __ldg(src + 1);
-          }
-        }
-        tc::bar_wait_wd(empty, (tile_g & 1) ^ 1);   // the MMAs that read the previous tile have completed
-        AP_STAMP(1 + which, 3 * t + 1);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int cmb = 2 * j + wp, g8 = cmb & 7, pl = cmb >> 3;
-          if (4 * pl + cq >= C::C8) continue;   // (HD = 112: the last plane is half used)
-          const uint32_t hofs = (uint32_t)(pl * (KT * 128) + g8 * 1024);
-          sts128(h_off0 + hofs, f4_bits(va[j]));
-          sts128(h_off1 + hofs, f4_bits(vb[j]));
-          const uint4 xb = bf16x8(va[j], vb[j]), rb = bf16x8(rest4(va[j]), rest4(vb[j]));
-          if (which == 1) {
-            sts128(c_offA + hofs, rb);
-            sts128(c_offB + hofs, xb);
-          } else {
-            const uint32_t cofs = (uint32_t)((pl >> 1) * (2 * KT * 128) + ((g8 >> 1) * 32 + (g8 & 1) * 8) * 128);
-            const uint32_t ca = (pl & 1) ? c_offB : c_offA;
-            sts128(ca + cofs, rb);
-            sts128(ca + cofs + 16 * 128, xb);
-          }
-        }
-        tc::fence_proxy_async();
-        tc::bar_arrive(full);
-        AP_STAMP(1 + which, 3 * t + 2);
-      }
-      ++item_g;
-    }
-  } else if (warp >= 12) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");   // all four warps of the group (three of them only exist for this)
-  }
-  if (warp == 12) {
+  } else if (warp == 8) {
     // =============================== MMA issuer: warp-uniform control flow, one elected lane ===============================
     constexpr uint32_t id_o = tc::idesc_tf32(BQ, HD) | B_MN_MAJOR, id_oc = tc::idesc_bf16(BQ, HD) | B_MN_MAJOR;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const bool leader = tc::elect_one();
-    const uint32_t qc_a = sbase + C::OFF_QC, kh_a = sbase + C::OFF_KH, kc_a = sbase + C::OFF_KC;
-    const uint32_t vh_a = sbase + C::OFF_VH, vc_a = sbase + C::OFF_VC;
-    uint32_t item_g = 0, tile_g = 0;
+    const uint64_t kh_desc = tc::desc_sw128(sbase + C::OFF_KH), qc_desc = tc::desc_sw128(sbase + C::OFF_QC);
+    const uint64_t kc_desc = tc::desc_sw128(sbase + C::OFF_KC);
+    const uint64_t vh_desc = desc_sw128b32_mn(sbase + C::OFF_VH, KT * 128), vc_desc = desc_sw128_mn(sbase + C::OFF_VC, 2 * KT * 128);
+    uint32_t item_g = 0, tile_g = 0, s_cnt = 0, q_seen = 0;
     long long *prof = (blockIdx.x == 0 && lane == 0) ? g_atc_prof : nullptr;
 
-    const uint64_t kh_desc = tc::desc_sw128(kh_a), qc_desc = tc::desc_sw128(qc_a), kc_desc = tc::desc_sw128(kc_a);
-    const uint64_t vh_desc = desc_sw128b32_mn(vh_a, KT * 128), vc_desc = desc_sw128_mn(vc_a, 2 * KT * 128);
-    // S = Q K^T of the tile with running index tg (of whichever item it belongs to); `last`: the item's last tile
-    auto issue_qk = [&](uint32_t tg, bool last, int slot) {
-      const uint32_t buf = tg & 1;
-      tc::bar_wait_wd(BAR(B_KFULL), tg & 1);
-      tc::tc_fence_after();
-      AP_STAMP(4, slot);
-      atc::issue_qk<HD>(leader, tb + COL_S + 64 * buf, tb + COL_Q, kh_desc, qc_desc, kc_desc);
-      if (leader) {
-        tc::umma_commit(BAR(B_SFULL0 + buf));
-        tc::umma_commit(BAR(B_KEMPTY));
-        if (last) tc::umma_commit(BAR(B_QFREE));
-      }
-      __syncwarp();
-    };
-
-    Item cur, nxt;
-    int cur_i = next_active(blockIdx.x, cur);
-    if (cur_i < n_items) {
-      tc::bar_wait_wd(BAR(B_QREADY), 0);
-      tc::tc_fence_after();
-      AP_STAMP(4, 0);
-      issue_qk(0, cur.nt == 1, 1);
-    }
-    while (cur_i < n_items) {
-      const int nxt_i = next_active(cur_i + gridDim.x, nxt);
-      bool nxt_started = false;
+    // cs: the next S tile to issue (kept one ahead of the P V position cp)
+    Cursor cs, cp;
+    cursor_first(cs, sq, blockIdx.x);
+    cp = cs;
+    bool started = false;
+    while (cp.valid) {
+      const int nt = cp.it.nt;
 #pragma unroll 1
-      for (int t = 0; t < cur.nt; ++t, ++tile_g) {
-        // keep one S tile ahead of the softmax: the next tile of this item, or -- on the last tile -- the first tile of the
-        // next item if its Q has already landed (otherwise after this tile's P V)
-        if (t + 1 < cur.nt) {
-          issue_qk(tile_g + 1, t + 2 == cur.nt, 2 + 6 * t);
-        } else if (nxt_i < n_items && __all_sync(0xffffffffu, tc::bar_try_wait(BAR(B_QREADY), (item_g + 1) & 1))) {
+      for (int t = started ? 0 : -1; t < nt; ++t) {
+        if (cs.valid) {
+          // S = Q K^T of the sequence's next tile: one ahead of the softmax
+          if (cs.t == 0) {   // the tile opens a new item: its Q must have landed
+            bar_wait(BAR(B_QREADY), q_seen & 1);
+            ++q_seen;
+          }
+          const uint32_t sbuf = s_cnt & 1;
+          bar_wait(BAR(B_KFULL), s_cnt & 1);
           tc::tc_fence_after();
-          issue_qk(tile_g + 1, nxt.nt == 1, 2 + 6 * t);
-          nxt_started = true;
+          AP_STAMP(4, 1 + 4 * (t + 1));
+          issue_qk<HD>(leader, tb + COL_S + 64 * sbuf, tb + COL_Q, kh_desc, qc_desc, kc_desc);
+          if (leader) {
+            tc::umma_commit(BAR(B_SFULL0 + sbuf));
+            tc::umma_commit(BAR(B_KEMPTY));
+            if (cs.t == cs.it.nt - 1) tc::umma_commit(BAR(B_QFREE));   // the item's last S product
+          }
+          __syncwarp();
+#ifdef MTS_ATTN_TIMELINE   // diagnostic: how long does the S product take to execute?
+          AP_STAMP(4, 20 + (t + 1));
+          bar_wait(BAR(B_SFULL0 + sbuf), (s_cnt >> 1) & 1);
+          AP_STAMP(4, 26 + (t + 1));
+#endif
+          ++s_cnt;
+          cursor_advance(cs, sq);
         }
-        AP_STAMP(4, 3 + 6 * t);
+        if (t < 0) {
+          started = true;
+          continue;
+        }
         const uint32_t buf = tile_g & 1;
-        tc::bar_wait_wd(BAR(B_PREADY0 + buf), (tile_g >> 1) & 1);
-        AP_STAMP(4, 4 + 6 * t);
-        tc::bar_wait_wd(BAR(B_VFULL), tile_g & 1);
-        AP_STAMP(4, 5 + 6 * t);
-        tc::bar_wait_wd(BAR(B_OREADY), tile_g & 1);   // O rescaled for this tile (t > 0) / free to be overwritten (t == 0)
+        bar_wait(BAR(B_PREADY0 + buf), (tile_g >> 1) & 1);
+        AP_STAMP(4, 2 + 4 * t);
+        bar_wait(BAR(B_VFULL), tile_g & 1);
+        if (t == 0) bar_wait(BAR(B_OFREE), (item_g & 1) ^ 1);   // the previous item's epilogue has read O
         tc::tc_fence_after();
-        AP_STAMP(4, 6 + 6 * t);
+        AP_STAMP(4, 3 + 4 * t);
         const uint32_t d_o = tb + COL_O;
 #pragma unroll
         for (int kg = 0; kg < KT / 8; ++kg) {
@@ -683,26 +758,28 @@ __global__ void __launch_bounds__(THREADS, 1)
           if (leader) tc::umma_bf16_ts(d_o, tb + COL_PC + 64 * buf + 8 * j, bd, id_oc, 1);
         }
         if (leader) {
-          tc::umma_commit(BAR(B_OFULL));
           tc::umma_commit(BAR(B_VEMPTY));
+          if (t == nt - 1) tc::umma_commit(BAR(B_ODONE));
         }
         __syncwarp();
-        AP_STAMP(4, 7 + 6 * t);
+#ifdef MTS_ATTN_TIMELINE   // diagnostic: how long does the P V product take to execute?
+        AP_STAMP(4, 32 + t);
+        bar_wait(BAR(B_VEMPTY), tile_g & 1);
+        AP_STAMP(4, 36 + t);
+#endif
+        ++tile_g;
+        AP_STAMP(4, 4 + 4 * t);
       }
       ++item_g;
-      if (nxt_i < n_items && !nxt_started) {
-        tc::bar_wait_wd(BAR(B_QREADY), item_g & 1);
-        tc::tc_fence_after();
-        issue_qk(tile_g, nxt.nt == 1, 1);
-      }
-      cur = nxt;
-      cur_i = nxt_i;
+      // P V position: on to the next active item
+      cp.t = nt - 1;
+      cursor_advance(cp, sq);
     }
   }
 #undef BAR
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == 8) {
     tc::tc_fence_after();
     tc::tmem_dealloc<512>(tmem_base);
   }
