@@ -21,7 +21,7 @@
 //   packed correction, K-major: N = keys, K = head dim) and the V tile (raw + packed correction, MN-major: N = head
 //   dim, K = keys; tf32 MN-major operands exist in the SWIZZLE_128B_BASE32B layout only).
 //
-// Warps: 8 UNIFORM worker warps + 1 MMA-issuing warp.  (A first version gave every job its own warps -- softmax, rescale,
+// Warps: 8 UNIFORM worker warps + 1 MMA-issuing warp + 2 loader warps (one thread each: TMA requests for the raw K / V tiles).  (A first version gave every job its own warps -- softmax, rescale,
 // loaders -- with one warp per scheduler and job: correct, but bound by instruction fetch at 0.2 IPC, ncu: 2.5 stalled
 // "no instruction" warp-cycles per issued instruction, instruction-cache hit rate 65-72 %.  Now all CUDA-core work is
 // done by the same eight warps running the same code, phase after phase, two warps per scheduler.)
@@ -37,6 +37,7 @@
 //   After the last tile: o / l transposed through shared memory, row-contiguous stores of o (+ the packed correction
 //   operand the next GEMM wants) and the log-sum-exp.
 //   The tensor pipe works on S_{t+1} during the softmax of tile t and on P V of tile t during the next tile's phase 1.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "tcgen05_utils.cuh"
@@ -79,7 +80,8 @@ struct Cfg {
   static constexpr int SMEM = (USED + 1024) > 120 * 1024 ? (USED + 1024) : 120 * 1024;
 };
 
-enum { B_QREADY = 0, B_QFREE, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL0, B_SFULL1, B_PREADY0, B_PREADY1, B_ODONE, B_OFREE, B_COUNT };
+enum { B_QREADY = 0, B_QFREE, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL0, B_SFULL1, B_PREADY0, B_PREADY1, B_ODONE, B_OFREE,
+       B_KRAW, B_VRAW, B_COUNT };
 static_assert(B_COUNT <= 16, "barrier block holds 16 mbarriers");
 
 // MN-major SWIZZLE_128B descriptor (16-bit operands): LBO = byte stride between 128-byte chunks along N, SBO = between
@@ -147,6 +149,17 @@ __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
@@ -294,63 +307,47 @@ __device__ __noinline__ void issue_qk(bool leader, uint32_t d_s, uint32_t q_tmem
   }
 }
 
+// First key of tile t of an item.  The raw K / V tiles arrive by TMA as full 64-row boxes; the box of the last tile is shifted
+// up so that it ENDS at kend -- it never reads a row behind the episode (behind the buffer, for the last episode of the
+// ragged layout).  Rows it re-reads (keys already covered by the previous tile, or -- negative coordinates, zero-filled --
+// rows before the buffer) are masked like every other key outside the band.
+__device__ __forceinline__ int tile_k0(const Item &it, int t) { return min(it.kbeg + t * KT, it.kend - KT); }
+
 __device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
 
-// A key / value tile share of one worker warp: rows 8 w .. 8 w + 7 of the tile.  One warp instruction covers whole rows:
-// lane = 16-byte piece p of a row (HD / 4 pieces; 32 / (HD / 4) rows per instruction), because the L1 pipe serves one
-// 128-byte line per cycle: a load or store that touches 16 lines for 512 bytes costs 4x one that touches 4.
-template <int HD>
-struct TileRegs {
-  static constexpr int LPR = HD / 4;                    // 16-byte pieces per row
-  static constexpr int RPI = 32 / LPR > 0 ? 32 / LPR : 1;   // rows per warp instruction
-  static constexpr int NI = 8 / RPI;                    // instructions per warp and tile
-  float4 v[NI];
-};
-
-// global -> registers.  gthread = qkv + (first row of the episode) * ld + (k or v block) + head * HD + 4 p; keys beyond kend
-// load as zeros (P is 0 there; 0 * garbage could be NaN)
-template <int HD>
-__device__ __forceinline__ void tile_fetch(TileRegs<HD> &tr, const float *__restrict__ gthread, int64_t ld, int row0, int kend,
-                                           int lane) {
-  using T = TileRegs<HD>;
-  const int rsub = lane / T::LPR;
-#pragma unroll
-  for (int i = 0; i < T::NI; ++i) {
-    const int row = row0 + i * T::RPI + rsub;
-    tr.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rsub < T::RPI && row < kend) tr.v[i] = __ldg(reinterpret_cast<const float4 *>(gthread + (int64_t)row * ld));
-  }
-}
-
-// registers -> raw plane + packed correction plane (tile-local row = 8 wk + i * RPI + rsub, piece p = columns 4 p .. 4 p + 3)
+// Packed correction plane of a K / V tile from its raw plane (both in shared memory; the raw plane arrived by TMA).
+// Worker warp wk takes rows 8 wk .. 8 wk + 7; lane = 16-byte piece p of a row (HD / 4 pieces; 32 / (HD / 4) rows per pass).
 //   raw plane     K (K-major, SWIZZLE_128B): 16-byte chunk (p & 7) XOR (row & 7) of plane p >> 3
-//                 V (MN-major tf32, SWIZZLE_128B_BASE32B): 32-byte unit ((p >> 1) & 3) XOR (row & 3), half p & 1
+//                 V (MN-major tf32, SWIZZLE_128B_BASE32B = TMA's 128B_ATOM_32B): 32-byte unit ((p >> 1) & 3) XOR (row & 3), half p & 1
 //   correction    K (K-major packed, B side: per 16 columns [bf16(rest) x16 | bf16(x) x16]): 8 bytes at 8 (p & 3) of the
 //                   rest half / the x half of 64-byte block (p >> 2) & 1 of plane p >> 3
 //                 V (MN-major packed: K' rows per 16 keys [rest v x16 | v x16], 64 head columns per 128-byte row): 8 bytes at
 //                   column byte 8 (p & 15) of K' row (key >> 4) * 32 + (key & 15) (+ 16 for the v half), plane p >> 4
 template <int HD, bool IS_V>
-__device__ __forceinline__ void tile_store(const TileRegs<HD> &tr, uint32_t hi_base, uint32_t co_base, int wk, int lane) {
-  using T = TileRegs<HD>;
-  const int rsub = lane / T::LPR, p = lane % T::LPR;
-  if (rsub >= T::RPI) return;
+__device__ __forceinline__ void tile_correction(uint32_t hi_base, uint32_t co_base, int wk, int lane) {
+  constexpr int LPR = HD / 4, RPI = 32 / LPR > 0 ? 32 / LPR : 1, NI = 8 / RPI;
+  const int rsub = lane / LPR, p = lane % LPR;
+  if (rsub >= RPI) return;
+  uint4 raw[NI];
 #pragma unroll
-  for (int i = 0; i < T::NI; ++i) {
-    const int row = 8 * wk + i * T::RPI + rsub;
-    const float4 x = tr.v[i];
+  for (int i = 0; i < NI; ++i) {
+    const int row = 8 * wk + i * RPI + rsub;
+    const uint32_t prow = hi_base + (uint32_t)((p >> 3) * (KT * 128) + row * 128);
+    raw[i] = lds128(prow + (uint32_t)(IS_V ? (((((p >> 1) & 3) ^ (row & 3)) << 5) + 16 * (p & 1)) : (((p & 7) ^ (row & 7)) << 4)));
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int row = 8 * wk + i * RPI + rsub;
+    const float4 x = make_float4(__uint_as_float(raw[i].x), __uint_as_float(raw[i].y), __uint_as_float(raw[i].z), __uint_as_float(raw[i].w));
     const uint2 xb = make_uint2(bf16x2_bits(x.x, x.y), bf16x2_bits(x.z, x.w));
     const uint2 rb = make_uint2(bf16x2_bits(tf32_rest_exact(x.x), tf32_rest_exact(x.y)),
                                 bf16x2_bits(tf32_rest_exact(x.z), tf32_rest_exact(x.w)));
-    const uint32_t prow = (uint32_t)((p >> 3) * (KT * 128) + row * 128);
     if (!IS_V) {
-      sts128(hi_base + prow + (uint32_t)(((p & 7) ^ (row & 7)) << 4), f4_bits(x));
+      const uint32_t prow = co_base + (uint32_t)((p >> 3) * (KT * 128) + row * 128);
       const int chunk = ((p >> 2) & 1) * 4 + ((p & 3) >> 1);
-      const uint32_t ca = co_base + prow + (uint32_t)(((chunk ^ (row & 7)) << 4) + 8 * (p & 1));
-      const uint32_t cx = co_base + prow + (uint32_t)((((chunk + 2) ^ (row & 7)) << 4) + 8 * (p & 1));
-      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ca), "r"(rb.x), "r"(rb.y) : "memory");
-      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(cx), "r"(xb.x), "r"(xb.y) : "memory");
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(prow + (uint32_t)(((chunk ^ (row & 7)) << 4) + 8 * (p & 1))), "r"(rb.x), "r"(rb.y) : "memory");
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(prow + (uint32_t)((((chunk + 2) ^ (row & 7)) << 4) + 8 * (p & 1))), "r"(xb.x), "r"(xb.y) : "memory");
     } else {
-      sts128(hi_base + prow + (uint32_t)(((((p >> 1) & 3) ^ (row & 3)) << 5) + 16 * (p & 1)), f4_bits(x));
       const int rr = (row >> 4) * 32 + (row & 15);
       const uint32_t ca = co_base + (uint32_t)((p >> 4) * (2 * KT * 128) + rr * 128 + (((((p & 15) >> 1)) ^ (rr & 7)) << 4) + 8 * (p & 1));
       asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ca), "r"(rb.x), "r"(rb.y) : "memory");
@@ -361,7 +358,8 @@ __device__ __forceinline__ void tile_store(const TileRegs<HD> &tr, uint32_t hi_b
 
 template <int HD>
 __global__ void __launch_bounds__(THREADS, 1)
-    band_attn_fwd_tc_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths,
+    band_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                            const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths,
                             const int32_t *__restrict__ offsets, int B, int S, int nheads, int w, float *__restrict__ out,
                             float *__restrict__ out_hi, float *__restrict__ out_lo, int Kp, float *__restrict__ lse) {
   using C = Cfg<HD>;
@@ -404,6 +402,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     tc::bar_init(BAR(B_PREADY1), WORKERS);
     tc::bar_init(BAR(B_ODONE), 1);
     tc::bar_init(BAR(B_OFREE), WORKERS);
+    tc::bar_init(BAR(B_KRAW), 1);
+    tc::bar_init(BAR(B_VRAW), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) tc::tmem_alloc<512>(tc::s_u32(tmem_slot));
@@ -424,21 +424,13 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t tr = sbase + (uint32_t)(C::OFF_TR + warp * 32 * TRS * 4);   // my warp's transposition buffer (shared-space address:
                                                                              // a generic pointer makes every access a generic LD / ST)
     const float inv_scale = 1.0f / sqrtf((float)HD);   // HF divides q by sqrt(head_dim) (:513); the product differs by <= 1 ulp
-    const int pce = lane % TileRegs<HD>::LPR;         // tile share: my 16-byte piece of the rows 8 warp .. 8 warp + 7
     long long *prof = (blockIdx.x == 0 && threadIdx.x == 0) ? g_atc_prof : nullptr;
     uint32_t item_g = 0, tile_g = 0;                 // items / tiles completed (softmax view)
     uint32_t k_cnt = 0, v_cnt = 0, q_cnt = 0;        // K tiles, V tiles, Q blocks handed over so far
 
-    // ck: the tile whose K share sits in kreg (the next one to hand over); cv: the tile whose V share is fetched next
-    Cursor ck, cv;
-    TileRegs<HD> kreg, vreg;
+    // ck: the next S tile of the sequence whose operands are to be handed over
+    Cursor ck;
     cursor_first(ck, sq, blockIdx.x);
-    cv = ck;
-    if (ck.valid) {
-      tile_fetch<HD>(kreg, qkv + ck.it.row0 * ld + d + ck.it.head * HD + 4 * pce, ld, ck.it.kbeg + 8 * warp, ck.it.kend, lane);
-      tile_fetch<HD>(vreg, qkv + cv.it.row0 * ld + 2 * d + cv.it.head * HD + 4 * pce, ld, cv.it.kbeg + 8 * warp, cv.it.kend, lane);
-      cursor_advance(cv, sq);
-    }
     bool started = false;   // the sequence's first tile still needs its S operands (done by a virtual pass t = -1)
     Item it;
     for (item_first(it, sq, blockIdx.x); it.idx < sq.n_items; item_step(it, sq)) {
@@ -449,7 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         float m_run = -INFINITY, l_run = 0.0f;
 #pragma unroll 1
         for (int t = started ? 0 : -1; t < it.nt; ++t) {
-          // ---- phase 1: operands of the NEXT S tile of the sequence (its K share is in kreg already) -------------------
+          // ---- phase 1: operands of the NEXT S tile of the sequence (its raw K tile arrives by TMA) ----------------------
           if (ck.valid) {
             if (ck.t == 0) {
               // The tile opens a new item: its Q (16-column chunks c = ch, ch + 2, ...).  Coalesced loads (a warp instruction =
@@ -518,18 +510,14 @@ __global__ void __launch_bounds__(THREADS, 1)
               AP_STAMP(0, 24);
               ++q_cnt;
             }
-            bar_wait(BAR(B_KEMPTY), (k_cnt & 1) ^ 1);   // the S product that read the previous K tile has completed
+            bar_wait(BAR(B_KRAW), k_cnt & 1);   // the raw K tile has landed (requested by the loader warp when its buffer fell free)
             AP_STAMP(0, 25);
-            tile_store<HD, false>(kreg, sbase + C::OFF_KH, sbase + C::OFF_KC, warp, lane);
+            tile_correction<HD, false>(sbase + C::OFF_KH, sbase + C::OFF_KC, warp, lane);
             tc::fence_proxy_async();
             tc::bar_arrive(BAR(B_KFULL));
             AP_STAMP(0, 26);
             ++k_cnt;
             cursor_advance(ck, sq);
-            AP_STAMP(0, 27);
-            if (ck.valid)   // prefetch the K share of the S tile after that
-              tile_fetch<HD>(kreg, qkv + ck.it.row0 * ld + d + ck.it.head * HD + 4 * pce, ld, ck.it.kbeg + ck.t * KT + 8 * warp,
-                             ck.it.kend, lane);
           }
           if (t < 0) {   // virtual pass: only the operands of the sequence's first S tile
             started = true;
@@ -538,9 +526,10 @@ __global__ void __launch_bounds__(THREADS, 1)
           AP_STAMP(0, 1 + 4 * t);
           // ---- phase 2: softmax of tile t, my 32 rows x 32 columns -------------------------------------------------------
           const int buf = tile_g & 1;
-          const int k0 = it.kbeg + t * KT + 32 * ch;   // first key of my column half
-          // valid column range [clo, clo + nvalid) of my row inside my half: band |i - j| <= w, j < kend (<= len)
-          const int clo = max(0, i - w - k0);
+          const int k0 = tile_k0(it, t) + 32 * ch;     // first key of my column half
+          // valid column range [clo, clo + nvalid) of my row inside my half: band |i - j| <= w, j < kend (<= len), and not a
+          // key the previous tile has covered already (the last tile's box is shifted up to end at kend)
+          const int clo = max(max(0, i - w - k0), it.kbeg + t * KT - k0);
           const int chi = (i < it.len) ? min(it.kend - k0, i + w + 1 - k0) : 0;
           const unsigned nvalid = (unsigned)max(min(chi, 32) - clo, 0);
           bar_wait(BAR(B_SFULL0 + buf), (tile_g >> 1) & 1);
@@ -619,16 +608,11 @@ __global__ void __launch_bounds__(THREADS, 1)
           tc::bar_arrive(BAR(B_PREADY0 + buf));
           AP_STAMP(0, 3 + 4 * t);
           // ---- phase 3: V tile of tile t (prefetched), then prefetch the next V tile of the sequence --------------------
-          bar_wait(BAR(B_VEMPTY), (v_cnt & 1) ^ 1);   // the P V product that read the previous V tile has completed
-          tile_store<HD, true>(vreg, sbase + C::OFF_VH, sbase + C::OFF_VC, warp, lane);
+          bar_wait(BAR(B_VRAW), v_cnt & 1);   // the raw V tile has landed
+          tile_correction<HD, true>(sbase + C::OFF_VH, sbase + C::OFF_VC, warp, lane);
           tc::fence_proxy_async();
           tc::bar_arrive(BAR(B_VFULL));
           ++v_cnt;
-          if (cv.valid) {
-            tile_fetch<HD>(vreg, qkv + cv.it.row0 * ld + 2 * d + cv.it.head * HD + 4 * pce, ld, cv.it.kbeg + cv.t * KT + 8 * warp,
-                           cv.it.kend, lane);
-            cursor_advance(cv, sq);
-          }
           ++tile_g;
           AP_STAMP(0, 4 + 4 * t);
         }
@@ -690,6 +674,27 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       if (ch == 0 && lse && it.q0 + r < S) lse[((int64_t)it.b * nheads + it.head) * S + it.q0 + r] = lse_v;
     }
+  } else if (warp == 9 || warp == 10) {
+    // =============================== loader warps: raw K (warp 9) / V (warp 10) tiles by TMA ===============================
+    // One request per tile as soon as its buffer falls free (the S / P V product that read the previous tile has completed),
+    // i.e. a whole softmax phase before the workers need it: 64 rows x 32 columns per plane, swizzled by the TMA unit the way
+    // the tensor core wants the operand.
+    if (lane == 0) {
+      const bool is_v = warp == 10;
+      const CUtensorMap *map = is_v ? &map_v : &map_k;
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+      const uint32_t dst = sbase + (uint32_t)(is_v ? C::OFF_VH : C::OFF_KH);
+      const uint32_t raw_bar = BAR(is_v ? B_VRAW : B_KRAW), empty_bar = BAR(is_v ? B_VEMPTY : B_KEMPTY);
+      Cursor cl;
+      uint32_t n = 0;
+      for (cursor_first(cl, sq, blockIdx.x); cl.valid; cursor_advance(cl, sq), ++n) {
+        bar_wait(empty_bar, (n & 1) ^ 1);
+        tc::bar_expect_tx(raw_bar, C::NP * KT * 128);
+        const int c0 = (is_v ? 2 : 1) * d + cl.it.head * HD, c1 = (int)cl.it.row0 + tile_k0(cl.it, cl.t);
+#pragma unroll
+        for (int j = 0; j < C::NP; ++j) tma_load_2d(dst + j * (KT * 128), map, c0 + 32 * j, c1, raw_bar);
+      }
+    }
   } else if (warp == 8) {
     // =============================== MMA issuer: warp-uniform control flow, one elected lane ===============================
     constexpr uint32_t id_o = tc::idesc_tf32(BQ, HD) | B_MN_MAJOR, id_oc = tc::idesc_bf16(BQ, HD) | B_MN_MAJOR;
@@ -717,6 +722,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             ++q_seen;
           }
           const uint32_t sbuf = s_cnt & 1;
+          bar_wait(BAR(B_KRAW), s_cnt & 1);    // (complete by now; orders the TMA writes before this thread's MMAs)
           bar_wait(BAR(B_KFULL), s_cnt & 1);
           tc::tc_fence_after();
           AP_STAMP(4, 1 + 4 * (t + 1));
@@ -742,6 +748,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const uint32_t buf = tile_g & 1;
         bar_wait(BAR(B_PREADY0 + buf), (tile_g >> 1) & 1);
         AP_STAMP(4, 2 + 4 * t);
+        bar_wait(BAR(B_VRAW), tile_g & 1);
         bar_wait(BAR(B_VFULL), tile_g & 1);
         if (t == 0) bar_wait(BAR(B_OFREE), (item_g & 1) ^ 1);   // the previous item's epilogue has read O
         tc::tc_fence_after();
@@ -785,14 +792,47 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// qkv as a 2-D fp32 tensor [rows, 3 d] (row stride ld); box = 64 rows x 32 columns = one raw operand plane.  `rows` is an
+// upper bound (B * S): by construction no box ends behind its episode (tile_k0), so nothing behind the buffer is read.
+static int make_map(CUtensorMap *map, const float *qkv, int64_t ld, int width, int64_t rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("band_attn_fwd_tc: cuTensorMapEncodeTiled not available"); return MTS_E_NODEVICE; }
+  cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)KT};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("band_attn_fwd_tc: cuTensorMapEncodeTiled failed"); return MTS_E_BADARG; }
+  return 0;
+}
+
 template <int HD>
 static int launch(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int w,
                   float *out, float *out_hi, float *out_lo, int Kp, float *lse, cudaStream_t st) {
   using C = Cfg<HD>;
+  CUtensorMap map_k, map_v;
+  int rc;
+  if ((rc = make_map(&map_k, qkv, ld, 3 * nheads * HD, (int64_t)B * S, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&map_v, qkv, ld, 3 * nheads * HD, (int64_t)B * S, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   MTS_CUDA(cudaFuncSetAttribute(band_attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   const int n_items = B * ((S + BQ - 1) / BQ) * nheads;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
-  band_attn_fwd_tc_kernel<HD><<<grid, THREADS, C::SMEM, st>>>(qkv, ld, lengths, offsets, B, S, nheads, w, out, out_hi, out_lo, Kp, lse);
+  band_attn_fwd_tc_kernel<HD><<<grid, THREADS, C::SMEM, st>>>(map_k, map_v, qkv, ld, lengths, offsets, B, S, nheads, w, out, out_hi,
+                                                             out_lo, Kp, lse);
   MTS_LAUNCH_CHECK();
   return 0;
 }
