@@ -692,6 +692,66 @@ def saturating_leg(ctx):
             "shape": f"B episodes x {T} sentences, one layer, both directions, inference"}
 
 
+def bf16_leg(ctx, steps):
+    """The headline batch through the explicit bf16 switch (ops.set_precision("bf16")): bf16 x bf16 products in the input
+    projections and the recurrence (fp32 state, gates, accumulation, outputs), embeddings stored and shipped as bf16.  Reported
+    BESIDE the f32 headline, never instead of it; tolerances in DESIGN.md, measured by tests/test_gpu_config_shapes.py."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    m, dev = ctx.m, ctx.dev
+    c = CFG
+    torch.manual_seed(0)
+    seg = m.TextSegmenter(2, c["D1"] + c["D2"], c["H"], num_layers=c["L"], architecture="BiLSTM", loss_fn="FocalLoss",
+                          threshold=0.5).to(dev)
+    seg.model.th = 0.5
+    model = seg.model
+    n_sets = 4
+    host = [synth(500 + 100 * ctx.rank + i, c["B"], c["T"], c["D1"], c["D2"]) for i in range(n_sets)]
+    pinned = [(a.to(torch.bfloat16).pin_memory(), b.to(torch.bfloat16).pin_memory(), l) for a, b, l in host]
+    dev_sets = [(a.to(dev), b.to(dev), ops.Lengths(l, dev, c["T"])) for a, b, l in pinned]
+    n_sent = c["B"] * c["T"]
+    ops.set_precision("bf16")
+    try:
+        def step(i):
+            x1, x2, lens = dev_sets[i % n_sets]
+            return model.decode_device((x1, x2), lens)
+
+        ms, launches = ctx.timed(step, steps, warm=3)
+        prof = ctx.profile(step, n=4)
+        prefetcher = m.DevicePrefetcher(None, dev)
+
+        def batches(n):
+            for i in range(n):
+                a, b, l = pinned[i % n_sets]
+                yield {"src_tokens": (a, b), "src_lengths": l}
+
+        def e2e(n):
+            for _ in seg.predict_batches(prefetcher.iterate(batches(n))):
+                pass
+
+        e2e(4)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        e2e(steps)
+        ctx.barrier()
+        e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    finally:
+        ops.set_precision("f32")
+    h2d = c["B"] * c["T"] * (c["D1"] + c["D2"]) * 2 + c["B"] * 8
+    rec = "mts_lstm_rec_fwd_tc_bf16"
+    return {"metric": "segmented sentences/sec", "dtype": "bf16", "value": n_sent * ctx.world / (ms / 1e3), "unit": "sentences/s",
+            "ms_per_step": ms, "gpu_launches_per_step": launches, "workload": WORKLOAD + " -- bf16 path, bf16 embeddings, eager launches",
+            "e2e": {"value": n_sent * steps * ctx.world / e2e_s, "unit": "sentences/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": c["B"] * c["T"]},
+            "kernel_ms_per_call": {k: sum(v) / len(v) for k, v in prof.items()},
+            "roofline": {"kernel": "lstm_fwd_tc_kernel, bf16 mode (32 MMAs per step)", "bound": "hbm",
+                         "achieved": n_sent * ALGO_BYTES_PER_SENTENCE_REC / (sum(prof[rec]) / len(prof[rec]) / 1e3) / 1e9 if rec in prof else None,
+                         "peak": peaks()[0], "unit": "GB/s",
+                         "note": "gx and h stay fp32 in HBM: same algorithmic bytes as the f32 path, shorter step"},
+            "tolerance": "logits within 2e-2 of the logit scale of the fp32 oracle (measured 5e-3), boundary flips <= 0.5 % (measured 0.1 %) (tests/test_gpu_config_shapes.py::"
+                         "test_bf16_path_tolerance_and_flips prints the measured values)"}
+
+
 def library_gpu_info(ctx):
     """Information only: what torch's own GPU libraries (cuDNN RNN, cuBLAS; TF32 off) need for the
     headline batch and for the configs[1] training step on this same GPU.  Not a contract arm."""
@@ -759,7 +819,7 @@ def run_ours(args, rank, world, local_rank):
     ops.device_ok()
     ctx = Ctx(m, dev, rank, world, local_rank)
     legs = set(args.legs.split(",")) if args.legs != "all" else {"train", "train_crf", "latefusion", "long", "crf", "transformer",
-                                                                 "saturating", "library"}
+                                                                 "saturating", "library", "bf16"}
     if args.skip_transformer:
         legs.discard("transformer")
     try:
@@ -912,6 +972,8 @@ def run_ours(args, rank, world, local_rank):
         if "latefusion" in legs:
             for key in ("latefusion_train", "latefusion_train_b64", "latefusion_crf_train"):
                 results[key] = train_leg(ctx, key, heavy)
+        if "bf16" in legs:
+            results["bf16"] = bf16_leg(ctx, args.steps)
         if "crf" in legs:
             results["crf"] = crf_leg(ctx, heavy)
         if "long" in legs:
@@ -963,6 +1025,11 @@ def run_ours(args, rank, world, local_rank):
                 legs_short[short.replace("_sps", "_e2e_sps")] = results[key]["e2e"]["value"]
     if "crf" in results:
         legs_short["bilstm_crf_decode_sps"] = results["crf"]["bilstm_crf_decode"]["value"]
+    if "bf16" in results:
+        legs_short["bf16_sps"] = results["bf16"]["value"]
+        legs_short["bf16_e2e_sps"] = results["bf16"]["e2e"]["value"]
+        if results["bf16"]["roofline"]["achieved"]:
+            results["bf16"]["roofline"]["frac"] = results["bf16"]["roofline"]["achieved"] / results["bf16"]["roofline"]["peak"]
     line = {
         "metric": "segmented sentences/sec", "value": value, "unit": "sentences/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -1004,7 +1071,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="all", help="comma list of train,train_crf,latefusion,long,crf,transformer,saturating,library "
+    ap.add_argument("--legs", default="all", help="comma list of train,train_crf,latefusion,long,crf,transformer,saturating,library,bf16 "
                                                    "(the headline leg always runs); 'none' = headline only")
     ap.add_argument("--skip-transformer", action="store_true", help="skip the configs[2] windowed-attention leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")

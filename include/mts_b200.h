@@ -123,6 +123,26 @@ int mts_lstm_rec_fwd(const float *gx, const float *w_hh, const int32_t *lengths,
 int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
                         int B, int T, int H, float *y, float *gates, float *y_corr, void *stream);
 
+/* ---- bf16 path (explicit precision switch; fp32 stays the default and the parity contract) -----------------------
+ * The same kernels with bf16 operands on kind::f16 MMAs only: per product one bf16 x bf16 term instead of the
+ * error-compensated TF32 + bf16 pair.  State, gates, accumulation and every output stay fp32.  Tolerances per kernel
+ * (measured against the fp32 oracle at T = 300 and T = 8192) are listed in DESIGN.md.
+ *   mts_lstm_rec_fwd_tc_bf16 : nn.LSTM recurrence (NeuralArchitectures.py:113) with bf16(W_hh) bf16(h) products: 32 instead of
+ *                              64 MMAs per step.  Same arguments as mts_lstm_rec_fwd_tc.
+ *   mts_gemm_bf16p           : C = A B^T (+ bias, epilogues as mts_gemm_tf32x3) from the PACKED operands alone: A_lo as every
+ *                              producer writes it (side 0), B_lo = the weights packed with side 0 too.  The raw fp32 arrays
+ *                              are not read: half the operand bytes, half the MMAs.
+ *   mts_pack_rows_bf16in     : early-fusion concat + crop of BF16 embedding tensors (src1 [B,*,D1], src2 [B,*,D2], strides in
+ *                              elements) straight into the packed operand: embeddings stored and shipped as bf16 halve the
+ *                              host->device bytes of the path (utils/load_datasets_precomputed.py:158-161 is where the
+ *                              reference concatenates fp32). */
+int mts_lstm_rec_fwd_tc_bf16(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
+                             int B, int T, int H, float *y, float *gates, float *y_corr, void *stream);
+int mts_gemm_bf16p(const float *A_lo, const float *B_lo, const float *bias, float *C, int M, int N, int Kp, int64_t ldc,
+                   int epilogue, int accumulate, void *stream);
+int mts_pack_rows_bf16in(const void *src1, int64_t bstride1, int D1, const void *src2, int64_t bstride2, int D2, int B, int T,
+                         int Kp, float *lo, void *stream);
+
 /* Profiling hook of the tensor-core recurrence: installs (or, with NULL, removes) a device buffer of 4 x 12 int64
  * into which CTA 0 writes clock64() stamps of the phases of steps 8..11 (see csrc/lstm_rec_tc.cu). */
 int mts_debug_rec_profile(long long *buf);

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
-                       int epilogue, int accumulate, int splits) {
+                       int epilogue, int accumulate, int splits, int bf16_only) {
   using Cfg = TcCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -291,16 +291,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int kb = kb0; kb < kb1; ++kb) {
           bar_wait(s_u32(&empty_bar[stage]), phase ^ 1);  // CL == 2: BOTH CTAs have consumed this stage
           const uint32_t fb = s_u32(&full_bar[stage]);
-          bar_expect_tx(fb, Cfg::kStageBytes);
+          bar_expect_tx(fb, bf16_only ? Cfg::kStageBytes / 2 : Cfg::kStageBytes);   // bf16 mode: the raw fp32 tiles are not loaded
           const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
-          tma_load_2d(base, &map_a_hi, kb * TC_BK, m0, fb);
+          if (!bf16_only) tma_load_2d(base, &map_a_hi, kb * TC_BK, m0, fb);
           tma_load_2d(base + Cfg::kABytes, &map_a_lo, kb * 2 * TC_BK, m0, fb);  // bf16 elements: 64 per k-block
           if (CL == 1) {
-            tma_load_2d(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
+            if (!bf16_only) tma_load_2d(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
             tma_load_2d(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * 2 * TC_BK, n0, fb);
           } else {  // my 1/CL slice of the B tile (rows n0 + crank * BN/CL ...), delivered to every CTA at the same offsets
             const uint32_t part = crank * (uint32_t)(Cfg::kBBytes / CL);
-            tma_load_2d_mc(base + 2 * Cfg::kABytes + part, &map_b_hi, kb * TC_BK, n0 + (int)crank * (BN / CL), fb, kMask);
+            if (!bf16_only)
+              tma_load_2d_mc(base + 2 * Cfg::kABytes + part, &map_b_hi, kb * TC_BK, n0 + (int)crank * (BN / CL), fb, kMask);
             tma_load_2d_mc(base + 2 * Cfg::kABytes + Cfg::kBBytes + part, &map_b_lo, kb * 2 * TC_BK,
                            n0 + (int)crank * (BN / CL), fb, kMask);
           }
@@ -333,8 +334,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);  // +32 B per k-step inside the swizzle row
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));  // K = 8 fp32 = 32 B
-            umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_c, 1);                     // K = 16 bf16 = 32 B
+            if (!bf16_only) umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));  // K = 8 fp32 = 32 B
+            umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_c, !bf16_only || (kb != kb0) || (k != 0));  // K = 16 bf16 = 32 B
           }
           if (CL == 1) umma_commit(s_u32(&empty_bar[stage]));  // smem slot free once these MMAs have read it
           else umma_commit_mc(s_u32(&empty_bar[stage]), kMask);  // ... tells both producers (the peer writes B here too)
@@ -442,7 +443,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_2sm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                            const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
-                           int epilogue, int accumulate, int splits) {
+                           int epilogue, int accumulate, int splits, int bf16_only) {
   using Cfg = Tc2Cfg;
   constexpr int BN = Cfg::BN, kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -498,11 +499,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           bar_wait(s_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
           // the leader arms ITS barrier for both CTAs' bytes; the peer's loads report to the same barrier
-          if (leader) bar_expect_tx(s_u32(&full_bar[stage]), 2 * Cfg::kStageBytes);
+          if (leader) bar_expect_tx(s_u32(&full_bar[stage]), bf16_only ? Cfg::kStageBytes : 2 * Cfg::kStageBytes);
           const uint32_t fb = mapa_u32(s_u32(&full_bar[stage]), 0);
-          tma_load_2d_2sm(base, &map_a_hi, kb * TC_BK, m0, fb);
+          if (!bf16_only) tma_load_2d_2sm(base, &map_a_hi, kb * TC_BK, m0, fb);
           tma_load_2d_2sm(base + Cfg::kABytes, &map_a_lo, kb * 2 * TC_BK, m0, fb);
-          tma_load_2d_2sm(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
+          if (!bf16_only) tma_load_2d_2sm(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
           tma_load_2d_2sm(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * 2 * TC_BK, n0, fb);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -534,8 +535,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
-            umma2_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));
-            umma2_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_c, 1);
+            if (!bf16_only) umma2_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));
+            umma2_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_c, !bf16_only || (kb != kb0) || (k != 0));
           }
           umma2_commit_mc(s_u32(&empty_bar[stage]), 3);  // both producers may refill this stage
           if (kb == kb1 - 1) umma2_commit_mc(s_u32(&tfull_bar[acc_stage]), 3);
@@ -615,7 +616,8 @@ __global__ void __launch_bounds__(256) zero_matrix_kernel(float *__restrict__ C,
 
 template <int BN>
 static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
-                     float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, cudaStream_t st) {
+                     float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, cudaStream_t st,
+                     int bf16_only = 0) {
   using Cfg = TcCfg<BN>;
   const int tiles_m1 = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
   // clusters of 2 (B tile multicast) whenever there are at least two row tiles; MTS_GEMM_CLUSTER=1 keeps single CTAs
@@ -681,13 +683,13 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
     cfg.dynamicSmemBytes = Tc2Cfg::kSmemBytes;
     cfg.numAttrs = 0;  // the cluster shape is compiled into the kernel
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_2sm_kernel, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits));
+                                accumulate, splits, bf16_only));
   } else if (CL == 2) {
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits));
+                                accumulate, splits, bf16_only));
   } else {
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 1>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits));
+                                accumulate, splits, bf16_only));
   }
   MTS_LAUNCH_CHECK();
   return 0;
@@ -709,4 +711,21 @@ extern "C" int mts_gemm_tf32x3(const float *A_hi, const float *A_lo, const float
   cudaStream_t st = (cudaStream_t)stream;
   if (N >= 256) return launch_tc<256>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st);
   return launch_tc<128>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st);
+}
+
+// bf16 path (explicit precision switch, tolerance stated per kernel in DESIGN.md): C = bf16(A) bf16(B)^T (+ bf16(rest A)
+// bf16(rest B)^T, negligible) on kind::f16 MMAs only, fp32 accumulation.  A_lo = packed operand of A as every producer
+// writes it (side 0: per 16 columns [bf16(x) | bf16(rest)]); B_lo = the weights packed with side 0 as well, so that
+// the halves pair up x * w.  Half the MMAs and half the operand bytes of mts_gemm_tf32x3; the raw fp32 arrays are
+// not read at all.
+extern "C" int mts_gemm_bf16p(const float *A_lo, const float *B_lo, const float *bias, float *C, int M, int N, int Kp,
+                              int64_t ldc, int epilogue, int accumulate, void *stream) {
+  MTS_REQUIRE(A_lo && B_lo && C, MTS_E_BADARG, "gemm_bf16p: null pointer");
+  MTS_REQUIRE(M > 0 && N > 0 && Kp > 0, MTS_E_BADARG, "gemm_bf16p: empty shape");
+  MTS_REQUIRE(Kp % TC_BK == 0, MTS_E_UNSUPPORTED, "gemm_bf16p: Kp must be a multiple of 32");
+  MTS_REQUIRE(epilogue == 0 || bias, MTS_E_BADARG, "gemm_bf16p: epilogue needs a bias");
+  MTS_REQUIRE((((uintptr_t)A_lo | (uintptr_t)B_lo) & 15) == 0, MTS_E_BADARG, "gemm_bf16p: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N >= 256) return launch_tc<256>(A_lo, A_lo, B_lo, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st, 1);
+  return launch_tc<128>(A_lo, A_lo, B_lo, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st, 1);
 }

@@ -65,7 +65,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
     lstm_fwd_tc_kernel(const float *__restrict__ gx, const float *__restrict__ w_hh,
                        const int32_t *__restrict__ lengths, const int32_t *__restrict__ order, int B, int T, int n_enc,
                        int n_tiles, int ept, float *__restrict__ y, float *__restrict__ gates,
-                       float *__restrict__ y_corr) {
+                       float *__restrict__ y_corr, int bf16_mode) {
+  // bf16_mode (explicit precision switch): the step's product is bf16(W_hh) bf16(h) only -- the 32 kind::tf32 MMAs are
+  // skipped and the packed operand of h carries [bf16(h) | 0] instead of [bf16(rest h) | bf16(h)], so that the packed
+  // halves pair up W * h.  32 instead of 64 MMAs per step; tolerance stated in DESIGN.md.
   // ept = episodes per tile (<= TR_NB).  With fewer sequences than 16 x the resident clusters the host spreads them over
   // ALL clusters: the MMAs cost the same at any N <= 16, while the gate phase, the h exchange and the correction-operand
   // derivation shrink with the number of episodes a cluster carries.  Rows >= ept of the operand buffers stay zero.
@@ -220,15 +223,16 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t bd = tc::desc_sw128(bhi_a + kb * (TR_NB * 128) + k * 32);
-              if (leader) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, (kb | k) != 0);
+              if (leader && !bf16_mode) tc::umma_tf32_ts(d_tmem, tb + (uint32_t)(kb * 32 + k * 8), bd, idesc, (kb | k) != 0);
             }
           }
         }
         TR_STAMP(2);
-        if (s > 0) {  // at s == 0 both h and h_lo are the zero-filled buffers: the h_lo product contributes nothing
+        if (s > 0 || bf16_mode) {  // at s == 0 both h and h_lo are the zero-filled buffers: the h_lo product contributes nothing
+                                   // (bf16 mode: it is the only product, and it zeroes the accumulator)
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            tc::bar_wait_wd(tc::s_u32(&lo_ready[g]), ph_lo);
+            if (s > 0) tc::bar_wait_wd(tc::s_u32(&lo_ready[g]), ph_lo);
             if (g == 1) TR_STAMP(3);
             tc::tc_fence_after();
 #pragma unroll
@@ -238,7 +242,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
                 // correction product: 64 bf16 per slot = 4 MMAs of K = 16; A = packed (W | rest W), B = packed (rest h | h)
                 const uint64_t bd = tc::desc_sw128(blo_a + kb * (TR_NB * 128) + k * 32);
                 if (leader) {
-                  if (kb < 7) tc::umma_bf16_ts(d_tmem, tb + (uint32_t)(TR_WLO_COL + kb * 32 + k * 8), bd, idesc_c, 1);
+                  const uint32_t acc = (bf16_mode && (kb | k) == 0) ? 0u : 1u;
+                  if (kb < 7) tc::umma_bf16_ts(d_tmem, tb + (uint32_t)(TR_WLO_COL + kb * 32 + k * 8), bd, idesc_c, acc);
                   else tc::umma_bf16_ss(d_tmem, tc::desc_sw128(tail_a + k * 32), bd, idesc_c, 1);
                 }
               }
@@ -307,10 +312,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(TR_SUB_THREAD
               const int blk = c >> 2, kk = (c & 3) * 4;              // 16-k block, first k inside it
               uint8_t *rowp = reinterpret_cast<uint8_t *>(dst) + (f4 >> 7) * (TR_NB * 128) + e * 128;
               const int off_lo = blk * 64 + kk * 2, off_hb = off_lo + 32;   // byte offsets inside the 128-byte row
-              *reinterpret_cast<uint2 *>(rowp + ((((off_lo >> 4) ^ (e & 7)) << 4) | (off_lo & 15))) =
-                  make_uint2(bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y)), bf16x2_bits(tf32_rest_exact(v.z), tf32_rest_exact(v.w)));
-              *reinterpret_cast<uint2 *>(rowp + ((((off_hb >> 4) ^ (e & 7)) << 4) | (off_hb & 15))) =
-                  make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
+              const uint2 hb = make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
+              const uint2 rb = make_uint2(bf16x2_bits(tf32_rest_exact(v.x), tf32_rest_exact(v.y)), bf16x2_bits(tf32_rest_exact(v.z), tf32_rest_exact(v.w)));
+              // B side: [bf16(rest h) | bf16(h)] pairs with A's [bf16(W) | bf16(rest W)]; bf16 mode: [bf16(h) | 0] -> W * h only
+              *reinterpret_cast<uint2 *>(rowp + ((((off_lo >> 4) ^ (e & 7)) << 4) | (off_lo & 15))) = bf16_mode ? hb : rb;
+              *reinterpret_cast<uint2 *>(rowp + ((((off_hb >> 4) ^ (e & 7)) << 4) | (off_hb & 15))) = bf16_mode ? make_uint2(0u, 0u) : hb;
             }
             tc::fence_proxy_async();   // generic-proxy writes of h_lo -> visible to tcgen05.mma
             tc::bar_arrive(tc::s_u32(&lo_ready[g]));
@@ -440,9 +446,22 @@ extern "C" int mts_debug_rec_profile(long long *buf) {
   return 0;
 }
 
+static int rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc, int B, int T,
+                      int H, float *y, float *gates, float *y_corr, void *stream, int bf16_mode);
+
 // tensor-core forward recurrence; same arguments as mts_lstm_rec_fwd, H must be 256
 extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order,
                                    int n_enc, int B, int T, int H, float *y, float *gates, float *y_corr, void *stream) {
+  return rec_fwd_tc(gx, w_hh, lengths, order, n_enc, B, T, H, y, gates, y_corr, stream, 0);
+}
+// the bf16 path of the same kernel (explicit precision switch): bf16(W_hh) bf16(h) products only, fp32 state and gates
+extern "C" int mts_lstm_rec_fwd_tc_bf16(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order,
+                                        int n_enc, int B, int T, int H, float *y, float *gates, float *y_corr, void *stream) {
+  return rec_fwd_tc(gx, w_hh, lengths, order, n_enc, B, T, H, y, gates, y_corr, stream, 1);
+}
+
+static int rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc, int B, int T,
+                      int H, float *y, float *gates, float *y_corr, void *stream, int bf16_mode) {
   MTS_REQUIRE(gx && w_hh && lengths && y, MTS_E_BADARG, "lstm_rec_fwd_tc: null pointer");
   MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0, MTS_E_BADARG, "lstm_rec_fwd_tc: bad shape");
   MTS_REQUIRE(H == kH, MTS_E_UNSUPPORTED, "lstm_rec_fwd_tc: the tensor-core recurrence serves H == 256");
@@ -477,13 +496,13 @@ extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int
   const bool two = force ? (force[0] == '2') : (items1 > cap);
   if (!two) {
     const unsigned grid = (unsigned)((items1 < cap ? items1 : cap) * kCluster);
-    if (gates) lstm_fwd_tc_kernel<true, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr);
-    else lstm_fwd_tc_kernel<false, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr);
+    if (gates) lstm_fwd_tc_kernel<true, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr, bf16_mode);
+    else lstm_fwd_tc_kernel<false, 1><<<grid, TR_SUB_THREADS, tr_smem<1>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr, bf16_mode);
   } else {
     const int items2 = ((n_tiles + 1) / 2) * 2 * n_enc;
     const unsigned grid = (unsigned)((items2 < cap ? items2 : cap) * kCluster);
-    if (gates) lstm_fwd_tc_kernel<true, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr);
-    else lstm_fwd_tc_kernel<false, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr);
+    if (gates) lstm_fwd_tc_kernel<true, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr, bf16_mode);
+    else lstm_fwd_tc_kernel<false, 2><<<grid, 2 * TR_SUB_THREADS, tr_smem<2>(), st>>>(gx, w_hh, lengths, order, B, T, n_enc, n_tiles, ept, y, gates, y_corr, bf16_mode);
   }
   MTS_LAUNCH_CHECK();
   return 0;

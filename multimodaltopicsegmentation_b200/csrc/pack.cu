@@ -45,10 +45,35 @@ __global__ void __launch_bounds__(256) pack_rows_split_v8_kernel(const float *__
       v0 = __ldcs(reinterpret_cast<const float4 *>(p));      // streamed once: do not keep in L2 ahead of the GEMM operands
       v1 = __ldcs(reinterpret_cast<const float4 *>(p) + 1);
     }
-    float4 *h = reinterpret_cast<float4 *>(hi + row * Kp + k);
-    h[0] = v0;
-    h[1] = v1;
+    if (hi) {   // (bf16 path: only the packed operand is wanted)
+      float4 *h = reinterpret_cast<float4 *>(hi + row * Kp + k);
+      h[0] = v0;
+      h[1] = v1;
+    }
     corr_store8(lo + row * Kp, k, v0, v1, 0);
+  }
+}
+
+// bf16 sources (embeddings stored and transferred as bf16: half the host->device bytes of the path): the packed operand only
+__global__ void __launch_bounds__(256) pack_rows_bf16in_kernel(const uint16_t *__restrict__ src1, int64_t bstride1, int D1,
+                                                               const uint16_t *__restrict__ src2, int64_t bstride2, int D2,
+                                                               int B, int T, int Kp, float *__restrict__ lo) {
+  const int k8n = Kp >> 3;
+  const int64_t total = (int64_t)B * T * k8n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % k8n) << 3;
+    const int64_t row = idx / k8n;
+    const int b = (int)(row / T), t = (int)(row % T);
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    const uint16_t *p = nullptr;
+    if (k < D1) p = src1 + (int64_t)b * bstride1 + (int64_t)t * D1 + k;
+    else if (k < D1 + D2) p = src2 + (int64_t)b * bstride2 + (int64_t)t * D2 + (k - D1);
+    if (p) raw = __ldcs(reinterpret_cast<const uint4 *>(p));
+    // a bf16 value is exact in TF32, so its remainder is zero: [bf16(x) x8 | 0 x8] at this 8-column half of the block
+    uint16_t *dst = reinterpret_cast<uint16_t *>(lo + row * Kp) + (k >> 4) * 32 + (k & 15);
+    *reinterpret_cast<uint4 *>(dst) = raw;
+    *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -173,12 +198,14 @@ static unsigned grid_for(int64_t total) {
 
 extern "C" int mts_pack_rows_split(const float *src1, int64_t bstride1, int D1, const float *src2, int64_t bstride2,
                                    int D2, int B, int T, int Kp, float *hi, float *lo, void *stream) {
-  MTS_REQUIRE(src1 && hi && lo, MTS_E_BADARG, "pack_rows_split: null pointer");
+  MTS_REQUIRE(src1 && lo, MTS_E_BADARG, "pack_rows_split: null pointer");
   MTS_REQUIRE(D2 == 0 || src2, MTS_E_BADARG, "pack_rows_split: D2 > 0 without src2");
   MTS_REQUIRE(B > 0 && T > 0 && D1 > 0 && D2 >= 0, MTS_E_BADARG, "pack_rows_split: bad shape");
   MTS_REQUIRE(Kp % 32 == 0 && Kp >= D1 + D2, MTS_E_BADARG, "pack_rows_split: Kp must be a multiple of 32 and >= D1 + D2");
   const bool al16 = ((((uintptr_t)src1 | (uintptr_t)src2 | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0) &&
                     bstride1 % 4 == 0 && bstride2 % 4 == 0;
+  MTS_REQUIRE(hi || (al16 && D1 % 8 == 0 && D2 % 8 == 0), MTS_E_UNSUPPORTED,
+              "pack_rows_split: the packed-operand-only form needs widths that are multiples of 8 and 16-byte aligned rows");
   if (al16 && D1 % 8 == 0 && D2 % 8 == 0) {
     pack_rows_split_v8_kernel<<<grid_for((int64_t)B * T * (Kp / 8)), 256, 0, (cudaStream_t)stream>>>(
         src1, bstride1, D1, src2, bstride2, D2, B, T, Kp, hi, lo);
@@ -186,6 +213,21 @@ extern "C" int mts_pack_rows_split(const float *src1, int64_t bstride1, int D1, 
     pack_rows_split_kernel<<<grid_for((int64_t)B * T * Kp), 256, 0, (cudaStream_t)stream>>>(src1, bstride1, D1, src2,
                                                                                            bstride2, D2, B, T, Kp, hi, lo);
   }
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mts_pack_rows_bf16in(const void *src1, int64_t bstride1, int D1, const void *src2, int64_t bstride2, int D2,
+                                    int B, int T, int Kp, float *lo, void *stream) {
+  MTS_REQUIRE(src1 && lo, MTS_E_BADARG, "pack_rows_bf16in: null pointer");
+  MTS_REQUIRE(D2 == 0 || src2, MTS_E_BADARG, "pack_rows_bf16in: D2 > 0 without src2");
+  MTS_REQUIRE(B > 0 && T > 0 && D1 > 0 && D2 >= 0, MTS_E_BADARG, "pack_rows_bf16in: bad shape");
+  MTS_REQUIRE(Kp % 32 == 0 && Kp >= D1 + D2, MTS_E_BADARG, "pack_rows_bf16in: Kp must be a multiple of 32 and >= D1 + D2");
+  MTS_REQUIRE(D1 % 8 == 0 && D2 % 8 == 0 && bstride1 % 8 == 0 && bstride2 % 8 == 0 &&
+                  ((((uintptr_t)src1 | (uintptr_t)src2 | (uintptr_t)lo) & 15) == 0),
+              MTS_E_UNSUPPORTED, "pack_rows_bf16in: widths must be multiples of 8 and rows 16-byte aligned");
+  pack_rows_bf16in_kernel<<<grid_for((int64_t)B * T * (Kp / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t *)src1, bstride1, D1, (const uint16_t *)src2, bstride2, D2, B, T, Kp, lo);
   MTS_LAUNCH_CHECK();
   return 0;
 }

@@ -91,7 +91,8 @@ class RNN(nn.Module):
             x1 = F.dropout(x1, p=self.dropout_in)  # active in eval too, as in the reference
             x2 = F.dropout(x2, p=self.dropout_in) if x2 is not None else None
         packed = self.packed()
-        out = ops.bilstm_stack(ops._check(x1, "input"), x2, None, lens, packed, 1)
+        out = ops.bilstm_stack(ops._check(x1, "input", x1.dtype if x1.dtype == torch.bfloat16 else torch.float32), x2, None, lens,
+                               packed, 1)
         if self.dropout_out:
             out = F.dropout(out, p=self.dropout_out)
         return out
@@ -193,7 +194,8 @@ class BiLSTMLateFusion(nn.Module):
         p_in = self.model1.dropout_in
         if p_in:
             x1, x2 = F.dropout(x1, p=p_in), F.dropout(x2, p=p_in)
-        out = ops.bilstm_stack(ops._check(x1, "x1"), None, ops._check(x2, "x2"), lens, self._packed, 2)
+        dt = x1.dtype if x1.dtype == torch.bfloat16 else torch.float32   # bf16 embeddings: the bf16 path (ops.set_precision)
+        out = ops.bilstm_stack(ops._check(x1, "x1", dt), None, ops._check(x2, "x2", dt), lens, self._packed, 2)
         if self.model1.dropout_out:
             out = F.dropout(out, p=self.model1.dropout_out)
         return out

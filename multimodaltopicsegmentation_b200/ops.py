@@ -33,6 +33,19 @@ GEMM_IMPL = __import__("os").environ.get("MTS_GEMM_IMPL", "tcgen05")
 REC_IMPL = __import__("os").environ.get("MTS_REC_IMPL", "tc")
 
 
+# Arithmetic of the LSTM path: "f32" (default; the parity contract: error-compensated TF32 + bf16 products, fp32-grade) or
+# "bf16" (explicit switch, inference only: bf16 x bf16 products in the input projections and the recurrence, fp32 state and
+# accumulation; tolerances per kernel in DESIGN.md).  MTS_PRECISION=bf16 or set_precision("bf16").
+PRECISION = __import__("os").environ.get("MTS_PRECISION", "f32")
+
+
+def set_precision(name):
+    global PRECISION
+    if name not in ("f32", "bf16"):
+        raise ValueError("precision must be 'f32' or 'bf16'")
+    PRECISION = name
+
+
 def _call(name, *args):
     global _LAUNCHES
     _LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
@@ -128,12 +141,32 @@ def _rows_ok(x, name, B, T):
     stride(2) == 1).  A view that is not (e.g. x[:, :, :D1] of a fused tensor) is made contiguous here."""
     if x is None:
         return None
-    _check(x, name)
+    _check(x, name, torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32)
+    if x.dtype == torch.bfloat16 and PRECISION != "bf16":
+        raise TypeError(f"{name}: bfloat16 embeddings belong to the bf16 path (ops.set_precision('bf16')); the fp32 path takes fp32")
     if x.dim() != 3 or x.shape[0] < B or x.shape[1] < T:
         raise ValueError(f"{name}: expected [B >= {B}, T >= {T}, D], got {tuple(x.shape)}")
     if x.stride(2) != 1 or x.stride(1) != x.shape[2]:
         x = x.contiguous()
     return x
+
+
+def pack_rows_packed(x1, x2, B, T):
+    """bf16 path: [x1[b,:T] | x2[b,:T]] -> the packed operand alone [B*T, pad32(D1+D2)].  The sources may be fp32 or -- embeddings
+    stored and shipped as bf16 -- bfloat16 tensors."""
+    D1 = x1.shape[2]
+    D2 = 0 if x2 is None else x2.shape[2]
+    kp = _pad32(D1 + D2)
+    lo = torch.empty((B * T, kp), device=x1.device, dtype=torch.float32)
+    if x1.dtype == torch.bfloat16:
+        if x2 is not None and x2.dtype != torch.bfloat16:
+            raise TypeError("both modalities must have the same dtype")
+        _call("mts_pack_rows_bf16in", _ptr(x1), x1.stride(0), D1, _ptr(x2), 0 if x2 is None else x2.stride(0), D2, B, T, kp,
+              _ptr(lo), _stream())
+    else:
+        _call("mts_pack_rows_split", _ptr(x1), x1.stride(0), D1, _ptr(x2), 0 if x2 is None else x2.stride(0), D2, B, T, kp,
+              0, _ptr(lo), _stream())
+    return lo
 
 
 def pack_rows_split(x1, x2, B, T):
@@ -241,6 +274,24 @@ class PackedLstm:
                 out.extend(self._params(rnn, layer))
         return out
 
+    def wih_packed_a(self, layer, e):
+        """bf16 path: W_ih of (layer, encoder e), both directions stacked, packed like an A operand (side 0) so that the
+        packed halves of activations and weights pair up x * w.  Made on first use per weight version."""
+        ent = self.get()[layer]
+        cache = ent.setdefault("wih_bf", {})
+        if e not in cache:
+            w_f, _, _, _, w_r = self._params(self.rnns[e], layer)[:5]
+            D = w_f.shape[1]
+            kp = _pad32(D)
+            H4 = w_f.shape[0]
+            bf = torch.empty((2, 2 * H4, kp), device=w_f.device, dtype=torch.float32)
+            with torch.no_grad():
+                for d, w in enumerate((w_f, w_r)):
+                    wc = w.detach().contiguous()
+                    _call("mts_split_tf32", _ptr(wc), D, H4, D, kp, A_SIDE, _ptr(bf[0, d * H4:]), _ptr(bf[1, d * H4:]), _stream())
+            cache[e] = bf[1]
+        return cache[e]
+
     def get(self):
         key = tuple((p.data_ptr(), p._version) for p in self.flat_params())
         if key == self.key:
@@ -279,9 +330,23 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
     layers = packed.get()
     saved = []
     y_prev = y_corr = None
+    bf16 = PRECISION == "bf16"
+    if bf16 and (save or H != 256 or REC_IMPL != "tc" or GEMM_IMPL == "simt"):
+        raise NotImplementedError("the bf16 path serves inference with H == 256 on the tensor-core kernels; train in fp32")
     for layer in range(L):
         gx = torch.empty((n_enc, B * T, 8 * H), device=dev, dtype=torch.float32)
         for e in range(n_enc):
+            if bf16:
+                if layer == 0:
+                    a_lo = pack_rows_packed(x1, x2, B, T) if n_enc == 1 else pack_rows_packed(x1 if e == 0 else xs2, None, B, T)
+                elif y_corr is not None:
+                    a_lo = y_corr
+                else:
+                    src = y_prev.view(B * T, n_enc * 2 * H)[:, e * 2 * H:(e + 1) * 2 * H]
+                    a_lo = split_tf32(src, cols=2 * H, ld=n_enc * 2 * H, rows=B * T)[1]
+                _call("mts_gemm_bf16p", _ptr(a_lo), _ptr(packed.wih_packed_a(layer, e)), _ptr(layers[layer]["bias"][e]), _ptr(gx[e]),
+                      B * T, 8 * H, a_lo.shape[1], 8 * H, 1, 0, _stream())
+                continue
             if layer == 0:
                 if n_enc == 1:
                     a_hi, a_lo = pack_rows_split(x1, x2, B, T)
@@ -306,8 +371,8 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
             # early fusion, more layers above: the kernel also writes the GEMM operand of the next layer's input
             y_corr = (torch.empty((B * T, 2 * H), device=dev, dtype=torch.float32)
                       if (n_enc == 1 and layer + 1 < L and GEMM_IMPL != "simt") else None)
-            _call("mts_lstm_rec_fwd_tc", _ptr(gx), _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order), n_enc, B, T,
-                  H, _ptr(y), _ptr(gates), _ptr(y_corr), _stream())
+            _call("mts_lstm_rec_fwd_tc_bf16" if bf16 else "mts_lstm_rec_fwd_tc", _ptr(gx), _ptr(layers[layer]["whh"]),
+                  _ptr(lens.dev), _ptr(lens.order), n_enc, B, T, H, _ptr(y), _ptr(gates), _ptr(y_corr), _stream())
         else:
             y_corr = None
             _call("mts_lstm_rec_fwd", _ptr(gx), _ptr(layers[layer]["whh"]), _ptr(lens.dev), _ptr(lens.order), n_enc, B, T,
