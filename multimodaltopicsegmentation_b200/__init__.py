@@ -4,7 +4,7 @@ The package mirrors the reference's Python interface for the segmentation-model 
 (`TextSegmenter`, the segmenter classes of models/CRF.py, the `EncoderDataset` batch layout) and runs
 its arithmetic in hand-written CUDA kernels behind the C ABI of include/mts_b200.h.
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, ops, results_io  # noqa: F401
 from .EncoderDataset import AudioPortionDataset, AudioPortionDatasetInference, DevicePrefetcher, to_device  # noqa: F401
 from .lightning_model import TextSegmenter  # noqa: F401
 from .load_datasets_precomputed import (ResidentDataset, cross_validation_split, load_dataset_for_inference,  # noqa: F401

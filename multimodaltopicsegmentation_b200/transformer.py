@@ -204,9 +204,31 @@ def _ln(mode, a, b, typ, gamma, beta, B, S, d, want_split, save, lens=None):
 LAYOUT = __import__("os").environ.get("MTS_XF_LAYOUT", "ragged")
 
 
-def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
+# Keep-masks of the hidden-state dropout: callable (site, rows, d, p, device) -> bool/uint8/float [rows, d].
+# None = Bernoulli(1 - p) from torch's CUDA generator.  Tests install a function that replays recorded masks.
+DROPOUT_MASK_FN = None
+
+
+def _keep_mask(site, rows, d, p, device):
+    if DROPOUT_MASK_FN is not None:
+        return DROPOUT_MASK_FN(site, rows, d, p, device)
+    return torch.rand((rows, d), device=device) >= p
+
+
+def _drop(t, site, p, masks):
+    """In-place inverted dropout of a [rows, d] activation; the keep-mask is remembered for the backward pass."""
+    keep = _keep_mask(site, t.shape[0], t.shape[1], p, t.device)
+    t.mul_(keep).mul_(1.0 / (1.0 - p))
+    masks.append(keep)
+    return t
+
+
+def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hidden=0.0):
     """x [B,S,d] -> last hidden state [B,S,d].  `reaches[l]` = one-sided window of layer l.
-    With save=True also returns what the backward pass needs."""
+    With save=True also returns what the backward pass needs.
+    p_hidden > 0 applies HF's `hidden_dropout_prob` at its three sites (after the embeddings LayerNorm and on the
+    two dense outputs that feed a residual LayerNorm: modeling_longformer.py LongformerEmbeddings / SelfOutput /
+    Output) as plain element-wise passes -- a training-time regulariser, not part of the timed inference path."""
     B, S, d = x.shape
     ragged = LAYOUT == "ragged"
     M = lens.N if ragged else B * S
@@ -219,7 +241,13 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
     h, h_hi, h_lo, pre0, st0 = _ln(0, x, emb.position_embeddings.weight.detach(), emb.token_type_embeddings.weight.detach()[0],
                                    emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), B, S, d, True, save,
                                    lens if ragged else None)
-    saved = {"emb": (pre0, st0), "layers": [], "ragged": ragged}
+    masks = []
+    if p_hidden > 0:
+        h = _drop(h, 0, p_hidden, masks)
+        h_hi, h_lo = ops.split_tf32(h)
+        if _pad32(d) == d:
+            h_hi = h
+    saved = {"emb": (pre0, st0), "layers": [], "ragged": ragged, "masks": masks, "p_hidden": p_hidden}
     for l, ent in enumerate(layers):
         lyr = m.encoder.layer[l]
         F = lyr.intermediate.dense.out_features
@@ -242,6 +270,8 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
             _call("mts_split_tf32", _ptr(a), d, M, d, kp, ops.A_SIDE, _ptr(a_hi), _ptr(a_lo), _stream())
         t = torch.empty((M, d), device=dev, dtype=torch.float32)
         ops.gemm_tf32x3(a_hi, a_lo, ent["wo"][0], ent["wo"][1], ent["bo"], t, M, d, epilogue=1)
+        if p_hidden > 0:
+            _drop(t, 1 + 2 * l, p_hidden, masks)
         ln1 = lyr.attention.output.LayerNorm
         y, y_hi, y_lo, pre1, st1 = _ln(1, t, h, None, ln1.weight.detach(), ln1.bias.detach(), M, 1, d, True, save)
         zp = torch.empty((M, F), device=dev, dtype=torch.float32)
@@ -252,6 +282,8 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save):
         _call("mts_gelu_split", _ptr(zp), F, M, F, kf, _ptr(z), _ptr(z_hl[0]), _ptr(z_hl[1]), _stream())
         u = torch.empty((M, d), device=dev, dtype=torch.float32)
         ops.gemm_tf32x3(z_hl[0], z_hl[1], ent["w2"][0], ent["w2"][1], ent["b2"], u, M, d, epilogue=1)
+        if p_hidden > 0:
+            _drop(u, 2 + 2 * l, p_hidden, masks)
         ln2 = lyr.output.LayerNorm
         h_in = h
         last = l == len(layers) - 1
@@ -270,9 +302,9 @@ class EncoderFn(torch.autograd.Function):
     """Differentiable w.r.t. the encoder parameters (the input embeddings are data)."""
 
     @staticmethod
-    def forward(ctx, x, lens, packed, nheads, reaches, *params):
+    def forward(ctx, x, lens, packed, nheads, reaches, p_hidden, *params):
         need = any(ctx.needs_input_grad)
-        out, saved = encoder_forward(x, lens, packed, nheads, reaches, save=need)
+        out, saved = encoder_forward(x, lens, packed, nheads, reaches, save=need, p_hidden=p_hidden)
         if need:
             ctx.saved, ctx.lens, ctx.packed, ctx.nheads, ctx.reaches = saved, lens, packed, nheads, reaches
             ctx.shape = x.shape
@@ -284,7 +316,7 @@ class EncoderFn(torch.autograd.Function):
 
         grads = encoder_backward(ctx, dout.contiguous())
         ctx.saved = None
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)
 
 
 class Longformer_Local_Attention(nn.Module):
@@ -318,17 +350,18 @@ class Longformer_Local_Attention(nn.Module):
         if x.shape[1] + 2 > self.max_positions:
             raise IndexError(f"sequence length {x.shape[1]} exceeds the position table ({self.max_positions} rows, "
                              "position ids start at 2)")
-        if self.training and (self.hidden_dropout > 0 or self.attention_dropout > 0):
-            raise NotImplementedError("dropout inside the windowed encoder is not implemented on the B200 path; "
-                                      "train with dropout_in = dropout_out = 0")
+        if self.training and self.attention_dropout > 0:
+            raise NotImplementedError("dropout on the attention probabilities is not implemented on the B200 path "
+                                      "(the probabilities never leave tensor memory); train with dropout_out = 0")
+        p_hidden = self.hidden_dropout if self.training else 0.0
         if x.stride(2) != 1 or x.stride(1) != x.shape[2]:
             x = x.contiguous()
         lens = lengths if isinstance(lengths, ops.Lengths) else ops.Lengths(lengths, x.device, x.shape[1])
         packed = self.packed()
         params = packed.used_parameters()
         if not (torch.is_grad_enabled() and any(p.requires_grad for p in params)):  # inference: nothing saved
-            return encoder_forward(x, lens, packed, self.nhead, self.reaches, save=False)[0]
-        return EncoderFn.apply(x, lens, packed, self.nhead, self.reaches, *params)
+            return encoder_forward(x, lens, packed, self.nhead, self.reaches, save=False, p_hidden=p_hidden)[0]
+        return EncoderFn.apply(x, lens, packed, self.nhead, self.reaches, p_hidden, *params)
 
 
 class Transformer_segmenter(nn.Module):

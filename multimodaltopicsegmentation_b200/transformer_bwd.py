@@ -59,6 +59,15 @@ def encoder_backward(ctx, dout):
     n_layers = len(m.encoder.layer)
     per = packed.PER_LAYER
     grads = [None] * (4 + per * n_layers)
+    masks, p_hidden = saved.get("masks", []), saved.get("p_hidden", 0.0)
+
+    def through_dropout(dpre, site):
+        """gradient of the dense output that was dropped before the residual add: (d, (hi, lo)) of d * keep / (1 - p);
+        the skip path keeps the unmasked dpre."""
+        g = (dpre * masks[site]).mul_(1.0 / (1.0 - p_hidden))
+        hl = ops.split_tf32(g)
+        return g, ((g if _pad32(d) == d else hl[0]), hl[1])
+
     if ragged:  # gradient rows of the valid sentences only, in the forward pass's ragged order
         dh = torch.empty((M, d), device=dev, dtype=torch.float32)
         _call("mts_ragged_copy", _ptr(dout), _ptr(dh), _ptr(lens.dev), _ptr(lens.offs), B, S, d, 0, 0.0, _stream())
@@ -75,9 +84,10 @@ def encoder_backward(ctx, dout):
         dpre2, dpre2_hl, dg2, db2 = _ln_bwd(dh, sv["pre2"], sv["st2"], lyr.output.LayerNorm.weight.detach(), M, d)
         grads[base + 14], grads[base + 15] = dg2, db2
         # ---- u = z W2^T + b2 -----------------------------------------------------------------------------
-        grads[base + 12], grads[base + 13] = _dense_param_grads(dpre2, sv["z"], M, d, F)
+        du, du_hl = through_dropout(dpre2, 2 + 2 * l) if p_hidden > 0 else (dpre2, dpre2_hl)
+        grads[base + 12], grads[base + 13] = _dense_param_grads(du, sv["z"], M, d, F)
         dz = torch.empty((M, F), device=dev, dtype=torch.float32)
-        ops.gemm_tf32x3(dpre2_hl[0], dpre2_hl[1], ent["w2_t"][0], ent["w2_t"][1], None, dz, M, F)
+        ops.gemm_tf32x3(du_hl[0], du_hl[1], ent["w2_t"][0], ent["w2_t"][1], None, dz, M, F)
         # ---- z = GELU(zp) ---------------------------------------------------------------------------------
         dzp = torch.empty((M, F), device=dev, dtype=torch.float32)
         dzp_hl = torch.empty((2, M, kf), device=dev, dtype=torch.float32)
@@ -90,9 +100,10 @@ def encoder_backward(ctx, dout):
         dpre1, dpre1_hl, dg1, db1 = _ln_bwd(dy, sv["pre1"], sv["st1"], lyr.attention.output.LayerNorm.weight.detach(), M, d)
         grads[base + 8], grads[base + 9] = dg1, db1
         # ---- t = a Wo^T + bo ---------------------------------------------------------------------------------
-        grads[base + 6], grads[base + 7] = _dense_param_grads(dpre1, sv["a"], M, d, d)
+        dt, dt_hl = through_dropout(dpre1, 1 + 2 * l) if p_hidden > 0 else (dpre1, dpre1_hl)
+        grads[base + 6], grads[base + 7] = _dense_param_grads(dt, sv["a"], M, d, d)
         da = torch.empty((M, d), device=dev, dtype=torch.float32)
-        ops.gemm_tf32x3(dpre1_hl[0], dpre1_hl[1], ent["wo_t"][0], ent["wo_t"][1], None, da, M, d)
+        ops.gemm_tf32x3(dt_hl[0], dt_hl[1], ent["wo_t"][0], ent["wo_t"][1], None, da, M, d)
         # ---- banded attention ----------------------------------------------------------------------------------
         dqkv = torch.empty((M, 3 * d), device=dev, dtype=torch.float32)
         delta = torch.empty((B, nheads, S), device=dev, dtype=torch.float32)
@@ -108,6 +119,8 @@ def encoder_backward(ctx, dout):
     # ---- embeddings: h0 = LN(x + P[2 + t] + E_type[0]) ---------------------------------------------------------
     emb = m.embeddings
     pre0, st0 = saved["emb"]
+    if p_hidden > 0:
+        dh = (dh * masks[0]).mul_(1.0 / (1.0 - p_hidden))
     dpre0, _, dg0, db0 = _ln_bwd(dh, pre0, st0, emb.LayerNorm.weight.detach(), M, d)
     dpos = torch.zeros_like(emb.position_embeddings.weight)
     _call("mts_embed_bwd", _ptr(dpre0), B, S, d, dpos.data_ptr() + 4 * 2 * d, _ptr(lens.dev) if ragged else 0, offs,

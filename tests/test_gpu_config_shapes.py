@@ -383,3 +383,60 @@ def test_bf16_path_tolerance_and_flips(dev, B, T, D):
     scale = float(s_ref.abs().max())
     assert worst <= 2e-2 * scale, (worst, scale)     # contract of the bf16 path: 2e-2 of the logit scale (measured 5e-3; fp32 path 1e-4)
     assert flips <= max(2, n_dec // 200)             # <= 0.5 % of the boundary decisions (measured 0.11 - 0.14 %)
+
+
+@pytest.mark.parametrize("loss_fn", ["BinaryCrossEntropy", "CrossEntropy"])
+def test_predict_flow_from_experiment_directory(dev, tmp_path, loss_fn):
+    """results.txt + a Lightning-layout checkpoint + a folder of .npy embeddings ->
+    Predictor -> per-file tags (reference predict.py:131-347), against the oracle's forward of the same weights.
+    The CrossEntropy checkpoint exercises the reference's second load attempt (predict.py:242-258)."""
+    from multimodaltopicsegmentation_b200 import TextSegmenter, results_io as rio
+    from multimodaltopicsegmentation_b200.predict import Predictor
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(21)
+    D, H, L = 192, 256, 2          # "ecapa" embeddings
+    seg = TextSegmenter(2, D, H, num_layers=L, architecture="BiLSTM", loss_fn=loss_fn, threshold=0.5)
+    ckpt = tmp_path / "epoch=3-valid_loss=0.21-threshold=0.50.ckpt"
+    torch.save({"state_dict": seg.state_dict(), "epoch": 3}, ckpt)
+    hyper = rio.write_results_txt(str(tmp_path), rio.summary_lines("exp", "ecapa", "BiLSTM", 8, H, 0.0, 0.0, L, "Adam",
+                                                                   {"Pk": 0.3, "F1": 0.4, "WD": 0.35}))
+    emb_dir = tmp_path / "emb"
+    emb_dir.mkdir()
+    g = np.random.default_rng(5)
+    for i, n in enumerate((40, 7, 133, 2, 64)):
+        np.save(emb_dir / f"file{i}.npy", g.standard_normal((n, 1, D)).astype(np.float32))   # extractor layout: squeezed at load
+
+    p = Predictor(hyper, str(ckpt), threshold=0.4, device=dev)
+    assert (p.encoder, p.architecture, p.th) == ("ecapa", "BiLSTM", 0.4)
+    results = p.predict(str(emb_dir), str(tmp_path / "run1"), batch_size=2)
+    assert len(results) == 3 and [len(r) for r in results] == [2, 2, 1]
+    with pytest.raises(AssertionError):
+        p.predict(str(emb_dir), str(tmp_path / "run1"))
+    with pytest.raises(NotImplementedError):
+        p.predict(str(emb_dir), str(tmp_path / "run2"), write_audio_segments=True)
+
+    th = 0.4 if loss_fn == "BinaryCrossEntropy" else 0.5
+    ref = rt.Segmenter(2, D, H, num_layers=L, loss_fn=loss_fn, threshold=th)
+    ref.load_state_dict({k[len("model."):]: v for k, v in seg.state_dict().items()})
+    flat = [tags for batch in results for tags in batch]
+    skipped = 0
+    for name, tags in zip(p.file_names, flat):
+        x = torch.from_numpy(np.load(emb_dir / name).squeeze()).reshape(-1, D)[None]
+        n = x.shape[1]
+        with torch.no_grad():
+            s_ref, t_ref = ref(x, torch.tensor([n]))
+        prob = torch.sigmoid(s_ref)[0, :, 0] if loss_fn == "BinaryCrossEntropy" else torch.softmax(s_ref, -1)[0, :, 1]
+        assert len(tags) == n
+        for t in range(n):
+            if abs(float(prob[t]) - th) <= 1e-6:
+                skipped += 1
+            else:
+                assert bool(tags[t]) == bool(t_ref[0][t]), (name, t, float(prob[t]))
+    print(f"  {sum(len(t) for t in flat)} decisions over {len(flat)} files, {skipped} skipped as near-ties")
+
+    bad = tmp_path / "bad.txt"
+    rio.write_results_txt(str(tmp_path), rio.summary_lines("exp", "ecapa", "Transformer", 8, H, 0.0, 0.0, L, "Adam",
+                                                           {"Pk": 0.3, "F1": 0.4, "WD": 0.35}), name="bad.txt")
+    with pytest.raises(NotImplementedError):
+        Predictor(str(bad), str(ckpt), device=dev)

@@ -754,6 +754,87 @@ def test_transformer_training_vs_hf_twin(dev, xf_layout):
     assert checked >= 4 + 15 * nl + 2
 
 
+def test_transformer_hidden_dropout_training_vs_hf_twin(dev, xf_layout, monkeypatch):
+    """dropout_in > 0 (HF hidden_dropout_prob: after the embeddings LayerNorm and on both dense outputs that feed a
+    residual LayerNorm) under training: loss and every gradient against HF with the SAME keep-masks replayed on both
+    sides (RNG parity with torch's CPU generator is not a goal, mask placement and scaling are).  Also: eval ignores
+    the probability, and attention-probability dropout stays refused."""
+    from multimodaltopicsegmentation_b200 import transformer
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(31)
+    g = torch.Generator().manual_seed(32)
+    B, S, d, F, nl, nh, w, p = 3, 96, 64, 48, 3, 4, 8, 0.25
+    ref = rt.WindowedSegmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="FocalLoss", window_size=w, dropout_in=p).train()
+    ours = Transformer_segmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="FocalLoss", window_size=w, dropout_in=p)
+    missing, _ = ours.load_state_dict(ref.state_dict(), strict=False)
+    assert not missing, missing
+    ours = ours.to(dev).train()
+    x = torch.randn(B, S, d, generator=g)
+    lengths = torch.tensor([96, 40, 7])
+    y = (torch.rand(B, S, generator=g) < 0.2).float()
+    keep = [(torch.rand(B, S, d, generator=g) >= p) for _ in range(1 + 2 * nl)]
+
+    class Replay(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, t):
+            assert t.shape == self.m.shape
+            return t * self.m / (1.0 - p)
+
+    hf = ref.model.model
+    assert isinstance(hf.embeddings.dropout, torch.nn.Dropout) and hf.embeddings.dropout.p == p
+    hf.embeddings.dropout = Replay(keep[0])
+    for l, lyr in enumerate(hf.encoder.layer):
+        assert lyr.attention.output.dropout.p == p and lyr.output.dropout.p == p
+        lyr.attention.output.dropout = Replay(keep[1 + 2 * l])
+        lyr.output.dropout = Replay(keep[2 + 2 * l])
+    used = []
+
+    def replay(site, rows, width, prob, device):
+        assert prob == p and width == d
+        m = keep[site]
+        m = torch.cat([m[b, :n] for b, n in enumerate(lengths.tolist())]) if xf_layout == "ragged" else m.reshape(B * S, d)
+        assert m.shape[0] == rows
+        used.append(site)
+        return m.to(device)
+
+    monkeypatch.setattr(transformer, "DROPOUT_MASK_FN", replay)
+    l_ref = ref.loss(x, lengths, y)
+    l_ref.backward()
+    l = ours.loss(x.to(dev), lengths, y.to(dev))
+    l.backward()
+    assert used == list(range(1 + 2 * nl))
+    close(l, l_ref)
+    ref_named = dict(ref.named_parameters())
+    checked = 0
+    for k, prm in ours.named_parameters():
+        r = ref_named[k].grad
+        if r is None or float(r.abs().max()) == 0.0:
+            continue
+        if k.endswith("attention.self.key.bias"):
+            assert float(prm.grad.abs().max()) < 1e-9 and float(r.abs().max()) < 1e-9
+            continue
+        close(prm.grad, r, rtol=2e-4, atol=1e-4 * float(r.abs().max()), msg=k)
+        checked += 1
+    assert checked >= 4 + 15 * nl + 2
+
+    # the default generator path: a different mask every call, same expectation scale; eval is dropout-free
+    monkeypatch.setattr(transformer, "DROPOUT_MASK_FN", None)
+    with torch.no_grad():
+        a = ours.model(x.to(dev), lengths)
+        b = ours.model(x.to(dev), lengths)
+        assert not torch.equal(a, b)
+        ours.eval()
+        c = ours.model(x.to(dev), lengths)
+        assert torch.equal(c, ours.model(x.to(dev), lengths))
+    with pytest.raises(NotImplementedError):
+        Transformer_segmenter(2, d, F, num_layers=1, nheads=nh, window_size=w, dropout_out=0.1).to(dev).train().model(x.to(dev), lengths)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # tensor-core recurrence (tcgen05, W_hh in tensor memory) against the exact-fp32 FMA kernel and float64
 # ----------------------------------------------------------------------------------------------------------

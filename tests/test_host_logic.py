@@ -166,3 +166,77 @@ def test_reference_mask_loop_equals_vectorised_mask():
     m = rt.reference_mask_loop(12, lengths)
     assert m.shape == (4, 12) and m.dtype == torch.int64
     assert torch.equal(m.bool(), rt.length_mask(12, lengths))
+
+
+def test_result_files_round_trip(tmp_path):
+    """results.txt / logs / all_results.json / all_scores.json in the reference's formats
+    (train_fit.py:399-412, 436-451, 583-624) and the hyper-parameter parse predict.py:168-177 performs on the first."""
+    from multimodaltopicsegmentation_b200 import results_io as rio
+
+    best = {"Pk": 0.25, "F1": 0.5, "WD": 0.375}
+    lines = rio.summary_lines("exp1", "x-vectors", "BiLSTM", 64, 256, 0.2, 0.1, 2, "Adam", best)
+    path = rio.write_results_txt(str(tmp_path), lines)
+    text = open(path).read()
+    assert text == ("\nResults for experiment exp1 with following parameters:\n\nSentence encoder: x-vectors\n"
+                    "\nNeural architecture: BiLSTM\n\nBatch size: 64\n\nHidden units: 256\n\nDropout in: 0.2\n"
+                    "\nDropout out: 0.1\n\nNumber of layers: 2\n\nOptimizer: Adam\n\nMean Pk obtained is 0.25\n"
+                    "\nMean F1 obtained is 0.5\n\nMean WD obtained is 0.375\n")
+    hp = rio.read_hyperparameters(path)
+    assert (hp.encoder, hp.architecture, hp.hidden_units, hp.num_layers) == ("x-vectors", "BiLSTM", 256, 2)
+
+    conf = {"Pk": 0.01, "F1": 0.02, "WD": 0.03, "B": 0.04}
+    cv = rio.summary_lines("e", "enc", "Transformer", 8, 32, 0.0, 0.0, 1, "SGD", dict(best, B=0.7), confidence=conf, metric="B",
+                           zero_shot_labels=["a", "b"])
+    assert cv[9] == "Mean Precision obtained is 0.25 with a 95% confidence interval of +- 0.01"
+    assert cv[11] == "Mean Recall obtained is 0.375 with a 95% confidence interval of +- 0.03"
+    assert cv[12] == "Mean Boundary Similarity obtained is 0.7 with a 95% confidence interval of +- 0.04"
+    assert cv[13] == "Labels: ['a', 'b']"
+    with pytest.raises(ValueError):
+        rio.read_hyperparameters(rio.write_results_txt(str(tmp_path), cv[:3], name="short.txt"))
+
+    # the tuned metric travels as 'test_loss' (train_fit.py:375-397)
+    logged_f1 = {"Pk_loss": 0.2, "WD_loss": 0.3, "test_loss": 0.9, "threshold": 0.4}
+    logged_pk = {"F1_loss": 0.9, "WD_loss": 0.3, "test_loss": 0.2, "threshold": 0.4}
+    assert rio.fold_metrics(logged_f1, "F1") == rio.fold_metrics(logged_pk, "Pk") == {"Pk": 0.2, "WD": 0.3, "F1": 0.9}
+    rio.append_fold_log(str(tmp_path), 0, logged_f1, "F1")
+    rio.append_fold_log(str(tmp_path), 1, logged_pk, "Pk")
+    assert open(tmp_path / "logs").read() == ("Results for fold number 0\nPK score: 0.2\nWD score: 0.3\nF1 score: 0.9\n"
+                                              "Results for fold number 1\nPK score: 0.2\nWD score: 0.3\nF1 score: 0.9\n")
+    assert rio.read_fold_logs(str(tmp_path / "logs")) == [(0, {"PK": 0.2, "WD": 0.3, "F1": 0.9}), (1, {"PK": 0.2, "WD": 0.3, "F1": 0.9})]
+    rio.append_fold_log(str(tmp_path), 0, {"b_precision": 1.0, "b_recall": 0.5, "b_f1": 0.6, "test_loss": 0.4}, "B", name="logs_b")
+    assert open(tmp_path / "logs_b").read().splitlines()[1:] == ["B_precision score: 1.0", "B_recall score: 0.5", "B_F1 score: 0.6",
+                                                                 "B Similarity score: 0.4"]
+
+    files = [(None, None, "a.npy"), (None, None, "b.npy")]
+    per_file = [{"Pk_loss": 0.1, "WD_loss": 0.2, "test_loss": torch.tensor(0.5), "threshold": 0.4},
+                {"Pk_loss": 0.3, "WD_loss": 0.4, "test_loss": 0.25, "threshold": 0.4}]
+    scores = [np.array([0.5, 0.25], dtype=np.float32), torch.tensor([0.125])]
+    res, sc = rio.collect_per_file(files, per_file, scores, metric="F1")
+    assert res["a.npy"] == {"Pk_loss": 0.1, "WD_loss": 0.2, "threshold": 0.4, "F1": 0.5} and "test_loss" not in res["b.npy"]
+    rio.write_per_file_json(str(tmp_path), res, sc)
+    back_res, back_sc = rio.read_per_file_json(str(tmp_path))
+    assert back_res == res and back_sc == {"a.npy": [0.5, 0.25], "b.npy": [0.125]}
+
+
+def test_segment_ranges_and_encoder_table():
+    """Sample ranges of predict.py:105-127 (hand-worked cases) and the encoder -> width table of predict.py:184-216."""
+    from multimodaltopicsegmentation_b200.predict import encoder_embedding_dim, segment_ranges
+
+    # 5.5 s of audio at sr 10, 1-s units, boundaries after units 1 and 3: remainder appended as the last segment
+    assert segment_ranges(55, [0, 1, 0, 1, 0], sr=10) == [(0, 20), (20, 40), (40, 55)]
+    # fewer predictions than units: stops at the end of the predictions (the reference's IndexError branch)
+    assert segment_ranges(55, [1], sr=10) == [(0, 10), (10, 55)]
+    assert segment_ranges(55, [0, 0, 0, 0, 0], sr=10) == [(0, 55)]
+    assert segment_ranges(40, [0, 1, 0, 1], sr=10, interval=2) == [(0, 40), (40, 40)]
+    # adaptive: 100 chunks of n // 100 samples, no trailing remainder
+    seg = [0] * 100
+    seg[9] = seg[99] = 1
+    assert segment_ranges(1000, seg, adaptive=True) == [(0, 100), (100, 1000)]
+    with pytest.raises(IndexError):
+        segment_ranges(1000, [0] * 50, adaptive=True)
+    for name, dim in (("x-vectors", 512), ("ecapa", 192), ("wav2vec", 768), ("wav2vec_std", 1536), ("openl3_std", 1024),
+                      ("openl3", 512), ("crepe_std", 512), ("crepe", 256), ("mfcc", 200), ("prosodic", 167)):
+        assert encoder_embedding_dim(name) == dim
+    assert encoder_embedding_dim("anything", pca_reduce=True, pca_value=33) == 33
+    with pytest.raises(ValueError):
+        encoder_embedding_dim("roberta")
