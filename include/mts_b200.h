@@ -123,6 +123,13 @@ int mts_lstm_rec_fwd(const float *gx, const float *w_hh, const int32_t *lengths,
 int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
                         int B, int T, int H, float *y, float *gates, float *y_corr, void *stream);
 
+/* LongformerIntermediate (HF modeling_longformer.py:1103-1116: dense + GELU(erf)) when its output feeds the next dense
+ * layer: C [M,N] = gelu(A B^T + bias) in fp32 -- which is its own `hi` operand -- and C_lo [M,N] = the packed correction
+ * operand of C (A side), both written by the GEMM epilogue.  Replaces mts_gemm_tf32x3 + mts_gelu_split in inference
+ * (training keeps the pre-activation).  N % 32 == 0, Kp % 32 == 0, Kp <= 3072, rows of C and C_lo dense (stride N). */
+int mts_gemm_tf32x3_gelu_pair(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
+                              float *C, float *C_lo, int M, int N, int Kp, void *stream);
+
 /* ---- bf16 path (explicit precision switch; fp32 stays the default and the parity contract) -----------------------
  * The same kernels with bf16 operands on kind::f16 MMAs only: per product one bf16 x bf16 term instead of the
  * error-compensated TF32 + bf16 pair.  State, gates, accumulation and every output stay fp32.  Tolerances per kernel
@@ -249,7 +256,9 @@ int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *pos, const 
                      const float *beta, int B, int S, int d, float eps, float *y, float *y_hi, float *y_lo, int Kp,
                      float *sum_out, float *stats, const int32_t *lengths, const int32_t *offsets, void *stream);
 /* LongformerSelfOutput / LongformerOutput (:1060-1071, :1119-1130): y = LN(a + res); a is the dense output
- *   (bias already added by the GEMM epilogue).  sum_out may alias a. */
+ *   (bias already added by the GEMM epilogue).  sum_out may alias a.  res may be NULL: a then already holds the
+ *   sum (the dense layer accumulated onto the residual in its epilogue: mts_gemm_tf32x3 with accumulate = 1), which
+ *   spares this kernel one of its two input reads. */
 int mts_add_ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, int M, int d, float eps,
                    float *y, float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats, void *stream);
 /* LongformerIntermediate (:1103-1116) activation fused with the operand split: hi/lo [rows,Kp] of GELU(src);

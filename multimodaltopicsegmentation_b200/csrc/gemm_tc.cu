@@ -36,6 +36,7 @@ struct TcCfg {
   static constexpr int kBBytes = BN * TC_BK * 4;          // 16/32 KB per half
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kTmemCols = 2 * BN;                // two accumulator stages
+  static constexpr int kAccStride = BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 32 * 4 /*epilogue*/;
 };
 
@@ -161,21 +162,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 constexpr int TC_EPI_STAGE_BYTES = 4 * 32 * 32 * 4;  // 4 epilogue warps x (32 rows x 32 fp32)
 
 template <int BN>
-__device__ __forceinline__ void tc_store_tile(uint32_t tmem_base, int acc_stage, int q, int lane, int m0, int n0, int sp,
+__device__ __forceinline__ void tc_store_tile(uint32_t tmem_base, int acc_col, int q, int lane, int m0, int n0, int sp,
                                               const float *__restrict__ bias, float *__restrict__ C, int M, int N,
-                                              int64_t ldc, int epilogue, int accumulate, int splits, float4 *stg) {
+                                              int64_t ldc, int epilogue, int accumulate, int splits, float4 *stg,
+                                              float *__restrict__ C_lo) {
   const int rsub = lane >> 3, ch = lane & 7;
   const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     if (n0 + c0 >= N) break;
+    const int n = n0 + c0 + 4 * ch;  // this lane's 4 columns, the same for all 8 row groups
+    const bool vec = vec_ok && (n + 4 <= N);
+    // accumulate: the 8 previous values of this lane are requested BEFORE the accumulator is read and transposed, all in
+    // flight together (a load -> add -> store chain per row made the epilogue longer than the main loop: measured 2x
+    // on the encoder's residual-folding GEMMs)
+    float4 prev[8];
+    const bool acc_vec = accumulate && splits == 1 && vec;
+    if (acc_vec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + q * 32 + 4 * i + rsub;
+        prev[i] = m < M ? *reinterpret_cast<const float4 *>(C + (int64_t)m * ldc + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     float v[32];
-    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN + c0), v);
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_col + c0), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
-    const int n = n0 + c0 + 4 * ch;  // this lane's 4 columns, the same for all 8 row groups
-    const bool vec = vec_ok && (n + 4 <= N);
     float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (epilogue >= 1 && sp == 0) {
 #pragma unroll
@@ -204,8 +218,11 @@ __device__ __forceinline__ void tc_store_tile(uint32_t tmem_base, int acc_stage,
           }
         } else if (vec) {
           float4 w = make_float4(o[0], o[1], o[2], o[3]);
-          if (accumulate) { const float4 p = *reinterpret_cast<const float4 *>(dst); w.x += p.x; w.y += p.y; w.z += p.z; w.w += p.w; }
+          if (accumulate) { const float4 p = prev[i]; w.x += p.x; w.y += p.y; w.z += p.z; w.w += p.w; }
           *reinterpret_cast<float4 *>(dst) = w;
+          // operand pair of the output for the next GEMM: C itself is `hi`, the packed correction operand goes to C_lo
+          // (same row stride; the launcher guarantees N % 32 == 0, so every row is whole 16-column blocks)
+          if (C_lo) corr_store4(C_lo + (int64_t)m * ldc, n, w, 0);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
@@ -233,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
-                       int epilogue, int accumulate, int splits, int bf16_only) {
+                       int epilogue, int accumulate, int splits, int bf16_only, float *__restrict__ C_lo) {
   using Cfg = TcCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -323,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (kb0 >= kb1) continue;  // empty trailing split: nothing to add (the epilogue skips it too)
         bar_wait(s_u32(&tempty_bar[acc_stage]), acc_phase ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * Cfg::kAccStride);
         for (int kb = kb0; kb < kb1; ++kb) {
           bar_wait(s_u32(&full_bar[stage]), phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int m0 = ((tile / tiles_n) * CL + (int)crank) * TC_BM, n0 = (tile % tiles_n) * BN;
       bar_wait(s_u32(&tfull_bar[acc_stage]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc_store_tile<BN>(tmem_base, acc_stage, q, lane, m0, n0, sp, bias, C, M, N, ldc, epilogue, accumulate, splits, stg);
+      tc_store_tile<BN>(tmem_base, acc_stage * BN, q, lane, m0, n0, sp, bias, C, M, N, ldc, epilogue, accumulate, splits, stg, C_lo);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) bar_arrive(s_u32(&tempty_bar[acc_stage]));
@@ -382,14 +399,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 // (the cta_group::2 form of the TMA load), the leader's commits multicast to both CTAs' empty / accumulator-full
 // barriers, and all 8 epilogue warps of the pair arrive on the leader's accumulator-empty barrier.
 // ---------------------------------------------------------------------------------------------------------
+// BN2 = 224 serves widths that 256 pads badly (896 = 4 x 224, 2688 = 12 x 224: the encoder's d and 3d): an MMA's cost is
+// proportional to its N (accumulator read-modify-write), so a narrower tile costs nothing per useful column.
+template <int BN2>
 struct Tc2Cfg {
-  static constexpr int BN = 256;
+  static constexpr int BN = BN2;
+  static constexpr int kAccStride = 256;                    // accumulator stages at TMEM columns 0 and 256
   static constexpr int kStages = 3;
   static constexpr int kABytes = TC_BM * TC_BK * 4;         // 16 KB: my 128 A rows, raw fp32 (and as much packed bf16)
-  static constexpr int kBBytes = (BN / 2) * TC_BK * 4;      // 16 KB: my 128 of the 256 B rows
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 64 KB
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kBBytes = (BN / 2) * TC_BK * 4;      // 16 (14) KB: my half of the B rows
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 64 (60) KB, a multiple of 1024 (swizzle atoms)
+  static constexpr int kTmemCols = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 4 * 32 * 32 * 4;
+  static_assert(BN % 32 == 0 && kBBytes % 1024 == 0, "B half tile must be whole swizzle atoms");
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -439,12 +461,13 @@ __device__ __forceinline__ bool bar_try_wait_cluster(uint32_t bar, uint32_t pari
   return ok != 0;
 }
 
+template <int BN2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_2sm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                            const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
-                           int epilogue, int accumulate, int splits, int bf16_only) {
-  using Cfg = Tc2Cfg;
+                           int epilogue, int accumulate, int splits, int bf16_only, float *__restrict__ C_lo) {
+  using Cfg = Tc2Cfg<BN2>;
   constexpr int BN = Cfg::BN, kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -524,7 +547,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         while (!bar_try_wait_cluster(s_u32(&tempty_bar[acc_stage]), acc_phase ^ 1)) {
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * Cfg::kAccStride);
         for (int kb = kb0; kb < kb1; ++kb) {
           bar_wait(s_u32(&full_bar[stage]), phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -557,7 +580,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const int m0 = ((tile / tiles_n) * 2 + (int)crank) * TC_BM, n0 = (tile % tiles_n) * BN;
       bar_wait(s_u32(&tfull_bar[acc_stage]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc_store_tile<BN>(tmem_base, acc_stage, q, lane, m0, n0, sp, bias, C, M, N, ldc, epilogue, accumulate, splits, stg);
+      tc_store_tile<BN>(tmem_base, acc_stage * Cfg::kAccStride, q, lane, m0, n0, sp, bias, C, M, N, ldc, epilogue, accumulate, splits,
+                        stg, C_lo);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) bar_arrive_cluster(mapa_u32(s_u32(&tempty_bar[acc_stage]), 0));
@@ -617,9 +641,9 @@ __global__ void __launch_bounds__(256) zero_matrix_kernel(float *__restrict__ C,
 template <int BN>
 static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
                      float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, cudaStream_t st,
-                     int bf16_only = 0) {
+                     int bf16_only = 0, float *C_lo = nullptr) {
   using Cfg = TcCfg<BN>;
-  const int tiles_m1 = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
+  const int tiles_m1 = (M + TC_BM - 1) / TC_BM;
   // clusters of 2 (B tile multicast) whenever there are at least two row tiles; MTS_GEMM_CLUSTER=1 keeps single CTAs
   static const char *force = getenv("MTS_GEMM_CLUSTER");
   int CL = tiles_m1 >= 2 ? 2 : 1;
@@ -631,17 +655,25 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
   static const char *two = getenv("MTS_GEMM_2SM");
   const bool use_2sm = BN == 256 && tiles_m1 >= 2 && !(two && atoi(two) == 0);
   if (use_2sm) CL = 2;
+  // tile width of the 2-SM kernel: 224 when it pads N less than 256 does (MTS_GEMM_BN2=256 keeps the wide tile)
+  static const char *bn2_env = getenv("MTS_GEMM_BN2");
+  int bn = BN;
+  if (use_2sm && !(bn2_env && atoi(bn2_env) == 256) && N % 256 != 0 && (N + 223) / 224 == (N + 255) / 256)
+    bn = 224;  // same number of column tiles, less padding (N = 896: 4 x 224).  More, narrower tiles were measured SLOWER
+               // (N = 2688 as 12 x 224: 1.81 vs 1.77 ms) -- every extra column tile re-reads A, and the kernel sits on the L2 cap
+  const int tiles_n = (N + bn - 1) / bn;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if ((rc = make_map(&ma_hi, A_hi, M, Kp, TC_BM))) return rc;
   if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM, true))) return rc;
-  if ((rc = make_map(&mb_hi, B_hi, N, Kp, BN / CL))) return rc;
-  if ((rc = make_map(&mb_lo, B_lo, N, Kp, BN / CL, true))) return rc;
+  if ((rc = make_map(&mb_hi, B_hi, N, Kp, bn / CL))) return rc;
+  if ((rc = make_map(&mb_lo, B_lo, N, Kp, bn / CL, true))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::kSmemBytes));
+    MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_2sm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<256>::kSmemBytes));
+    MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_2sm_kernel<224>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<224>::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ((tiles_m1 + CL - 1) / CL) * tiles_n;  // cluster work items before the K split
@@ -652,7 +684,7 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
   // summed with round-to-nearest atomics keep the product inside the 2e-5 contract at any K.
   int splits = 1;
   const int num_kb = Kp / TC_BK;
-  if (epilogue != 2) {
+  if (epilogue != 2 && !C_lo) {
     if (tiles * 2 <= slots && num_kb >= 32) {
       splits = slots / tiles;
       if (splits > num_kb / 8) splits = num_kb / 8;
@@ -680,16 +712,22 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   if (use_2sm) {
-    cfg.dynamicSmemBytes = Tc2Cfg::kSmemBytes;
     cfg.numAttrs = 0;  // the cluster shape is compiled into the kernel
-    MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_2sm_kernel, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits, bf16_only));
+    if (bn == 224) {
+      cfg.dynamicSmemBytes = Tc2Cfg<224>::kSmemBytes;
+      MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_2sm_kernel<224>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
+                                  accumulate, splits, bf16_only, C_lo));
+    } else {
+      cfg.dynamicSmemBytes = Tc2Cfg<256>::kSmemBytes;
+      MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_2sm_kernel<256>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
+                                  accumulate, splits, bf16_only, C_lo));
+    }
   } else if (CL == 2) {
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits, bf16_only));
+                                accumulate, splits, bf16_only, C_lo));
   } else {
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 1>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits, bf16_only));
+                                accumulate, splits, bf16_only, C_lo));
   }
   MTS_LAUNCH_CHECK();
   return 0;
@@ -711,6 +749,22 @@ extern "C" int mts_gemm_tf32x3(const float *A_hi, const float *A_lo, const float
   cudaStream_t st = (cudaStream_t)stream;
   if (N >= 256) return launch_tc<256>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st);
   return launch_tc<128>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st);
+}
+
+// Dense layer + GELU(erf) whose output feeds another mts_gemm_tf32x3: C = gelu(A B^T + bias) as fp32 [M, N] (which is
+// its own `hi` operand) and C_lo [M, N] = the packed correction operand of C (A side), written by the same epilogue --
+// replaces GEMM -> mts_gelu_split (one pass over the activation less).  N % 32 == 0, ldc == N, no K split.
+extern "C" int mts_gemm_tf32x3_gelu_pair(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo,
+                                         const float *bias, float *C, float *C_lo, int M, int N, int Kp, void *stream) {
+  MTS_REQUIRE(A_hi && A_lo && B_hi && B_lo && bias && C && C_lo, MTS_E_BADARG, "gemm_tf32x3_gelu_pair: null pointer");
+  MTS_REQUIRE(M > 0 && N > 0 && Kp > 0, MTS_E_BADARG, "gemm_tf32x3_gelu_pair: empty shape");
+  MTS_REQUIRE(Kp % TC_BK == 0 && N % 32 == 0, MTS_E_UNSUPPORTED, "gemm_tf32x3_gelu_pair: Kp and N must be multiples of 32");
+  MTS_REQUIRE(Kp <= 3072, MTS_E_UNSUPPORTED, "gemm_tf32x3_gelu_pair: K beyond 3072 needs the split-K path (no fused activation)");
+  MTS_REQUIRE((((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C | (uintptr_t)C_lo) & 15) == 0,
+              MTS_E_BADARG, "gemm_tf32x3_gelu_pair: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N >= 256) return launch_tc<256>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, N, 2, 0, st, 0, C_lo);
+  return launch_tc<128>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, N, 2, 0, st, 0, C_lo);
 }
 
 // bf16 path (explicit precision switch, tolerance stated per kernel in DESIGN.md): C = bf16(A) bf16(B)^T (+ bf16(rest A)

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
       pb = reinterpret_cast<const float4 *>(b + (int64_t)(t + 2) * d);
     } else {
       pa = reinterpret_cast<const float4 *>(a + (int64_t)row * d);
-      pb = reinterpret_cast<const float4 *>(b + (int64_t)row * d);
+      pb = b ? reinterpret_cast<const float4 *>(b + (int64_t)row * d) : nullptr;  // null: `a` already holds the sum
     }
     // float4 column of register i: lanes own PAIRS of adjacent float4 (8 consecutive elements), so that the packed
     // correction operand goes out in 16-byte pieces (corr_store8)
@@ -64,8 +64,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
       const int c = LN_COL(i);
       if (c < nv) {
         float4 x = __ldg(pa + c);
-        const float4 r = __ldg(pb + c);
-        x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+        if (MODE == 0 || pb) {
+          const float4 r = __ldg(pb + c);
+          x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+        }
         if (MODE == 0) {
           const float4 e = __ldg(reinterpret_cast<const float4 *>(typ) + c);
           x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
@@ -663,7 +665,7 @@ extern "C" int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *
 extern "C" int mts_add_ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, int M, int d,
                               float eps, float *y, float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats,
                               void *stream) {
-  MTS_REQUIRE(a && res && gamma && beta && y, MTS_E_BADARG, "add_ln_fwd: null pointer");
+  MTS_REQUIRE(a && gamma && beta && y, MTS_E_BADARG, "add_ln_fwd: null pointer");  // res may be null: a = the sum
   int rc = ln_args_ok("add_ln_fwd", M, d, y_hi, y_lo, Kp);
   if (rc) return rc;
   const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);

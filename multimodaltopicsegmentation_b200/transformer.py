@@ -202,6 +202,10 @@ def _ln(mode, a, b, typ, gamma, beta, B, S, d, want_split, save, lens=None):
 # [B*S] layout.  Valid positions come out identical either way (padded keys are masked); with the ragged layout the
 # padded positions of the returned hidden state are exact zeros instead of the reference's don't-care values.
 LAYOUT = __import__("os").environ.get("MTS_XF_LAYOUT", "ragged")
+# Folding the residual adds into the dense layers' epilogues (LayerNorm then reads one tensor instead of two) is
+# bit-identical but NOT faster: measured at configs[2] LayerNorm 5.05 -> 4.46 ms, GEMMs 17.0 -> 17.9 ms per step -- the
+# GEMM sits on the L2 throughput cap, so the residual read costs there what it saves here.  Off by default.
+FOLD_RESIDUAL = __import__("os").environ.get("MTS_XF_FOLD", "0") == "1"
 
 
 # Keep-masks of the hidden-state dropout: callable (site, rows, d, p, device) -> bool/uint8/float [rows, d].
@@ -248,6 +252,9 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hid
         if _pad32(d) == d:
             h_hi = h
     saved = {"emb": (pre0, st0), "layers": [], "ragged": ragged, "masks": masks, "p_hidden": p_hidden}
+    # Optional (MTS_XF_FOLD=1), inference only: the two residual adds folded into the dense layers' epilogues
+    # (accumulate onto the residual, which is dead as an operand by then) -- bit-identical sums, see FOLD_RESIDUAL.
+    fold = FOLD_RESIDUAL and not save and p_hidden == 0 and _pad32(d) == d
     for l, ent in enumerate(layers):
         lyr = m.encoder.layer[l]
         F = lyr.intermediate.dense.out_features
@@ -268,26 +275,39 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hid
             _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), offs, B, S, nheads, hd, reaches[l], _ptr(a), 0, 0,
                   0, _ptr(lse), _stream())
             _call("mts_split_tf32", _ptr(a), d, M, d, kp, ops.A_SIDE, _ptr(a_hi), _ptr(a_lo), _stream())
-        t = torch.empty((M, d), device=dev, dtype=torch.float32)
-        ops.gemm_tf32x3(a_hi, a_lo, ent["wo"][0], ent["wo"][1], ent["bo"], t, M, d, epilogue=1)
-        if p_hidden > 0:
-            _drop(t, 1 + 2 * l, p_hidden, masks)
         ln1 = lyr.attention.output.LayerNorm
-        y, y_hi, y_lo, pre1, st1 = _ln(1, t, h, None, ln1.weight.detach(), ln1.bias.detach(), M, 1, d, True, save)
-        zp = torch.empty((M, F), device=dev, dtype=torch.float32)
-        ops.gemm_tf32x3(y_hi, y_lo, ent["w1"][0], ent["w1"][1], ent["b1"], zp, M, F, epilogue=1)
+        if fold:  # t + h formed by the GEMM epilogue, in h (its operand role ended with the QKV product)
+            ops.gemm_tf32x3(a_hi, a_lo, ent["wo"][0], ent["wo"][1], ent["bo"], h, M, d, epilogue=1, accumulate=True)
+            y, y_hi, y_lo, pre1, st1 = _ln(1, h, None, None, ln1.weight.detach(), ln1.bias.detach(), M, 1, d, True, False)
+        else:
+            t = torch.empty((M, d), device=dev, dtype=torch.float32)
+            ops.gemm_tf32x3(a_hi, a_lo, ent["wo"][0], ent["wo"][1], ent["bo"], t, M, d, epilogue=1)
+            if p_hidden > 0:
+                _drop(t, 1 + 2 * l, p_hidden, masks)
+            y, y_hi, y_lo, pre1, st1 = _ln(1, t, h, None, ln1.weight.detach(), ln1.bias.detach(), M, 1, d, True, save)
         kf = _pad32(F)
         z_hl = torch.empty((2, M, kf), device=dev, dtype=torch.float32)
-        z = torch.empty((M, F), device=dev, dtype=torch.float32) if save else None
-        _call("mts_gelu_split", _ptr(zp), F, M, F, kf, _ptr(z), _ptr(z_hl[0]), _ptr(z_hl[1]), _stream())
-        u = torch.empty((M, d), device=dev, dtype=torch.float32)
-        ops.gemm_tf32x3(z_hl[0], z_hl[1], ent["w2"][0], ent["w2"][1], ent["b2"], u, M, d, epilogue=1)
-        if p_hidden > 0:
-            _drop(u, 2 + 2 * l, p_hidden, masks)
+        if not save and kf == F and y_hi.shape[1] <= 3072:  # inference: GELU and the operand pair of z in the GEMM epilogue
+            zp = z = None
+            _call("mts_gemm_tf32x3_gelu_pair", _ptr(y_hi), _ptr(y_lo), _ptr(ent["w1"][0]), _ptr(ent["w1"][1]), _ptr(ent["b1"]),
+                  _ptr(z_hl[0]), _ptr(z_hl[1]), M, F, y_hi.shape[1], _stream())
+        else:
+            zp = torch.empty((M, F), device=dev, dtype=torch.float32)
+            ops.gemm_tf32x3(y_hi, y_lo, ent["w1"][0], ent["w1"][1], ent["b1"], zp, M, F, epilogue=1)
+            z = torch.empty((M, F), device=dev, dtype=torch.float32) if save else None
+            _call("mts_gelu_split", _ptr(zp), F, M, F, kf, _ptr(z), _ptr(z_hl[0]), _ptr(z_hl[1]), _stream())
         ln2 = lyr.output.LayerNorm
         h_in = h
         last = l == len(layers) - 1
-        h, h_hi, h_lo, pre2, st2 = _ln(1, u, y, None, ln2.weight.detach(), ln2.bias.detach(), M, 1, d, not last, save)
+        if fold:
+            ops.gemm_tf32x3(z_hl[0], z_hl[1], ent["w2"][0], ent["w2"][1], ent["b2"], y, M, d, epilogue=1, accumulate=True)
+            h, h_hi, h_lo, pre2, st2 = _ln(1, y, None, None, ln2.weight.detach(), ln2.bias.detach(), M, 1, d, not last, False)
+        else:
+            u = torch.empty((M, d), device=dev, dtype=torch.float32)
+            ops.gemm_tf32x3(z_hl[0], z_hl[1], ent["w2"][0], ent["w2"][1], ent["b2"], u, M, d, epilogue=1)
+            if p_hidden > 0:
+                _drop(u, 2 + 2 * l, p_hidden, masks)
+            h, h_hi, h_lo, pre2, st2 = _ln(1, u, y, None, ln2.weight.detach(), ln2.bias.detach(), M, 1, d, not last, save)
         if save:
             saved["layers"].append({"h_in": h_in, "qkv": qkv, "lse": lse, "a": a, "pre1": pre1, "st1": st1,
                                     "y": y, "zp": zp, "z": z, "pre2": pre2, "st2": st2})

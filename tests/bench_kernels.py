@@ -106,6 +106,21 @@ if __name__ == "__main__":
         a_hi, a_lo = ops.split_tf32(a); b_hi, b_lo = ops.split_tf32(b, side=ops.B_SIDE)
         ms = timeit(lambda: ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, c, M, N, epilogue=1))
         print(f"{M} x {N} x {K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s fp32-equivalent")
+    elif what == "xf_gemms":  # the four dense layers of a configs[2] encoder layer on its 135 428 valid tokens
+        M = 135428
+        tot = 0.0
+        for name, N, K in (("qkv", 2688, 896), ("out-proj", 896, 896), ("ffn1", 256, 896), ("ffn2", 896, 256)):
+            a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev) * 0.05; bias = torch.randn(N, device=dev)
+            c = torch.empty(M, N, device=dev)
+            a_hi, a_lo = ops.split_tf32(a); b_hi, b_lo = ops.split_tf32(b, side=ops.B_SIDE)
+            ms = timeit(lambda: ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, c, M, N, epilogue=1))
+            rows = torch.randint(0, M, (512,), device=dev)
+            rows[0], rows[1] = M - 1, 0
+            ref = a[rows].double() @ b.double().t() + bias.double()
+            err = float((c[rows].double() - ref).abs().max() / ref.abs().max())
+            tot += ms
+            print(f"{name:9s} {M} x {N} x {K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s fp32-equivalent  norm-wise err {err:.2e}")
+        print(f"sum per layer {tot:.3f} ms, x 6 layers = {6 * tot:.2f} ms")
     elif what == "gemm_one":
         M, N, K = 19200, 2048, 896
         a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)

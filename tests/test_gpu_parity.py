@@ -114,6 +114,34 @@ def test_gemm_tf32x3(dev, M, N, K):
         close(c3, torch.nn.functional.gelu(ref).float(), rtol=1e-5, atol=2e-5 * scale)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 256, 896), (1000, 64, 96), (135, 896, 256), (4100, 512, 128)])
+def test_gemm_gelu_pair_epilogue_equals_gemm_then_gelu_split(dev, M, N, K):
+    """mts_gemm_tf32x3_gelu_pair (dense + GELU + operand pair in one epilogue) against the two-kernel form it replaces in
+    inference: bit-identical activation and correction operand."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev, generator=g)
+    b = torch.randn(N, K, device=dev, generator=g) * 0.1
+    bias = torch.randn(N, device=dev, generator=g)
+    a_hi, a_lo = ops.split_tf32(a)
+    b_hi, b_lo = ops.split_tf32(b, side=ops.B_SIDE)
+    zp = torch.empty(M, N, device=dev)
+    ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, zp, M, N, epilogue=1)
+    two = torch.full((2, M, N), float("nan"), device=dev)
+    ops._call("mts_gelu_split", zp.data_ptr(), N, M, N, N, 0, two[0].data_ptr(), two[1].data_ptr(), ops._stream())
+    one = torch.full((2, M, N), float("nan"), device=dev)
+    ops._call("mts_gemm_tf32x3_gelu_pair", a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), bias.data_ptr(),
+              one[0].data_ptr(), one[1].data_ptr(), M, N, a_hi.shape[1], ops._stream())
+    assert torch.equal(one[0], two[0])
+    assert torch.equal(one[1].view(torch.int32), two[1].view(torch.int32))
+    check_operand_pair(one[0], one[1], one[0], side=0)
+    from multimodaltopicsegmentation_b200 import _lib
+    with pytest.raises(_lib.MtsError):
+        ops._call("mts_gemm_tf32x3_gelu_pair", a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), bias.data_ptr(),
+                  one[0].data_ptr(), one[1].data_ptr(), M, N - 8, a_hi.shape[1], ops._stream())
+
+
 @pytest.mark.parametrize("rows,cols,T,shift", [(100, 40, 100, 0), (3 * 37, 65, 37, -1), (3 * 37, 65, 37, 1), (2048, 896, 2048, 0)])
 def test_transpose_split(dev, rows, cols, T, shift):
     from multimodaltopicsegmentation_b200 import ops
@@ -752,6 +780,28 @@ def test_transformer_training_vs_hf_twin(dev, xf_layout):
         close(p.grad, r, rtol=2e-4, atol=1e-4 * float(r.abs().max()), msg=k)
         checked += 1
     assert checked >= 4 + 15 * nl + 2
+
+
+def test_transformer_inference_fusions_are_bit_identical(dev, xf_layout, monkeypatch):
+    """Inference puts the GELU + operand split into the FFN1 epilogue and can fold the residual adds into the dense layers'
+    epilogues (MTS_XF_FOLD=1; LayerNorm then reads one tensor); training keeps the separate tensors.  Same arithmetic in the same order:
+    the hidden states must agree bit for bit with the unfused inference path and with the training-mode forward."""
+    from multimodaltopicsegmentation_b200 import ops, transformer
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+
+    torch.manual_seed(5)
+    B, S, d, F, nl, nh, w = 4, 120, 64, 96, 3, 4, 8
+    m = Transformer_segmenter(2, d, F, num_layers=nl, nheads=nh, loss_fn="FocalLoss", window_size=w).to(dev).eval()
+    x = torch.randn(B, S, d, device=dev)
+    lengths = torch.tensor([120, 64, 1, 33])
+    with torch.no_grad():
+        monkeypatch.setattr(transformer, "FOLD_RESIDUAL", True)
+        fused = m.model(x, lengths)
+        monkeypatch.setattr(transformer, "FOLD_RESIDUAL", False)
+        unfolded = m.model(x, lengths)
+    saved = transformer.encoder_forward(x, ops.Lengths(lengths, dev, S), m.model.packed(), nh, m.model.reaches, save=True)[0]
+    assert torch.equal(fused, unfolded)
+    assert torch.equal(fused, saved)
 
 
 def test_transformer_hidden_dropout_training_vs_hf_twin(dev, xf_layout, monkeypatch):
