@@ -43,6 +43,8 @@ ALGO_BYTES_PER_SENTENCE_REC = 10240  # read gx 8 H x 4 B
 # profiles/r01_ncu_summary.md: 159.46 MB read + 25.64 MB written (algorithmic: 157.3 MB gx in + 39.3 MB h out; part of
 # the output is still in L2 when the kernel ends)
 NCU_REC_DRAM_BYTES = 159459840 + 25640448
+# the same for lstm_fwd_h3_kernel (profiles/r02_ncu_summary.md); None until captured
+NCU_REC_H3_DRAM_BYTES = None
 
 
 def synth(seed, B, T, D1, D2, ragged=False):
@@ -273,7 +275,8 @@ def rec_roofline(prof, n_sent, note=None):
     ms = sum(prof[name]) / len(prof[name])
     nbytes = n_sent * ALGO_BYTES_PER_SENTENCE_REC
     achieved = nbytes / (ms / 1e3) / 1e9
-    out = {"kernel": ("lstm_fwd_tc_kernel" if name.endswith("_tc") else "lstm_fwd_cluster_kernel") + " (one launch per layer, both directions)",
+    tc_kernel = "lstm_fwd_tc_kernel" if os.environ.get("MTS_REC_TC", "").startswith("t") else "lstm_fwd_h3_kernel"
+    out = {"kernel": (tc_kernel if name.endswith("_tc") else "lstm_fwd_cluster_kernel") + " (one launch per layer, both directions)",
            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
            "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": ms}
     if note:
@@ -1007,9 +1010,10 @@ def run_ours(args, rank, world, local_rank):
     roof = rec_roofline(prof_lists, n_sent_step,
                         "latency-bound at 64 episodes per GPU (T serial steps; per step: tcgen05 MMAs, DSMEM all-gather of h, "
                         "gate epilogue): see DESIGN.md section 4; `saturating` = the batch at which the fraction stops growing")
-    roof["traffic"] = NCU_REC_DRAM_BYTES if roof["kernel"].startswith("lstm_fwd_tc") else None
-    roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one lstm_fwd_tc_kernel launch at this shape, "
-                              "ncu --set full (profiles/r01_ncu_summary.md)")
+    roof["traffic"] = (NCU_REC_DRAM_BYTES if roof["kernel"].startswith("lstm_fwd_tc")
+                       else NCU_REC_H3_DRAM_BYTES if roof["kernel"].startswith("lstm_fwd_h3") else None)
+    roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, ncu --set full "
+                              "(profiles/r01_ncu_summary.md for lstm_fwd_tc_kernel, profiles/r02_ncu_summary.md for lstm_fwd_h3_kernel)")
     if "saturating" in results:
         sat = results.pop("saturating")
         roof["saturating"] = sat
@@ -1037,7 +1041,8 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "per_gpu_batch": c["B"], "global_batch": c["B"] * world,
                    "l2": "4 rotating input sets (275 MB) exceed the 126 MB L2", "gemm": "tcgen05 TF32 + bf16 correction",
                    "launch": f"one CUDA graph per input set ({launches_per_step} kernels)" if graphs is not None else "eager launches",
-                   "recurrence": "tcgen05 TF32 + bf16 correction, W_hh resident in TMEM" if roof["kernel"].startswith("lstm_fwd_tc") else "packed-fp32 FMA",
+                   "recurrence": ("tcgen05 fp16-split operands (3 kind::f16 products), W_hh resident in TMEM" if roof["kernel"].startswith("lstm_fwd_h3")
+                                  else "tcgen05 TF32 + bf16 correction, W_hh resident in TMEM" if roof["kernel"].startswith("lstm_fwd_tc") else "packed-fp32 FMA"),
                    "parallelism": (f"dp{world} (episodes sharded, no collective inside the step, ONE all_gather of the tags after "
                                    "the last step, inside the timed region)") if world > 1 else "single GPU",
                    "numa_node_of_rank0": numa},

@@ -115,13 +115,17 @@ int mts_colsum(const float *X, int64_t ld, int M, int N, float *out, int accumul
 int mts_lstm_rec_fwd(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
                      int B, int T, int H, float *y, float *gates, void *stream);
 
-/* The same recurrence on the tensor cores (H == 256 only): W_hh split for 3xTF32 and kept on chip for the whole
- * sequence (hi half in shared memory, lo half in tensor memory), tiles of 16 episodes per 8-CTA cluster,
- * tcgen05.mma per step, h exchanged through distributed shared memory.  Same arguments and results (to fp32
- * rounding) as mts_lstm_rec_fwd, plus y_corr [B*T, 2H] or NULL (n_enc == 1 only): the packed bf16 correction operand
- * of y (A side), so that the next layer's input projection reads (y, y_corr) directly -- no split pass. */
+/* The same recurrence on the tensor cores (H == 256 only): W_hh kept on chip (tensor memory) for the whole sequence,
+ * tiles of up to 16 episodes per 8-CTA cluster, tcgen05.mma per step, h exchanged through distributed shared memory.
+ * Same arguments and results (to fp32 rounding) as mts_lstm_rec_fwd, plus y_corr [B*T, 2H] or NULL (n_enc == 1 only):
+ * the packed bf16 correction operand of y (A side), so that the next layer's input projection reads (y, y_corr)
+ * directly -- no split pass.  Two formulations exist: the default is the fp16-split kernel (mts_lstm_rec_fwd_h3 below,
+ * 48 MMAs per step); MTS_REC_TC=tf32 in the environment selects mts_lstm_rec_fwd_tf32 (one TF32 product + one bf16
+ * correction product, 64 MMAs per step, csrc/lstm_rec_tc.cu). */
 int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
                         int B, int T, int H, float *y, float *gates, float *y_corr, void *stream);
+int mts_lstm_rec_fwd_tf32(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
+                          int B, int T, int H, float *y, float *gates, float *y_corr, void *stream);
 
 /* LongformerIntermediate (HF modeling_longformer.py:1103-1116: dense + GELU(erf)) when its output feeds the next dense
  * layer: C [M,N] = gelu(A B^T + bias) in fp32 -- which is its own `hi` operand -- and C_lo [M,N] = the packed correction
@@ -134,8 +138,8 @@ int mts_gemm_tf32x3_gelu_pair(const float *A_hi, const float *A_lo, const float 
  * The same kernels with bf16 operands on kind::f16 MMAs only: per product one bf16 x bf16 term instead of the
  * error-compensated TF32 + bf16 pair.  State, gates, accumulation and every output stay fp32.  Tolerances per kernel
  * (measured against the fp32 oracle at T = 300 and T = 8192) are listed in DESIGN.md.
- *   mts_lstm_rec_fwd_tc_bf16 : nn.LSTM recurrence (NeuralArchitectures.py:113) with bf16(W_hh) bf16(h) products: 32 instead of
- *                              64 MMAs per step.  Same arguments as mts_lstm_rec_fwd_tc.
+ *   mts_lstm_rec_fwd_tc_bf16 : nn.LSTM recurrence (NeuralArchitectures.py:113) with bf16(W_hh) bf16(h) products: 16 instead of
+ *                              48 MMAs per step, half the h exchange.  Same arguments as mts_lstm_rec_fwd_tc.
  *   mts_gemm_bf16p           : C = A B^T (+ bias, epilogues as mts_gemm_tf32x3) from the PACKED operands alone: A_lo as every
  *                              producer writes it (side 0), B_lo = the weights packed with side 0 too.  The raw fp32 arrays
  *                              are not read: half the operand bytes, half the MMAs.
@@ -153,6 +157,16 @@ int mts_pack_rows_bf16in(const void *src1, int64_t bstride1, int D1, const void 
 /* Profiling hook of the tensor-core recurrence: installs (or, with NULL, removes) a device buffer of 4 x 12 int64
  * into which CTA 0 writes clock64() stamps of the phases of steps 8..11 (see csrc/lstm_rec_tc.cu). */
 int mts_debug_rec_profile(long long *buf);
+
+/* The tensor-core recurrence with fp16-split operands (csrc/lstm_rec_h3.cu; nn.LSTM at NeuralArchitectures.py:113-115).
+ * W_hh rows (scaled by an exact per-row power of two) and h are each written as two fp16 pieces; W h = W1 h1 + W2 h1 +
+ * W1 h2 runs as 48 kind::f16 MMAs per step (relative error ~2^-22), both W pieces resident in tensor memory, and the
+ * sender of h_t writes the fp16 pieces straight into the operand buffers of all 8 CTAs of the cluster -- the receivers
+ * derive nothing and issue the MMAs of a K-slot as soon as it lands.  Same arguments and results (to fp32 rounding) as
+ * mts_lstm_rec_fwd_tc; precision 0 = the fp32-parity path, 1 = one bf16 x bf16 product (the explicit bf16 path). */
+int mts_lstm_rec_fwd_h3(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
+                        int B, int T, int H, float *y, float *gates, float *y_corr, int precision, void *stream);
+int mts_debug_rec_profile_h3(long long *buf);
 
 /* Backward through time of the same layer.
  *   dy      [B, T, n_enc*2H]    gradient w.r.t. y (ignored at t >= len_b)

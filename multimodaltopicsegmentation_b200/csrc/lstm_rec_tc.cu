@@ -449,15 +449,26 @@ extern "C" int mts_debug_rec_profile(long long *buf) {
 static int rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc, int B, int T,
                       int H, float *y, float *gates, float *y_corr, void *stream, int bf16_mode);
 
-// tensor-core forward recurrence; same arguments as mts_lstm_rec_fwd, H must be 256
-extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order,
-                                   int n_enc, int B, int T, int H, float *y, float *gates, float *y_corr, void *stream) {
+// The tensor-core forward recurrence behind the public names: the fp16-split kernel (lstm_rec_h3.cu) unless the
+// environment asks for this file's TF32 + bf16 formulation (MTS_REC_TC=tf32), which also stays callable by its own name.
+static bool use_tf32_formulation() {
+  static const char *v = getenv("MTS_REC_TC");
+  return v && v[0] == 't';
+}
+extern "C" int mts_lstm_rec_fwd_tf32(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order,
+                                     int n_enc, int B, int T, int H, float *y, float *gates, float *y_corr, void *stream) {
   return rec_fwd_tc(gx, w_hh, lengths, order, n_enc, B, T, H, y, gates, y_corr, stream, 0);
 }
-// the bf16 path of the same kernel (explicit precision switch): bf16(W_hh) bf16(h) products only, fp32 state and gates
+extern "C" int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order,
+                                   int n_enc, int B, int T, int H, float *y, float *gates, float *y_corr, void *stream) {
+  if (use_tf32_formulation()) return rec_fwd_tc(gx, w_hh, lengths, order, n_enc, B, T, H, y, gates, y_corr, stream, 0);
+  return mts_lstm_rec_fwd_h3(gx, w_hh, lengths, order, n_enc, B, T, H, y, gates, y_corr, 0, stream);
+}
+// the bf16 path (explicit precision switch): one bf16(W_hh) bf16(h) product per step, fp32 state and gates
 extern "C" int mts_lstm_rec_fwd_tc_bf16(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order,
                                         int n_enc, int B, int T, int H, float *y, float *gates, float *y_corr, void *stream) {
-  return rec_fwd_tc(gx, w_hh, lengths, order, n_enc, B, T, H, y, gates, y_corr, stream, 1);
+  if (use_tf32_formulation()) return rec_fwd_tc(gx, w_hh, lengths, order, n_enc, B, T, H, y, gates, y_corr, stream, 1);
+  return mts_lstm_rec_fwd_h3(gx, w_hh, lengths, order, n_enc, B, T, H, y, gates, y_corr, 1, stream);
 }
 
 static int rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc, int B, int T,

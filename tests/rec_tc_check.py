@@ -12,6 +12,19 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multimodaltopicsegmentation_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
+# which tensor-core forward kernel the checks exercise: "mts_lstm_rec_fwd_tc" (TF32 + bf16 correction) or
+# "mts_lstm_rec_fwd_h3" (fp16-split operands)
+TC_NAME = os.environ.get("REC_TC_NAME", "mts_lstm_rec_fwd_h3")
+PROF_NAME = "mts_debug_rec_profile_h3" if TC_NAME.endswith("_h3") else "mts_debug_rec_profile"
+
+
+def _extra(name):
+    """trailing arguments between `gates` and the stream"""
+    if name.endswith("_h3"):
+        return (0, int(os.environ.get("REC_H3_PRECISION", "0")))          # y_corr, precision (+ debug bits)
+    if name.endswith("_tc"):
+        return (0,)            # y_corr
+    return ()
 
 
 def trunc_check():
@@ -58,21 +71,24 @@ def run(name, gx, whh, lens, B, T, H, n_enc, save):
     y = torch.full((B, T, n_enc * 2 * H), float("nan"), device=dev)
     gates = torch.full((n_enc, 2, B, T, 5, H), float("nan"), device=dev) if save else None
     ops._call(name, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T, H,
-              y.data_ptr(), 0 if gates is None else gates.data_ptr(), *((0,) if name.endswith("_tc") else ()), ops._stream())
+              y.data_ptr(), 0 if gates is None else gates.data_ptr(), *_extra(name), ops._stream())
     torch.cuda.synchronize()
     return y, gates
 
 
-def compare(B, T, lengths, n_enc=1, save=False, check64=False):
+def compare(B, T, lengths, n_enc=1, save=False, check64=False, mixed_rows=False):
     H = 256
     g = torch.Generator(device=dev).manual_seed(B * 1000 + T)
     gx = torch.randn((n_enc, B * T, 8 * H), device=dev, generator=g)
     whh = torch.randn((n_enc, 2, 4 * H, H), device=dev, generator=g) * 0.06
+    if mixed_rows:   # rows of very different magnitude (the fp16-split kernel scales every row by its own power of two)
+        whh = whh * (10.0 ** (torch.rand((n_enc, 2, 4 * H, 1), device=dev, generator=g) * 5.0 - 4.0))
+        whh[:, :, 5, :] = 0.0
     lens = ops.Lengths(lengths, dev, T)
     y_f, g_f = run("mts_lstm_rec_fwd", gx, whh, lens, B, T, H, n_enc, save)
-    y_t, g_t = run("mts_lstm_rec_fwd_tc", gx, whh, lens, B, T, H, n_enc, save)
+    y_t, g_t = run(TC_NAME, gx, whh, lens, B, T, H, n_enc, save)
     err = float((y_f - y_t).abs().max())
-    msg = f"B={B} T={T} n_enc={n_enc} save={save}: max |fma - tc| = {err:.3e}"
+    msg = f"B={B} T={T} n_enc={n_enc} save={save}{' mixed-rows' if mixed_rows else ''}: max |fma - tc| = {err:.3e}"
     ok = err < 2e-5 and not bool(torch.isnan(y_t).any())
     if save:
         valid = ~torch.isnan(g_f)
@@ -156,9 +172,9 @@ def sweep():
         lens = ops.Lengths([T] * B, dev, T)
         y = torch.empty((B, T, 2 * H), device=dev)
         call = lambda name: ops._call(name, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), 1,
-                                      B, T, H, y.data_ptr(), 0, *((0,) if name.endswith("_tc") else ()), ops._stream())
-        a = timeit(lambda: call("mts_lstm_rec_fwd"))
-        b = timeit(lambda: call("mts_lstm_rec_fwd_tc"))
+                                      B, T, H, y.data_ptr(), 0, *_extra(name), ops._stream())
+        a = timeit(lambda: call("mts_lstm_rec_fwd")) if B <= 256 else float("nan")
+        b = timeit(lambda: call(TC_NAME))
         print(f"{B:5d} {a:9.3f} ({a * 1e3 / T:6.2f}) {b:9.3f} ({b * 1e3 / T:6.2f}) {B * T * 10240 / b / 1e6:10.1f}", flush=True)
 
 
@@ -170,20 +186,24 @@ def timeline(B=16, T=40):
     whh = torch.randn((1, 2, 4 * H, H), device=dev, generator=g) * 0.05
     lens = ops.Lengths([T] * B, dev, T)
     y = torch.empty((B, T, 2 * H), device=dev)
-    buf = torch.zeros(4 * 12, dtype=torch.int64, device=dev)
-    call = lambda: ops._call("mts_lstm_rec_fwd_tc", gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
-                             lens.order.data_ptr(), 1, B, T, H, y.data_ptr(), 0, 0, ops._stream())
+    nsl = 16 if TC_NAME.endswith("_h3") else 12
+    buf = torch.zeros(4 * nsl, dtype=torch.int64, device=dev)
+    call = lambda: ops._call(TC_NAME, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
+                             lens.order.data_ptr(), 1, B, T, H, y.data_ptr(), 0, *_extra(TC_NAME), ops._stream())
     call(); call()
-    ops._call("mts_debug_rec_profile", buf.data_ptr())
+    ops._call(PROF_NAME, buf.data_ptr())
     call()
     torch.cuda.synchronize()
-    ops._call("mts_debug_rec_profile", 0)
-    st = buf.cpu().view(4, 12)
+    ops._call(PROF_NAME, 0)
+    st = buf.cpu().view(4, nsl)
     names = ["mma:start", "mma:h_full", "mma:hi issued", "mma:lo_ready", "mma:commit", "epi:start", "epi:h_full",
              "epi:lo done", "epi:acc_full", "epi:tmem ld", "epi:act+bar", "epi:sent"]
+    if TC_NAME.endswith("_h3"):
+        names = ["mma:start", "half0", "half1", "issued0", "issued1", "commit", "-", "-", "-", "-", "epi:acc_full", "tmem ld",
+                 "act+bar", "cell", "sent", "-"]
     t0 = int(st[0, 0])
     for i in range(4):
-        print(f"step {8 + i}: " + "  ".join(f"{n}={int(st[i, k]) - t0}" for k, n in enumerate(names)))
+        print(f"step {8 + i}: " + "  ".join(f"{n}={int(st[i, k]) - t0}" for k, n in enumerate(names) if n != "-"))
 
 
 if __name__ == "__main__":
@@ -197,6 +217,8 @@ if __name__ == "__main__":
         ok = compare(37, 61, [61] + [int(x) for x in torch.randint(1, 62, (36,))], save=True) and ok
         ok = compare(20, 33, [33] + [int(x) for x in torch.randint(1, 34, (19,))], n_enc=2, save=True) and ok
         ok = compare(300, 50, [50] * 300) and ok
+        ok = compare(16, 40, [40] * 16, check64=True, mixed_rows=True) and ok
+        ok = compare(70, 30, [30] * 70, check64=True) and ok
     if what in ("all", "bwd"):
         ok = compare_bwd(3, 5, [5, 3, 1]) and ok
         ok = compare_bwd(16, 40, [40] * 16) and ok
@@ -207,6 +229,7 @@ if __name__ == "__main__":
             sweep_bwd()
     if what in ("all", "timeline"):
         timeline()
+        timeline(B=10 * 7, T=40)   # cfg1-like: 10 episodes per tile
     if what in ("all", "sweep") and ok:
         sweep()
     sys.exit(0 if ok else 1)

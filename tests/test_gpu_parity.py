@@ -888,15 +888,19 @@ def test_transformer_hidden_dropout_training_vs_hf_twin(dev, xf_layout, monkeypa
 # ----------------------------------------------------------------------------------------------------------
 # tensor-core recurrence (tcgen05, W_hh in tensor memory) against the exact-fp32 FMA kernel and float64
 # ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("entry", ["mts_lstm_rec_fwd_tc", "mts_lstm_rec_fwd_tf32"])   # default = fp16-split kernel; TF32 + bf16 kernel
 @pytest.mark.parametrize("B,T,n_enc,save", [(3, 5, 1, False), (16, 40, 1, True), (37, 61, 1, True), (20, 33, 2, True),
-                                            (300, 50, 1, False)])
-def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save):
+                                            (300, 50, 1, False), (70, 30, 1, False), (1000, 9, 1, False)])
+def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save, entry):
     from multimodaltopicsegmentation_b200 import ops
 
     H = 256
     g = torch.Generator(device=dev).manual_seed(B * 1000 + T)
     gx = torch.randn((n_enc, B * T, 8 * H), device=dev, generator=g)
     whh = torch.randn((n_enc, 2, 4 * H, H), device=dev, generator=g) * 0.06
+    if B == 70:   # rows of very different magnitude, one zero row: the fp16-split kernel scales every row by its own power of two
+        whh = whh * (10.0 ** (torch.rand((n_enc, 2, 4 * H, 1), device=dev, generator=g) * 5.0 - 4.0))
+        whh[:, :, 5, :] = 0.0
     hg = torch.Generator().manual_seed(B + T)
     lengths = [T] + [int(v) for v in torch.randint(1, T + 1, (B - 1,), generator=hg)]
     lens = ops.Lengths(lengths, dev, T)
@@ -905,15 +909,15 @@ def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save):
         y = torch.full((B, T, n_enc * 2 * H), float("nan"), device=dev)
         gates = torch.full((n_enc, 2, B, T, 5, H), float("nan"), device=dev) if save else None
         ops._call(name, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T, H,
-                  y.data_ptr(), 0 if gates is None else gates.data_ptr(), *((0,) if name.endswith("_tc") else ()), ops._stream())
+                  y.data_ptr(), 0 if gates is None else gates.data_ptr(), *(() if name == "mts_lstm_rec_fwd" else (0,)), ops._stream())
         return y, gates
 
     y_f, g_f = run("mts_lstm_rec_fwd")
-    y_t, g_t = run("mts_lstm_rec_fwd_tc")
+    y_t, g_t = run(entry)
     if n_enc == 1:  # fused operand of the next layer's input projection: (y, y_corr) is a valid A-side operand pair
         y2 = torch.full((B, T, 2 * H), float("nan"), device=dev)
         corr = torch.full((B * T, 2 * H), float("nan"), device=dev)
-        ops._call("mts_lstm_rec_fwd_tc", gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H,
+        ops._call(entry, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H,
                   y2.data_ptr(), 0, corr.data_ptr(), ops._stream())
         assert torch.equal(y2, y_t)
         check_operand_pair(y2.view(B * T, 2 * H), corr, y2.view(B * T, 2 * H), side=0)
