@@ -43,8 +43,8 @@ ALGO_BYTES_PER_SENTENCE_REC = 10240  # read gx 8 H x 4 B
 # profiles/r01_ncu_summary.md: 159.46 MB read + 25.64 MB written (algorithmic: 157.3 MB gx in + 39.3 MB h out; part of
 # the output is still in L2 when the kernel ends)
 NCU_REC_DRAM_BYTES = 159459840 + 25640448
-# the same for lstm_fwd_h3_kernel (profiles/r02_ncu_summary.md); None until captured
-NCU_REC_H3_DRAM_BYTES = None
+# the same for lstm_fwd_h3_kernel (profiles/r02_ncu_summary.md, capture r02b): 159.63 MB read + 25.96 MB written
+NCU_REC_H3_DRAM_BYTES = 159627264 + 25957120
 
 
 def synth(seed, B, T, D1, D2, ragged=False):

@@ -11,5 +11,6 @@ from .load_datasets_precomputed import (ResidentDataset, cross_validation_split,
                                         load_dataset_from_precomputed)
 from .metrics import compute_Pk, compute_window_diff, get_boundaries  # noqa: F401
 from .modules import CRF, RNN, BiLSTM, BiLSTMLateFusion, BiLSTMLateFusionCrf, BiRnnCrf  # noqa: F401
+from .recurrent_longformer import RecurrentLongformer, RecurrentLongformerBlock  # noqa: F401
 
 __version__ = "0.1.0"

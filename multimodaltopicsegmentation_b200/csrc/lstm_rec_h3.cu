@@ -343,7 +343,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(HR_SUB_THREAD
     const float sg = __fdividef(1.0f, 1.0f + exp2f(z * zs));                  \
     act[(q * HR_NB + e) * 32 + lane] = fmaf(sg, oa, ob);                      \
   }
-        if (ept > 8) { HR_ACT(16) } else if (ept > 4) { HR_ACT(8) } else { HR_ACT(4) }
+        // fully unrolled over the columns in use (uniform choice): the MUFU pipe bounds this phase, its latency needs the
+        // independent chains (a branch per column group was measured 60 % slower)
+        if (ept > 14) { HR_ACT(16) } else if (ept > 12) { HR_ACT(14) } else if (ept > 10) { HR_ACT(12) } else if (ept > 8) { HR_ACT(10) }
+        else if (ept > 6) { HR_ACT(8) } else if (ept > 4) { HR_ACT(6) } else if (ept > 2) { HR_ACT(4) } else { HR_ACT(2) }
 #undef HR_ACT
         if (sub == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");

@@ -87,8 +87,14 @@ class TextSegmenter(_Base):
                                                loss_fn=loss_fn, positional_encoding=positional_encoding, nheads=nheads,
                                                threshold=threshold, alpha=alpha, gamma=gamma,
                                                window_size=attention_window)
+        elif architecture == "BiLSTMRestrictedMHA":   # lightning_model.py:215-216
+            from .recurrent_longformer import RecurrentLongformer
+
+            self.model = RecurrentLongformer(tagset_size, embedding_dim, hidden_dim, num_layers=num_layers, dropout_in=dropout_in,
+                                             dropout_out=dropout_out, batch_first=batch_first, loss_fn=loss_fn, nheads=nheads,
+                                             threshold=threshold, alpha=alpha, gamma=gamma, window_size=attention_window)
         else:
-            # SimpleBiLSTM, MLP, Transformer-CRF, RecurrentLongT5, BiLSTMRestrictedMHA, SwitchBiLSTM, SheikhBiLSTM:
+            # SimpleBiLSTM, MLP, Transformer-CRF, RecurrentLongT5, SwitchBiLSTM, SheikhBiLSTM:
             # outside the hot path this package accelerates
             raise ValueError("No other architectures implemented yet")
         self.learning_rate = lr

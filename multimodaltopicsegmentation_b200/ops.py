@@ -389,15 +389,16 @@ def bilstm_stack(x1, x2, xs2, lens, packed, n_enc):
     x1, x2, xs2 = (_rows_ok(x1, "input", lens.B, lens.T), _rows_ok(x2, "second input", lens.B, lens.T),
                    _rows_ok(xs2, "second encoder input", lens.B, lens.T))
     flat = packed.flat_params()
-    if not (torch.is_grad_enabled() and any(p.requires_grad for p in flat)):
+    if not (torch.is_grad_enabled() and (any(p.requires_grad for p in flat) or x1.requires_grad)):
         rnn0 = packed.rnns[0]
         return _lstm_stack_forward(x1, x2, xs2, lens, packed, rnn0.hidden_size, rnn0.num_layers, n_enc, save=False)[0]
     return BiLstmStackFn.apply(x1, x2, xs2, lens, packed, n_enc, *flat)
 
 
 class BiLstmStackFn(torch.autograd.Function):
-    """Differentiable (w.r.t. the LSTM parameters) bi-LSTM stack.  Inputs are data, so layer-0 dX is skipped
-    (SURVEY.md section 8a')."""
+    """Differentiable (w.r.t. the LSTM parameters) bi-LSTM stack.  Embedding inputs are data, so layer-0 dX is skipped
+    (SURVEY.md section 8a') -- unless the single input of an early-fusion stack itself requires a gradient (the stacked
+    blocks of RecurrentLongformer feed one block's attention output into the next block's LSTM)."""
 
     @staticmethod
     def forward(ctx, x1, x2, xs2, lens, packed, n_enc, *flat):
@@ -421,6 +422,7 @@ class BiLstmStackFn(torch.autograd.Function):
         dev = dy.device
         dy = dy.contiguous()
         grads = [[None] * (8 * L) for _ in range(n_enc)]
+        dx_in = None
         splits = max(1, min(16, N // 2048))
         tensor_core = GEMM_IMPL != "simt"
         ycols = n_enc * 2 * H
@@ -493,6 +495,19 @@ class BiLstmStackFn(torch.autograd.Function):
                         gemm_f32(dg.data_ptr() + 4 * d * 4 * H, 8 * H, yo.data_ptr() + 4 * (e * 2 * H + d * H),
                                  ycols, None, _ptr(dwhh[d]), H, 4 * H, H, N, layout=3, splits=splits, shift=shift,
                                  T=T, lengths=lens.dev)
+                if layer == 0 and ctx.needs_input_grad[0] and n_enc == 1 and ctx.x2 is None:
+                    # gradient to the stack's own input: dgx W_ih (same product as between layers)
+                    wcat = torch.cat([w_f.detach(), w_r.detach()], dim=0)
+                    dxt = torch.empty((N, D), device=dev, dtype=torch.float32)
+                    if tensor_core:
+                        wt = split_tf32(wcat.t().contiguous(), side=B_SIDE)
+                        dg_hl = split_tf32(dg)
+                        gemm_tf32x3(dg_hl[0], dg_hl[1], wt[0], wt[1], None, dxt, N, D)
+                    else:
+                        gemm_f32(_ptr(dg), 8 * H, _ptr(wcat), D, None, _ptr(dxt), D, N, D, 8 * H, layout=2)
+                    dx_in = dxt.view(B, T, D)
+                    if ctx.x1.shape[1] != T:
+                        dx_in = torch.nn.functional.pad(dx_in, (0, 0, 0, ctx.x1.shape[1] - T))
                 base = 8 * layer
                 g = grads[e]
                 g[base + 0], g[base + 1] = dwih[:4 * H], dwhh[0]
@@ -504,7 +519,7 @@ class BiLstmStackFn(torch.autograd.Function):
             dy = dy_next
         flat = [g for e in range(n_enc) for g in grads[e]]
         ctx.saved = None
-        return (None, None, None, None, None, None, *flat)
+        return (dx_in, None, None, None, None, None, *flat)
 
 
 # --------------------------------------------------------------------------------------------------------

@@ -12,6 +12,9 @@ autograd gradients come from the same library calls, arranged as the reference a
     LateFusion        <- models/CRF.py:371-479   (BiLSTMLateFusion)
     EncoderCRF        <- models/CRF.py:243-272   (BiRnnCrf, with the obviously intended wiring)
     WindowedSegmenter <- models/CRF.py:508-610 + models/RestrictedTransformerLayer.py:65-133
+    RecurrentLongformer <- models/CRF.py:636-684, 764-858 + the FFN-less layer of models/longformer_noffn.py (source-less:
+                         restated from the byte code of models/__pycache__/longformer_noffn.cpython-310.pyc; PARITY
+                         UNPINNED against the reference class itself, which cannot be imported)
 
 Parameter names and shapes are those of the reference state dict so golden
 parameters load with `load_state_dict`.  Pinned by tests/test_oracle_golden.py against
@@ -265,6 +268,107 @@ class WindowedSegmenter(_Head):
 
     def forward(self, xs, lengths, threshold=0.4):
         return self._decode(self.classification(self.model(xs, lengths)), lengths, threshold)
+
+
+class _Redirect(nn.Module):
+    """Stands in for `self.key` during one call: ignores the (already transposed) hidden states HF hands it and projects
+    the external input instead -- longformer_noffn's `key_vectors = self.key(external_input.transpose(0, 1))`."""
+
+    def __init__(self, linear, external):
+        super().__init__()
+        self.linear, self.external = linear, external
+
+    def forward(self, _hidden_states):
+        return self.linear(self.external.transpose(0, 1))
+
+
+class NoffnLayer(nn.Module):
+    """models/longformer_noffn.py LongformerLayer as its byte code reads: only `attention.self` exists; forward returns the
+    sliding-window self-attention output itself -- no output dense, no residual, no LayerNorm, no feed-forward -- with
+    query = Q(hidden), key = K(external_input) if given else K(hidden), value = V(hidden).  Everything after the three
+    projections is HF's own LongformerSelfAttention.forward (the installed transformers), called unmodified."""
+
+    def __init__(self, d_model, nhead, window):
+        super().__init__()
+        from transformers import LongformerConfig
+        from transformers.models.longformer.modeling_longformer import LongformerSelfAttention
+
+        cfg = LongformerConfig()
+        cfg.attention_window = [window]
+        cfg.hidden_size = d_model
+        cfg.num_attention_heads = nhead
+        cfg.attention_probs_dropout_prob = 0.0
+        holder = nn.Module()
+        holder.self = LongformerSelfAttention(cfg, layer_id=0)
+        self.attention = holder
+
+    def forward(self, hidden_states, lengths, external_input=None):
+        import inspect
+
+        sa = self.attention.self
+        mask = length_mask(hidden_states.shape[1], lengths).long() - 1        # RestrictedTransformerLayer.py:126: 0 valid, -1 padded
+        is_index_masked = mask < 0
+        kw = dict(attention_mask=mask, is_index_masked=is_index_masked, is_index_global_attn=mask > 0, is_global_attn=False)
+        if "layer_head_mask" in inspect.signature(sa.forward).parameters:
+            kw["layer_head_mask"] = None
+        key = sa._modules["key"]
+        if external_input is not None:
+            sa._modules["key"] = _Redirect(key, external_input)
+        try:
+            out = sa(hidden_states, **kw)
+        finally:
+            sa._modules["key"] = key
+        return out[0]
+
+
+class _RLBlock(nn.Module):
+    """RecurrentLongformerBlock (CRF.py:636-684) with separate_forward_backward (forward states = queries / values,
+    backward states = keys); the re-padding to 3600 rows is the caller's padded time axis."""
+
+    def __init__(self, embedding_dim, hidden_dim, nheads, window, sep_fb=True):
+        super().__init__()
+        self.lstm = Encoder(embedding_dim, hidden_dim, 1)
+        self.sep_fb = sep_fb
+        holder = nn.Module()
+        holder.model = NoffnLayer(hidden_dim if sep_fb else 2 * hidden_dim, nheads, window)
+        self.transformer = holder
+
+    def forward(self, x, lengths):
+        S = x.shape[1]
+        y = self.lstm(x, lengths)
+        y = F.pad(y, (0, 0, 0, S - y.shape[1]))                       # pad_to_window_multiple (CRF.py:660-668)
+        if self.sep_fb:
+            bs, sl, _ = y.shape
+            y = y.view(bs, sl, 2, -1)
+            return self.transformer.model(y[:, :, 0, :], lengths, external_input=y[:, :, 1, :])
+        return self.transformer.model(y, lengths)
+
+
+class RecurrentLongformer(_Head):
+    """CRF.py:764-858 (`BiLSTMRestrictedMHA`): num_layers blocks, a last bi-LSTM, the classification head."""
+
+    def __init__(self, tagset_size, embedding_dim, hidden_dim, num_layers=6, nheads=8, loss_fn="CrossEntropy", threshold=None,
+                 window_size=16, alpha=0.9, gamma=2, last_bilstm=True):
+        super().__init__()
+        blocks = [_RLBlock(embedding_dim, hidden_dim, nheads, window_size)]
+        blocks += [_RLBlock(hidden_dim, hidden_dim, nheads, window_size) for _ in range(num_layers - 1)]
+        self.model = nn.ModuleList(blocks)
+        self.last_bilstm = last_bilstm
+        if last_bilstm:
+            self.model.append(Encoder(hidden_dim, hidden_dim, 1))
+        self._init_head(2 * hidden_dim if last_bilstm else hidden_dim, tagset_size, loss_fn, threshold, alpha, gamma)
+
+    def features(self, x, lengths):
+        S = x.shape[1]
+        for block in self.model:
+            x = block(x, lengths)
+        return F.pad(x, (0, 0, 0, S - x.shape[1]))
+
+    def loss(self, x, lengths, tags):
+        return self._loss_from_logits(self.classification(self.features(x, lengths)), lengths, tags)
+
+    def forward(self, x, lengths, threshold=0.4):
+        return self._decode(self.classification(self.features(x, lengths)), lengths, threshold)
 
 
 def load_golden_params(module, fixture, strict=False):

@@ -440,3 +440,69 @@ def test_predict_flow_from_experiment_directory(dev, tmp_path, loss_fn):
                                                            {"Pk": 0.3, "F1": 0.4, "WD": 0.35}), name="bad.txt")
     with pytest.raises(NotImplementedError):
         Predictor(str(bad), str(ckpt), device=dev)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# BiLSTMRestrictedMHA (RecurrentLongformer, models/CRF.py:636-684, 764-858)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,nheads,D,S,window,layers", [(256, 8, 40, 64, 16, 2), (8, 2, 12, 32, 8, 3), (256, 4, 64, 96, 32, 1)])
+def test_recurrent_longformer_vs_oracle(dev, H, nheads, D, S, window, layers):
+    """bi-LSTM -> FFN-less windowed attention (forward states = queries and values, backward states = keys) blocks, a last
+    bi-LSTM and the head: scores, tags, loss and every gradient (the chain needs the LSTM's gradient to its INPUT)
+    against the oracle, which runs HF's own LongformerSelfAttention with the key projection redirected as the byte code of
+    the reference's source-less longformer_noffn module does.  S is a multiple of the window because HF needs it."""
+    from multimodaltopicsegmentation_b200 import RecurrentLongformer
+    from oracle import ref_torch as rt
+
+    torch.manual_seed(31 + H)
+    g = torch.Generator().manual_seed(77 + H)
+    B = 5
+    ref = rt.RecurrentLongformer(2, D, H, num_layers=layers, nheads=nheads, loss_fn="FocalLoss", window_size=window)
+    ours = RecurrentLongformer(2, D, H, num_layers=layers, nheads=nheads, loss_fn="FocalLoss", window_size=window)
+    assert set(ours.state_dict().keys()) == set(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev)
+    x = torch.randn(B, S, D, generator=g)
+    lengths = torch.randint(3, S + 1, (B,), generator=g)
+    lengths[1] = S
+    y = (torch.rand(B, S, generator=g) < 0.15).float()
+    for b, n in enumerate(lengths.tolist()):
+        y[b, n:] = -1
+    ref.th = ours.th = 0.5
+    s_ref, tags_ref = ref(x, lengths)
+    s, tags = ours(x.to(dev), lengths)
+    err, scale, _ = _report("scores", s[:, :, :], s_ref)
+    assert err <= 1e-4 * scale + 2e-5
+    _tags_agree(tags, tags_ref, s_ref.detach(), lengths, 0.5)
+    loss_ref = ref.loss(x, lengths, y)
+    loss_ref.backward()
+    loss = ours.loss(x.to(dev), lengths, y.to(dev))
+    loss.backward()
+    print(f"  loss {float(loss):.7f} vs oracle {float(loss_ref):.7f}")
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    ref_grads = dict(ref.named_parameters())
+    worst = 0.0
+    for k, prm in ours.named_parameters():
+        if "_global" in k:        # allocated by HF, never read (no gradient on either side)
+            assert prm.grad is None and ref_grads[k].grad is None
+            continue
+        e, sc, _ = _report("grad " + k, prm.grad, ref_grads[k].grad)
+        # key biases shift every score of a query by the same amount: their gradient is rounding noise on both sides
+        tol = 1e-4 * sc + 1e-7 if "key.bias" not in k else 1e-6
+        assert e <= tol, (k, e, sc)
+        if "key.bias" not in k and sc > 1e-6:   # gradients that vanished through the stacked blocks (~1e-9) are fp32 noise on both sides
+            worst = max(worst, e / sc)
+    print(f"  worst norm-wise gradient error over tensors with scale > 1e-6: {worst:.2e} (contract 1e-04)")
+    assert worst <= 1e-4
+
+
+def test_text_segmenter_dispatches_bilstm_restricted_mha(dev):
+    """lightning_model.py:215-216: architecture 'BiLSTMRestrictedMHA' builds RecurrentLongformer; predict-style call runs."""
+    from multimodaltopicsegmentation_b200 import RecurrentLongformer, TextSegmenter
+
+    seg = TextSegmenter(architecture="BiLSTMRestrictedMHA", tagset_size=2, embedding_dim=24, hidden_dim=16, num_layers=2,
+                        loss_fn="FocalLoss", nheads=4, attention_window=8, threshold=0.5).to(dev)
+    assert isinstance(seg.model, RecurrentLongformer)
+    x = torch.randn(2, 40, 24, device=dev)
+    scores, tags = seg.model(x, torch.tensor([40, 17]))
+    assert scores.shape == (2, 40, 1) and [len(t) for t in tags] == [40, 17]

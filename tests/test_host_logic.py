@@ -240,3 +240,30 @@ def test_segment_ranges_and_encoder_table():
     assert encoder_embedding_dim("anything", pca_reduce=True, pca_value=33) == 33
     with pytest.raises(ValueError):
         encoder_embedding_dim("roberta")
+
+
+def test_recurrent_longformer_parameter_tree_and_constructor_checks():
+    """`BiLSTMRestrictedMHA` (models/CRF.py:764-858): state-dict keys of the blocks / the FFN-less attention layer as the
+    reference names them, the reference's constructor assertions, and the TextSegmenter dispatch (lightning_model.py:215)."""
+    import pytest
+
+    from multimodaltopicsegmentation_b200 import RecurrentLongformer, TextSegmenter
+
+    m = RecurrentLongformer(2, 24, 16, num_layers=2, nheads=4, loss_fn="FocalLoss", window_size=8)
+    keys = set(m.state_dict().keys())
+    for blk in (0, 1):
+        for d in ("", "_reverse"):
+            for w in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                assert f"model.{blk}.lstm.rnn.{w}_l0{d}" in keys
+        for proj in ("query", "key", "value", "query_global", "key_global", "value_global"):
+            assert f"model.{blk}.transformer.model.attention.self.{proj}.weight" in keys
+        assert not any(k.startswith(f"model.{blk}.transformer.model.attention.output") for k in keys)   # no dense / LayerNorm
+    assert "model.2.rnn.weight_ih_l0" in keys and "classification.weight" in keys
+    assert m.model[0].lstm.rnn.input_size == 24 and m.model[1].lstm.rnn.input_size == 16
+    assert m.model[0].transformer.model.attention.self.query.weight.shape == (16, 16)   # separate forward / backward: d = H
+    assert m.classification.in_features == 32
+    with pytest.raises(AssertionError):      # RestrictedTransformerLayer.py:77-80 (the reference's default 127 trips it too)
+        RecurrentLongformer(2, 24, 16, num_layers=1, nheads=4, window_size=127)
+    seg = TextSegmenter(architecture="BiLSTMRestrictedMHA", tagset_size=2, embedding_dim=24, hidden_dim=16, num_layers=1,
+                        loss_fn="FocalLoss", nheads=4, attention_window=8)
+    assert isinstance(seg.model, RecurrentLongformer)
