@@ -127,6 +127,16 @@ int mts_lstm_rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengt
 int mts_lstm_rec_fwd_tf32(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
                           int B, int T, int H, float *y, float *gates, float *y_corr, void *stream);
 
+/* Early-fusion input projection without a concatenated copy (utils/load_datasets_precomputed.py:158-161 concatenates the
+ * text and audio embeddings, NeuralArchitectures.py:113 projects them): C = [A1 | A2] B^T with the raw fp32 A operand
+ * read in place from its one or two source matrices (A1 [M, D1] row stride ld1, A2 [M, D2] row stride ld2 or NULL) by the
+ * TMA producer -- k-blocks below D1 / 32 from A1, the others from A2 -- and only the packed correction operand
+ * A_lo [M, Kp], Kp = pad32(D1 + D2), prepared beforehand (mts_pack_rows_split with hi == NULL).  D1 % 32 == 0 when A2 is
+ * given; row strides multiples of 4 floats.  Other arguments as mts_gemm_tf32x3. */
+int mts_gemm_tf32x3_srcs(const float *A1, int D1, int64_t ld1, const float *A2, int D2, int64_t ld2, const float *A_lo,
+                         const float *B_hi, const float *B_lo, const float *bias, float *C, int M, int N, int Kp, int64_t ldc,
+                         int epilogue, int accumulate, void *stream);
+
 /* LongformerIntermediate (HF modeling_longformer.py:1103-1116: dense + GELU(erf)) when its output feeds the next dense
  * layer: C [M,N] = gelu(A B^T + bias) in fp32 -- which is its own `hi` operand -- and C_lo [M,N] = the packed correction
  * operand of C (A side), both written by the GEMM epilogue.  Replaces mts_gemm_tf32x3 + mts_gelu_split in inference

@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
-                       int epilogue, int accumulate, int splits, int bf16_only, float *__restrict__ C_lo) {
+                       int epilogue, int accumulate, int splits, int bf16_only, float *__restrict__ C_lo,
+                       const __grid_constant__ CUtensorMap map_a_hi2, int a_split_kb) {
+  // map_a_hi2 / a_split_kb: the raw fp32 A operand may live in TWO source matrices split along K (early fusion: text
+  // embeddings | audio embeddings) -- k-blocks below a_split_kb come from map_a_hi, the others from map_a_hi2 at
+  // k-block (kb - a_split_kb); no concatenated copy of the input is ever written.
   using Cfg = TcCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -310,7 +314,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const uint32_t fb = s_u32(&full_bar[stage]);
           bar_expect_tx(fb, bf16_only ? Cfg::kStageBytes / 2 : Cfg::kStageBytes);   // bf16 mode: the raw fp32 tiles are not loaded
           const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
-          if (!bf16_only) tma_load_2d(base, &map_a_hi, kb * TC_BK, m0, fb);
+          if (!bf16_only) {
+            if (kb < a_split_kb) tma_load_2d(base, &map_a_hi, kb * TC_BK, m0, fb);
+            else tma_load_2d(base, &map_a_hi2, (kb - a_split_kb) * TC_BK, m0, fb);   // second source matrix of A
+          }
           tma_load_2d(base + Cfg::kABytes, &map_a_lo, kb * 2 * TC_BK, m0, fb);  // bf16 elements: 64 per k-block
           if (CL == 1) {
             if (!bf16_only) tma_load_2d(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
@@ -466,7 +473,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     gemm_tf32x3_2sm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                            const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
-                           int epilogue, int accumulate, int splits, int bf16_only, float *__restrict__ C_lo) {
+                           int epilogue, int accumulate, int splits, int bf16_only, float *__restrict__ C_lo,
+                           const __grid_constant__ CUtensorMap map_a_hi2, int a_split_kb) {
   using Cfg = Tc2Cfg<BN2>;
   constexpr int BN = Cfg::BN, kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -524,7 +532,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           // the leader arms ITS barrier for both CTAs' bytes; the peer's loads report to the same barrier
           if (leader) bar_expect_tx(s_u32(&full_bar[stage]), bf16_only ? Cfg::kStageBytes : 2 * Cfg::kStageBytes);
           const uint32_t fb = mapa_u32(s_u32(&full_bar[stage]), 0);
-          if (!bf16_only) tma_load_2d_2sm(base, &map_a_hi, kb * TC_BK, m0, fb);
+          if (!bf16_only) {
+            if (kb < a_split_kb) tma_load_2d_2sm(base, &map_a_hi, kb * TC_BK, m0, fb);
+            else tma_load_2d_2sm(base, &map_a_hi2, (kb - a_split_kb) * TC_BK, m0, fb);   // second source matrix of A
+          }
           tma_load_2d_2sm(base + Cfg::kABytes, &map_a_lo, kb * 2 * TC_BK, m0, fb);
           if (!bf16_only) tma_load_2d_2sm(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
           tma_load_2d_2sm(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * 2 * TC_BK, n0, fb);
@@ -618,11 +629,16 @@ static EncodeTiledFn get_encode_fn() {
 
 // corr = false: fp32 [rows, Kp], box 32 x box_rows;  corr = true: the packed bf16 correction operand, [rows, 2 Kp] bf16
 // in the same bytes, box 64 x box_rows.  Either way one box row is one 128-byte swizzle row.
-static int make_map(CUtensorMap *map, const float *ptr, int rows, int Kp, int box_rows, bool corr = false) {
+// cols / ld (fp32 elements): a source matrix narrower than its k-blocks (columns beyond `cols` read as zeros: TMA fills
+// out-of-bounds elements) with row stride ld; 0 = the dense [rows, Kp] operand array.
+static int make_map(CUtensorMap *map, const float *ptr, int rows, int Kp, int box_rows, bool corr = false, int cols = 0,
+                    int64_t ld = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled not available"); return MTS_E_NODEVICE; }
-  cuuint64_t dims[2] = {(cuuint64_t)(corr ? 2 * Kp : Kp), (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(float)};
+  if (cols == 0) cols = Kp;
+  if (ld == 0) ld = Kp;
+  cuuint64_t dims[2] = {(cuuint64_t)(corr ? 2 * cols : cols), (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)(corr ? 2 * TC_BK : TC_BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, corr ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
@@ -638,10 +654,16 @@ __global__ void __launch_bounds__(256) zero_matrix_kernel(float *__restrict__ C,
     C[(i / N) * ldc + (i % N)] = 0.0f;
 }
 
+// The raw fp32 A operand given as one or two source matrices split along K (mts_gemm_tf32x3_srcs)
+struct ASources {
+  const float *a1; int d1; int64_t ld1;   // columns [0, d1) of A: d1 a multiple of 32 when a2 follows
+  const float *a2; int d2; int64_t ld2;   // columns [d1, d1 + d2), or NULL
+};
+
 template <int BN>
 static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
                      float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, cudaStream_t st,
-                     int bf16_only = 0, float *C_lo = nullptr) {
+                     int bf16_only = 0, float *C_lo = nullptr, const ASources *srcs = nullptr) {
   using Cfg = TcCfg<BN>;
   const int tiles_m1 = (M + TC_BM - 1) / TC_BM;
   // clusters of 2 (B tile multicast) whenever there are at least two row tiles; MTS_GEMM_CLUSTER=1 keeps single CTAs
@@ -664,7 +686,19 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
   const int tiles_n = (N + bn - 1) / bn;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, A_hi, M, Kp, TC_BM))) return rc;
+  CUtensorMap ma_hi2;
+  int a_split_kb = 1 << 30;
+  if (srcs) {
+    if ((rc = make_map(&ma_hi, srcs->a1, M, Kp, TC_BM, false, srcs->d1, srcs->ld1))) return rc;
+    ma_hi2 = ma_hi;
+    if (srcs->a2) {
+      if ((rc = make_map(&ma_hi2, srcs->a2, M, Kp, TC_BM, false, srcs->d2, srcs->ld2))) return rc;
+      a_split_kb = srcs->d1 / TC_BK;
+    }
+  } else {
+    if ((rc = make_map(&ma_hi, A_hi, M, Kp, TC_BM))) return rc;
+    ma_hi2 = ma_hi;
+  }
   if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM, true))) return rc;
   if ((rc = make_map(&mb_hi, B_hi, N, Kp, bn / CL))) return rc;
   if ((rc = make_map(&mb_lo, B_lo, N, Kp, bn / CL, true))) return rc;
@@ -716,18 +750,18 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
     if (bn == 224) {
       cfg.dynamicSmemBytes = Tc2Cfg<224>::kSmemBytes;
       MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_2sm_kernel<224>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                  accumulate, splits, bf16_only, C_lo));
+                                  accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb));
     } else {
       cfg.dynamicSmemBytes = Tc2Cfg<256>::kSmemBytes;
       MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_2sm_kernel<256>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                  accumulate, splits, bf16_only, C_lo));
+                                  accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb));
     }
   } else if (CL == 2) {
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits, bf16_only, C_lo));
+                                accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb));
   } else {
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 1>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits, bf16_only, C_lo));
+                                accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb));
   }
   MTS_LAUNCH_CHECK();
   return 0;
@@ -749,6 +783,29 @@ extern "C" int mts_gemm_tf32x3(const float *A_hi, const float *A_lo, const float
   cudaStream_t st = (cudaStream_t)stream;
   if (N >= 256) return launch_tc<256>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st);
   return launch_tc<128>(A_hi, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st);
+}
+
+// The same product with the raw fp32 A operand read IN PLACE from one or two source matrices split along K: A = [A1 | A2],
+// A1 [M, D1] (row stride ld1), A2 [M, D2] (row stride ld2) or NULL.  Early fusion (utils/load_datasets_precomputed.py:
+// 158-161 concatenates text and audio embeddings; NeuralArchitectures.py:113 projects the result): the TMA producer takes
+// k-blocks below D1 / 32 from A1 and the others from A2, so neither the concatenation nor an fp32 operand copy is ever
+// written -- only the packed correction operand A_lo [M, Kp], Kp = pad32(D1 + D2) (mts_pack_rows_split with hi == NULL).
+// D1 % 32 == 0 when A2 is given; ld1 % 4 == 0, ld2 % 4 == 0; columns beyond D1 + D2 read as zeros.
+extern "C" int mts_gemm_tf32x3_srcs(const float *A1, int D1, int64_t ld1, const float *A2, int D2, int64_t ld2, const float *A_lo,
+                                    const float *B_hi, const float *B_lo, const float *bias, float *C, int M, int N, int Kp,
+                                    int64_t ldc, int epilogue, int accumulate, void *stream) {
+  MTS_REQUIRE(A1 && A_lo && B_hi && B_lo && C, MTS_E_BADARG, "gemm_tf32x3_srcs: null pointer");
+  MTS_REQUIRE(M > 0 && N > 0 && Kp > 0 && D1 > 0 && (A2 ? D2 > 0 : D2 == 0), MTS_E_BADARG, "gemm_tf32x3_srcs: bad shape");
+  MTS_REQUIRE(Kp % TC_BK == 0 && D1 + D2 <= Kp && Kp - (D1 + D2) < TC_BK, MTS_E_BADARG, "gemm_tf32x3_srcs: Kp must be pad32(D1 + D2)");
+  MTS_REQUIRE(!A2 || D1 % TC_BK == 0, MTS_E_UNSUPPORTED, "gemm_tf32x3_srcs: the first source must be a whole number of 32-wide k-blocks");
+  MTS_REQUIRE(ld1 % 4 == 0 && ld1 >= D1 && (!A2 || (ld2 % 4 == 0 && ld2 >= D2)), MTS_E_BADARG, "gemm_tf32x3_srcs: row strides must be multiples of 4 floats");
+  MTS_REQUIRE(epilogue == 0 || bias, MTS_E_BADARG, "gemm_tf32x3_srcs: epilogue needs a bias");
+  MTS_REQUIRE((((uintptr_t)A1 | (uintptr_t)A2 | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo) & 15) == 0, MTS_E_BADARG,
+              "gemm_tf32x3_srcs: operands must be 16-byte aligned");
+  const ASources srcs = {A1, D1, ld1, A2, D2, ld2};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N >= 256) return launch_tc<256>(A1, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st, 0, nullptr, &srcs);
+  return launch_tc<128>(A1, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st, 0, nullptr, &srcs);
 }
 
 // Dense layer + GELU(erf) whose output feeds another mts_gemm_tf32x3: C = gelu(A B^T + bias) as fp32 [M, N] (which is

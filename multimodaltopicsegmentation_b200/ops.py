@@ -181,6 +181,39 @@ def pack_rows_split(x1, x2, B, T):
     return out[0], out[1]
 
 
+# The layer-0 input projection reads the embeddings in place (two TMA maps split along K) and only the packed correction
+# operand is written beforehand; MTS_PROJ_DIRECT=0 restores the concat + operand-pair packing pass.
+PROJ_DIRECT = __import__("os").environ.get("MTS_PROJ_DIRECT", "1") != "0"
+
+
+def _direct_sources_ok(x1, x2, B, T):
+    """In-place reading needs [B*T, D_i] to be plain matrices: no time crop, dense rows, 16-byte row pitch, and -- when a second
+    source follows -- a first width that is a whole number of 32-wide k-blocks."""
+    for x in (x1, x2):
+        if x is None:
+            continue
+        if x.dtype != torch.float32 or x.shape[0] != B or x.shape[1] != T or not x.is_contiguous() or x.shape[2] % 8 != 0:
+            return False    # (the packed-operand-only packing kernel works on 8-element units)
+        if x.data_ptr() % 16 != 0:
+            return False
+    return x2 is None or x1.shape[2] % 32 == 0
+
+
+def input_projection(x1, x2, B, T, w_hi, w_lo, bias, out, N):
+    """out [B*T, N] = [x1 | x2] W^T + bias: early-fusion concat + linear projection (load_datasets_precomputed.py:158-161 +
+    NeuralArchitectures.py:113) with the embeddings read in place by the GEMM's TMA producer."""
+    x1, x2 = _rows_ok(x1, "input", B, T), _rows_ok(x2, "second input", B, T)
+    if not (PROJ_DIRECT and _direct_sources_ok(x1, x2, B, T)):
+        a_hi, a_lo = pack_rows_split(x1, x2, B, T)
+        return gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias, out, B * T, N, epilogue=1, ldc=N)
+    D1 = x1.shape[2]
+    D2 = 0 if x2 is None else x2.shape[2]
+    a_lo = pack_rows_packed(x1, x2, B, T)     # the packed correction operand alone (hi == NULL)
+    _call("mts_gemm_tf32x3_srcs", _ptr(x1), D1, D1, _ptr(x2), D2, D2, _ptr(a_lo), _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(out),
+          B * T, N, a_lo.shape[1], N, 1, 0, _stream())
+    return out
+
+
 def transpose_split(src_ptr, bstride, ld, rows, cols, T, device, shift=0, lengths=None, side=A_SIDE):
     """(hi, lo) [cols, pad32(rows)] of the transposed (optionally time-shifted / length-masked) source: the K-major
     operand of a GEMM that contracts over tokens (weight gradients)."""
@@ -346,6 +379,13 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
                     a_lo = split_tf32(src, cols=2 * H, ld=n_enc * 2 * H, rows=B * T)[1]
                 _call("mts_gemm_bf16p", _ptr(a_lo), _ptr(packed.wih_packed_a(layer, e)), _ptr(layers[layer]["bias"][e]), _ptr(gx[e]),
                       B * T, 8 * H, a_lo.shape[1], 8 * H, 1, 0, _stream())
+                continue
+            if layer == 0 and GEMM_IMPL != "simt":
+                w_hi, w_lo = layers[layer]["wih"][e]
+                if n_enc == 1:
+                    input_projection(x1, x2, B, T, w_hi, w_lo, layers[layer]["bias"][e], gx[e], 8 * H)
+                else:
+                    input_projection(x1 if e == 0 else xs2, None, B, T, w_hi, w_lo, layers[layer]["bias"][e], gx[e], 8 * H)
                 continue
             if layer == 0:
                 if n_enc == 1:

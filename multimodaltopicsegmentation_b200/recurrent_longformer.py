@@ -27,8 +27,9 @@ Superset notes: the reference asserts `inputs.shape[1] == 3600` and re-pads ever
 re-padding produces.  HF's sliding chunks additionally need S to be a multiple of the window; the kernels do not.
 The reference's CrossEntropy branch reads `self.tagset_size`, which `RecurrentLongformer.__init__` never sets
 (AttributeError on construction); here it is set from the constructor argument.
-Parity: pinned against `oracle/ref_torch.RecurrentLongformer` (HF's own LongformerSelfAttention with the key projection
-redirected as the byte code does); the reference class itself cannot be imported (source-less module), DESIGN.md.
+Parity: the GPU tests compare with the torch twin of this composition (HF's own LongformerSelfAttention with the key
+projection redirected as the byte code does); the reference class itself cannot be imported (source-less module) --
+"parity unpinned" for this row, DESIGN.md.
 """
 from __future__ import annotations
 
