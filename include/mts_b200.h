@@ -178,6 +178,14 @@ int mts_lstm_rec_fwd_h3(const float *gx, const float *w_hh, const int32_t *lengt
                         int B, int T, int H, float *y, float *gates, float *y_corr, int precision, void *stream);
 int mts_debug_rec_profile_h3(long long *buf);
 
+/* The fp16-split recurrence with the h tile shared by CTA PAIRS (csrc/lstm_rec_h3p.cu): the two CTAs of a pair issue one
+ * M = 256 tcgen05.mma.cta_group::2 stream whose B operand (the 16 episodes' h rows) is split between them, so every CTA
+ * receives only half of the rows and every sender addresses 4 CTAs instead of 8 -- half the distributed-shared-memory bytes
+ * per step.  Same arguments and results as mts_lstm_rec_fwd_h3. */
+int mts_lstm_rec_fwd_h3p(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc,
+                         int B, int T, int H, float *y, float *gates, float *y_corr, int precision, void *stream);
+int mts_debug_rec_profile_h3p(long long *buf);
+
 /* Backward through time of the same layer.
  *   dy      [B, T, n_enc*2H]    gradient w.r.t. y (ignored at t >= len_b)
  *   gates   as saved by the forward call

@@ -42,6 +42,8 @@ SIGNATURES = {
     "mts_pack_rows_bf16in": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
     "mts_debug_rec_profile": (c_int, [_P]),
     "mts_debug_rec_profile_h3": (c_int, [_P]),
+    "mts_lstm_rec_fwd_h3p": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P]),
+    "mts_debug_rec_profile_h3p": (c_int, [_P]),
     "mts_lstm_rec_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "mts_lstm_rec_bwd_tc": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "mts_head_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),

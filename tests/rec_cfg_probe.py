@@ -18,7 +18,7 @@ gx = torch.randn((1, B * T, 8 * H), device=dev, generator=g) * 0.5
 whh = torch.randn((1, 2, 4 * H, H), device=dev, generator=g) * 0.05
 lens = ops.Lengths([T] * B, dev, T)
 y = torch.empty((B, T, 2 * H), device=dev)
-extra = (0, 0) if NAME.endswith("_h3") else (0,)
+extra = (0, 0) if NAME.endswith(("_h3", "_h3p")) else (0,)
 call = lambda: ops._call(NAME, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H,
                          y.data_ptr(), 0, *extra, ops._stream())
 for _ in range(3):

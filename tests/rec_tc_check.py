@@ -15,12 +15,13 @@ dev = torch.device("cuda:0")
 # which tensor-core forward kernel the checks exercise: "mts_lstm_rec_fwd_tc" (TF32 + bf16 correction) or
 # "mts_lstm_rec_fwd_h3" (fp16-split operands)
 TC_NAME = os.environ.get("REC_TC_NAME", "mts_lstm_rec_fwd_h3")
-PROF_NAME = "mts_debug_rec_profile_h3" if TC_NAME.endswith("_h3") else "mts_debug_rec_profile"
+PROF_NAME = ("mts_debug_rec_profile_h3p" if TC_NAME.endswith("_h3p") else "mts_debug_rec_profile_h3" if TC_NAME.endswith("_h3")
+             else "mts_debug_rec_profile")
 
 
 def _extra(name):
     """trailing arguments between `gates` and the stream"""
-    if name.endswith("_h3"):
+    if name.endswith(("_h3", "_h3p")):
         return (0, int(os.environ.get("REC_H3_PRECISION", "0")))          # y_corr, precision (+ debug bits)
     if name.endswith("_tc"):
         return (0,)            # y_corr
@@ -186,7 +187,7 @@ def timeline(B=16, T=40):
     whh = torch.randn((1, 2, 4 * H, H), device=dev, generator=g) * 0.05
     lens = ops.Lengths([T] * B, dev, T)
     y = torch.empty((B, T, 2 * H), device=dev)
-    nsl = 16 if TC_NAME.endswith("_h3") else 12
+    nsl = 16 if TC_NAME.endswith(("_h3", "_h3p")) else 12
     buf = torch.zeros(4 * nsl, dtype=torch.int64, device=dev)
     call = lambda: ops._call(TC_NAME, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
                              lens.order.data_ptr(), 1, B, T, H, y.data_ptr(), 0, *_extra(TC_NAME), ops._stream())
@@ -198,7 +199,7 @@ def timeline(B=16, T=40):
     st = buf.cpu().view(4, nsl)
     names = ["mma:start", "mma:h_full", "mma:hi issued", "mma:lo_ready", "mma:commit", "epi:start", "epi:h_full",
              "epi:lo done", "epi:acc_full", "epi:tmem ld", "epi:act+bar", "epi:sent"]
-    if TC_NAME.endswith("_h3"):
+    if TC_NAME.endswith(("_h3", "_h3p")):
         names = ["mma:start", "half0", "half1", "issued0", "issued1", "commit", "-", "-", "-", "-", "epi:acc_full", "tmem ld",
                  "act+bar", "cell", "sent", "-"]
     t0 = int(st[0, 0])

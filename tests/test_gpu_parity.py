@@ -888,7 +888,8 @@ def test_transformer_hidden_dropout_training_vs_hf_twin(dev, xf_layout, monkeypa
 # ----------------------------------------------------------------------------------------------------------
 # tensor-core recurrence (tcgen05, W_hh in tensor memory) against the exact-fp32 FMA kernel and float64
 # ----------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("entry", ["mts_lstm_rec_fwd_tc", "mts_lstm_rec_fwd_tf32"])   # default = fp16-split kernel; TF32 + bf16 kernel
+# default = fp16-split kernels (pair kernel from ~113 sequences per direction on); the TF32 + bf16 kernel; the pair kernel at every size
+@pytest.mark.parametrize("entry", ["mts_lstm_rec_fwd_tc", "mts_lstm_rec_fwd_tf32", "mts_lstm_rec_fwd_h3p"])
 @pytest.mark.parametrize("B,T,n_enc,save", [(3, 5, 1, False), (16, 40, 1, True), (37, 61, 1, True), (20, 33, 2, True),
                                             (300, 50, 1, False), (70, 30, 1, False), (1000, 9, 1, False)])
 def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save, entry):
@@ -909,7 +910,8 @@ def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save, entry):
         y = torch.full((B, T, n_enc * 2 * H), float("nan"), device=dev)
         gates = torch.full((n_enc, 2, B, T, 5, H), float("nan"), device=dev) if save else None
         ops._call(name, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T, H,
-                  y.data_ptr(), 0 if gates is None else gates.data_ptr(), *(() if name == "mts_lstm_rec_fwd" else (0,)), ops._stream())
+                  y.data_ptr(), 0 if gates is None else gates.data_ptr(),
+                  *(() if name == "mts_lstm_rec_fwd" else (0, 0) if name.endswith("_h3p") else (0,)), ops._stream())
         return y, gates
 
     y_f, g_f = run("mts_lstm_rec_fwd")
@@ -918,7 +920,7 @@ def test_recurrence_tensor_core_vs_fma(dev, B, T, n_enc, save, entry):
         y2 = torch.full((B, T, 2 * H), float("nan"), device=dev)
         corr = torch.full((B * T, 2 * H), float("nan"), device=dev)
         ops._call(entry, gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), 1, B, T, H,
-                  y2.data_ptr(), 0, corr.data_ptr(), ops._stream())
+                  y2.data_ptr(), 0, corr.data_ptr(), *((0,) if entry.endswith("_h3p") else ()), ops._stream())
         assert torch.equal(y2, y_t)
         check_operand_pair(y2.view(B * T, 2 * H), corr, y2.view(B * T, 2 * H), side=0)
     assert not bool(torch.isnan(y_t).any())          # every position written (zeros beyond len_b)
