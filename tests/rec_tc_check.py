@@ -229,8 +229,11 @@ if __name__ == "__main__":
         if ok:
             sweep_bwd()
     if what in ("all", "timeline"):
-        timeline()
-        timeline(B=10 * 7, T=40)   # cfg1-like: 10 episodes per tile
+        if len(sys.argv) > 3:
+            timeline(B=int(sys.argv[2]), T=int(sys.argv[3]))
+        else:
+            timeline()
+            timeline(B=10 * 7, T=40)   # cfg1-like: 10 episodes per tile
     if what in ("all", "sweep") and ok:
         sweep()
     sys.exit(0 if ok else 1)
