@@ -452,7 +452,7 @@ def transformer_leg(ctx, steps):
     hbm_peak, _ = peaks()
     tokens = c["B"] * c["S"]
     attn = prof.get("mts_band_attn_fwd", [])
-    gemm = prof.get("mts_gemm_tf32x3", [])
+    gemm = prof.get("mts_gemm_tf32x3", []) + prof.get("mts_gemm_tf32x3_gelu_pair", []) + prof.get("mts_gemm_f16x3", [])
     out = {"metric": "segmented sentences/sec", "value": n_sent * ctx.world / (ms / 1e3), "unit": "sentences/s",
            "ms_per_step": ms, "steps": steps, "workload": XF_WORKLOAD, "valid_sentences_per_step_per_gpu": n_sent,
            "tokens_per_step_per_gpu": tokens, "gpu_launches_per_step": launches,
@@ -473,11 +473,14 @@ def transformer_leg(ctx, steps):
 
         rows = n_sent if xf.LAYOUT == "ragged" else tokens   # the dense layers only see the valid sentences
         tf = rows * XF_GEMM_FLOPS_PER_TOKEN * c["L"] / (sum(gemm) / 1e3) / 1e12
-        out["roofline_dense"] = {"kernel": "gemm_tf32x3_2sm_kernel / gemm_tf32x3_kernel", "bound": "tensor",
+        out["roofline_dense"] = {"kernel": "gemm_tf32x3_2sm_kernel (out-proj, output dense: TF32 + bf16 correction) and the same kernel "
+                                           "in its fp16-split mode (q/k/v, intermediate dense: three kind::f16 products)", "bound": "tensor",
                                  "rows_per_launch": rows, "token_layout": xf.LAYOUT, "launches": len(gemm),
-                                 "achieved_tflops_fp32_equiv": tf, "achieved_tflops_issued": 2 * tf,
-                                 "note": "error-compensated TF32: one TF32 product + one bf16 correction product per "
-                                         "fp32-grade product (issued = 2x)"}
+                                 "achieved_tflops_fp32_equiv": tf,
+                                 "ms_by_entry": {k: sum(prof[k]) for k in ("mts_gemm_f16x3", "mts_gemm_tf32x3", "mts_gemm_tf32x3_gelu_pair")
+                                                 if k in prof},
+                                 "note": "fp32-grade products on the tensor cores: TF32 + one bf16 correction product (2 MMA streams "
+                                         "per product, K = 8 / 16) or three fp16 products over split operands (K = 16 each)"}
     return out
 
 

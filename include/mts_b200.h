@@ -137,6 +137,16 @@ int mts_gemm_tf32x3_srcs(const float *A1, int D1, int64_t ld1, const float *A2, 
                          const float *B_hi, const float *B_lo, const float *bias, float *C, int M, int N, int Kp, int64_t ldc,
                          int epilogue, int accumulate, void *stream);
 
+/* Dense layer over FP16-SPLIT operands (HF LongformerSelfAttention q/k/v projections :514-516 and LongformerIntermediate
+ * :1103-1116 in inference, where the A operand comes from a LayerNorm that knows its row): x = x1 + x2 with x1 = fp16(x s),
+ * x2 = fp16(x s - x1), s an exact power-of-two scale per operand row.  C = (A1 B1^T + A2 B1^T + A1 B2^T) rs[m] cs[n] (+ bias,
+ * epilogue 2: GELU): three kind::f16 tcgen05 products -- 6 instead of 8 MMAs per 32 k and half the operand bytes of
+ * mts_gemm_tf32x3, relative error ~2^-22.  A_pieces [M][2][K] fp16 (mts_add_ln_fwd_f16 / mts_embed_ln_fwd_f16 write it),
+ * B_pieces [N][2][K], row_scale [M] / col_scale [N] = 1 / s or NULL; K % 64 == 0, K <= 3072, M, N >= 256.  C_lo (optional):
+ * the packed bf16 correction operand of C, for a following mts_gemm_tf32x3 (dense rows, N % 32 == 0). */
+int mts_gemm_f16x3(const void *A_pieces, const void *B_pieces, const float *row_scale, const float *col_scale, const float *bias,
+                   float *C, float *C_lo, int M, int N, int K, int64_t ldc, int epilogue, void *stream);
+
 /* LongformerIntermediate (HF modeling_longformer.py:1103-1116: dense + GELU(erf)) when its output feeds the next dense
  * layer: C [M,N] = gelu(A B^T + bias) in fp32 -- which is its own `hi` operand -- and C_lo [M,N] = the packed correction
  * operand of C (A side), both written by the GEMM epilogue.  Replaces mts_gemm_tf32x3 + mts_gelu_split in inference
@@ -293,6 +303,14 @@ int mts_embed_ln_fwd(const float *x, int64_t x_bstride, const float *pos, const 
  *   spares this kernel one of its two input reads. */
 int mts_add_ln_fwd(const float *a, const float *res, const float *gamma, const float *beta, int M, int d, float eps,
                    float *y, float *y_hi, float *y_lo, int Kp, float *sum_out, float *stats, void *stream);
+/* The same two LayerNorms writing, next to y, the FP16-SPLIT operand of mts_gemm_f16x3 instead of the (hi, lo) pair:
+ *   pieces [rows][2][K64] fp16 (K64 % 64 == 0, zero beyond d): fp16(y s) and fp16(y s - fp16(y s)), s = the exact power of two
+ *   that puts the row's largest |y| into [2^13, 2^14); row_scale [rows] = 1 / s.  d <= 1024.  Inference only (no saved tensors). */
+int mts_embed_ln_fwd_f16(const float *x, int64_t x_bstride, const float *pos, const float *typ, const float *gamma,
+                         const float *beta, int B, int S, int d, float eps, float *y, void *pieces, int K64, float *row_scale,
+                         const int32_t *lengths, const int32_t *offsets, void *stream);
+int mts_add_ln_fwd_f16(const float *a, const float *res, const float *gamma, const float *beta, int M, int d, float eps, float *y,
+                       void *pieces, int K64, float *row_scale, void *stream);
 /* LongformerIntermediate (:1103-1116) activation fused with the operand split: hi/lo [rows,Kp] of GELU(src);
  * act [rows,cols] or NULL: GELU(src) in fp32, kept for the weight gradient of the next dense layer. */
 int mts_gelu_split(const float *src, int64_t ld, int rows, int cols, int Kp, float *act, float *hi, float *lo,

@@ -107,6 +107,10 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // kind::f16 with bf16 inputs (a_format = b_format = 1), fp32 accumulate, K-major
+// kind::f16 with fp16 operands (format code 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -165,7 +169,9 @@ template <int BN>
 __device__ __forceinline__ void tc_store_tile(uint32_t tmem_base, int acc_col, int q, int lane, int m0, int n0, int sp,
                                               const float *__restrict__ bias, float *__restrict__ C, int M, int N,
                                               int64_t ldc, int epilogue, int accumulate, int splits, float4 *stg,
-                                              float *__restrict__ C_lo) {
+                                              float *__restrict__ C_lo, const float *__restrict__ row_scale = nullptr,
+                                              const float *__restrict__ col_scale = nullptr) {
+  // row_scale / col_scale (fp16-split operands): the accumulator holds (A / rs) (B / cs)^T, power-of-two scales per operand row
   const int rsub = lane >> 3, ch = lane & 7;
   const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
@@ -196,11 +202,19 @@ __device__ __forceinline__ void tc_store_tile(uint32_t tmem_base, int acc_col, i
       for (int e = 0; e < 4; ++e)
         if (n + e < N) bv[e] = __ldg(bias + n + e);
     }
+    float cv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    if (col_scale) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < N) cv[e] = __ldg(col_scale + n + e);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = 4 * i + rsub, m = m0 + q * 32 + row;
       const float4 t = stg[row * 8 + (ch ^ (row & 7))];
-      float o[4] = {t.x + bv[0], t.y + bv[1], t.z + bv[2], t.w + bv[3]};
+      const float rsv = (row_scale && m < M) ? __ldg(row_scale + m) : 1.0f;
+      float o[4] = {fmaf(t.x, rsv * cv[0], bv[0]), fmaf(t.y, rsv * cv[1], bv[1]), fmaf(t.z, rsv * cv[2], bv[2]),
+                    fmaf(t.w, rsv * cv[3], bv[3])};
       if (epilogue == 2) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = gelu_erf(o[e]);
@@ -251,7 +265,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
                        int epilogue, int accumulate, int splits, int bf16_only, float *__restrict__ C_lo,
-                       const __grid_constant__ CUtensorMap map_a_hi2, int a_split_kb) {
+                       const __grid_constant__ CUtensorMap map_a_hi2, int a_split_kb,
+                       const float *__restrict__ row_scale, const float *__restrict__ col_scale) {
   // map_a_hi2 / a_split_kb: the raw fp32 A operand may live in TWO source matrices split along K (early fusion: text
   // embeddings | audio embeddings) -- k-blocks below a_split_kb come from map_a_hi, the others from map_a_hi2 at
   // k-block (kb - a_split_kb); no concatenated copy of the input is ever written.
@@ -381,7 +396,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int m0 = ((tile / tiles_n) * CL + (int)crank) * TC_BM, n0 = (tile % tiles_n) * BN;
       bar_wait(s_u32(&tfull_bar[acc_stage]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc_store_tile<BN>(tmem_base, acc_stage * BN, q, lane, m0, n0, sp, bias, C, M, N, ldc, epilogue, accumulate, splits, stg, C_lo);
+      tc_store_tile<BN>(tmem_base, acc_stage * BN, q, lane, m0, n0, sp, bias, C, M, N, ldc, epilogue, accumulate, splits, stg, C_lo,
+                        row_scale, col_scale);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) bar_arrive(s_u32(&tempty_bar[acc_stage]));
@@ -474,7 +490,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                            const float *__restrict__ bias, float *__restrict__ C, int M, int N, int Kp, int64_t ldc,
                            int epilogue, int accumulate, int splits, int bf16_only, float *__restrict__ C_lo,
-                           const __grid_constant__ CUtensorMap map_a_hi2, int a_split_kb) {
+                           const __grid_constant__ CUtensorMap map_a_hi2, int a_split_kb,
+                           const float *__restrict__ row_scale, const float *__restrict__ col_scale) {
   using Cfg = Tc2Cfg<BN2>;
   constexpr int BN = Cfg::BN, kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -530,14 +547,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           bar_wait(s_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t base = s_u32(smem + stage * Cfg::kStageBytes);
           // the leader arms ITS barrier for both CTAs' bytes; the peer's loads report to the same barrier
-          if (leader) bar_expect_tx(s_u32(&full_bar[stage]), bf16_only ? Cfg::kStageBytes : 2 * Cfg::kStageBytes);
+          if (leader) bar_expect_tx(s_u32(&full_bar[stage]), bf16_only == 1 ? Cfg::kStageBytes : 2 * Cfg::kStageBytes);
           const uint32_t fb = mapa_u32(s_u32(&full_bar[stage]), 0);
-          if (!bf16_only) {
+          if (bf16_only == 2) {   // fp16-split operands: all four tiles are 2-byte matrices of 64 elements per k-block
+            tma_load_2d_2sm(base, &map_a_hi, kb * 2 * TC_BK, m0, fb);
+          } else if (!bf16_only) {
             if (kb < a_split_kb) tma_load_2d_2sm(base, &map_a_hi, kb * TC_BK, m0, fb);
             else tma_load_2d_2sm(base, &map_a_hi2, (kb - a_split_kb) * TC_BK, m0, fb);   // second source matrix of A
           }
           tma_load_2d_2sm(base + Cfg::kABytes, &map_a_lo, kb * 2 * TC_BK, m0, fb);
-          if (!bf16_only) tma_load_2d_2sm(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
+          if (bf16_only == 2) tma_load_2d_2sm(base + 2 * Cfg::kABytes, &map_b_hi, kb * 2 * TC_BK, n0, fb);
+          else if (!bf16_only) tma_load_2d_2sm(base + 2 * Cfg::kABytes, &map_b_hi, kb * TC_BK, n0, fb);
           tma_load_2d_2sm(base + 2 * Cfg::kABytes + Cfg::kBBytes, &map_b_lo, kb * 2 * TC_BK, n0, fb);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -547,6 +567,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(2 * TC_BM, BN), idesc_c = make_idesc_bf16(2 * TC_BM, BN);
+      constexpr uint32_t idesc_h = make_idesc_f16(2 * TC_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc_stage = 0;
@@ -569,8 +590,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
-            if (!bf16_only) umma2_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));
-            umma2_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_c, !bf16_only || (kb != kb0) || (k != 0));
+            if (bf16_only == 2) {   // x = x1 + x2 (fp16 pieces): A B^T ~= A1 B1^T + A2 B1^T + A1 B2^T, three K = 16 products
+              umma2_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc_h, (kb != kb0) || (k != 0));
+              umma2_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc_h, 1);
+              umma2_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc_h, 1);
+            } else {
+              if (!bf16_only) umma2_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb != kb0) || (k != 0));
+              umma2_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_c, !bf16_only || (kb != kb0) || (k != 0));
+            }
           }
           umma2_commit_mc(s_u32(&empty_bar[stage]), 3);  // both producers may refill this stage
           if (kb == kb1 - 1) umma2_commit_mc(s_u32(&tfull_bar[acc_stage]), 3);
@@ -592,7 +619,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       bar_wait(s_u32(&tfull_bar[acc_stage]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       tc_store_tile<BN>(tmem_base, acc_stage * Cfg::kAccStride, q, lane, m0, n0, sp, bias, C, M, N, ldc, epilogue, accumulate, splits,
-                        stg, C_lo);
+                        stg, C_lo, row_scale, col_scale);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) bar_arrive_cluster(mapa_u32(s_u32(&tempty_bar[acc_stage]), 0));
@@ -663,7 +690,8 @@ struct ASources {
 template <int BN>
 static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, const float *B_lo, const float *bias,
                      float *C, int M, int N, int Kp, int64_t ldc, int epilogue, int accumulate, cudaStream_t st,
-                     int bf16_only = 0, float *C_lo = nullptr, const ASources *srcs = nullptr) {
+                     int bf16_only = 0, float *C_lo = nullptr, const ASources *srcs = nullptr, const float *row_scale = nullptr,
+                     const float *col_scale = nullptr) {
   using Cfg = TcCfg<BN>;
   const int tiles_m1 = (M + TC_BM - 1) / TC_BM;
   // clusters of 2 (B tile multicast) whenever there are at least two row tiles; MTS_GEMM_CLUSTER=1 keeps single CTAs
@@ -696,12 +724,14 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
       a_split_kb = srcs->d1 / TC_BK;
     }
   } else {
-    if ((rc = make_map(&ma_hi, A_hi, M, Kp, TC_BM))) return rc;
+    // fp16-split: 2-byte matrices like the correction operands; the two pieces of a row sit side by side ([row][piece][K]),
+    // so both maps have the row pitch of the pair (2 Kp floats)
+    if ((rc = make_map(&ma_hi, A_hi, M, Kp, TC_BM, bf16_only == 2, 0, bf16_only == 2 ? 2 * Kp : 0))) return rc;
     ma_hi2 = ma_hi;
   }
-  if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM, true))) return rc;
-  if ((rc = make_map(&mb_hi, B_hi, N, Kp, bn / CL))) return rc;
-  if ((rc = make_map(&mb_lo, B_lo, N, Kp, bn / CL, true))) return rc;
+  if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM, true, 0, bf16_only == 2 ? 2 * Kp : 0))) return rc;
+  if ((rc = make_map(&mb_hi, B_hi, N, Kp, bn / CL, bf16_only == 2, 0, bf16_only == 2 ? 2 * Kp : 0))) return rc;
+  if ((rc = make_map(&mb_lo, B_lo, N, Kp, bn / CL, true, 0, bf16_only == 2 ? 2 * Kp : 0))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -750,18 +780,18 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
     if (bn == 224) {
       cfg.dynamicSmemBytes = Tc2Cfg<224>::kSmemBytes;
       MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_2sm_kernel<224>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                  accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb));
+                                  accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb, row_scale, col_scale));
     } else {
       cfg.dynamicSmemBytes = Tc2Cfg<256>::kSmemBytes;
       MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_2sm_kernel<256>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                  accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb));
+                                  accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb, row_scale, col_scale));
     }
   } else if (CL == 2) {
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb));
+                                accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb, row_scale, col_scale));
   } else {
     MTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BN, 1>, ma_hi, ma_lo, mb_hi, mb_lo, bias, C, M, N, Kp, ldc, epilogue,
-                                accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb));
+                                accumulate, splits, bf16_only, C_lo, ma_hi2, a_split_kb, row_scale, col_scale));
   }
   MTS_LAUNCH_CHECK();
   return 0;
@@ -806,6 +836,26 @@ extern "C" int mts_gemm_tf32x3_srcs(const float *A1, int D1, int64_t ld1, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (N >= 256) return launch_tc<256>(A1, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st, 0, nullptr, &srcs);
   return launch_tc<128>(A1, A_lo, B_hi, B_lo, bias, C, M, N, Kp, ldc, epilogue, accumulate, st, 0, nullptr, &srcs);
+}
+
+// The product over FP16-SPLIT operands: x = x1 + x2 with x1 = fp16(x s), x2 = fp16(x s - x1), s an exact power-of-two scale per
+// operand ROW (so that the row's largest entry sits in [2^13, 2^14): fp16's range is never left, both pieces of the large
+// entries are normal).  C = (A1 B1^T + A2 B1^T + A1 B2^T) rs[m] cs[n] (+ bias, GELU): three kind::f16 products of K = 16 --
+// 6 instead of 8 MMAs per 32 k, half the operand bytes of mts_gemm_tf32x3, relative error ~2^-22 (the dropped A2 B2^T).
+// A_pieces [M][2][K] fp16 (the two pieces of a row side by side), B_pieces [N][2][K], K % 64 == 0; row_scale [M] / col_scale [N]
+// = 1 / s (NULL = 1).  Activations whose producer knows the row (LayerNorm) and weights use it; served by the 2-SM kernel
+// (M >= 256, N >= 256).  C_lo (optional, epilogue 2): the packed bf16 correction operand of C for a following mts_gemm_tf32x3.
+extern "C" int mts_gemm_f16x3(const void *A_pieces, const void *B_pieces, const float *row_scale, const float *col_scale,
+                              const float *bias, float *C, float *C_lo, int M, int N, int K, int64_t ldc, int epilogue, void *stream) {
+  MTS_REQUIRE(A_pieces && B_pieces && C, MTS_E_BADARG, "gemm_f16x3: null pointer");
+  MTS_REQUIRE(M >= 256 && N >= 256 && K > 0 && K % 64 == 0, MTS_E_UNSUPPORTED, "gemm_f16x3: M, N >= 256, K a multiple of 64");
+  MTS_REQUIRE(K <= 3072, MTS_E_UNSUPPORTED, "gemm_f16x3: K beyond 3072 needs the split-K path of mts_gemm_tf32x3");
+  MTS_REQUIRE(epilogue == 0 || bias, MTS_E_BADARG, "gemm_f16x3: epilogue needs a bias");
+  MTS_REQUIRE(!C_lo || (N % 32 == 0 && ldc == N), MTS_E_BADARG, "gemm_f16x3: the operand-pair output needs dense rows, N % 32 == 0");
+  MTS_REQUIRE((((uintptr_t)A_pieces | (uintptr_t)B_pieces | (uintptr_t)C) & 15) == 0, MTS_E_BADARG, "gemm_f16x3: operands must be 16-byte aligned");
+  const uint16_t *a = (const uint16_t *)A_pieces, *b = (const uint16_t *)B_pieces;
+  return launch_tc<256>((const float *)a, (const float *)(a + K), (const float *)b, (const float *)(b + K), bias, C, M, N, K / 2, ldc,
+                        epilogue, 0, (cudaStream_t)stream, 2, C_lo, nullptr, row_scale, col_scale);
 }
 
 // Dense layer + GELU(erf) whose output feeds another mts_gemm_tf32x3: C = gelu(A B^T + bias) as fp32 [M, N] (which is

@@ -14,6 +14,8 @@
 // q,k,v (12d) and writes o (4d, or the two operand halves) per token and only ever touches in-window keys.
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mts {
@@ -27,7 +29,10 @@ namespace mts {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 16;  // float4 per lane -> d <= 2048 (MAXV = 8 serves d <= 1024 with half the registers)
 
-template <int MODE, int MAXV>
+// PIECES: instead of the (hi, lo) pair the kernel writes the fp16-split operand of mts_gemm_f16x3 -- y_lo then points to
+// __half pieces [M][2][Kp] (Kp a multiple of 64: fp16 elements) and row_scale [M] receives 2^-s, where 2^s is the exact
+// power of two that puts the row's largest |y| into [2^13, 2^14) (a warp owns a row, so its maximum is one shuffle tree away).
+template <int MODE, int MAXV, bool PIECES = false>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a, int64_t a_bstride,
                                                      const float *__restrict__ b, const float *__restrict__ typ,
                                                      const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -35,7 +40,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
                                                      float *__restrict__ y_hi, float *__restrict__ y_lo, int Kp,
                                                      float *__restrict__ sum_out, float *__restrict__ stats,
                                                      const int32_t *__restrict__ lengths,
-                                                     const int32_t *__restrict__ offsets) {
+                                                     const int32_t *__restrict__ offsets, float *__restrict__ row_scale = nullptr) {
   const int lane = threadIdx.x & 31;
   const int nv = d >> 2;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -87,6 +92,46 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float *__restrict__ a
     }
     const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + eps);
     if (stats && lane == 0) { stats[2 * (int64_t)row] = mean; stats[2 * (int64_t)row + 1] = rstd; }
+    if (PIECES) {
+      // normalised values in place, the row's largest magnitude, its power-of-two scale, then y and the two fp16 pieces
+      float mx = 0.0f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = LN_COL(i);
+        if (c < nv) {
+          if (sum_out) reinterpret_cast<float4 *>(sum_out + (int64_t)row * d)[c] = v[i];
+          const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + c);
+          const float4 be = __ldg(reinterpret_cast<const float4 *>(beta) + c);
+          v[i].x = (v[i].x - mean) * rstd * g.x + be.x;
+          v[i].y = (v[i].y - mean) * rstd * g.y + be.y;
+          v[i].z = (v[i].z - mean) * rstd * g.z + be.z;
+          v[i].w = (v[i].w - mean) * rstd * g.w + be.w;
+          reinterpret_cast<float4 *>(y + (int64_t)row * d)[c] = v[i];
+          mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[i].x), fabsf(v[i].y))), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
+        }
+      }
+      mx = warp_max(mx);
+      const int ex = (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+      int sexp = ex == 0 ? 0 : 127 + 13 - ex;
+      sexp = sexp > 110 ? 110 : (sexp < -110 ? -110 : sexp);
+      const float sc = __uint_as_float((uint32_t)(127 + sexp) << 23);
+      if (lane == 0) row_scale[row] = __uint_as_float((uint32_t)(127 - sexp) << 23);
+      __half *p1 = reinterpret_cast<__half *>(y_lo) + (int64_t)row * 2 * Kp, *p2 = p1 + Kp;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = LN_COL(i);
+        if (c < nv) {
+          const float4 x = make_float4(v[i].x * sc, v[i].y * sc, v[i].z * sc, v[i].w * sc);
+          const __half2 a0 = __floats2half2_rn(x.x, x.y), a1 = __floats2half2_rn(x.z, x.w);
+          const float2 f0 = __half22float2(a0), f1 = __half22float2(a1);
+          const __half2 b0 = __floats2half2_rn(x.x - f0.x, x.y - f0.y), b1 = __floats2half2_rn(x.z - f1.x, x.w - f1.y);
+          *reinterpret_cast<uint2 *>(p1 + 4 * c) = make_uint2(*reinterpret_cast<const uint32_t *>(&a0), *reinterpret_cast<const uint32_t *>(&a1));
+          *reinterpret_cast<uint2 *>(p2 + 4 * c) = make_uint2(*reinterpret_cast<const uint32_t *>(&b0), *reinterpret_cast<const uint32_t *>(&b1));
+        }
+      }
+      for (int c = d + lane; c < Kp; c += 32) { p1[c] = __float2half(0.0f); p2[c] = __float2half(0.0f); }
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < MAXV; i += 2) {
       const int c = LN_COL(i);   // even float4 column; c + 1 is register i + 1
@@ -675,6 +720,35 @@ extern "C" int mts_add_ln_fwd(const float *a, const float *res, const float *gam
   else
     ln_fwd_kernel<1, 16><<<grid, 256, 0, (cudaStream_t)stream>>>(a, 0, res, nullptr, gamma, beta, M, 0, d, eps, y, y_hi, y_lo,
                                                                   Kp, sum_out, stats, nullptr, nullptr);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+// The same two kernels writing the fp16-split operand of mts_gemm_f16x3 (pieces [rows][2][K64] fp16 + row_scale [rows]) next to y
+extern "C" int mts_embed_ln_fwd_f16(const float *x, int64_t x_bstride, const float *pos, const float *typ, const float *gamma,
+                                    const float *beta, int B, int S, int d, float eps, float *y, void *pieces, int K64,
+                                    float *row_scale, const int32_t *lengths, const int32_t *offsets, void *stream) {
+  MTS_REQUIRE(x && pos && typ && gamma && beta && y && pieces && row_scale, MTS_E_BADARG, "embed_ln_fwd_f16: null pointer");
+  MTS_REQUIRE(!offsets || lengths, MTS_E_BADARG, "embed_ln_fwd_f16: ragged output needs the lengths");
+  MTS_REQUIRE(B > 0 && S > 0 && d > 0 && d % 4 == 0 && d <= 1024, MTS_E_UNSUPPORTED, "embed_ln_fwd_f16: width must be a multiple of 4 and <= 1024");
+  MTS_REQUIRE(K64 % 64 == 0 && K64 >= d, MTS_E_BADARG, "embed_ln_fwd_f16: K64 must be a multiple of 64 and >= d");
+  const int M = B * S;
+  const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);
+  ln_fwd_kernel<0, 8, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bstride, pos, typ, gamma, beta, M, S, d, eps, y, nullptr,
+                                                                     reinterpret_cast<float *>(pieces), K64, nullptr, nullptr, lengths,
+                                                                     offsets, row_scale);
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mts_add_ln_fwd_f16(const float *a, const float *res, const float *gamma, const float *beta, int M, int d, float eps,
+                                  float *y, void *pieces, int K64, float *row_scale, void *stream) {
+  MTS_REQUIRE(a && gamma && beta && y && pieces && row_scale, MTS_E_BADARG, "add_ln_fwd_f16: null pointer");
+  MTS_REQUIRE(M > 0 && d > 0 && d % 4 == 0 && d <= 1024, MTS_E_UNSUPPORTED, "add_ln_fwd_f16: width must be a multiple of 4 and <= 1024");
+  MTS_REQUIRE(K64 % 64 == 0 && K64 >= d, MTS_E_BADARG, "add_ln_fwd_f16: K64 must be a multiple of 64 and >= d");
+  const unsigned grid = (unsigned)min((int64_t)(M + 7) / 8, (int64_t)kNumSMs * 8);
+  ln_fwd_kernel<1, 8, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a, 0, res, nullptr, gamma, beta, M, 0, d, eps, y, nullptr,
+                                                                     reinterpret_cast<float *>(pieces), K64, nullptr, nullptr, nullptr,
+                                                                     nullptr, row_scale);
   MTS_LAUNCH_CHECK();
   return 0;
 }

@@ -214,6 +214,33 @@ def input_projection(x1, x2, B, T, w_hi, w_lo, bias, out, N):
     return out
 
 
+def f16_pieces(w):
+    """fp32 matrix [N, K] -> (pieces [N, 2, K64] fp16, scale [N]): the fp16-split operand of mts_gemm_f16x3.  Row n is scaled by the
+    exact power of two 2^s that puts its largest magnitude into [2^13, 2^14); pieces = fp16(w 2^s), fp16(w 2^s - piece 1);
+    scale = 2^-s.  (Weight packing: once per parameter version, plain torch ops.)"""
+    N, K = w.shape
+    K64 = (K + 63) // 64 * 64
+    amax = w.abs().amax(dim=1)
+    _, e = torch.frexp(amax)                     # amax = m 2^e, m in [0.5, 1)
+    sexp = torch.where(amax > 0, 14 - e, torch.zeros_like(e)).clamp(-110, 110)
+    scale = torch.ldexp(torch.ones_like(amax), sexp)
+    ws = w * scale[:, None]
+    pieces = torch.zeros((N, 2, K64), device=w.device, dtype=torch.float16)
+    w1 = ws.half()
+    pieces[:, 0, :K] = w1
+    pieces[:, 1, :K] = (ws - w1.float()).half()
+    return pieces.contiguous(), (1.0 / scale).contiguous()
+
+
+def gemm_f16x3(a_pieces, a_scale, b_pieces, b_scale, bias, out, M, N, epilogue=0, out_lo=None):
+    """out [M, N] = A B^T (+ bias; epilogue 2: GELU) over fp16-split operands (include/mts_b200.h, mts_gemm_f16x3)."""
+    K64 = a_pieces.shape[-1]
+    assert b_pieces.shape[-1] == K64
+    _call("mts_gemm_f16x3", _ptr(a_pieces), _ptr(b_pieces), _ptr(a_scale), _ptr(b_scale), _ptr(bias), _ptr(out), _ptr(out_lo), M, N,
+          K64, out.stride(-2), epilogue if bias is not None else 0, _stream())
+    return out
+
+
 def transpose_split(src_ptr, bstride, ld, rows, cols, T, device, shift=0, lengths=None, side=A_SIDE):
     """(hi, lo) [cols, pad32(rows)] of the transposed (optionally time-shifted / length-masked) source: the K-major
     operand of a GEMM that contracts over tokens (weight gradients)."""

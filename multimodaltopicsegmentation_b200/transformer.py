@@ -158,6 +158,19 @@ class PackedEncoder:
         self.key, self.layers = key, layers
         return layers
 
+    def pieces(self, l):
+        """fp16-split copies of the two weights whose A operand comes from a LayerNorm (q/k/v and the intermediate dense):
+        made on first use per weight version, inference only."""
+        ent = self.get()[l]
+        if "wqkv_p" not in ent:
+            lyr = self.params.encoder.layer[l]
+            sa = lyr.attention.self
+            with torch.no_grad():
+                wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], dim=0)
+                ent["wqkv_p"] = ops.f16_pieces(wqkv.detach())
+                ent["w1_p"] = ops.f16_pieces(lyr.intermediate.dense.weight.detach())
+        return ent
+
     def transposed(self, l):
         """hi/lo of W^T for the dX GEMMs of the backward pass (made on first use per weight version)."""
         ent = self.get()[l]
@@ -197,6 +210,30 @@ def _ln(mode, a, b, typ, gamma, beta, B, S, d, want_split, save, lens=None):
     return y, (y if (want_split and hi is None) else hi), lo, pre, stats
 
 
+def _ln_f16(mode, a, b, typ, gamma, beta, B, S, d, lens=None):
+    """_ln for inference with the fp16-split operand of mts_gemm_f16x3 as the second output: (y, pieces [M, 2, K64], scale [M])."""
+    M = lens.N if lens is not None else B * S
+    dev = a.device
+    k64 = (d + 63) // 64 * 64
+    y = torch.empty((M, d), device=dev, dtype=torch.float32)
+    pieces = torch.empty((M, 2, k64), device=dev, dtype=torch.float16)
+    scale = torch.empty((M,), device=dev, dtype=torch.float32)
+    if mode == 0:
+        _call("mts_embed_ln_fwd_f16", _ptr(a), a.stride(0), _ptr(b), _ptr(typ), _ptr(gamma), _ptr(beta), B, S, d, LN_EPS, _ptr(y),
+              _ptr(pieces), k64, _ptr(scale), _ptr(lens.dev) if lens is not None else 0, _ptr(lens.offs) if lens is not None else 0,
+              _stream())
+    else:
+        _call("mts_add_ln_fwd_f16", _ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), M, d, LN_EPS, _ptr(y), _ptr(pieces), k64, _ptr(scale),
+              _stream())
+    return y, pieces, scale
+
+
+# The dense layers fed by a LayerNorm (q/k/v projection, intermediate dense) run over fp16-split operands in inference
+# (mts_gemm_f16x3: 6 instead of 8 MMAs per 32 k, half the operand bytes; 1.27x on those products at configs[2]);
+# MTS_XF_F16X3=0 keeps every product on mts_gemm_tf32x3.
+F16X3 = __import__("os").environ.get("MTS_XF_F16X3", "1") != "0"
+
+
 # Token layout inside the encoder: "ragged" (default) keeps rows only for the sum(len) valid sentences, so the dense
 # layers, LayerNorms and GELU do no work on padding (45 % of the rows at configs[2]); "padded" is the reference's
 # [B*S] layout.  Valid positions come out identical either way (padded keys are masked); with the ragged layout the
@@ -227,6 +264,72 @@ def _drop(t, site, p, masks):
     return t
 
 
+def _f16x3_eligible(M, d, F, ops_mod):
+    """mts_gemm_f16x3 is served by the 2-SM GEMM (M, N >= 256) and the fp16-pieces LayerNorm (d <= 1024); the out-proj and the
+    output dense keep mts_gemm_tf32x3 (their A operands come from the attention kernel / the GELU epilogue)."""
+    return (F16X3 and ops_mod.GEMM_IMPL != "simt" and ops_mod.PRECISION != "bf16" and M >= 256 and d % 4 == 0 and d <= 1024
+            and 3 * d >= 256 and _pad32(d) == d)
+
+
+def encoder_forward_f16(x, lens, packed: PackedEncoder, nheads, reaches):
+    """Inference pass of the encoder with the LayerNorm-fed dense layers on fp16-split operands:
+
+        emb LN -> (h, h pieces) -> QKV [f16x3] -> banded attention -> out-proj [tf32x3] -> LN(t + h) -> (y, y pieces)
+               -> intermediate dense + GELU [f16x3 when F >= 256, writes (z, z_lo)] -> output dense [tf32x3] -> LN(u + y) -> ...
+
+    Same arithmetic contract as encoder_forward (fp32-grade products: relative error ~2^-22 instead of ~2^-19)."""
+    B, S, d = x.shape
+    ragged = LAYOUT == "ragged"
+    M = lens.N if ragged else B * S
+    offs = _ptr(lens.offs) if ragged else 0
+    dev = x.device
+    hd = d // nheads
+    m = packed.params
+    emb = m.embeddings
+    h, h_p, h_s = _ln_f16(0, x, emb.position_embeddings.weight.detach(), emb.token_type_embeddings.weight.detach()[0],
+                          emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), B, S, d, lens if ragged else None)
+    n_layers = len(m.encoder.layer)
+    for l in range(n_layers):
+        lyr = m.encoder.layer[l]
+        ent = packed.pieces(l)
+        F = lyr.intermediate.dense.out_features
+        qkv = torch.empty((M, 3 * d), device=dev, dtype=torch.float32)
+        ops.gemm_f16x3(h_p, h_s, ent["wqkv_p"][0], ent["wqkv_p"][1], ent["bqkv"], qkv, M, 3 * d, epilogue=1)
+        a = torch.empty((M, d), device=dev, dtype=torch.float32)
+        a_lo = torch.empty((M, d), device=dev, dtype=torch.float32)
+        _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), offs, B, S, nheads, hd, reaches[l], 0, _ptr(a), _ptr(a_lo), d,
+              0, _stream())
+        t = torch.empty((M, d), device=dev, dtype=torch.float32)
+        ops.gemm_tf32x3(a, a_lo, ent["wo"][0], ent["wo"][1], ent["bo"], t, M, d, epilogue=1)
+        ln1 = lyr.attention.output.LayerNorm
+        kf = _pad32(F)
+        z_hl = torch.empty((2, M, kf), device=dev, dtype=torch.float32)
+        if F >= 256 and kf == F:
+            y, y_p, y_s = _ln_f16(1, t, h, None, ln1.weight.detach(), ln1.bias.detach(), M, 1, d)
+            ops.gemm_f16x3(y_p, y_s, ent["w1_p"][0], ent["w1_p"][1], ent["b1"], z_hl[0], M, F, epilogue=2, out_lo=z_hl[1])
+        else:   # narrow feed-forward: the TF32 + bf16 product (GELU + operand pair in its epilogue when the width allows)
+            y, y_hi, y_lo, _, _ = _ln(1, t, h, None, ln1.weight.detach(), ln1.bias.detach(), M, 1, d, True, False)
+            if kf == F:
+                _call("mts_gemm_tf32x3_gelu_pair", _ptr(y_hi), _ptr(y_lo), _ptr(ent["w1"][0]), _ptr(ent["w1"][1]), _ptr(ent["b1"]),
+                      _ptr(z_hl[0]), _ptr(z_hl[1]), M, F, y_hi.shape[1], _stream())
+            else:
+                zp = torch.empty((M, F), device=dev, dtype=torch.float32)
+                ops.gemm_tf32x3(y_hi, y_lo, ent["w1"][0], ent["w1"][1], ent["b1"], zp, M, F, epilogue=1)
+                _call("mts_gelu_split", _ptr(zp), F, M, F, kf, 0, _ptr(z_hl[0]), _ptr(z_hl[1]), _stream())
+        u = torch.empty((M, d), device=dev, dtype=torch.float32)
+        ops.gemm_tf32x3(z_hl[0], z_hl[1], ent["w2"][0], ent["w2"][1], ent["b2"], u, M, d, epilogue=1)
+        ln2 = lyr.output.LayerNorm
+        if l + 1 < n_layers:
+            h, h_p, h_s = _ln_f16(1, u, y, None, ln2.weight.detach(), ln2.bias.detach(), M, 1, d)
+        else:
+            h = _ln(1, u, y, None, ln2.weight.detach(), ln2.bias.detach(), M, 1, d, False, False)[0]
+    if ragged:  # back to the caller's [B,S,d] layout, padded sentences zero
+        out = torch.empty((B, S, d), device=dev, dtype=torch.float32)
+        _call("mts_ragged_copy", _ptr(h), _ptr(out), _ptr(lens.dev), _ptr(lens.offs), B, S, d, 1, 0.0, _stream())
+        return out
+    return h.view(B, S, d)
+
+
 def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hidden=0.0):
     """x [B,S,d] -> last hidden state [B,S,d].  `reaches[l]` = one-sided window of layer l.
     With save=True also returns what the backward pass needs.
@@ -236,6 +339,8 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hid
     B, S, d = x.shape
     ragged = LAYOUT == "ragged"
     M = lens.N if ragged else B * S
+    if not save and p_hidden == 0 and not FOLD_RESIDUAL and _f16x3_eligible(M, d, 0, ops):
+        return encoder_forward_f16(x, lens, packed, nheads, reaches), None
     offs = _ptr(lens.offs) if ragged else 0
     dev = x.device
     hd = d // nheads

@@ -121,6 +121,21 @@ if __name__ == "__main__":
             tot += ms
             print(f"{name:9s} {M} x {N} x {K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s fp32-equivalent  norm-wise err {err:.2e}")
         print(f"sum per layer {tot:.3f} ms, x 6 layers = {6 * tot:.2f} ms")
+    elif what == "gemm_f16x3":  # timing + accuracy probe of the fp16-split product against the TF32 + bf16 one
+        for M, N, K in ((19200, 2048, 896), (19200, 2048, 512), (135428, 2688, 896), (135428, 896, 896), (135428, 256, 896), (135428, 896, 256)):
+            a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev) * 0.05; bias = torch.randn(N, device=dev)
+            c = torch.empty(M, N, device=dev); c2 = torch.empty(M, N, device=dev)
+            a_hi, a_lo = ops.split_tf32(a); b_hi, b_lo = ops.split_tf32(b, side=ops.B_SIDE)
+            ms0 = timeit(lambda: ops.gemm_tf32x3(a_hi, a_lo, b_hi, b_lo, bias, c, M, N, epilogue=1))
+            (ap, asc), (bp, bsc) = ops.f16_pieces(a), ops.f16_pieces(b)
+            call = lambda: ops.gemm_f16x3(ap, asc, bp, bsc, bias, c2, M, N, epilogue=1)
+            ms1 = timeit(call)
+            rows = torch.randint(0, M, (512,), device=dev)
+            ref = a[rows].double() @ b.double().t() + bias.double()
+            e0 = float((c[rows].double() - ref).abs().max() / ref.abs().max())
+            e1 = float((c2[rows].double() - ref).abs().max() / ref.abs().max())
+            print(f"{M} x {N} x {K}: tf32+bf16 {ms0:.3f} ms ({2.0 * M * N * K / ms0 / 1e9:.0f} TF, err {e0:.1e})   "
+                  f"fp16x3 {ms1:.3f} ms ({2.0 * M * N * K / ms1 / 1e9:.0f} TF, err {e1:.1e})", flush=True)
     elif what == "gemm_one":
         M, N, K = 19200, 2048, 896
         a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)

@@ -1243,3 +1243,91 @@ def test_input_projection_reads_sources_in_place(dev, B, T, D1, D2, N):
     xc = xl[:, :T] if x2 is None else torch.cat([xl[:, :T], x2], dim=2)
     ref_c = xc.reshape(B * T, -1).double() @ w.double().T + bias.double()
     assert float((out_c.double() - ref_c).abs().max()) / float(ref_c.abs().max()) < 2e-5
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fp16-split dense layers (mts_gemm_f16x3) and the LayerNorms that produce their operand
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(300, 256, 64), (1000, 2688, 896), (513, 256, 896), (4096, 2048, 512), (700, 896, 200)])
+def test_gemm_f16x3(dev, M, N, K):
+    """(A1 B1^T + A2 B1^T + A1 B2^T) rs cs + bias against a float64 product: rows of A and of B spanning six decades (every row
+    carries its own power-of-two scale), K padded to 64 with zeros; the GELU + operand-pair epilogue against torch."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = torch.randn((M, K), device=dev, generator=g) * (10.0 ** (torch.rand((M, 1), device=dev, generator=g) * 6 - 3))
+    b = torch.randn((N, K), device=dev, generator=g) * (10.0 ** (torch.rand((N, 1), device=dev, generator=g) * 6 - 4))
+    a[3] = 0.0
+    bias = torch.randn((N,), device=dev, generator=g)
+    ap, asc = ops.f16_pieces(a)
+    bp, bsc = ops.f16_pieces(b)
+    # the pieces reproduce the scaled operand to ~2^-22 of the row maximum
+    rec = (ap[:, 0, :K].float() + ap[:, 1, :K].float()) * asc[:, None]
+    assert float(((rec - a).abs() / a.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)).max()) < 2.0 ** -21
+    out = torch.full((M, N), float("nan"), device=dev)
+    ops.gemm_f16x3(ap, asc, bp, bsc, bias, out, M, N, epilogue=1)
+    ref = a.double() @ b.double().T + bias.double()
+    # error relative to |a_m| . |b_n| (what an fp32 product of these rows can promise), worst over the matrix
+    bound = (a.double().abs() @ b.double().abs().T) + bias.double().abs()
+    err = float(((out.double() - ref).abs() / bound.clamp_min(1e-30)).max())
+    print(f"  gemm_f16x3 {M} x {N} x {K}: worst |err| / (|a| . |b|) = {err:.2e}")
+    assert err < 1e-5, err
+    if N % 32 == 0:
+        z = torch.full((M, N), float("nan"), device=dev)
+        z_lo = torch.full((M, N), float("nan"), device=dev)
+        ops.gemm_f16x3(ap, asc, bp, bsc, bias, z, M, N, epilogue=2, out_lo=z_lo)
+        zr = torch.nn.functional.gelu(ref.float())
+        close(z, zr, rtol=1e-4, atol=2e-5 * float(zr.abs().max()))
+        check_operand_pair(z, z_lo, z, side=0)
+
+
+@pytest.mark.parametrize("M,d", [(300, 896), (64, 100), (1000, 1024)])
+def test_layernorm_writes_fp16_split_operand(dev, M, d):
+    """mts_add_ln_fwd_f16: y bit-equal to mts_add_ln_fwd's, pieces + row scale reproduce y to ~2^-22 of the row maximum, zero
+    padding up to K64."""
+    from multimodaltopicsegmentation_b200 import transformer as tr
+
+    g = torch.Generator(device=dev).manual_seed(M + d)
+    a = torch.randn((M, d), device=dev, generator=g) * 3.0
+    r = torch.randn((M, d), device=dev, generator=g)
+    gamma = torch.randn((d,), device=dev, generator=g)
+    beta = torch.randn((d,), device=dev, generator=g) * 0.1
+    gamma[::7] *= 1e-3
+    y_ref = tr._ln(1, a, r, None, gamma, beta, M, 1, d, False, False)[0]
+    y, pieces, scale = tr._ln_f16(1, a, r, None, gamma, beta, M, 1, d)
+    assert torch.equal(y, y_ref)
+    rec = (pieces[:, 0, :d].float() + pieces[:, 1, :d].float()) * scale[:, None]
+    rel = (rec - y).abs() / y.abs().amax(dim=1, keepdim=True)
+    assert float(rel.max()) < 2.0 ** -21, float(rel.max())
+    assert float(pieces[:, :, d:].abs().max() if pieces.shape[2] > d else 0.0) == 0.0
+    lg = torch.log2(scale)
+    assert torch.equal(lg, lg.round())                      # exact powers of two
+    top = y.abs().amax(dim=1) / scale
+    assert float(top.min()) >= 2.0 ** 13 and float(top.max()) < 2.0 ** 14
+
+
+def test_encoder_fp16_split_path_equals_tf32_path(dev):
+    """The inference encoder with the LayerNorm-fed dense layers on fp16-split operands against the same encoder with every
+    product on mts_gemm_tf32x3 (both fp32-grade: they must agree far inside the 1e-4 contract), ragged batch, 3 layers."""
+    from multimodaltopicsegmentation_b200 import transformer as tr
+
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(55)
+    d, F, nh, w = 256, 256, 8, 8
+    seg = tr.Transformer_segmenter(2, d, F, num_layers=3, nheads=nh, loss_fn="FocalLoss", window_size=w).to(dev).eval()
+    x = torch.randn(6, 96, d, generator=g).to(dev)
+    lengths = torch.tensor([96, 50, 77, 96, 13, 64])
+    outs = []
+    for flag in (True, False):
+        tr.F16X3 = flag
+        try:
+            n0 = tr.ops.launch_count()
+            with torch.no_grad():
+                outs.append(seg.model(x, lengths))
+        finally:
+            tr.F16X3 = True
+    err = float((outs[0] - outs[1]).abs().max()) / float(outs[1].abs().max())
+    print(f"  encoder fp16-split vs tf32 path: norm-wise difference {err:.2e}")
+    assert err < 2e-5
+    for b, n in enumerate(lengths.tolist()):
+        assert float(outs[0][b, n:].abs().max() if n < 96 else 0.0) == 0.0
