@@ -137,7 +137,7 @@ if __name__ == "__main__":
             print(f"{M} x {N} x {K}: tf32+bf16 {ms0:.3f} ms ({2.0 * M * N * K / ms0 / 1e9:.0f} TF, err {e0:.1e})   "
                   f"fp16x3 {ms1:.3f} ms ({2.0 * M * N * K / ms1 / 1e9:.0f} TF, err {e1:.1e})", flush=True)
     elif what == "gemm_one":
-        M, N, K = 19200, 2048, 896
+        M, N, K = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (19200, 2048, 896)
         a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)
         c = torch.empty(M, N, device=dev)
         a_hi, a_lo = ops.split_tf32(a); b_hi, b_lo = ops.split_tf32(b, side=ops.B_SIDE)

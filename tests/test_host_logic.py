@@ -267,3 +267,27 @@ def test_recurrent_longformer_parameter_tree_and_constructor_checks():
     seg = TextSegmenter(architecture="BiLSTMRestrictedMHA", tagset_size=2, embedding_dim=24, hidden_dim=16, num_layers=1,
                         loss_fn="FocalLoss", nheads=4, attention_window=8)
     assert isinstance(seg.model, RecurrentLongformer)
+
+
+def test_f16_pieces_weight_packing():
+    """ops.f16_pieces (host-side weight packing of mts_gemm_f16x3, plain torch): exact power-of-two row scales that put the
+    row maximum into [2^13, 2^14), pieces that reproduce the scaled row to ~2^-22 of its maximum, zero K padding, zero rows."""
+    import torch
+
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(37, 100, generator=g) * (10.0 ** (torch.rand(37, 1, generator=g) * 8 - 5))
+    w[5] = 0.0
+    pieces, scale = ops.f16_pieces(w)
+    assert pieces.shape == (37, 2, 128) and pieces.dtype == torch.float16 and scale.shape == (37,)
+    lg = torch.log2(scale)
+    assert torch.equal(lg, lg.round())
+    top = w.abs().amax(dim=1) / scale
+    keep = w.abs().amax(dim=1) > 0
+    assert float(top[keep].min()) >= 2.0 ** 13 and float(top[keep].max()) < 2.0 ** 14
+    rec = (pieces[:, 0, :100].float() + pieces[:, 1, :100].float()) * scale[:, None]
+    rel = (rec - w).abs() / w.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)
+    assert float(rel.max()) < 2.0 ** -21
+    assert float(pieces[:, :, 100:].abs().max()) == 0.0 and float(pieces[5].abs().max()) == 0.0
+    assert torch.isfinite(pieces.float()).all()
