@@ -1044,7 +1044,7 @@ def run_ours(args, rank, world, local_rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": c["B"], "global_batch": c["B"] * world,
-                   "l2": "4 rotating input sets (275 MB) exceed the 126 MB L2", "gemm": "tcgen05 TF32 + bf16 correction",
+                   "l2": "4 rotating input sets (275 MB) exceed the 126 MB L2", "gemm": "tcgen05: layer-0 projection over fp16-split operands (3 kind::f16 products), layer 1 TF32 + bf16 correction",
                    "launch": f"one CUDA graph per input set ({launches_per_step} kernels)" if graphs is not None else "eager launches",
                    "recurrence": ("tcgen05 fp16-split operands (3 kind::f16 products), W_hh resident in TMEM" if roof["kernel"].startswith("lstm_fwd_h3")
                                   else "tcgen05 TF32 + bf16 correction, W_hh resident in TMEM" if roof["kernel"].startswith("lstm_fwd_tc") else "packed-fp32 FMA"),

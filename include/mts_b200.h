@@ -144,6 +144,11 @@ int mts_gemm_tf32x3_srcs(const float *A1, int D1, int64_t ld1, const float *A2, 
  * mts_gemm_tf32x3, relative error ~2^-22.  A_pieces [M][2][K] fp16 (mts_add_ln_fwd_f16 / mts_embed_ln_fwd_f16 write it),
  * B_pieces [N][2][K], row_scale [M] / col_scale [N] = 1 / s or NULL; K % 64 == 0, K <= 3072, M, N >= 256.  C_lo (optional):
  * the packed bf16 correction operand of C, for a following mts_gemm_tf32x3 (dense rows, N % 32 == 0). */
+/* Early-fusion concat + crop (utils/load_datasets_precomputed.py:158-161, NeuralArchitectures.py:115) straight into the
+ * fp16-split operand: pieces [B*T][2][K64] fp16 and row_scale [B*T] of the rows [src1[b, t, :] | src2[b, t, :]], t < T
+ * (a warp owns a row: its maximum fixes the row's power-of-two scale).  D1, D2 % 4 == 0, D1 + D2 <= 2048, K64 % 64 == 0. */
+int mts_pack_rows_f16(const float *src1, int64_t bstride1, int D1, const float *src2, int64_t bstride2, int D2, int B, int T,
+                      int K64, void *pieces, float *row_scale, void *stream);
 int mts_gemm_f16x3(const void *A_pieces, const void *B_pieces, const float *row_scale, const float *col_scale, const float *bias,
                    float *C, float *C_lo, int M, int N, int K, int64_t ldc, int epilogue, void *stream);
 

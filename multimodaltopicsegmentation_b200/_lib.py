@@ -37,6 +37,7 @@ SIGNATURES = {
     "mts_lstm_rec_fwd_h3": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P]),
     "mts_gemm_tf32x3_srcs": (c_int, [_P, c_int, c_int64, _P, c_int, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int,
                                      c_int, _P]),
+    "mts_pack_rows_f16": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "mts_gemm_f16x3": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
     "mts_gemm_tf32x3_gelu_pair": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "mts_gemm_bf16p": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, c_int, _P]),

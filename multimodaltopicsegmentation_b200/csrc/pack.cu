@@ -2,6 +2,8 @@
 // The reference materialises the concat on the host at load time (utils/load_datasets_precomputed.py:158-161);
 // here the two modality tensors stay separate and the concat happens while the GEMM operand is written.
 // Pure streaming kernels: 4(D1+D2) bytes read, 8 Kp bytes written per sentence.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mts {
@@ -213,6 +215,77 @@ extern "C" int mts_pack_rows_split(const float *src1, int64_t bstride1, int D1, 
     pack_rows_split_kernel<<<grid_for((int64_t)B * T * Kp), 256, 0, (cudaStream_t)stream>>>(src1, bstride1, D1, src2,
                                                                                            bstride2, D2, B, T, Kp, hi, lo);
   }
+  MTS_LAUNCH_CHECK();
+  return 0;
+}
+
+// Early-fusion concat + crop straight into the FP16-SPLIT operand of mts_gemm_f16x3: a warp owns one (episode, sentence) row of
+// [x1 | x2], finds its largest magnitude, scales by the exact power of two that puts it into [2^13, 2^14) and writes
+// pieces [row][2][K64] (fp16(x s), fp16(x s - piece 1), zero beyond D1 + D2) and row_scale [row] = 1 / s.  D1, D2 % 4 == 0,
+// D1 + D2 <= 2048.
+constexpr int PF_MAXV = 16;   // float4 per lane: D1 + D2 <= 2048 (8 serves widths <= 1024 with half the registers)
+template <int MAXV>
+__global__ void __launch_bounds__(256) pack_rows_f16_kernel(const float *__restrict__ src1, int64_t bstride1, int D1,
+                                                            const float *__restrict__ src2, int64_t bstride2, int D2, int B, int T,
+                                                            int K64, __half *__restrict__ pieces, float *__restrict__ row_scale) {
+  const int lane = threadIdx.x & 31;
+  const int nv1 = D1 >> 2, nv = (D1 + D2) >> 2;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int rows = B * T;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const int b = row / T, t = row % T;
+    const float4 *p1 = reinterpret_cast<const float4 *>(src1 + (int64_t)b * bstride1 + (int64_t)t * D1);
+    const float4 *p2 = src2 ? reinterpret_cast<const float4 *>(src2 + (int64_t)b * bstride2 + (int64_t)t * D2) : nullptr;
+    float4 v[MAXV];
+    float mx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        v[i] = c < nv1 ? __ldg(p1 + c) : __ldg(p2 + (c - nv1));
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[i].x), fabsf(v[i].y))), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
+      }
+    }
+    mx = warp_max(mx);
+    const int ex = (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+    int sexp = ex == 0 ? 0 : 127 + 13 - ex;
+    sexp = sexp > 110 ? 110 : (sexp < -110 ? -110 : sexp);
+    const float sc = __uint_as_float((uint32_t)(127 + sexp) << 23);
+    if (lane == 0) row_scale[row] = __uint_as_float((uint32_t)(127 - sexp) << 23);
+    __half *q1 = pieces + (int64_t)row * 2 * K64, *q2 = q1 + K64;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float4 x = make_float4(v[i].x * sc, v[i].y * sc, v[i].z * sc, v[i].w * sc);
+        const __half2 a0 = __floats2half2_rn(x.x, x.y), a1 = __floats2half2_rn(x.z, x.w);
+        const float2 f0 = __half22float2(a0), f1 = __half22float2(a1);
+        const __half2 b0 = __floats2half2_rn(x.x - f0.x, x.y - f0.y), b1 = __floats2half2_rn(x.z - f1.x, x.w - f1.y);
+        *reinterpret_cast<uint2 *>(q1 + 4 * c) = make_uint2(*reinterpret_cast<const uint32_t *>(&a0), *reinterpret_cast<const uint32_t *>(&a1));
+        *reinterpret_cast<uint2 *>(q2 + 4 * c) = make_uint2(*reinterpret_cast<const uint32_t *>(&b0), *reinterpret_cast<const uint32_t *>(&b1));
+      }
+    }
+    for (int c = D1 + D2 + lane; c < K64; c += 32) { q1[c] = __float2half(0.0f); q2[c] = __float2half(0.0f); }
+  }
+}
+
+extern "C" int mts_pack_rows_f16(const float *src1, int64_t bstride1, int D1, const float *src2, int64_t bstride2, int D2, int B,
+                                 int T, int K64, void *pieces, float *row_scale, void *stream) {
+  MTS_REQUIRE(src1 && pieces && row_scale, MTS_E_BADARG, "pack_rows_f16: null pointer");
+  MTS_REQUIRE(D2 == 0 || src2, MTS_E_BADARG, "pack_rows_f16: D2 > 0 without src2");
+  MTS_REQUIRE(B > 0 && T > 0 && D1 > 0 && D2 >= 0, MTS_E_BADARG, "pack_rows_f16: bad shape");
+  MTS_REQUIRE(K64 % 64 == 0 && K64 >= D1 + D2, MTS_E_BADARG, "pack_rows_f16: K64 must be a multiple of 64 and >= D1 + D2");
+  MTS_REQUIRE(D1 % 4 == 0 && D2 % 4 == 0 && D1 + D2 <= 128 * PF_MAXV && bstride1 % 4 == 0 && bstride2 % 4 == 0 &&
+                  ((((uintptr_t)src1 | (uintptr_t)src2 | (uintptr_t)pieces) & 15) == 0),
+              MTS_E_UNSUPPORTED, "pack_rows_f16: widths must be multiples of 4 (sum <= 2048) and rows 16-byte aligned");
+  const int64_t rows = (int64_t)B * T;
+  const unsigned grid = (unsigned)((rows + 7) / 8 < (int64_t)kNumSMs * 16 ? (rows + 7) / 8 : (int64_t)kNumSMs * 16);
+  if (D1 + D2 <= 1024)
+    pack_rows_f16_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(src1, bstride1, D1, src2, bstride2, D2, B, T, K64,
+                                                                     reinterpret_cast<__half *>(pieces), row_scale);
+  else
+    pack_rows_f16_kernel<PF_MAXV><<<grid, 256, 0, (cudaStream_t)stream>>>(src1, bstride1, D1, src2, bstride2, D2, B, T, K64,
+                                                                           reinterpret_cast<__half *>(pieces), row_scale);
   MTS_LAUNCH_CHECK();
   return 0;
 }

@@ -199,10 +199,35 @@ def _direct_sources_ok(x1, x2, B, T):
     return x2 is None or x1.shape[2] % 32 == 0
 
 
-def input_projection(x1, x2, B, T, w_hi, w_lo, bias, out, N):
+# The same projection over fp16-split operands (mts_pack_rows_f16 -> mts_gemm_f16x3: 6 instead of 8 MMAs per 32 k, 1.27x at
+# cfg1's 19 200 x 2048 x 896); MTS_PROJ_F16X3=0 keeps the TF32 + bf16 product.
+PROJ_F16X3 = __import__("os").environ.get("MTS_PROJ_F16X3", "1") != "0"
+
+
+def _f16_projection_ok(x1, x2, B, T, N):
+    D = x1.shape[2] + (0 if x2 is None else x2.shape[2])
+    for x in (x1, x2):
+        if x is not None and (x.dtype != torch.float32 or x.shape[2] % 4 != 0 or x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0):
+            return False
+    return PROJ_F16X3 and PRECISION != "bf16" and B * T >= 256 and N >= 256 and D <= 2048
+
+
+def input_projection(x1, x2, B, T, w_hi, w_lo, bias, out, N, w_pieces=None):
     """out [B*T, N] = [x1 | x2] W^T + bias: early-fusion concat + linear projection (load_datasets_precomputed.py:158-161 +
-    NeuralArchitectures.py:113) with the embeddings read in place by the GEMM's TMA producer."""
+    NeuralArchitectures.py:113).  w_pieces: callable returning the fp16-split weights (pieces, scale); with it and a large
+    enough product the operand is packed as fp16 pieces and the product runs in the GEMM's fp16-split mode; otherwise the
+    embeddings are read in place by the TF32 + bf16 GEMM's TMA producer."""
     x1, x2 = _rows_ok(x1, "input", B, T), _rows_ok(x2, "second input", B, T)
+    if w_pieces is not None and _f16_projection_ok(x1, x2, B, T, N):
+        D1 = x1.shape[2]
+        D2 = 0 if x2 is None else x2.shape[2]
+        k64 = (D1 + D2 + 63) // 64 * 64
+        pieces = torch.empty((B * T, 2, k64), device=x1.device, dtype=torch.float16)
+        scale = torch.empty((B * T,), device=x1.device, dtype=torch.float32)
+        _call("mts_pack_rows_f16", _ptr(x1), x1.stride(0), D1, _ptr(x2), 0 if x2 is None else x2.stride(0), D2, B, T, k64,
+              _ptr(pieces), _ptr(scale), _stream())
+        wp, ws = w_pieces()
+        return gemm_f16x3(pieces, scale, wp, ws, bias, out, B * T, N, epilogue=1)
     if not (PROJ_DIRECT and _direct_sources_ok(x1, x2, B, T)):
         a_hi, a_lo = pack_rows_split(x1, x2, B, T)
         return gemm_tf32x3(a_hi, a_lo, w_hi, w_lo, bias, out, B * T, N, epilogue=1, ldc=N)
@@ -334,6 +359,17 @@ class PackedLstm:
                 out.extend(self._params(rnn, layer))
         return out
 
+    def wih_pieces(self, layer, e):
+        """fp16-split copy of W_ih of (layer, encoder e), both directions stacked: (pieces [8H, 2, K64], scale [8H]) for
+        mts_gemm_f16x3.  Made on first use per weight version."""
+        ent = self.get()[layer]
+        cache = ent.setdefault("wih_p", {})
+        if e not in cache:
+            w_f, _, _, _, w_r = self._params(self.rnns[e], layer)[:5]
+            with torch.no_grad():
+                cache[e] = f16_pieces(torch.cat([w_f.detach(), w_r.detach()], dim=0))
+        return cache[e]
+
     def wih_packed_a(self, layer, e):
         """bf16 path: W_ih of (layer, encoder e), both directions stacked, packed like an A operand (side 0) so that the
         packed halves of activations and weights pair up x * w.  Made on first use per weight version."""
@@ -409,10 +445,12 @@ def _lstm_stack_forward(x1, x2, xs2, lens, packed, H, L, n_enc, save):
                 continue
             if layer == 0 and GEMM_IMPL != "simt":
                 w_hi, w_lo = layers[layer]["wih"][e]
+                wp = lambda e=e: packed.wih_pieces(0, e)
                 if n_enc == 1:
-                    input_projection(x1, x2, B, T, w_hi, w_lo, layers[layer]["bias"][e], gx[e], 8 * H)
+                    input_projection(x1, x2, B, T, w_hi, w_lo, layers[layer]["bias"][e], gx[e], 8 * H, w_pieces=wp)
                 else:
-                    input_projection(x1 if e == 0 else xs2, None, B, T, w_hi, w_lo, layers[layer]["bias"][e], gx[e], 8 * H)
+                    input_projection(x1 if e == 0 else xs2, None, B, T, w_hi, w_lo, layers[layer]["bias"][e], gx[e], 8 * H,
+                                     w_pieces=wp)
                 continue
             if layer == 0:
                 if n_enc == 1:

@@ -1331,3 +1331,33 @@ def test_encoder_fp16_split_path_equals_tf32_path(dev):
     assert err < 2e-5
     for b, n in enumerate(lengths.tolist()):
         assert float(outs[0][b, n:].abs().max() if n < 96 else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("B,T,Tmax,D1,D2,N", [(7, 50, 50, 384, 512, 2048), (3, 100, 117, 64, 40, 2048), (5, 60, 60, 100, 0, 512)])
+def test_input_projection_fp16_split(dev, B, T, Tmax, D1, D2, N):
+    """mts_pack_rows_f16 + mts_gemm_f16x3 as the layer-0 projection: [x1 | x2] W^T + b from time-cropped sources whose rows span
+    five decades, against float64; the packed pieces reproduce the cropped, concatenated rows."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(D1 * 3 + D2)
+    x1 = torch.randn((B, Tmax, D1), device=dev, generator=g) * (10.0 ** (torch.rand((B, Tmax, 1), device=dev, generator=g) * 5 - 3))
+    x2 = (torch.randn((B, Tmax, D2), device=dev, generator=g) * 3.0) if D2 else None
+    w = torch.randn((N, D1 + D2), device=dev, generator=g) * 0.05
+    bias = torch.randn((N,), device=dev, generator=g)
+    w_hi, w_lo = ops.split_tf32(w, side=ops.B_SIDE)
+    wp = ops.f16_pieces(w)
+    out = torch.full((B * T, N), float("nan"), device=dev)
+    ops.PROFILE, prof = {}, None
+    try:
+        ops.input_projection(x1, x2, B, T, w_hi, w_lo, bias, out, N, w_pieces=lambda: wp)
+        prof = set(ops.PROFILE)
+    finally:
+        ops.PROFILE = None
+    assert "mts_gemm_f16x3" in prof and "mts_pack_rows_f16" in prof       # the fp16-split path really ran
+    x = x1[:, :T] if x2 is None else torch.cat([x1[:, :T], x2[:, :T]], dim=2)
+    xr = x.reshape(B * T, -1).double()
+    ref = xr @ w.double().T + bias.double()
+    bound = xr.abs() @ w.double().abs().T + bias.double().abs()
+    err = float(((out.double() - ref).abs() / bound).max())
+    print(f"  fp16-split input projection {B * T} x {N} x {D1 + D2}: worst |err| / (|x| . |w|) = {err:.2e}")
+    assert err < 1e-5, err
