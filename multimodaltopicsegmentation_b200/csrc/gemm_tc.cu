@@ -174,6 +174,115 @@ __device__ __forceinline__ void tc_store_tile(uint32_t tmem_base, int acc_col, i
   // row_scale / col_scale (fp16-split operands): the accumulator holds (A / rs) (B / cs)^T, power-of-two scales per operand row
   const int rsub = lane >> 3, ch = lane & 7;
   const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  // The common case -- plain or bias epilogue, one K split, no accumulation, no operand-pair output, whole float4 columns --
+  // has its own compact loop: with every variant (GELU polynomials, atomics, operand packing) inlined into ONE loop body the
+  // epilogue warps stalled on instruction fetch (ncu on a K = 256 product: "no instruction" 2.1 and "branch resolving" 1.4
+  // stalled warps per issued instruction, tensor pipe 30 % busy, 32 k cycles per tile against 8.6 k of MMAs).
+  if (vec_ok && splits == 1 && !accumulate && !C_lo && epilogue <= 1 && (N & 3) == 0) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
+      const int n = n0 + c0 + 4 * ch;
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_col + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      const bool col_ok = n < N;   // N % 4 == 0: a float4 column is inside or outside as a whole
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), cv = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (col_ok && epilogue == 1) bv = make_float4(__ldg(bias + n), __ldg(bias + n + 1), __ldg(bias + n + 2), __ldg(bias + n + 3));
+      if (col_ok && col_scale) cv = make_float4(__ldg(col_scale + n), __ldg(col_scale + n + 1), __ldg(col_scale + n + 2), __ldg(col_scale + n + 3));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + rsub, m = m0 + q * 32 + row;
+        const float4 t = stg[row * 8 + (ch ^ (row & 7))];
+        if (m < M && col_ok) {
+          const float rsv = row_scale ? __ldg(row_scale + m) : 1.0f;
+          *reinterpret_cast<float4 *>(C + (int64_t)m * ldc + n) =
+              make_float4(fmaf(t.x, rsv * cv.x, bv.x), fmaf(t.y, rsv * cv.y, bv.y), fmaf(t.z, rsv * cv.z, bv.z), fmaf(t.w, rsv * cv.w, bv.w));
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  // accumulate onto C (the gradient arriving through a residual path) / split K (weight gradients: partial products meet in C
+  // through vector reductions): the two forms the backward pass uses, each with its own compact loop too
+  if (vec_ok && !C_lo && epilogue <= 1 && (N & 3) == 0 && (accumulate || splits > 1)) {
+    const bool red = splits > 1;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
+      const int n = n0 + c0 + 4 * ch;
+      const bool col_ok = n < N;
+      float4 prev[8];
+      if (!red) {   // the 8 previous values of this lane: requested before the accumulator is read, all in flight together
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + q * 32 + 4 * i + rsub;
+          prev[i] = (m < M && col_ok) ? *reinterpret_cast<const float4 *>(C + (int64_t)m * ldc + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_col + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), cv = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (col_ok && epilogue == 1 && sp == 0) bv = make_float4(__ldg(bias + n), __ldg(bias + n + 1), __ldg(bias + n + 2), __ldg(bias + n + 3));
+      if (col_ok && col_scale) cv = make_float4(__ldg(col_scale + n), __ldg(col_scale + n + 1), __ldg(col_scale + n + 2), __ldg(col_scale + n + 3));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + rsub, m = m0 + q * 32 + row;
+        const float4 t = stg[row * 8 + (ch ^ (row & 7))];
+        if (m < M && col_ok) {
+          const float rsv = row_scale ? __ldg(row_scale + m) : 1.0f;
+          float4 w = make_float4(fmaf(t.x, rsv * cv.x, bv.x), fmaf(t.y, rsv * cv.y, bv.y), fmaf(t.z, rsv * cv.z, bv.z), fmaf(t.w, rsv * cv.w, bv.w));
+          float *dst = C + (int64_t)m * ldc + n;
+          if (red) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
+          } else {
+            const float4 p = prev[i];
+            w.x += p.x; w.y += p.y; w.z += p.z; w.w += p.w;
+            *reinterpret_cast<float4 *>(dst) = w;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  // the second common case: dense + GELU whose output feeds the next dense layer (C and the packed correction operand C_lo)
+  if (vec_ok && splits == 1 && !accumulate && C_lo && epilogue == 2 && (N & 3) == 0) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
+      const int n = n0 + c0 + 4 * ch;
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_col + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      const bool col_ok = n < N;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), cv = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (col_ok) bv = make_float4(__ldg(bias + n), __ldg(bias + n + 1), __ldg(bias + n + 2), __ldg(bias + n + 3));
+      if (col_ok && col_scale) cv = make_float4(__ldg(col_scale + n), __ldg(col_scale + n + 1), __ldg(col_scale + n + 2), __ldg(col_scale + n + 3));
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + rsub, m = m0 + q * 32 + row;
+        const float4 t = stg[row * 8 + (ch ^ (row & 7))];
+        if (m < M && col_ok) {
+          const float rsv = row_scale ? __ldg(row_scale + m) : 1.0f;
+          const float4 w = make_float4(gelu_erf(fmaf(t.x, rsv * cv.x, bv.x)), gelu_erf(fmaf(t.y, rsv * cv.y, bv.y)),
+                                       gelu_erf(fmaf(t.z, rsv * cv.z, bv.z)), gelu_erf(fmaf(t.w, rsv * cv.w, bv.w)));
+          *reinterpret_cast<float4 *>(C + (int64_t)m * ldc + n) = w;
+          corr_store4(C_lo + (int64_t)m * ldc, n, w, 0);
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     if (n0 + c0 >= N) break;
