@@ -483,6 +483,62 @@ def test_text_segmenter_steps(dev):
         TextSegmenter(2, 20, 256, architecture="nope")
 
 
+@pytest.mark.parametrize("name,kw,double", [
+    ("bilstm_pk", dict(architecture="BiLSTM", loss_fn="FocalLoss", metric="Pk", threshold=0.4), False),
+    ("bilstm_f1_eb", dict(architecture="BiLSTM", loss_fn="BinaryCrossEntropy", metric="F1", threshold=0.5, end_boundary=True), False),
+    ("bilstm_ce_wd", dict(architecture="BiLSTM", loss_fn="CrossEntropy", metric="WD", threshold=None), False),
+    ("late_pk", dict(architecture="BiLSTMLateFusion", loss_fn="FocalLoss", metric="Pk", threshold=0.3), True),
+])
+def test_text_segmenter_steps_equal_the_reference_steps(dev, golden, name, kw, double):
+    """training / validation / test / predict steps against the outputs of the reference's OWN `TextSegmenter`
+    (models/lightning_model.py:179-760, run unmodified behind a pytorch_lightning / segeval stub by
+    tests/golden/make_golden_steps.py): losses within rtol 1e-5, tags exact, and the logged result dict of test_step --
+    keys, threshold, F1 (sklearn on the reference side), Pk / WindowDiff averages incl. the 1- and 3-sentence episodes
+    where WindowDiff asserts and the reference substitutes Pk, and the end_boundary variant -- equal to 1e-12 on both the
+    device-count path and the host walk."""
+    from multimodaltopicsegmentation_b200 import TextSegmenter
+
+    fx = golden("steps")
+    emb = [10, 6] if double else 10
+    seg = TextSegmenter(2, emb, 8, num_layers=2, optimizer="Adam", lr=1e-3, all_results=True, **kw)
+    sd = {k[len(name) + 3:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith(name + ":p:")}
+    missing, unexpected = seg.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    seg = seg.to(dev)
+
+    def batch():
+        b = {"src_tokens": torch.from_numpy(fx[name + ":i:src_tokens"]).to(dev),
+             "tgt_tokens": torch.from_numpy(fx[name + ":i:tgt_tokens"]).to(dev),
+             "src_lengths": torch.from_numpy(fx[name + ":i:src_lengths"]), "src_tokens2": None}
+        if double:
+            b["src_tokens2"] = torch.from_numpy(fx[name + ":i:src_tokens2"]).to(dev)
+        return b
+
+    seg.train()
+    loss = seg.training_step(batch(), 0)
+    close(loss, fx[name + ":o:training_loss"], rtol=1e-5, atol=1e-7)
+    close(seg.logged["training_loss"], fx[name + ":o:logged_training_loss"], rtol=1e-5, atol=1e-7)
+    seg.eval()
+    val = seg.validation_step(batch(), 0)
+    close(val, fx[name + ":o:val_loss"], rtol=1e-5, atol=1e-7)
+    assert float(seg.logged["threshold"]) == float(fx[name + ":o:val_threshold"])
+    if not double:
+        tags_equal(seg.predict_step(batch(), 0), fx[name + ":o:predict_tags"])
+    keys = fx[name + ":o:result_keys"].tolist()
+    want = fx[name + ":o:result_values"]
+    for device_metrics in (True, False):
+        seg.device_metrics = device_metrics
+        seg.results = []
+        res = seg.test_step(batch(), 0)
+        assert sorted(res) == keys and seg.results[-1] is res
+        got = np.asarray([float(res[k]) for k in keys])
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12, err_msg=f"{name} device_metrics={device_metrics} {keys}")
+        assert sorted(k for k in seg.logged if k in keys) == keys
+    opt = seg.configure_optimizers()
+    assert [type(opt["optimizer"]).__name__, opt["lr_scheduler"]["monitor"], opt["lr_scheduler"]["scheduler"].mode] \
+        == fx[name + ":o:optimizer"].tolist()
+
+
 # ----------------------------------------------------------------------------------------------------------
 # pyramidal windowed-attention segmenter (HF LongformerModel in the reference)
 # ----------------------------------------------------------------------------------------------------------

@@ -31,6 +31,90 @@ def test_collater_layout_matches_reference_contract():
     assert set(b2) == {"id", "src_tokens", "src_lengths"} and b2["src_lengths"].tolist() == [5, 9, 2]
 
 
+def test_collaters_equal_the_reference_collaters(golden):
+    """Outputs of the UNMODIFIED reference collaters (EncoderDataset.py:91-152, 189-232; tests/golden/make_golden_steps.py
+    imports them behind a pytorch_lightning / segeval stub) on seeded ragged episodes: every field, dtype and shape."""
+    from multimodaltopicsegmentation_b200 import AudioPortionDataset, AudioPortionDatasetInference
+
+    fx = golden("steps")
+    n = 4
+    lines = [(torch.from_numpy(fx[f"cin:x{k}"]), fx[f"cin:t{k}"].tolist(), f"{k}abc.npy" if k % 2 == 0 else f"x{k}.npy")
+             for k in range(n)]
+    second = [(torch.from_numpy(fx[f"cin:x2{k}"]), None, None) for k in range(n)]
+
+    def check(ci, batch):
+        fields = {k.split(":")[1] for k in fx.files if k.startswith(f"c{ci}:")}
+        assert set(batch) == fields
+        for k, v in batch.items():
+            if f"c{ci}:{k}:none" in fx.files:
+                assert v is None, (ci, k)
+                continue
+            ref = fx[f"c{ci}:{k}"]
+            if torch.is_tensor(v):
+                assert v.numpy().dtype == ref.dtype and tuple(v.shape) == ref.shape, (ci, k, v.dtype, ref.dtype)
+                assert np.array_equal(v.numpy(), ref), (ci, k)
+            else:
+                assert list(v) == ref.tolist(), (ci, k)
+
+    cases = [dict(CRF=True, truncate=False, second=True, domain_adapt=True),
+             dict(CRF=False, truncate=False, second=True, domain_adapt=False),
+             dict(CRF=False, truncate=True, truncate_value=4, second=False, domain_adapt=False),
+             dict(CRF=True, truncate=True, truncate_value=12, second=True, domain_adapt=True)]
+    for ci, c in enumerate(cases):
+        ds = AudioPortionDataset(lines, {"0": 0, "1": 1}, CRF=c["CRF"], truncate=c["truncate"],
+                                 truncate_value=c.get("truncate_value", 100), second_input=second if c["second"] else None,
+                                 domain_adapt=c["domain_adapt"])
+        check(ci, ds.collater([ds[i] for i in (2, 0, 3, 1)]))
+    for ci, c in enumerate([dict(truncate=False), dict(truncate=True, truncate_value=4)], start=len(cases)):
+        ds = AudioPortionDatasetInference([ln[0] for ln in lines], **c)
+        check(ci, ds.collater([ds[i] for i in (1, 3, 0, 2)]))
+
+
+def _recorded_segeval_calls(flat):
+    flat = [int(v) for v in flat]
+    n, i, calls = flat[0], 1, []
+    for _ in range(n):
+        kind, nh = flat[i], flat[i + 1]
+        h = flat[i + 2: i + 2 + nh]
+        nt = flat[i + 2 + nh]
+        t = flat[i + 3 + nh: i + 3 + nh + nt]
+        calls.append((kind, h, t))
+        i += 3 + nh + nt
+    assert i == len(flat)
+    return calls
+
+
+def test_metrics_on_the_masses_the_reference_hands_to_segeval(golden):
+    """The reference's test_step (run unmodified for the fixture) reaches segeval with these (hypothesis, reference)
+    mass lists; the host metrics of the product, fed the equivalent boundary vectors, must return what the oracle's
+    segeval restatement returns on the masses -- including the window > length cases where WindowDiff asserts."""
+    from multimodaltopicsegmentation_b200 import metrics
+
+    fx = golden("steps")
+    n_calls = 0
+    for name in ("bilstm_pk", "bilstm_f1_eb", "bilstm_ce_wd", "late_pk"):
+        for kind, h, t in _recorded_segeval_calls(fx[name + ":masses"]):
+            assert sum(h) == sum(t)
+            hb = np.zeros(sum(h), dtype=int)
+            tb = np.zeros(sum(t), dtype=int)
+            hb[np.cumsum(h) - 1] = 1
+            tb[np.cumsum(t) - 1] = 1
+            assert metrics.get_boundaries(hb) == h and metrics.get_boundaries(tb) == t
+            hb[-1] = tb[-1] = 0   # compute_Pk / compute_window_diff force the last boundary themselves
+            if kind == 0:
+                assert metrics.compute_Pk(hb, tb) == rn.pk_masses(h, t)
+            else:
+                try:
+                    want = rn.window_diff_masses(h, t)
+                except AssertionError:
+                    with pytest.raises(AssertionError):
+                        metrics.compute_window_diff(hb, tb)
+                else:
+                    assert metrics.compute_window_diff(hb, tb) == want
+            n_calls += 1
+    assert n_calls >= 40
+
+
 def test_metrics_agree_with_oracle():
     from multimodaltopicsegmentation_b200 import compute_Pk, compute_window_diff, get_boundaries
 
