@@ -371,6 +371,19 @@ int mts_embed_bwd(const float *dpre, int B, int S, int d, float *dpos, const int
 int mts_band_attn_bwd(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
                       const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int hd, int w, float *dqkv,
                       float *delta_ws, void *stream);
+/* Training with dropout on the attention probabilities -- HF `attention_probs_dropout_prob`, set by the reference from
+ * `dropout_out` (models/CRF.py:531-536 -> models/RestrictedTransformerLayer.py:85-92; `nn.functional.dropout(attn_probs)`
+ * in modeling_longformer.py LongformerSelfAttention.forward).  Same contracts as mts_band_attn_fwd_simt / mts_band_attn_bwd
+ * with P V weighted by p * keep / (1 - p_drop); `lse` stays the log-sum-exp of the undropped scores.  keep(b, head, i, j)
+ * is a pure function of `seed` and the indices (csrc/common.cuh attn_keep_scale; oracle/ref_numpy.py attn_dropout_keep is
+ * its numpy restatement), so the backward call regenerates the forward mask from the same seed: no mask tensor.
+ * p_drop in [0, 1); p_drop == 0 is the plain kernel. */
+int mts_band_attn_fwd_dropout(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
+                              int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
+                              float p_drop, uint64_t seed, void *stream);
+int mts_band_attn_bwd_dropout(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
+                              const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int hd, int w,
+                              float *dqkv, float *delta_ws, float p_drop, uint64_t seed, void *stream);
 
 #ifdef __cplusplus
 }

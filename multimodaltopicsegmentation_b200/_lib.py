@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_float, c_int, c_int64, c_void_p
+from ctypes import c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmts_b200.so")
@@ -75,6 +75,10 @@ SIGNATURES = {
     "mts_ragged_copy": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     "mts_embed_bwd": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mts_band_attn_bwd": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "mts_band_attn_fwd_dropout": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, c_float,
+                                          c_uint64, _P]),
+    "mts_band_attn_bwd_dropout": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float,
+                                          c_uint64, _P]),
 }
 
 _lib = None

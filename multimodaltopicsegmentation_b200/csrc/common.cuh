@@ -107,6 +107,24 @@ __device__ __forceinline__ void corr_store8(float *row, int k, float4 a, float4 
                  bf16x2_bits(tf32_rest_exact(b.x), tf32_rest_exact(b.y)), bf16x2_bits(tf32_rest_exact(b.z), tf32_rest_exact(b.w)));
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Dropout on the attention probabilities (HF LongformerSelfAttention: nn.functional.dropout(attn_probs, p), inverted
+// scaling).  The keep decision of probability (episode b, head, query i, key j) is a pure function of a 64-bit seed and
+// those four indices -- a splitmix64 finaliser over  seed ^ (bh << 40 | i << 20 | j)  -- so the forward kernel and both
+// backward kernels regenerate the same mask from the seed and no mask tensor exists.  u = top 24 bits / 2^24 is kept
+// when u >= p.  The parity tests restate this hash in numpy on the checker side.  S <= 2^20.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float attn_keep_scale(uint64_t seed, uint32_t bh, uint32_t i, uint32_t j, uint32_t p24, float inv_keep) {
+  uint64_t x = seed ^ (((uint64_t)bh << 40) | ((uint64_t)i << 20) | (uint64_t)j);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return ((uint32_t)(x >> 40) >= p24) ? inv_keep : 0.0f;
+}
+
+// host side of attn_keep_scale: the 24-bit threshold of a drop probability
+inline uint32_t attn_drop_p24(float p) { return (uint32_t)((double)p * 16777216.0 + 0.5); }
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 }  // namespace mts

@@ -227,11 +227,14 @@ static size_t ba_smem_bytes(int hd) {
   return sizeof(float) * ((size_t)(BA_BQ + 2 * BA_TK) * ba_row_stride(hd) + BA_BQ * BA_PS + 3 * BA_BQ);
 }
 
+// DROP: dropout on the probabilities (training): the weights of P V are p * keep / (1 - p_drop), the softmax denominator
+// and the saved log-sum-exp stay those of the undropped probabilities (attn_keep_scale, common.cuh).
+template <bool DROP>
 __global__ void __launch_bounds__(BA_THREADS, 2)
     band_attn_fwd_kernel(const float *__restrict__ qkv, int64_t ld, const int32_t *__restrict__ lengths,
                          const int32_t *__restrict__ offsets, int S, int nheads, int hd, int w,
                          float *__restrict__ out, float *__restrict__ out_hi, float *__restrict__ out_lo, int Kp,
-                         float *__restrict__ lse) {
+                         float *__restrict__ lse, uint32_t p24, float inv_keep, uint64_t seed) {
   extern __shared__ __align__(16) float sm[];
   const int RS = ba_row_stride(hd);
   float *Qs = sm;
@@ -364,8 +367,14 @@ __global__ void __launch_bounds__(BA_THREADS, 2)
         const float m_new = fmaxf(m_run[a], mx[a]);
         const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
         const float p0 = expf(sc[a][0] - m_use), p1 = expf(sc[a][1] - m_use);
-        Ps[(4 * warp + a) * BA_PS + lane] = p0;
-        Ps[(4 * warp + a) * BA_PS + lane + 32] = p1;
+        float pv0 = p0, pv1 = p1;
+        if (DROP) {
+          const uint32_t bh = (uint32_t)(b * nheads + head), i = (uint32_t)(q0 + 4 * warp + a);
+          pv0 *= attn_keep_scale(seed, bh, i, (uint32_t)(k0 + lane), p24, inv_keep);
+          pv1 *= attn_keep_scale(seed, bh, i, (uint32_t)(k0 + lane + 32), p24, inv_keep);
+        }
+        Ps[(4 * warp + a) * BA_PS + lane] = pv0;
+        Ps[(4 * warp + a) * BA_PS + lane + 32] = pv1;
         ps[a] = p0 + p1;
         alpha[a] = expf(m_run[a] - m_use);
         m_run[a] = m_new;
@@ -800,9 +809,9 @@ extern "C" int mts_band_attn_fwd(const float *qkv, int64_t ld, const int32_t *le
   return mts_band_attn_fwd_simt(qkv, ld, lengths, offsets, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, stream);
 }
 
-extern "C" int mts_band_attn_fwd_simt(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B,
-                                      int S, int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp,
-                                      float *lse, void *stream) {
+static int band_attn_fwd_simt_impl(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B, int S,
+                                   int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse,
+                                   float p_drop, uint64_t seed, void *stream) {
   MTS_REQUIRE(qkv && lengths && (out || out_hi), MTS_E_BADARG, "band_attn_fwd: null pointer");
   MTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), MTS_E_BADARG, "band_attn_fwd: hi and lo go together");
   MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_fwd: bad shape");
@@ -812,15 +821,35 @@ extern "C" int mts_band_attn_fwd_simt(const float *qkv, int64_t ld, const int32_
   MTS_REQUIRE(!out_hi || (Kp % 32 == 0 && Kp >= nheads * hd), MTS_E_BADARG, "band_attn_fwd: Kp");
   MTS_REQUIRE(!out_hi || Kp == nheads * hd, MTS_E_UNSUPPORTED,
               "band_attn_fwd: the split output needs a model width that is a multiple of 32");
+  MTS_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, MTS_E_BADARG, "band_attn_fwd: dropout probability must be in [0, 1)");
+  MTS_REQUIRE(p_drop == 0.0f || S <= (1 << 20), MTS_E_UNSUPPORTED, "band_attn_fwd: dropout indices need S <= 2^20");
   const size_t smem = ba_smem_bytes(hd);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    MTS_CUDA(cudaFuncSetAttribute(band_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   const dim3 grid((S + BA_BQ - 1) / BA_BQ, nheads, B);
-  band_attn_fwd_kernel<<<grid, BA_THREADS, smem, (cudaStream_t)stream>>>(qkv, ld, lengths, offsets, S, nheads, hd, w, out,
-                                                                        out_hi, out_lo, Kp, lse);
+  if (p_drop > 0.0f) {
+    MTS_CUDA(cudaFuncSetAttribute(band_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    band_attn_fwd_kernel<true><<<grid, BA_THREADS, smem, (cudaStream_t)stream>>>(
+        qkv, ld, lengths, offsets, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, attn_drop_p24(p_drop), 1.0f / (1.0f - p_drop), seed);
+  } else {
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      MTS_CUDA(cudaFuncSetAttribute(band_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    band_attn_fwd_kernel<false><<<grid, BA_THREADS, smem, (cudaStream_t)stream>>>(qkv, ld, lengths, offsets, S, nheads, hd, w, out,
+                                                                                 out_hi, out_lo, Kp, lse, 0u, 1.0f, 0ull);
+  }
   MTS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mts_band_attn_fwd_simt(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B,
+                                      int S, int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp,
+                                      float *lse, void *stream) {
+  return band_attn_fwd_simt_impl(qkv, ld, lengths, offsets, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, 0.0f, 0ull, stream);
+}
+
+extern "C" int mts_band_attn_fwd_dropout(const float *qkv, int64_t ld, const int32_t *lengths, const int32_t *offsets, int B,
+                                         int S, int nheads, int hd, int w, float *out, float *out_hi, float *out_lo, int Kp,
+                                         float *lse, float p_drop, uint64_t seed, void *stream) {
+  return band_attn_fwd_simt_impl(qkv, ld, lengths, offsets, B, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, p_drop, seed, stream);
 }

@@ -154,11 +154,16 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc)
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
+// DROP (both kernels): the forward pass weighted P V by p * m with m = keep / (1 - p_drop) (attn_keep_scale, regenerated here
+// from the seed): dV = (P .* M)^T dO, dP = M .* (dO V^T), dS = P .* (dP - delta) with delta = rowsum(dO .* O) as before
+// (sum_j P_ij dP_ij = dO_i . O_i holds with the dropped weights too).
+template <bool DROP>
 __global__ void __launch_bounds__(BB_THREADS, 2)
     band_attn_bwd_dq_kernel(const float *__restrict__ qkv, int64_t ld, const float *__restrict__ o,
                             const float *__restrict__ dO, const float *__restrict__ lse,
                             const int32_t *__restrict__ lengths, const int32_t *__restrict__ offsets, int S,
-                            int nheads, int hd, int w, float *__restrict__ dqkv, float *__restrict__ delta) {
+                            int nheads, int hd, int w, float *__restrict__ dqkv, float *__restrict__ delta,
+                            uint32_t p24, float inv_keep, uint64_t seed) {
   extern __shared__ __align__(16) float sm[];
   const int RS = bb_row_stride(hd);
   float *Qs = sm;                       // [32][RS] scaled queries
@@ -271,7 +276,9 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
           const int kj = k0 + kg + 16 * j;
           const bool ok = (i < len) && (kj < kend) && (kj >= i - w) && (kj <= i + w);
           const float p = ok ? expf(as[a][j] - lse_s[r]) : 0.0f;
-          Ps[r * BB_PS + kg + 16 * j] = p * (ap[a][j] - del_s[r]);
+          float dp = ap[a][j];
+          if (DROP) dp *= attn_keep_scale(seed, (uint32_t)(b * nheads + head), (uint32_t)i, (uint32_t)kj, p24, inv_keep);
+          Ps[r * BB_PS + kg + 16 * j] = p * (dp - del_s[r]);
         }
       }
     }
@@ -309,11 +316,13 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
   }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(BB_THREADS, 2)
     band_attn_bwd_dkv_kernel(const float *__restrict__ qkv, int64_t ld, const float *__restrict__ dO,
                              const float *__restrict__ lse, const float *__restrict__ delta,
                              const int32_t *__restrict__ lengths, const int32_t *__restrict__ offsets, int S,
-                             int nheads, int hd, int w, float *__restrict__ dqkv) {
+                             int nheads, int hd, int w, float *__restrict__ dqkv, uint32_t p24, float inv_keep,
+                             uint64_t seed) {
   extern __shared__ __align__(16) float sm[];
   const int RS = bb_row_stride(hd);
   float *Ks = sm;                        // [32][RS] own keys
@@ -405,8 +414,10 @@ __global__ void __launch_bounds__(BB_THREADS, 2)
             const int qi = qq + 16 * j, i = t0 + qi;
             const bool ok = (kj < len) && (i < qend) && (kj >= i - w) && (kj <= i + w);
             const float p = ok ? expf(as[a][j] - lse_s[qi]) : 0.0f;
-            Pt[r * BB_PS + qi] = p;
-            St[r * BB_PS + qi] = p * (ap[a][j] - del_s[qi]);
+            float m = 1.0f;
+            if (DROP) m = attn_keep_scale(seed, (uint32_t)(b * nheads + head), (uint32_t)i, (uint32_t)kj, p24, inv_keep);
+            Pt[r * BB_PS + qi] = p * m;
+            St[r * BB_PS + qi] = p * (m * ap[a][j] - del_s[qi]);
           }
         }
       }
@@ -510,31 +521,50 @@ extern "C" int mts_embed_bwd(const float *dpre, int B, int S, int d, float *dpos
   return 0;
 }
 
-extern "C" int mts_band_attn_bwd(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
-                                 const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int hd, int w,
-                                 float *dqkv, float *delta_ws, void *stream) {
-  MTS_REQUIRE(qkv && o && d_o && lse && lengths && dqkv && delta_ws, MTS_E_BADARG, "band_attn_bwd: null pointer");
-  MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_bwd: bad shape");
-  MTS_REQUIRE(hd % 4 == 0 && hd <= 128, MTS_E_UNSUPPORTED, "band_attn_bwd: head dim must be a multiple of 4 and <= 128");
-  MTS_REQUIRE(ld % 4 == 0 && ld >= 3 * nheads * hd, MTS_E_BADARG, "band_attn_bwd: qkv row stride");
+template <bool DROP>
+static int band_attn_bwd_launch(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
+                                const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int hd, int w,
+                                float *dqkv, float *delta_ws, float p_drop, uint64_t seed, void *stream) {
   const int RS = bb_row_stride(hd);
   const size_t smem_dq = sizeof(float) * ((size_t)(2 * BB_OWN + 2 * BB_TILE) * RS + BB_OWN * BB_PS + 2 * BB_OWN);
   const size_t smem_dkv = sizeof(float) * ((size_t)(2 * BB_OWN + 2 * BB_TILE) * RS + 2 * BB_OWN * BB_PS + 2 * BB_TILE);
-  static size_t set_dq = 0, set_dkv = 0;
+  static size_t set_dq = 0, set_dkv = 0;   // one pair per instantiation
   if (smem_dq > set_dq) {
-    MTS_CUDA(cudaFuncSetAttribute(band_attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
+    MTS_CUDA(cudaFuncSetAttribute(band_attn_bwd_dq_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
     set_dq = smem_dq;
   }
   if (smem_dkv > set_dkv) {
-    MTS_CUDA(cudaFuncSetAttribute(band_attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv));
+    MTS_CUDA(cudaFuncSetAttribute(band_attn_bwd_dkv_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv));
     set_dkv = smem_dkv;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid((S + BB_OWN - 1) / BB_OWN, nheads, B);
-  band_attn_bwd_dq_kernel<<<grid, BB_THREADS, smem_dq, st>>>(qkv, ld, o, d_o, lse, lengths, offsets, S, nheads, hd, w,
-                                                             dqkv, delta_ws);
-  band_attn_bwd_dkv_kernel<<<grid, BB_THREADS, smem_dkv, st>>>(qkv, ld, d_o, lse, delta_ws, lengths, offsets, S, nheads,
-                                                               hd, w, dqkv);
+  const uint32_t p24 = DROP ? attn_drop_p24(p_drop) : 0u;
+  const float inv_keep = DROP ? 1.0f / (1.0f - p_drop) : 1.0f;
+  band_attn_bwd_dq_kernel<DROP><<<grid, BB_THREADS, smem_dq, st>>>(qkv, ld, o, d_o, lse, lengths, offsets, S, nheads, hd, w,
+                                                                   dqkv, delta_ws, p24, inv_keep, seed);
+  band_attn_bwd_dkv_kernel<DROP><<<grid, BB_THREADS, smem_dkv, st>>>(qkv, ld, d_o, lse, delta_ws, lengths, offsets, S, nheads,
+                                                                     hd, w, dqkv, p24, inv_keep, seed);
   MTS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mts_band_attn_bwd_dropout(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
+                                         const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int hd,
+                                         int w, float *dqkv, float *delta_ws, float p_drop, uint64_t seed, void *stream) {
+  MTS_REQUIRE(qkv && o && d_o && lse && lengths && dqkv && delta_ws, MTS_E_BADARG, "band_attn_bwd: null pointer");
+  MTS_REQUIRE(B > 0 && S > 0 && nheads > 0 && hd > 0 && w >= 0, MTS_E_BADARG, "band_attn_bwd: bad shape");
+  MTS_REQUIRE(hd % 4 == 0 && hd <= 128, MTS_E_UNSUPPORTED, "band_attn_bwd: head dim must be a multiple of 4 and <= 128");
+  MTS_REQUIRE(ld % 4 == 0 && ld >= 3 * nheads * hd, MTS_E_BADARG, "band_attn_bwd: qkv row stride");
+  MTS_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, MTS_E_BADARG, "band_attn_bwd: dropout probability must be in [0, 1)");
+  MTS_REQUIRE(p_drop == 0.0f || S <= (1 << 20), MTS_E_UNSUPPORTED, "band_attn_bwd: dropout indices need S <= 2^20");
+  if (p_drop > 0.0f)
+    return band_attn_bwd_launch<true>(qkv, ld, o, d_o, lse, lengths, offsets, B, S, nheads, hd, w, dqkv, delta_ws, p_drop, seed, stream);
+  return band_attn_bwd_launch<false>(qkv, ld, o, d_o, lse, lengths, offsets, B, S, nheads, hd, w, dqkv, delta_ws, 0.0f, 0ull, stream);
+}
+
+extern "C" int mts_band_attn_bwd(const float *qkv, int64_t ld, const float *o, const float *d_o, const float *lse,
+                                 const int32_t *lengths, const int32_t *offsets, int B, int S, int nheads, int hd, int w,
+                                 float *dqkv, float *delta_ws, void *stream) {
+  return mts_band_attn_bwd_dropout(qkv, ld, o, d_o, lse, lengths, offsets, B, S, nheads, hd, w, dqkv, delta_ws, 0.0f, 0ull, stream);
 }

@@ -38,6 +38,7 @@ import torch.nn as nn
 
 from . import ops
 from .modules import RNN, _build_head, _head_decode, _head_decode_device, _head_loss, _lens
+from .transformer import attn_seed, band_attention
 from .transformer_bwd import _dense_param_grads
 
 _ptr, _call, _stream, _pad32 = ops._ptr, ops._call, ops._stream, ops._pad32
@@ -97,7 +98,7 @@ class _PackedMha:
         return ent
 
 
-def _mha_forward(xq, xk, lens, packed: _PackedMha, nheads, reach, save):
+def _mha_forward(xq, xk, lens, packed: _PackedMha, nheads, reach, save, p_attn=0.0, seed=0):
     """xq, xk [B,S,d] (views with unit inner stride are fine) -> attention output [B,S,d]."""
     B, S, d = xq.shape
     M = B * S
@@ -114,8 +115,7 @@ def _mha_forward(xq, xk, lens, packed: _PackedMha, nheads, reach, save):
                         epilogue=1, ldc=3 * d)
     a = torch.empty((B, S, d), device=dev, dtype=torch.float32)
     lse = torch.empty((B, nheads, S), device=dev, dtype=torch.float32) if save else None
-    _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), 0, B, S, nheads, hd, reach, _ptr(a), 0, 0, 0, _ptr(lse),
-          _stream())
+    band_attention(qkv, 3 * d, lens, 0, B, S, nheads, hd, reach, a, None, None, 0, lse, p_attn, seed)
     return a, (xq2, xk2, qkv, lse)
 
 
@@ -123,11 +123,13 @@ class BandMhaFn(torch.autograd.Function):
     """Differentiable w.r.t. both inputs and the three projections."""
 
     @staticmethod
-    def forward(ctx, xq, xk, lens, packed, nheads, reach, *params):
+    def forward(ctx, xq, xk, lens, packed, nheads, reach, p_attn, *params):
         need = any(ctx.needs_input_grad)
-        a, saved = _mha_forward(xq, xk, lens, packed, nheads, reach, save=need)
+        seed = attn_seed(0) if p_attn > 0 else 0
+        a, saved = _mha_forward(xq, xk, lens, packed, nheads, reach, save=need, p_attn=p_attn, seed=seed)
         if need:
             ctx.saved, ctx.lens, ctx.packed, ctx.nheads, ctx.reach = saved + (a,), lens, packed, nheads, reach
+            ctx.p_attn, ctx.seed = p_attn, seed
             ctx.same = xk is xq
         return a
 
@@ -143,8 +145,8 @@ class BandMhaFn(torch.autograd.Function):
         da = dout.contiguous()
         dqkv = torch.empty((M, 3 * d), device=dev, dtype=torch.float32)
         delta = torch.empty((B, nheads, S), device=dev, dtype=torch.float32)
-        _call("mts_band_attn_bwd", _ptr(qkv), 3 * d, _ptr(a), _ptr(da), _ptr(lse), _ptr(lens.dev), 0, B, S, nheads, hd, reach,
-              _ptr(dqkv), _ptr(delta), _stream())
+        _call("mts_band_attn_bwd_dropout", _ptr(qkv), 3 * d, _ptr(a), _ptr(da), _ptr(lse), _ptr(lens.dev), 0, B, S, nheads, hd, reach,
+              _ptr(dqkv), _ptr(delta), float(ctx.p_attn), int(ctx.seed), _stream())
         grads = []
         for j, x in enumerate((xq2, xk2, xq2)):
             dw, db = _dense_param_grads(dqkv[:, j * d:(j + 1) * d], x, M, d, d)
@@ -155,7 +157,7 @@ class BandMhaFn(torch.autograd.Function):
             hl = ops.split_tf32(dqkv[:, j * d:(j + 1) * d], cols=d, ld=3 * d, rows=M)
             ops.gemm_tf32x3(hl[0], hl[1], ent["wt"][j][0], ent["wt"][j][1], None, dst.view(M, d), M, d, accumulate=acc)
         ctx.saved = None
-        return (dxq, None if ctx.same else dxk, None, None, None, None, *grads)
+        return (dxq, None if ctx.same else dxk, None, None, None, None, None, *grads)
 
 
 class Longformer_Local_Attention(nn.Module):
@@ -194,15 +196,14 @@ class Longformer_Local_Attention(nn.Module):
             raise ValueError(f"expected [B, S, {self.d_model}] hidden states, got {tuple(xq.shape)} / {tuple(xk.shape)}")
         if xq.stride(2) != 1 or xk.stride(2) != 1 or xq.stride(0) != xq.shape[1] * xq.stride(1) or xk.stride(0) != xk.shape[1] * xk.stride(1):
             xq, xk = xq.contiguous(), (xq.contiguous() if xk is xq else xk.contiguous())
-        if self.training and self.attention_dropout > 0:
-            raise NotImplementedError("dropout on the attention probabilities is not implemented on the B200 path "
-                                      "(the probabilities never leave tensor memory); train with dropout_out = 0")
+        p_attn = self.attention_dropout if self.training else 0.0
         lens = lengths if isinstance(lengths, ops.Lengths) else ops.Lengths(lengths, xq.device, xq.shape[1])
         packed = self.packed()
         params = packed.params()
         if not (torch.is_grad_enabled() and (any(p.requires_grad for p in params) or xq.requires_grad or xk.requires_grad)):
-            return _mha_forward(xq, xk, lens, packed, self.nhead, self.reach, save=False)[0]
-        return BandMhaFn.apply(xq, xk, lens, packed, self.nhead, self.reach, *params)
+            return _mha_forward(xq, xk, lens, packed, self.nhead, self.reach, save=False, p_attn=p_attn,
+                                seed=attn_seed(0) if p_attn > 0 else 0)[0]
+        return BandMhaFn.apply(xq, xk, lens, packed, self.nhead, self.reach, p_attn, *params)
 
 
 class RecurrentLongformerBlock(nn.Module):
@@ -214,11 +215,10 @@ class RecurrentLongformerBlock(nn.Module):
         transformer_in = hidden_dim if separate_forward_backward else hidden_dim * 2
         self.sep_fb = separate_forward_backward
         just_mha = True if separate_forward_backward else just_mha
-        # The reference does not pass `dropout_attention` here, so its wrapper default (0.1) becomes HF's
-        # attention_probs_dropout_prob while training.  The probabilities never leave the chip on this path: the block
-        # trains WITHOUT that regulariser (evaluation is identical); stated in DESIGN.md.
+        # The reference does not pass `dropout_attention` here (models/CRF.py:653-657), so its wrapper default (0.1) becomes
+        # HF's attention_probs_dropout_prob while training: same here (mts_band_attn_fwd_dropout); evaluation is dropout-free.
         self.transformer = Longformer_Local_Attention(transformer_in, nheads, 1, transformer_in, window_size=window_size,
-                                                      dropout=dropout_in, dropout_attention=0.0, layer_norm_eps=1e-12,
+                                                      dropout=dropout_in, layer_norm_eps=1e-12,
                                                       tagset_size=tagset_size, device=None, max_position_embedding=4096,
                                                       just_mha=just_mha)
 

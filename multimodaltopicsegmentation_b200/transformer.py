@@ -250,6 +250,29 @@ FOLD_RESIDUAL = __import__("os").environ.get("MTS_XF_FOLD", "0") == "1"
 DROPOUT_MASK_FN = None
 
 
+# Seeds of the attention-probability dropout: callable (layer) -> int below 2^63.  None = drawn from torch's CPU generator
+# (so torch.manual_seed makes a training run repeatable; no device synchronisation).  The keep-mask itself is a pure
+# function of the seed and the (episode, head, query, key) indices (csrc/common.cuh attn_keep_scale) and is regenerated
+# by the backward kernels: no mask tensor is stored.
+ATTN_SEED_FN = None
+
+
+def attn_seed(layer):
+    if ATTN_SEED_FN is not None:
+        return int(ATTN_SEED_FN(layer))
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def band_attention(qkv, ld, lens, offs, B, S, nheads, hd, reach, out, out_hi, out_lo, kp, lse, p_attn=0.0, seed=0):
+    """mts_band_attn_fwd, or its dropout form when p_attn > 0 (training)."""
+    if p_attn > 0:
+        _call("mts_band_attn_fwd_dropout", _ptr(qkv), ld, _ptr(lens.dev), offs, B, S, nheads, hd, reach, _ptr(out), _ptr(out_hi),
+              _ptr(out_lo), kp, _ptr(lse), float(p_attn), int(seed), _stream())
+    else:
+        _call("mts_band_attn_fwd", _ptr(qkv), ld, _ptr(lens.dev), offs, B, S, nheads, hd, reach, _ptr(out), _ptr(out_hi),
+              _ptr(out_lo), kp, _ptr(lse), _stream())
+
+
 def _keep_mask(site, rows, d, p, device):
     if DROPOUT_MASK_FN is not None:
         return DROPOUT_MASK_FN(site, rows, d, p, device)
@@ -330,16 +353,17 @@ def encoder_forward_f16(x, lens, packed: PackedEncoder, nheads, reaches):
     return h.view(B, S, d)
 
 
-def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hidden=0.0):
+def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hidden=0.0, p_attn=0.0):
     """x [B,S,d] -> last hidden state [B,S,d].  `reaches[l]` = one-sided window of layer l.
     With save=True also returns what the backward pass needs.
     p_hidden > 0 applies HF's `hidden_dropout_prob` at its three sites (after the embeddings LayerNorm and on the
     two dense outputs that feed a residual LayerNorm: modeling_longformer.py LongformerEmbeddings / SelfOutput /
-    Output) as plain element-wise passes -- a training-time regulariser, not part of the timed inference path."""
+    Output) as plain element-wise passes -- a training-time regulariser, not part of the timed inference path.
+    p_attn > 0 applies HF's `attention_probs_dropout_prob` inside the attention kernel (one seed per layer)."""
     B, S, d = x.shape
     ragged = LAYOUT == "ragged"
     M = lens.N if ragged else B * S
-    if not save and p_hidden == 0 and not FOLD_RESIDUAL and _f16x3_eligible(M, d, 0, ops):
+    if not save and p_hidden == 0 and p_attn == 0 and not FOLD_RESIDUAL and _f16x3_eligible(M, d, 0, ops):
         return encoder_forward_f16(x, lens, packed, nheads, reaches), None
     offs = _ptr(lens.offs) if ragged else 0
     dev = x.device
@@ -356,7 +380,7 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hid
         h_hi, h_lo = ops.split_tf32(h)
         if _pad32(d) == d:
             h_hi = h
-    saved = {"emb": (pre0, st0), "layers": [], "ragged": ragged, "masks": masks, "p_hidden": p_hidden}
+    saved = {"emb": (pre0, st0), "layers": [], "ragged": ragged, "masks": masks, "p_hidden": p_hidden, "p_attn": p_attn}
     # Optional (MTS_XF_FOLD=1), inference only: the two residual adds folded into the dense layers' epilogues
     # (accumulate onto the residual, which is dead as an operand by then) -- bit-identical sums, see FOLD_RESIDUAL.
     fold = FOLD_RESIDUAL and not save and p_hidden == 0 and _pad32(d) == d
@@ -367,18 +391,17 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hid
         ops.gemm_tf32x3(h_hi, h_lo, ent["wqkv"][0], ent["wqkv"][1], ent["bqkv"], qkv, M, 3 * d, epilogue=1)
         kp = _pad32(d)
         lse = torch.empty((B, nheads, S), device=dev, dtype=torch.float32) if save else None
+        seed = attn_seed(l) if p_attn > 0 else 0
         if kp == d:  # the attention output is its own `hi` operand; the kernel adds the correction operand
             a = torch.empty((M, d), device=dev, dtype=torch.float32)
             a_lo = torch.empty((M, kp), device=dev, dtype=torch.float32)
             a_hi = a
-            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), offs, B, S, nheads, hd, reaches[l], 0,
-                  _ptr(a_hi), _ptr(a_lo), kp, _ptr(lse), _stream())
+            band_attention(qkv, 3 * d, lens, offs, B, S, nheads, hd, reaches[l], None, a_hi, a_lo, kp, lse, p_attn, seed)
         else:  # widths that are not a multiple of 32: plain output, then the generic (zero-padding) split
             a = torch.empty((M, d), device=dev, dtype=torch.float32)
             a_hl = torch.empty((2, M, kp), device=dev, dtype=torch.float32)
             a_hi, a_lo = a_hl[0], a_hl[1]
-            _call("mts_band_attn_fwd", _ptr(qkv), 3 * d, _ptr(lens.dev), offs, B, S, nheads, hd, reaches[l], _ptr(a), 0, 0,
-                  0, _ptr(lse), _stream())
+            band_attention(qkv, 3 * d, lens, offs, B, S, nheads, hd, reaches[l], a, None, None, 0, lse, p_attn, seed)
             _call("mts_split_tf32", _ptr(a), d, M, d, kp, ops.A_SIDE, _ptr(a_hi), _ptr(a_lo), _stream())
         ln1 = lyr.attention.output.LayerNorm
         if fold:  # t + h formed by the GEMM epilogue, in h (its operand role ended with the QKV product)
@@ -414,7 +437,7 @@ def encoder_forward(x, lens, packed: PackedEncoder, nheads, reaches, save, p_hid
                 _drop(u, 2 + 2 * l, p_hidden, masks)
             h, h_hi, h_lo, pre2, st2 = _ln(1, u, y, None, ln2.weight.detach(), ln2.bias.detach(), M, 1, d, not last, save)
         if save:
-            saved["layers"].append({"h_in": h_in, "qkv": qkv, "lse": lse, "a": a, "pre1": pre1, "st1": st1,
+            saved["layers"].append({"h_in": h_in, "qkv": qkv, "lse": lse, "a": a, "attn_seed": seed, "pre1": pre1, "st1": st1,
                                     "y": y, "zp": zp, "z": z, "pre2": pre2, "st2": st2})
     if ragged:  # back to the caller's [B,S,d] layout, padded sentences zero
         out = torch.empty((B, S, d), device=dev, dtype=torch.float32)
@@ -427,9 +450,9 @@ class EncoderFn(torch.autograd.Function):
     """Differentiable w.r.t. the encoder parameters (the input embeddings are data)."""
 
     @staticmethod
-    def forward(ctx, x, lens, packed, nheads, reaches, p_hidden, *params):
+    def forward(ctx, x, lens, packed, nheads, reaches, p_hidden, p_attn, *params):
         need = any(ctx.needs_input_grad)
-        out, saved = encoder_forward(x, lens, packed, nheads, reaches, save=need, p_hidden=p_hidden)
+        out, saved = encoder_forward(x, lens, packed, nheads, reaches, save=need, p_hidden=p_hidden, p_attn=p_attn)
         if need:
             ctx.saved, ctx.lens, ctx.packed, ctx.nheads, ctx.reaches = saved, lens, packed, nheads, reaches
             ctx.shape = x.shape
@@ -441,7 +464,7 @@ class EncoderFn(torch.autograd.Function):
 
         grads = encoder_backward(ctx, dout.contiguous())
         ctx.saved = None
-        return (None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, *grads)
 
 
 class Longformer_Local_Attention(nn.Module):
@@ -475,18 +498,16 @@ class Longformer_Local_Attention(nn.Module):
         if x.shape[1] + 2 > self.max_positions:
             raise IndexError(f"sequence length {x.shape[1]} exceeds the position table ({self.max_positions} rows, "
                              "position ids start at 2)")
-        if self.training and self.attention_dropout > 0:
-            raise NotImplementedError("dropout on the attention probabilities is not implemented on the B200 path "
-                                      "(the probabilities never leave tensor memory); train with dropout_out = 0")
         p_hidden = self.hidden_dropout if self.training else 0.0
+        p_attn = self.attention_dropout if self.training else 0.0   # HF attention_probs_dropout_prob (RestrictedTransformerLayer.py:92)
         if x.stride(2) != 1 or x.stride(1) != x.shape[2]:
             x = x.contiguous()
         lens = lengths if isinstance(lengths, ops.Lengths) else ops.Lengths(lengths, x.device, x.shape[1])
         packed = self.packed()
         params = packed.used_parameters()
         if not (torch.is_grad_enabled() and any(p.requires_grad for p in params)):  # inference: nothing saved
-            return encoder_forward(x, lens, packed, self.nhead, self.reaches, save=False, p_hidden=p_hidden)[0]
-        return EncoderFn.apply(x, lens, packed, self.nhead, self.reaches, p_hidden, *params)
+            return encoder_forward(x, lens, packed, self.nhead, self.reaches, save=False, p_hidden=p_hidden, p_attn=p_attn)[0]
+        return EncoderFn.apply(x, lens, packed, self.nhead, self.reaches, p_hidden, p_attn, *params)
 
 
 class Transformer_segmenter(nn.Module):

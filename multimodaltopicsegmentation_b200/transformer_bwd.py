@@ -107,8 +107,9 @@ def encoder_backward(ctx, dout):
         # ---- banded attention ----------------------------------------------------------------------------------
         dqkv = torch.empty((M, 3 * d), device=dev, dtype=torch.float32)
         delta = torch.empty((B, nheads, S), device=dev, dtype=torch.float32)
-        _call("mts_band_attn_bwd", _ptr(sv["qkv"]), 3 * d, _ptr(sv["a"]), _ptr(da), _ptr(sv["lse"]), _ptr(lens.dev), offs, B, S,
-              nheads, hd, reaches[l], _ptr(dqkv), _ptr(delta), _stream())
+        _call("mts_band_attn_bwd_dropout", _ptr(sv["qkv"]), 3 * d, _ptr(sv["a"]), _ptr(da), _ptr(sv["lse"]), _ptr(lens.dev), offs,
+              B, S, nheads, hd, reaches[l], _ptr(dqkv), _ptr(delta), float(saved.get("p_attn", 0.0)), int(sv.get("attn_seed", 0)),
+              _stream())
         # ---- qkv = h_in Wqkv^T + b;  dh_in = dqkv Wqkv + dpre1 (skip path) ---------------------------------------
         dwqkv, dbqkv = _dense_param_grads(dqkv, sv["h_in"], M, 3 * d, d)
         for j in range(3):

@@ -462,6 +462,15 @@ def test_recurrent_longformer_vs_oracle(dev, H, nheads, D, S, window, layers):
     assert set(ours.state_dict().keys()) == set(ref.state_dict().keys())
     ours.load_state_dict(ref.state_dict())
     ours = ours.to(dev)
+    # like the reference's block, ours trains with the wrapper's default attention-probability dropout of 0.1; the
+    # oracle twin is built with 0 (its mask would come from torch's generator): compare the dropout-free arithmetic
+    n_attn = 0
+    for mod in ours.modules():
+        if hasattr(mod, "attention_dropout"):
+            assert mod.attention_dropout == pytest.approx(0.1)
+            mod.attention_dropout = 0.0
+            n_attn += 1
+    assert n_attn == layers
     x = torch.randn(B, S, D, generator=g)
     lengths = torch.randint(3, S + 1, (B,), generator=g)
     lengths[1] = S

@@ -686,8 +686,9 @@ def test_transformer_vs_hf_twin(dev, xf_layout):
     close(l, l_ref)
 
 
-def _dense_band_attention_torch(qkv, lens, B, S, h, hd, w):
-    """float64 autograd reference: dense scores with the band / length mask, zero rows for padded queries."""
+def _dense_band_attention_torch(qkv, lens, B, S, h, hd, w, prob_scale=None):
+    """float64 autograd reference: dense scores with the band / length mask, zero rows for padded queries;
+    prob_scale [B, h, S, S]: multiplier of the probabilities after the softmax (dropout keep / (1 - p))."""
     d = h * hd
     q, k, v = [t.view(B, S, h, hd).permute(0, 2, 1, 3) for t in (qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:])]
     s = (q / np.sqrt(hd)) @ k.transpose(-1, -2)
@@ -700,6 +701,8 @@ def _dense_band_attention_torch(qkv, lens, B, S, h, hd, w):
         sb = s[b].masked_fill(~allowed, float("-inf"))
         sb = torch.where(allowed.any(-1, keepdim=True), sb, torch.zeros_like(sb))
         p = torch.softmax(sb, dim=-1) * (idx < n)[None, :, None]
+        if prob_scale is not None:
+            p = p * prob_scale[b]
         outs.append(p @ v[b])
     return torch.stack(outs).permute(0, 2, 1, 3).reshape(B * S, d)
 
@@ -742,6 +745,118 @@ def test_band_attention_backward(dev, B, S, h, hd, w, lens, layout):
     assert bool(torch.isnan(dqkv[rows]).all())  # nothing written behind the last row
     scale = float(qkv.grad.abs().max())
     close(dqkv[:rows], pack(qkv.grad.float()), rtol=1e-4, atol=2e-5 * scale)
+
+
+@pytest.mark.parametrize("B,S,h,hd,w,lens,p", [
+    (2, 24, 4, 8, 4, [24, 13], 0.5),
+    (2, 150, 2, 112, 48, [150, 61], 0.1),
+    (3, 130, 3, 64, 8, [130, 31, 1], 0.1),
+    (1, 300, 1, 16, 120, [280], 0.25),
+])
+@pytest.mark.parametrize("layout", ["padded", "ragged"])
+def test_band_attention_dropout_forward_backward(dev, B, S, h, hd, w, lens, p, layout):
+    """Dropout on the attention probabilities (HF attention_probs_dropout_prob; the reference sets it from dropout_out,
+    models/CRF.py:531-536): forward output, saved log-sum-exp and dq / dk / dv of mts_band_attn_fwd_dropout /
+    mts_band_attn_bwd_dropout against float64 autograd through the dense masked softmax multiplied by the SAME keep-mask,
+    which the oracle regenerates from the seed (oracle/ref_numpy.py:attn_dropout_keep restates the device hash)."""
+    from multimodaltopicsegmentation_b200 import ops
+    from oracle import ref_numpy as rn
+
+    g = torch.Generator().manual_seed(S + hd + w + 7)
+    seed = 0x1234_5678_9ABC_DEF0 ^ (S * 7919 + hd)
+    d = h * hd
+    keep = rn.attn_dropout_keep(seed, B, h, S, p)
+    frac = 1.0 - keep.mean()
+    assert abs(frac - p) < 4 * np.sqrt(p * (1 - p) / keep.size) + 1e-3, (frac, p)
+    scale_mask = torch.from_numpy(keep.astype(np.float64)) / (1.0 - float(np.float32(p)))
+    qkv = torch.randn(B * S, 3 * d, generator=g, dtype=torch.float64).requires_grad_(True)
+    do = torch.randn(B * S, d, generator=g, dtype=torch.float64)
+    ragged = layout == "ragged"
+    if ragged:
+        for b, n in enumerate(lens):
+            do.view(B, S, d)[b, n:] = 0
+    ref = _dense_band_attention_torch(qkv, lens, B, S, h, hd, w, prob_scale=scale_mask)
+    ref.backward(do)
+    plain = _dense_band_attention_torch(qkv.detach(), lens, B, S, h, hd, w)
+    assert float((ref.detach() - plain).abs().max()) > 1e-3     # the mask does something
+    L = ops.Lengths(lens, dev, S)
+    offs = L.offs.data_ptr() if ragged else 0
+    pack = (lambda t: _to_ragged(t, lens, B, S)) if ragged else (lambda t: t)
+    qkv_d = pack(qkv.detach().float()).to(dev)
+    rows = qkv_d.shape[0]
+    out, out0 = torch.empty(rows, d, device=dev), torch.empty(rows, d, device=dev)
+    lse, lse0 = torch.empty(B, h, S, device=dev), torch.empty(B, h, S, device=dev)
+    ops._call("mts_band_attn_fwd_dropout", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), offs, B, S, h, hd, w, out.data_ptr(), 0, 0, 0,
+              lse.data_ptr(), p, seed, ops._stream())
+    close(out, pack(ref.detach().float()), rtol=1e-4, atol=2e-5)
+    ops._call("mts_band_attn_fwd_simt", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), offs, B, S, h, hd, w, out0.data_ptr(), 0, 0, 0,
+              lse0.data_ptr(), ops._stream())
+    assert torch.equal(lse, lse0)                               # the statistics are those of the undropped scores
+    out_p0 = torch.empty(rows, d, device=dev)
+    ops._call("mts_band_attn_fwd_dropout", qkv_d.data_ptr(), 3 * d, L.dev.data_ptr(), offs, B, S, h, hd, w, out_p0.data_ptr(), 0, 0, 0,
+              0, 0.0, seed, ops._stream())
+    assert torch.equal(out_p0, out0)                            # p = 0 is the plain kernel
+    dqkv = torch.full((rows + 1, 3 * d), float("nan"), device=dev)
+    delta = torch.empty(B, h, S, device=dev)
+    do_d = pack(do.float()).to(dev)
+    ops._call("mts_band_attn_bwd_dropout", qkv_d.data_ptr(), 3 * d, out.data_ptr(), do_d.data_ptr(), lse.data_ptr(),
+              L.dev.data_ptr(), offs, B, S, h, hd, w, dqkv.data_ptr(), delta.data_ptr(), p, seed, ops._stream())
+    assert bool(torch.isnan(dqkv[rows]).all())
+    scale = float(qkv.grad.abs().max())
+    close(dqkv[:rows], pack(qkv.grad.float()), rtol=1e-4, atol=2e-5 * scale)
+
+
+def test_attention_dropout_in_training(dev, monkeypatch):
+    """Transformer_segmenter(dropout_out = p) and the BiLSTMRestrictedMHA block (wrapper default 0.1, as in the reference)
+    train with dropped attention probabilities: repeatable under a fixed seed function, different from call to call with
+    the default generator, absent in eval mode; the gradient is the gradient of the dropped forward pass (directional
+    finite difference on the loss under a fixed seed)."""
+    from multimodaltopicsegmentation_b200 import RecurrentLongformer, transformer
+    from multimodaltopicsegmentation_b200.transformer import Transformer_segmenter
+
+    g = torch.Generator().manual_seed(5)
+    B, S, d, F, nh, w = 3, 48, 32, 16, 4, 8
+    x = torch.randn(B, S, d, generator=g).to(dev)
+    lengths = torch.tensor([48, 20, 33])
+    y = (torch.rand(B, S, generator=g) < 0.2).float()
+    for b, n in enumerate(lengths.tolist()):
+        y[b, n:] = -1
+    y = y.to(dev)
+    torch.manual_seed(3)
+    models = [Transformer_segmenter(2, d, F, num_layers=2, nheads=nh, loss_fn="FocalLoss", window_size=w, dropout_out=0.3).to(dev),
+              RecurrentLongformer(2, d, 16, num_layers=2, nheads=nh, loss_fn="FocalLoss", window_size=w).to(dev)]
+    for m in models:
+        m.train()
+        monkeypatch.setattr(transformer, "ATTN_SEED_FN", None)
+        with torch.no_grad():
+            a, b_ = float(m.loss(x, lengths, y)), float(m.loss(x, lengths, y))
+            assert a != b_
+        monkeypatch.setattr(transformer, "ATTN_SEED_FN", lambda layer: 1000 + layer)
+        loss = m.loss(x, lengths, y)
+        loss.backward()
+        with torch.no_grad():
+            assert float(m.loss(x, lengths, y)) == float(loss)
+            # directional derivative along the gradient, central difference (same seeds -> same masks)
+            params = [q for q in m.parameters() if q.grad is not None]
+            gnorm2 = sum(float((q.grad.double() ** 2).sum()) for q in params)
+            eps = 1e-2 / np.sqrt(gnorm2)
+            for sgn in (+1, -1):
+                for q in params:
+                    q.add_(sgn * eps * q.grad)
+                if sgn > 0:
+                    lp = float(m.loss(x, lengths, y).double())
+                    for q in params:
+                        q.sub_(eps * q.grad)
+                else:
+                    lm = float(m.loss(x, lengths, y).double())
+                    for q in params:
+                        q.add_(eps * q.grad)
+            fd = (lp - lm) / (2 * eps)
+            print(f"  {type(m).__name__}: directional derivative {fd:.6e} vs |grad|^2 {gnorm2:.6e}")
+            assert abs(fd - gnorm2) <= 2e-2 * gnorm2
+            m.eval()
+            monkeypatch.setattr(transformer, "ATTN_SEED_FN", None)
+            assert float(m.loss(x, lengths, y)) == float(m.loss(x, lengths, y))
 
 
 @pytest.mark.parametrize("M,d", [(37, 32), (1000, 896), (300, 1024), (64, 100)])
@@ -937,8 +1052,6 @@ def test_transformer_hidden_dropout_training_vs_hf_twin(dev, xf_layout, monkeypa
         ours.eval()
         c = ours.model(x.to(dev), lengths)
         assert torch.equal(c, ours.model(x.to(dev), lengths))
-    with pytest.raises(NotImplementedError):
-        Transformer_segmenter(2, d, F, num_layers=1, nheads=nh, window_size=w, dropout_out=0.1).to(dev).train().model(x.to(dev), lengths)
 
 
 # ----------------------------------------------------------------------------------------------------------
