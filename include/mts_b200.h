@@ -218,6 +218,15 @@ int mts_lstm_rec_bwd(const float *dy, const float *gates, const float *w_hh, con
  * memory.  Same results (to fp32 rounding) as mts_lstm_rec_bwd; needs no transposed copy of w_hh. */
 int mts_lstm_rec_bwd_tc(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
                         const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream);
+/* The same on fp16-split operands (csrc/lstm_bwd_h3.cu): W_hh^T dp = W1 D1 + W2 D1 + W1 D2 as 48 kind::f16 MMAs per step
+ * instead of 64 (TF32 + bf16), per-row power-of-two scale of the weight slice and a per-step, per-episode power-of-two scale
+ * of dp (column maximum by one warp-wide integer max), both undone in the reduce-scatter epilogue.  The default behind
+ * mts_lstm_rec_bwd_tc (MTS_BWD_IMPL=tf32 keeps the TF32 + bf16 kernel); same arguments and results (error ~2^-22 of the
+ * column scale). */
+int mts_lstm_rec_bwd_h3(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
+                        const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream);
+int mts_lstm_rec_bwd_tf32(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
+                          const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Head + decode  (models/CRF.py:340,361-369: Linear then sigmoid/softmax threshold)

@@ -48,6 +48,8 @@ SIGNATURES = {
     "mts_debug_rec_profile_h3p": (c_int, [_P]),
     "mts_lstm_rec_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "mts_lstm_rec_bwd_tc": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "mts_lstm_rec_bwd_h3": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "mts_lstm_rec_bwd_tf32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "mts_head_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
     "mts_head_bwd_ws_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "mts_head_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),

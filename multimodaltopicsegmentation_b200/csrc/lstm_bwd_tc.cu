@@ -14,6 +14,7 @@
 //               into that CTA's receive buffer with st.async (DSMEM) completing on its mbarrier -- 16 KB per CTA per
 //               step, the same volume as the forward all-gather.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "cluster_utils.cuh"
 #include "tcgen05_utils.cuh"
@@ -329,6 +330,14 @@ using namespace mts;
 
 extern "C" int mts_lstm_rec_bwd_tc(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
                                    const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream) {
+  // default: the fp16-split kernel (lstm_bwd_h3.cu); MTS_BWD_IMPL=tf32 keeps the TF32 + bf16 formulation of this file
+  static const char *impl = getenv("MTS_BWD_IMPL");
+  if (impl && impl[0] == 't') return mts_lstm_rec_bwd_tf32(dy, gates, w_hh, lengths, order, n_enc, B, T, H, dgx, stream);
+  return mts_lstm_rec_bwd_h3(dy, gates, w_hh, lengths, order, n_enc, B, T, H, dgx, stream);
+}
+
+extern "C" int mts_lstm_rec_bwd_tf32(const float *dy, const float *gates, const float *w_hh, const int32_t *lengths,
+                                     const int32_t *order, int n_enc, int B, int T, int H, float *dgx, void *stream) {
   MTS_REQUIRE(dy && gates && w_hh && lengths && dgx, MTS_E_BADARG, "lstm_rec_bwd_tc: null pointer");
   MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0, MTS_E_BADARG, "lstm_rec_bwd_tc: bad shape");
   MTS_REQUIRE(H == kH, MTS_E_UNSUPPORTED, "lstm_rec_bwd_tc: the tensor-core recurrence serves H == 256");

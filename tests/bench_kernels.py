@@ -70,9 +70,10 @@ def bench_rec():
         rec_call(gx, whh, lens, y, gates, Bb, T)
         dy = torch.randn_like(y)
         dgx = torch.empty_like(gx)
-        ms = timeit(lambda: ops._call("mts_lstm_rec_bwd_tc", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
-                                      lens.order.data_ptr(), 1, Bb, T, H, dgx.data_ptr(), ops._stream()))
-        print(f"backward, tensor-core kernel (mts_lstm_rec_bwd_tc) B={Bb} T=300: {ms:.3f} ms  ({ms * 1e3 / T:.2f} us/step)")
+        for name in ("mts_lstm_rec_bwd_h3", "mts_lstm_rec_bwd_tf32"):
+            ms = timeit(lambda: ops._call(name, dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
+                                          lens.order.data_ptr(), 1, Bb, T, H, dgx.data_ptr(), ops._stream()))
+            print(f"backward, tensor-core kernel ({name}) B={Bb} T=300: {ms:.3f} ms  ({ms * 1e3 / T:.2f} us/step)")
 
 
 def bench_gemm():

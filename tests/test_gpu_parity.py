@@ -1191,15 +1191,23 @@ def test_cfg5_long_episode_properties(dev):
     assert bool((stats[0] >= stats[1] * (1 - 3e-4)).all())     # log Z >= score of any single path
 
 
-@pytest.mark.parametrize("B,T,n_enc", [(3, 5, 1), (37, 61, 1), (20, 33, 2), (300, 50, 1)])
-def test_recurrence_backward_tensor_core_vs_fma(dev, B, T, n_enc):
-    """lstm_bwd_tc_kernel (tcgen05, transposed W_hh slice in tensor memory) against the packed-FMA BPTT kernel."""
+# default = fp16-split kernel (lstm_bwd_h3.cu); the TF32 + bf16 kernel of round 1
+@pytest.mark.parametrize("entry", ["mts_lstm_rec_bwd_tc", "mts_lstm_rec_bwd_tf32"])
+@pytest.mark.parametrize("B,T,n_enc,spread", [(3, 5, 1, 0), (37, 61, 1, 0), (20, 33, 2, 0), (300, 50, 1, 0), (10, 120, 1, 1), (37, 61, 2, 1)])
+def test_recurrence_backward_tensor_core_vs_fma(dev, B, T, n_enc, spread, entry):
+    """The tcgen05 BPTT kernels (transposed W_hh slice in tensor memory) against the packed-FMA BPTT kernel.  spread = 1:
+    upstream gradients whose magnitude differs by ten decades between episodes and by four along an episode, weight
+    columns spanning five decades and a zero column -- the fp16-split kernel rescales every dp column at every step."""
     from multimodaltopicsegmentation_b200 import ops
 
     H = 256
     g = torch.Generator(device=dev).manual_seed(B * 77 + T)
     gx = torch.randn((n_enc, B * T, 8 * H), device=dev, generator=g)
     whh = torch.randn((n_enc, 2, 4 * H, H), device=dev, generator=g) * 0.06
+    if spread:
+        colscale = 10.0 ** (-5.0 * torch.rand(H, device=dev, generator=g))
+        colscale[7] = 0.0
+        whh = whh * colscale.view(1, 1, 1, H)
     hg = torch.Generator().manual_seed(B + T)
     lengths = [T] + [int(v) for v in torch.randint(1, T + 1, (B - 1,), generator=hg)]
     lens = ops.Lengths(lengths, dev, T)
@@ -1208,17 +1216,27 @@ def test_recurrence_backward_tensor_core_vs_fma(dev, B, T, n_enc):
     ops._call("mts_lstm_rec_fwd_tc", gx.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(), lens.order.data_ptr(), n_enc, B, T,
               H, y.data_ptr(), gates.data_ptr(), 0, ops._stream())
     dy = torch.randn((B, T, n_enc * 2 * H), device=dev, generator=g)
+    if spread:
+        dy = dy * (10.0 ** (-10.0 * torch.rand(B, 1, 1, device=dev, generator=g))) * (10.0 ** (-4.0 * torch.rand(B, T, 1, device=dev, generator=g)))
     whh_t = whh.transpose(2, 3).contiguous()
     d_f = torch.full((n_enc, B * T, 8 * H), float("nan"), device=dev)
     d_t = torch.full((n_enc, B * T, 8 * H), float("nan"), device=dev)
     ops._call("mts_lstm_rec_bwd", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), whh_t.data_ptr(), lens.dev.data_ptr(),
               lens.order.data_ptr(), n_enc, B, T, H, d_f.data_ptr(), ops._stream())
-    ops._call("mts_lstm_rec_bwd_tc", dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
+    ops._call(entry, dy.data_ptr(), gates.data_ptr(), whh.data_ptr(), lens.dev.data_ptr(),
               lens.order.data_ptr(), n_enc, B, T, H, d_t.data_ptr(), ops._stream())
     assert not bool(torch.isnan(d_t).any())       # every row written, zeros at padded steps
     for b, n in enumerate(lengths):
         assert float(d_t[:, b * T + n:(b + 1) * T].abs().max() if n < T else 0.0) == 0.0
-    close(d_t, d_f, rtol=1e-4, atol=2e-5 * float(d_f.abs().max()))
+    # per episode: gradients of different episodes may differ by many decades, each is held to ITS OWN scale
+    worst = 0.0
+    for b in range(B):
+        f, t = d_f[:, b * T:(b + 1) * T], d_t[:, b * T:(b + 1) * T]
+        sc = float(f.abs().max())
+        if sc > 0:
+            worst = max(worst, float((f - t).abs().max()) / sc)
+    print(f"  {entry} B={B} T={T} n_enc={n_enc} spread={spread}: worst per-episode norm-wise error {worst:.2e} (contract 2e-5)")
+    assert worst <= 2e-5
 
 
 # ----------------------------------------------------------------------------------------------------------
