@@ -90,9 +90,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(THREADS, 1)
   uint64_t *bars = reinterpret_cast<uint64_t *>(sd + 2 * NB);
   uint64_t *part_full = bars;      // [2]  the 8 partial blocks of step s-1 landed in recv[s & 1]
   uint64_t *b_ready = bars + 2;    //      dp operand of the step written
-  uint64_t *acc_full = bars + 3;   //      the step's MMAs have completed
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
-  int *len_s = reinterpret_cast<int *>(bars + 6);
+  uint64_t *acc_full = bars + 3;   // [2]  the step's MMAs into accumulator 0 (hidden units 0-127) / 1 (128-255) have completed
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
+  int *len_s = reinterpret_cast<int *>(bars + 7);
   int *bq_s = len_s + NB;
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -107,7 +107,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(THREADS, 1)
     tc::bar_init(tc::s_u32(&part_full[0]), 1);
     tc::bar_init(tc::s_u32(&part_full[1]), 1);
     tc::bar_init(tc::s_u32(b_ready), EPI);
-    tc::bar_init(tc::s_u32(acc_full), 1);
+    tc::bar_init(tc::s_u32(&acc_full[0]), 1);
+    tc::bar_init(tc::s_u32(&acc_full[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tc::tmem_alloc<512>(tc::s_u32(tmem_slot));
@@ -210,8 +211,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(THREADS, 1)
               umma_f16_ts_p(d_tmem, a2, d1, dhi, idesc, 1);        // W2 D1
               umma_f16_ts_p(d_tmem, a1, d2, dhi, idesc, 1);        // W1 D2
             }
+            // one commit per accumulator: the reduce-scatter of the first overlaps the MMAs of the second
+            tc::umma_commit(tc::s_u32(&acc_full[mb]));
           }
-          tc::umma_commit(tc::s_u32(acc_full));
         }
         __syncwarp();
       }
@@ -244,6 +246,22 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(THREADS, 1)
           }
         }
       }
+      // Everything of the cell derivative that depends only on the SAVED activations is formed off the critical path (here for
+      // the first step, after the sends of a step for the next one, while the partial products are in flight):
+      //   d_o = dh tcv, dcv = dc + dh fA, dp_i = dcv fI, dp_f = dcv fF, dp_g = dcv fG, dp_o = dh fO, dc' = dcv f
+      float tcv[4], fA[4], fI[4], fF[4], fG[4], fO[4];
+      auto cell_factors = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tcv[i] = tanh_fast(c_cur[i]);
+          fA[i] = og[i] * (1.0f - tcv[i] * tcv[i]);
+          fI[i] = gg[i] * ig[i] * (1.0f - ig[i]);
+          fF[i] = c_prev[i] * fg[i] * (1.0f - fg[i]);
+          fG[i] = ig[i] * (1.0f - gg[i] * gg[i]);
+          fO[i] = tcv[i] * og[i] * (1.0f - og[i]);
+        }
+      };
+      cell_factors();
       // reduce-scatter addressing: this thread reads TMEM lane (32 q + lane) of both accumulators: hidden units
       // 32 q + lane (owner CTA q) and 128 + 32 q + lane (owner CTA q + 4); it lands in row `lane` of my source slot there
       const uint32_t row_off = (uint32_t)(((int)rank * 32 + lane) * ROW * 4);
@@ -275,13 +293,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(THREADS, 1)
         for (int i = 0; i < 4; ++i) {
           float dpi = 0.f, dpf = 0.f, dpg = 0.f, dpo = 0.f;
           if (i < n_i && s < len[i]) {
-            const float tcv = tanh_fast(c_cur[i]);
-            const float d_o = dh[i] * tcv;
-            const float dcv = dc[i] + dh[i] * og[i] * (1.0f - tcv * tcv);
-            dpi = dcv * gg[i] * ig[i] * (1.0f - ig[i]);
-            dpf = dcv * c_prev[i] * fg[i] * (1.0f - fg[i]);
-            dpg = dcv * ig[i] * (1.0f - gg[i] * gg[i]);
-            dpo = d_o * og[i] * (1.0f - og[i]);
+            const float dcv = fmaf(dh[i], fA[i], dc[i]);
+            dpi = dcv * fI[i];
+            dpf = dcv * fF[i];
+            dpg = dcv * fG[i];
+            dpo = dh[i] * fO[i];
             dc[i] = dcv * fg[i];
             const int t = dir ? s : len[i] - 1 - s;
             float *o = dgx + dgx_enc + ((size_t)bq[i] * T + t) * 8 * kH + gcol;
@@ -337,24 +353,25 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(THREADS, 1)
         }
         // ---- reduce-scatter of this step's partial products (scales undone: 2^-s of my weight row x 2^-k of the column) ----
         if (s + 1 < nsteps) {
-          tc::bar_wait_wd(tc::s_u32(acc_full), ph_acc); ph_acc ^= 1;
-          tc::tc_fence_after();
-          float d0[NB], d1[NB];
-          tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC0, d0);
-          tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC1, d1);
-          tc::tc_fence_before();
           const uint32_t boff = (uint32_t)((p ^ 1) * RECV_FLOATS * 4), moff = (uint32_t)((p ^ 1) * 8);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j >= nf4) break;
-            const float4 k4 = *reinterpret_cast<const float4 *>(sd + p * NB + 4 * j);
-            const float4 s0 = make_float4(k4.x * rsw0, k4.y * rsw0, k4.z * rsw0, k4.w * rsw0);
-            const float4 s1 = make_float4(k4.x * rsw1, k4.y * rsw1, k4.z * rsw1, k4.w * rsw1);
-            st_async_v4(r_addr0 + boff + 16 * j,
-                        make_float4(d0[4 * j] * s0.x, d0[4 * j + 1] * s0.y, d0[4 * j + 2] * s0.z, d0[4 * j + 3] * s0.w), r_bar0 + moff);
-            st_async_v4(r_addr1 + boff + 16 * j,
-                        make_float4(d1[4 * j] * s1.x, d1[4 * j + 1] * s1.y, d1[4 * j + 2] * s1.z, d1[4 * j + 3] * s1.w), r_bar1 + moff);
+          for (int mb = 0; mb < 2; ++mb) {
+            tc::bar_wait_wd(tc::s_u32(&acc_full[mb]), ph_acc);
+            tc::tc_fence_after();
+            float d[NB];
+            tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (mb ? COL_ACC1 : COL_ACC0), d);
+            tc::tc_fence_before();
+            const float rsw = mb ? rsw1 : rsw0;
+            const uint32_t r_addr = (mb ? r_addr1 : r_addr0) + boff, r_bar = (mb ? r_bar1 : r_bar0) + moff;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j >= nf4) break;
+              const float4 k4 = *reinterpret_cast<const float4 *>(sd + p * NB + 4 * j);
+              st_async_v4(r_addr + 16 * j, make_float4(d[4 * j] * (k4.x * rsw), d[4 * j + 1] * (k4.y * rsw), d[4 * j + 2] * (k4.z * rsw),
+                                                       d[4 * j + 3] * (k4.w * rsw)), r_bar);
+            }
           }
+          ph_acc ^= 1;
         }
         // ---- rotate the prefetched values in ------------------------------------------------------------------------
 #pragma unroll
@@ -363,6 +380,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(THREADS, 1)
           c_cur[i] = c_prev[i];
           c_prev[i] = n_cp[i];
         }
+        cell_factors();
       }
       // dgx of the padded tail: zeros (the weight-gradient GEMMs read every row)
 #pragma unroll
