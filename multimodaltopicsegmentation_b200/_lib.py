@@ -109,11 +109,16 @@ def load():
     return _lib
 
 
+_FN = {}
+
+
 def call(name, *args):
     """Invoke an int-returning entry point and turn a non-zero status into an exception."""
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
-        msg = lib.mts_last_error().decode("utf-8", "replace")
+        msg = load().mts_last_error().decode("utf-8", "replace")
         raise MtsError(f"{name} failed with status {rc}: {msg}")
     return rc
