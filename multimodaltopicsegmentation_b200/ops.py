@@ -260,6 +260,29 @@ def f16_pieces(w):
     return pieces.contiguous(), (1.0 / scale).contiguous()
 
 
+def f16_pieces_stacked(mats):
+    """f16_pieces of the row-wise concatenation of `mats` ([N_i, K] fp32 each) without forming it: one mts_pack_rows_f16
+    launch per matrix (warp per row: maximum, power-of-two scale, two pieces) into slices of the outputs.  In training the
+    weights change every step, so this runs once per step and LSTM layer: the torch formulation above costs ~15 small
+    launches each time.  Falls back to it for matrices the kernel does not take (width not a multiple of 4, unaligned)."""
+    K = mats[0].shape[1]
+    ok = all(m.is_cuda and m.dtype == torch.float32 and m.dim() == 2 and m.shape[1] == K and m.is_contiguous()
+             and m.data_ptr() % 16 == 0 for m in mats) and K % 4 == 0 and K <= 2048
+    if not ok:
+        return f16_pieces(torch.cat([m.detach() for m in mats], dim=0))
+    K64 = (K + 63) // 64 * 64
+    N = sum(m.shape[0] for m in mats)
+    pieces = torch.empty((N, 2, K64), device=mats[0].device, dtype=torch.float16)
+    scale = torch.empty((N,), device=mats[0].device, dtype=torch.float32)
+    row = 0
+    for m in mats:
+        n = m.shape[0]
+        _call("mts_pack_rows_f16", _ptr(m), n * K, K, 0, 0, 0, 1, n, K64, pieces.data_ptr() + row * 2 * K64 * 2,
+              scale.data_ptr() + row * 4, _stream())
+        row += n
+    return pieces, scale
+
+
 def gemm_f16x3(a_pieces, a_scale, b_pieces, b_scale, bias, out, M, N, epilogue=0, out_lo=None):
     """out [M, N] = A B^T (+ bias; epilogue 2: GELU) over fp16-split operands (include/mts_b200.h, mts_gemm_f16x3)."""
     K64 = a_pieces.shape[-1]
@@ -377,7 +400,7 @@ class PackedLstm:
         if e not in cache:
             w_f, _, _, _, w_r = self._params(self.rnns[e], layer)[:5]
             with torch.no_grad():
-                cache[e] = f16_pieces(torch.cat([w_f.detach(), w_r.detach()], dim=0))
+                cache[e] = f16_pieces_stacked([w_f.detach(), w_r.detach()])
         return cache[e]
 
     def wih_packed_a(self, layer, e):

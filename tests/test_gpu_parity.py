@@ -539,6 +539,27 @@ def test_text_segmenter_steps_equal_the_reference_steps(dev, golden, name, kw, d
         == fx[name + ":o:optimizer"].tolist()
 
 
+def test_f16_weight_pieces_kernel_equals_host_formulation(dev):
+    """ops.f16_pieces_stacked (mts_pack_rows_f16 per matrix, what the LSTM weight cache runs after every optimiser step)
+    against ops.f16_pieces (plain torch ops, CPU-tested in test_host_logic.py): identical bits, also for a zero row, rows
+    spanning ten decades and a width that needs K padding; unsupported widths fall back to the torch formulation."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    for K in (384, 896, 72, 1024 + 64):
+        mats = [torch.randn(1024, K, generator=g) * (10.0 ** (-10 * torch.rand(1024, 1, generator=g))) for _ in range(2)]
+        mats[1][5] = 0.0
+        dmats = [m.to(dev) for m in mats]
+        p, sc = ops.f16_pieces_stacked(dmats)
+        p_ref, sc_ref = ops.f16_pieces(torch.cat(dmats, dim=0))
+        assert p.shape == p_ref.shape and torch.equal(p.view(torch.int16), p_ref.view(torch.int16)), K
+        assert torch.equal(sc, sc_ref), K
+    odd = [torch.randn(8, 10, generator=g).to(dev)]
+    p, sc = ops.f16_pieces_stacked(odd)
+    p_ref, sc_ref = ops.f16_pieces(odd[0])
+    assert torch.equal(p.view(torch.int16), p_ref.view(torch.int16)) and torch.equal(sc, sc_ref)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # pyramidal windowed-attention segmenter (HF LongformerModel in the reference)
 # ----------------------------------------------------------------------------------------------------------
