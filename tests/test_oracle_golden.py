@@ -195,3 +195,34 @@ def test_pk_windowdiff_hand_cases():
                 assert wd == rn.Decimal(num) / den
             except AssertionError:
                 assert c_oracle.window_diff(h, r)[0] == -1
+
+
+def test_attention_dropout_keep_mask_restates_the_device_hash():
+    """oracle/ref_numpy.py:attn_dropout_keep against the hash written out with Python integers (the definition the device
+    function attn_keep_scale in csrc/common.cuh follows): splitmix64 finaliser of seed ^ (bh << 40 | i << 20 | j), top 24 bits
+    compared with round(p 2^24).  Plus the statistics a dropout mask needs."""
+    M = (1 << 64) - 1
+
+    def keep(seed, bh, i, j, p):
+        x = (seed ^ ((bh << 40) | (i << 20) | j)) & M
+        x ^= x >> 30
+        x = (x * 0xBF58476D1CE4E5B9) & M
+        x ^= x >> 27
+        x = (x * 0x94D049BB133111EB) & M
+        x ^= x >> 31
+        return (x >> 40) >= int(float(np.float32(p)) * 16777216.0 + 0.5)
+
+    seed, B, H, S, p = 0x1234_5678_9ABC_DEF0, 2, 3, 40, 0.25
+    got = rn.attn_dropout_keep(seed, B, H, S, p)
+    assert got.shape == (B, H, S, S) and got.dtype == bool
+    for b in range(B):
+        for h in range(H):
+            for i in (0, 7, 39):
+                for j in (0, 1, 38):
+                    assert bool(got[b, h, i, j]) == keep(seed, b * H + h, i, j, p), (b, h, i, j)
+    big = rn.attn_dropout_keep(seed, 2, 4, 256, 0.1)
+    assert abs((1.0 - big.mean()) - 0.1) < 3e-3
+    assert abs((1.0 - big[0, 0].mean()) - 0.1) < 1e-2 and abs((1.0 - big[:, :, 5].mean()) - 0.1) < 3e-2   # no head / row is special
+    other = rn.attn_dropout_keep(seed + 1, 2, 4, 256, 0.1)
+    assert 0.15 < (big != other).mean() < 0.21      # independent masks differ at 2 p (1 - p) = 0.18 of the positions
+    assert rn.attn_dropout_keep(seed, 1, 1, 16, 0.0).all()
