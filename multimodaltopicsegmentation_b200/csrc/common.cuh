@@ -38,6 +38,20 @@ void set_error(const char *msg);  // defined in abi.cu (thread-local message for
 
 constexpr int kNumSMs = 148;  // B200
 
+// Launch-site state that has to exist once per DEVICE: cudaFuncSetAttribute and the occupancy answers are per device, so a
+// process that drives several GPUs must configure each of them (the package's model is one process per GPU, where slot 0 of
+// these arrays is the only one used).  `MTS_PER_DEVICE(int, cap);` declares `cap` as a reference to the current device's slot
+// of a function-static, zero-initialised array.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+#define MTS_PER_DEVICE(type, name)                                  \
+  static type name##_per_device[::mts::kMaxDevices] = {};           \
+  type &name = name##_per_device[::mts::device_slot()]
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

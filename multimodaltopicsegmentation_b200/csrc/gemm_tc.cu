@@ -841,7 +841,7 @@ static int launch_tc(const float *A_hi, const float *A_lo, const float *B_hi, co
   if ((rc = make_map(&ma_lo, A_lo, M, Kp, TC_BM, true, 0, bf16_only == 2 ? 2 * Kp : 0))) return rc;
   if ((rc = make_map(&mb_hi, B_hi, N, Kp, bn / CL, bf16_only == 2, 0, bf16_only == 2 ? 2 * Kp : 0))) return rc;
   if ((rc = make_map(&mb_lo, B_lo, N, Kp, bn / CL, true, 0, bf16_only == 2 ? 2 * Kp : 0))) return rc;
-  static bool attr_set = false;
+  MTS_PER_DEVICE(bool, attr_set);
   if (!attr_set) {
     MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     MTS_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -337,7 +337,7 @@ extern "C" int mts_lstm_rec_bwd(const float *dy, const float *gates, const float
   cudaStream_t st = (cudaStream_t)stream;
   if (H == kH) {
     constexpr size_t smem1 = bwd_smem_bytes(1), smem2 = bwd_smem_bytes(2);
-    static int cap = 0;
+    MTS_PER_DEVICE(int, cap);
     if (!cap) {
       MTS_CUDA(cudaFuncSetAttribute(lstm_bwd_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       cap = max_active_clusters_bwd(lstm_bwd_cluster_kernel<1>, smem1);

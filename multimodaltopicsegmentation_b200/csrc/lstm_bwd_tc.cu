@@ -342,7 +342,7 @@ extern "C" int mts_lstm_rec_bwd_tf32(const float *dy, const float *gates, const 
   MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0, MTS_E_BADARG, "lstm_rec_bwd_tc: bad shape");
   MTS_REQUIRE(H == kH, MTS_E_UNSUPPORTED, "lstm_rec_bwd_tc: the tensor-core recurrence serves H == 256");
   cudaStream_t st = (cudaStream_t)stream;
-  static int cap = 0;
+  MTS_PER_DEVICE(int, cap);
   if (!cap) {
     MTS_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM));
     cudaLaunchConfig_t cfg = {};

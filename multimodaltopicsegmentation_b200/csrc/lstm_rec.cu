@@ -308,7 +308,7 @@ extern "C" int mts_lstm_rec_fwd(const float *gx, const float *w_hh, const int32_
   MTS_REQUIRE(n_enc >= 1 && B > 0 && T > 0 && H > 0, MTS_E_BADARG, "lstm_rec_fwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (H == kH) {
-    static int cap = 0;
+    MTS_PER_DEVICE(int, cap);
     if (!cap) cap = max_active_clusters(lstm_fwd_cluster_kernel<false, 1>);
     const int n_tiles = (B + kBT - 1) / kBT;
     const int items1 = n_tiles * 2 * n_enc;

@@ -455,7 +455,7 @@ extern "C" int mts_debug_rec_profile_h3(long long *buf) {
 template <bool BF16>
 static int launch_h3(const float *gx, const float *w_hh, const int32_t *lengths, const int32_t *order, int n_enc, int B, int T,
                      float *y, float *gates, float *y_corr, cudaStream_t st) {
-  static int cap = 0;
+  MTS_PER_DEVICE(int, cap);
   if (!cap) {
     MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_h3_kernel<false, 1, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, hr_smem<1>()));
     MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_h3_kernel<true, 1, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, hr_smem<1>()));

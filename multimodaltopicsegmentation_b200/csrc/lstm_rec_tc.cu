@@ -480,7 +480,7 @@ static int rec_fwd_tc(const float *gx, const float *w_hh, const int32_t *lengths
   MTS_REQUIRE((n_enc * 2 * kH) % 4 == 0 && (((uintptr_t)y | (uintptr_t)gx | (uintptr_t)w_hh) & 15) == 0, MTS_E_BADARG,
               "lstm_rec_fwd_tc: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  static int cap = 0;
+  MTS_PER_DEVICE(int, cap);
   if (!cap) {
     MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<1>()));
     MTS_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem<1>()));

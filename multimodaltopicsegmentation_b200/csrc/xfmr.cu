@@ -663,7 +663,7 @@ static int launch_band_mma(const float *qkv, int64_t ld, const int32_t *lengths,
                            int nheads, int w, float *out, float *out_hi, float *out_lo, int Kp, float *lse, cudaStream_t st) {
   constexpr int HD = NHD * 8;
   const size_t smem = sizeof(float) * 2 * BM_TK * (HD + 4);
-  static bool attr_set = false;
+  MTS_PER_DEVICE(bool, attr_set);
   if (!attr_set) {
     MTS_CUDA(cudaFuncSetAttribute(band_attn_fwd_mma_kernel<NHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -830,7 +830,7 @@ static int band_attn_fwd_simt_impl(const float *qkv, int64_t ld, const int32_t *
     band_attn_fwd_kernel<true><<<grid, BA_THREADS, smem, (cudaStream_t)stream>>>(
         qkv, ld, lengths, offsets, S, nheads, hd, w, out, out_hi, out_lo, Kp, lse, attn_drop_p24(p_drop), 1.0f / (1.0f - p_drop), seed);
   } else {
-    static size_t smem_set = 0;
+    MTS_PER_DEVICE(size_t, smem_set);
     if (smem > smem_set) {
       MTS_CUDA(cudaFuncSetAttribute(band_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set = smem;

@@ -528,7 +528,8 @@ static int band_attn_bwd_launch(const float *qkv, int64_t ld, const float *o, co
   const int RS = bb_row_stride(hd);
   const size_t smem_dq = sizeof(float) * ((size_t)(2 * BB_OWN + 2 * BB_TILE) * RS + BB_OWN * BB_PS + 2 * BB_OWN);
   const size_t smem_dkv = sizeof(float) * ((size_t)(2 * BB_OWN + 2 * BB_TILE) * RS + 2 * BB_OWN * BB_PS + 2 * BB_TILE);
-  static size_t set_dq = 0, set_dkv = 0;   // one pair per instantiation
+  MTS_PER_DEVICE(size_t, set_dq);   // one pair per instantiation and device
+  MTS_PER_DEVICE(size_t, set_dkv);
   if (smem_dq > set_dq) {
     MTS_CUDA(cudaFuncSetAttribute(band_attn_bwd_dq_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
     set_dq = smem_dq;
