@@ -375,3 +375,28 @@ def test_f16_pieces_weight_packing():
     assert float(rel.max()) < 2.0 ** -21
     assert float(pieces[:, :, 100:].abs().max()) == 0.0 and float(pieces[5].abs().max()) == 0.0
     assert torch.isfinite(pieces.float()).all()
+
+
+def test_weight_pieces_stacked_falls_back_to_the_host_formulation_off_device():
+    """ops.f16_pieces_stacked on matrices the packing kernel does not take (here: CPU tensors) is f16_pieces of their row-wise
+    concatenation -- the same bits the kernel path is held to on the GPU (test_f16_weight_pieces_kernel_equals_host_formulation)."""
+    from multimodaltopicsegmentation_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    mats = [torch.randn(12, 40, generator=g), torch.randn(20, 40, generator=g) * 1e-4]
+    p, sc = ops.f16_pieces_stacked(mats)
+    p_ref, sc_ref = ops.f16_pieces(torch.cat(mats, dim=0))
+    assert p.shape == (32, 2, 64) and torch.equal(p.view(torch.int16), p_ref.view(torch.int16)) and torch.equal(sc, sc_ref)
+    back = (p[:, 0, :40].double() + p[:, 1, :40].double()) * sc.double()[:, None]
+    assert float((back - torch.cat(mats).double()).abs().max() / torch.cat(mats).abs().max()) < 2 ** -21
+
+
+def test_attention_dropout_seeds_follow_the_torch_generator_or_the_hook(monkeypatch):
+    from multimodaltopicsegmentation_b200 import transformer
+
+    torch.manual_seed(123)
+    a = [transformer.attn_seed(l) for l in range(3)]
+    torch.manual_seed(123)
+    assert a == [transformer.attn_seed(l) for l in range(3)] and len(set(a)) == 3 and all(0 <= v < 2 ** 62 for v in a)
+    monkeypatch.setattr(transformer, "ATTN_SEED_FN", lambda layer: 40 + layer)
+    assert [transformer.attn_seed(l) for l in range(3)] == [40, 41, 42]
